@@ -1,0 +1,146 @@
+/* pasio_b200.h -- C ABI of the B200-native Pasio segmentation hot path.
+ *
+ * The reference (autosome-ru/pasio v1.1.3) is pure Python and has NO FFI of its own:
+ * its boundary for this path is three duck-typed Python protocols (reducer, splitter,
+ * scorer).  This header is the boundary a maintainer would bind instead
+ * (ctypes stub shown in INTEGRATION.md); every entry point names the reference code
+ * it replaces (paths under /root/reference/src/pasio/).
+ *
+ * Conventions: plain C symbols, plain pointers and sizes, no torch types.  Every
+ * function returns 0 on success or a negative pasio_status; pasio_last_error() gives
+ * the message.  All pointers are HOST pointers unless the name says `_device`; host
+ * buffers may be pageable or pinned (pinned is faster).  The caller owns every buffer.
+ * A context owns one CUDA stream and is not re-entrant.  No function falls back to
+ * the CPU: without a usable sm_100 device pasio_ctx_create fails.
+ */
+#ifndef PASIO_B200_H
+#define PASIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pasio_ctx pasio_ctx;
+
+typedef enum pasio_status {
+    PASIO_OK = 0,
+    PASIO_E_CUDA = -1,            /* CUDA runtime error (message has the detail)            */
+    PASIO_E_ARG = -2,             /* malformed argument                                     */
+    PASIO_E_COUNTS = -3,          /* negative count / empty contig   -> AssertionError
+                                     (log_marginal_likelyhood.py:30-34)                      */
+    PASIO_E_CANDIDATES = -4,      /* candidates not 0..n strictly ascending -> AssertionError
+                                     (log_marginal_likelyhood.py:36-40)                      */
+    PASIO_E_TABLE_TOO_SHORT = -5, /* a look-up table is shorter than the largest argument;
+                                     pasio_table_need() says how long they must be          */
+    PASIO_E_STATE = -6,           /* call out of order (no contig / no tables / ...)         */
+    PASIO_E_TOO_LARGE = -7,       /* contig >= 2^31-1 nt, total count >= 2^31, or window
+                                     larger than one CTA's shared memory                    */
+    PASIO_E_NOMEM = -8
+} pasio_status;
+
+/* Table ids for pasio_table_upload / pasio_table_need. */
+enum { PASIO_TAB_LOG = 0,          /* Lg[k] = log(k + beta)      cached_log.py:9  (LogComputer)            */
+       PASIO_TAB_LGAMMA = 1,       /* G[k]  = gammaln(k)         cached_log.py:36 (LogGammaComputer())     */
+       PASIO_TAB_LGAMMA_ALPHA = 2  /* Ga[k] = gammaln(k + alpha) cached_log.py:36 (shift=alpha)            */ };
+
+/* split_constraints of default_splitters.py:52-59 */
+enum { PASIO_CONSTRAINT_NONE = 0, PASIO_CONSTRAINT_ZEROS = 1, PASIO_CONSTRAINT_CONSTANTS = 2 };
+
+/* ---- context ------------------------------------------------------------------------ */
+int pasio_ctx_create(int device, pasio_ctx **out);
+int pasio_ctx_destroy(pasio_ctx *ctx);
+const char *pasio_last_error(const pasio_ctx *ctx);   /* never NULL; ctx may be NULL */
+int pasio_abi_version(void);
+
+/* ---- scorer parameters and tables ---------------------------------------------------
+ * Replaces ScorerFactory.__init__ (log_marginal_likelyhood.py:6-16) and the LogComputer /
+ * LogGammaComputer tables (cached_log.py:5-56).  The VALUES are produced on the host by
+ * the same numpy/scipy calls the reference makes, so they are bit-identical to what the
+ * reference would look up or compute; the device only gathers from them.
+ * alpha_is_int mirrors log_marginal_likelyhood.py:9-12,19.  segment_creation_cost is
+ * alpha*log(beta) - gammaln(alpha) (:62) evaluated by the host. */
+int pasio_set_params(pasio_ctx *ctx, int alpha_is_int, double alpha, double beta,
+                     double segment_creation_cost);
+int pasio_table_upload(pasio_ctx *ctx, int table_id, const double *values, int64_t n);
+/* After PASIO_E_TABLE_TOO_SHORT: minimum lengths (entries) the three tables need. */
+int pasio_table_need(const pasio_ctx *ctx, int64_t *n_log, int64_t *n_lgamma, int64_t *n_lgamma_alpha);
+
+/* ---- contig(s) ----------------------------------------------------------------------
+ * Replaces LogMarginalLikelyhoodComputer.__init__'s np.cumsum (log_marginal_likelyhood.py:57)
+ * and the change-point test of NotConstantReducer (constants_reducer.py:16-17), done once
+ * per contig instead of once per window.  counts: int64[n] >= 0.
+ * n_contigs > 1 loads a batch: contig c is counts[offsets[c] .. offsets[c+1]) and is
+ * segmented independently (process_bedgraph.py:69: one segments_with_scores per contig);
+ * offsets has n_contigs+1 entries, offsets[0]=0.  Pass offsets=NULL for one contig.
+ * Candidates are reset to "all positions" (segmentation.py:8). */
+int pasio_contig_load(pasio_ctx *ctx, const int64_t *counts, int64_t n,
+                      const int64_t *offsets, int64_t n_contigs);
+/* Same, from run-length intervals (the bedgraph form, process_bedgraph.py:46-60):
+ * run r covers [starts[r], starts[r+1]) with value values[r]; starts has n_runs+1 entries. */
+int pasio_contig_load_rle(pasio_ctx *ctx, const int64_t *starts, const int64_t *values,
+                          int64_t n_runs, const int64_t *offsets, int64_t n_contigs);
+int pasio_contig_info(const pasio_ctx *ctx, int64_t *n, int64_t *total_count, int64_t *n_contigs);
+/* cumsum[candidates] as the reference scorer exposes it (log_marginal_likelyhood.py:57). */
+int pasio_cumsum_at(pasio_ctx *ctx, const int64_t *positions, int64_t m, int64_t *out);
+
+/* ---- candidates ---------------------------------------------------------------------
+ * positions are in the concatenated coordinate space of the loaded batch (contig c starts
+ * at offsets[c]); contig boundaries are always candidates.  cands=NULL: all positions. */
+int pasio_candidates_set(pasio_ctx *ctx, const int64_t *cands, int64_t m);
+int pasio_candidates_count(const pasio_ctx *ctx, int64_t *m);
+int pasio_candidates_download(pasio_ctx *ctx, int64_t *out, int64_t capacity, int64_t *m);
+
+/* ---- one sliding-window round -------------------------------------------------------
+ * Replaces SlidingWindowReducer.reduce_candidate_list (sliding_window_reducer.py:21-29)
+ * with base reducer [NotConstantReducer|NotZeroReducer +] SquareSplitter
+ * (constants_reducer.py:5-21, square_splitter.py:67-109, dto/sliding_window.py:9-15):
+ * every window of the round is one DP, all windows run in one launch, survivors are
+ * united and compacted on the device.  Candidates stay device-resident.
+ * n_in / n_out: candidate counts before / after (round_reducer.py:21: the round loop's
+ * fixed-point test is n_in == n_out because the new list is a subset).
+ * cells: DP (i,j) cells evaluated in this round. */
+int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int constraint,
+                int64_t *n_in, int64_t *n_out, int64_t *cells);
+/* RoundReducer.reduce_candidate_list (round_reducer.py:10-31): rounds until fixed point or
+ * max_rounds (<=0: len(counts)).  Stops with PASIO_E_TABLE_TOO_SHORT when tables must grow
+ * (state is kept; call again after uploading longer tables).
+ * sizes (optional, capacity sizes_cap) receives the candidate count before each round run. */
+int pasio_rounds(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int constraint,
+                 int64_t max_rounds, int64_t *rounds_done, int64_t *n_out, int64_t *cells,
+                 int64_t *sizes, int64_t sizes_cap);
+
+/* ---- exact DP -----------------------------------------------------------------------
+ * Replaces SquareSplitter.split_without_normalizations + collect_split_points
+ * (square_splitter.py:67-109) over the CURRENT candidates of a single-contig context.
+ * out_splits (capacity cap) receives split positions; score = prefix_scores[-1].
+ * prefix_scores / previous_splits (optional, N entries each) expose the DP arrays. */
+int pasio_square_split(pasio_ctx *ctx, int64_t *out_splits, int64_t cap, int64_t *n_splits,
+                       double *score, double *prefix_scores, int64_t *previous_splits);
+/* LogMarginalLikelyhood*AlphaComputer.all_suffixes_self_score(stop)
+ * (log_marginal_likelyhood.py:105-115, :121-132) over the current candidates:
+ * out[0..stop). */
+int pasio_suffix_scores(pasio_ctx *ctx, int64_t stop, double *out);
+
+/* ---- per-segment outputs ------------------------------------------------------------
+ * Replaces scores(), mean_counts(), log_marginal_likelyhoods(), total_sum_logfac()
+ * (log_marginal_likelyhood.py:64-83) and NopSplitter.split (nop_splitter.py:15-18) over
+ * the CURRENT candidates taken as the final split points (m candidates -> m-1 segments;
+ * in a batch, the segment count is still m-1 because boundaries are shared).
+ * Any output pointer may be NULL.  logfac_cumsum has m entries. */
+int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *segment_counts,
+                         double *mean_counts, double *logfac_cumsum, int64_t capacity,
+                         int64_t *n_segments);
+
+/* ---- measurement hooks (bench.py / profiles) ------------------------------------------
+ * Device time (ms, CUDA events on the context's stream) and launch count accumulated per
+ * kernel family since the last reset: 0 scan, 1 window DP, 2 compaction+prepass,
+ * 3 exact DP, 4 scoring, 5 H2D, 6 D2H. */
+int pasio_timing_reset(pasio_ctx *ctx, int enable);
+int pasio_timing_get(pasio_ctx *ctx, int family, double *ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASIO_B200_H */

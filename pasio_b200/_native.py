@@ -1,0 +1,342 @@
+"""ctypes binding of libpasio_b200.so (include/pasio_b200.h) and the per-process Engine.
+
+The library is built in-tree (pasio_b200/libpasio_b200.so) by `__graft_entry__.build()` or
+`make -C pasio_b200/csrc`.  There is NO CPU fallback: if the library is missing, or no
+sm_100 device is visible, every LogML code path raises RuntimeError.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpasio_b200.so')
+
+OK = 0
+E_CUDA, E_ARG, E_COUNTS, E_CANDIDATES, E_TABLE_TOO_SHORT, E_STATE, E_TOO_LARGE, E_NOMEM = range(-1, -9, -1)
+TAB_LOG, TAB_LGAMMA, TAB_LGAMMA_ALPHA = 0, 1, 2
+CONSTRAINTS = {'none': 0, 'zeros': 1, 'constants': 2}
+TIMING_FAMILIES = ['scan', 'window_dp', 'compact', 'exact_dp', 'score', 'h2d', 'd2h']
+
+_i64 = ctypes.c_int64
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/pasio_b200.h declares
+SIGNATURES = {
+    'pasio_ctx_create': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    'pasio_ctx_destroy': (ctypes.c_int, [_vp]),
+    'pasio_last_error': (ctypes.c_char_p, [_vp]),
+    'pasio_abi_version': (ctypes.c_int, []),
+    'pasio_set_params': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    'pasio_table_upload': (ctypes.c_int, [_vp, ctypes.c_int, _f64p, _i64]),
+    'pasio_table_need': (ctypes.c_int, [_vp, _i64p, _i64p, _i64p]),
+    'pasio_contig_load': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _i64]),
+    'pasio_contig_load_rle': (ctypes.c_int, [_vp, _i64p, _i64p, _i64, _i64p, _i64]),
+    'pasio_contig_info': (ctypes.c_int, [_vp, _i64p, _i64p, _i64p]),
+    'pasio_cumsum_at': (ctypes.c_int, [_vp, _i64p, _i64, _i64p]),
+    'pasio_candidates_set': (ctypes.c_int, [_vp, _i64p, _i64]),
+    'pasio_candidates_count': (ctypes.c_int, [_vp, _i64p]),
+    'pasio_candidates_download': (ctypes.c_int, [_vp, _i64p, _i64, _i64p]),
+    'pasio_round': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64p, _i64p, _i64p]),
+    'pasio_rounds': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64, _i64p, _i64p, _i64p, _i64p, _i64]),
+    'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
+    'pasio_suffix_scores': (ctypes.c_int, [_vp, _i64, _f64p]),
+    'pasio_segment_scores': (ctypes.c_int, [_vp, _f64p, _i64p, _f64p, _f64p, _i64, _i64p]),
+    'pasio_timing_reset': (ctypes.c_int, [_vp, ctypes.c_int]),
+    'pasio_timing_get': (ctypes.c_int, [_vp, ctypes.c_int, _f64p, _i64p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the in-tree shared library and set every prototype.  Raises RuntimeError if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError('pasio_b200: %s is missing -- build it with `python -c "import __graft_entry__ as g; '
+                                   'g.build()"` or `make -C pasio_b200/csrc`; there is no CPU fallback' % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _ptr(arr, ct):
+    return arr.ctypes.data_as(ctypes.POINTER(ct))
+
+
+class PasioDeviceError(RuntimeError):
+    pass
+
+
+class Engine(object):
+    """One CUDA context + stream of this process: tables, one loaded contig batch, candidates."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        handle = _vp()
+        rc = self.lib.pasio_ctx_create(int(device), ctypes.byref(handle))
+        if rc != OK:
+            raise PasioDeviceError('pasio_b200: cannot create a device context (%s); the LogML path has no CPU '
+                                   'fallback' % self.lib.pasio_last_error(None).decode())
+        self.ctx = handle
+        self.device = device
+        self._params = None          # (alpha_is_int, alpha, beta, pen)
+        self._tables = {}            # table id -> (computer object, uploaded length)
+        self._scorer_source = None   # object providing the three computers
+        self._loaded = None          # strong ref to the loaded counts array (identity cache)
+        self._loaded_offsets = None
+        self._cands_obj = None       # array object the device candidates correspond to (identity cache)
+
+    def close(self):
+        if self.ctx:
+            self.lib.pasio_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    # -- errors ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc == OK:
+            return
+        msg = self.lib.pasio_last_error(self.ctx).decode()
+        if rc in (E_COUNTS, E_CANDIDATES):
+            raise AssertionError(msg)         # the reference asserts (log_marginal_likelyhood.py:30-40)
+        if rc == E_ARG:
+            raise ValueError(msg)
+        if rc == E_NOMEM:
+            raise MemoryError(msg)
+        raise PasioDeviceError('pasio_b200 error %d: %s' % (rc, msg))
+
+    # -- scorer parameters and tables --------------------------------------------------------
+    def use_scorer(self, source):
+        """source has .alpha (int or float), .beta, .log_computer, .log_gamma_computer,
+        .log_gamma_alpha_computer, .segment_creation_cost (ScorerFactory or a scorer)."""
+        alpha = source.alpha
+        is_int = isinstance(alpha, (int, np.integer)) and not isinstance(alpha, bool)
+        params = (int(is_int), float(alpha), float(source.log_computer.shift), float(source.segment_creation_cost))
+        if params != self._params:
+            self._check(self.lib.pasio_set_params(self.ctx, *params))
+            self._params = params
+        comps = {TAB_LOG: source.log_computer, TAB_LGAMMA: source.log_gamma_computer,
+                 TAB_LGAMMA_ALPHA: source.log_gamma_alpha_computer}
+        for tid, comp in comps.items():
+            have = self._tables.get(tid)
+            if have is None or have[0] is not comp:
+                self._upload_table(tid, comp, comp.cache_size)
+        self._scorer_source = source
+
+    def _upload_table(self, tid, comp, n):
+        tab = comp.table(n)
+        self._check(self.lib.pasio_table_upload(self.ctx, tid, _ptr(tab, ctypes.c_double), len(tab)))
+        self._tables[tid] = (comp, len(tab))
+
+    def _grow_tables(self):
+        need = [_i64(0), _i64(0), _i64(0)]
+        self._check(self.lib.pasio_table_need(self.ctx, *[ctypes.byref(x) for x in need]))
+        for tid in (TAB_LOG, TAB_LGAMMA, TAB_LGAMMA_ALPHA):
+            comp, have = self._tables[tid]
+            if need[tid].value > have:
+                self._upload_table(tid, comp, max(need[tid].value, int(have * 1.5)))
+
+    def _retry(self, fn):
+        """Call fn() until it stops asking for longer tables."""
+        while True:
+            rc = fn()
+            if rc != E_TABLE_TOO_SHORT:
+                self._check(rc)
+                return
+            self._grow_tables()
+
+    # -- contig ------------------------------------------------------------------------------
+    def load(self, counts, offsets=None):
+        """H2D + prefix scan + change-point bitmap; cached by array identity."""
+        if self._loaded is counts and offsets is None and self._loaded_offsets is None:
+            return
+        assert isinstance(counts, np.ndarray)
+        assert counts.dtype == int
+        assert len(counts) > 0
+        c = np.ascontiguousarray(counts)
+        self._loaded = None
+        self._cands_obj = None
+        if offsets is None:
+            rc = self.lib.pasio_contig_load(self.ctx, _ptr(c, ctypes.c_int64), len(c), None, 1)
+        else:
+            off = np.ascontiguousarray(offsets, dtype=np.int64)
+            rc = self.lib.pasio_contig_load(self.ctx, _ptr(c, ctypes.c_int64), len(c), _ptr(off, ctypes.c_int64),
+                                            len(off) - 1)
+        self._check(rc)
+        self._loaded = counts
+        self._loaded_offsets = None if offsets is None else np.array(offsets, dtype=np.int64)
+
+    def load_rle(self, starts, values, offsets=None):
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        values = np.ascontiguousarray(values, dtype=np.int64)
+        self._loaded = None
+        self._cands_obj = None
+        if offsets is None:
+            rc = self.lib.pasio_contig_load_rle(self.ctx, _ptr(starts, ctypes.c_int64), _ptr(values, ctypes.c_int64),
+                                                len(values), None, 1)
+        else:
+            off = np.ascontiguousarray(offsets, dtype=np.int64)
+            rc = self.lib.pasio_contig_load_rle(self.ctx, _ptr(starts, ctypes.c_int64), _ptr(values, ctypes.c_int64),
+                                                len(values), _ptr(off, ctypes.c_int64), len(off) - 1)
+        self._check(rc)
+        self._loaded = object()      # no host array corresponds to this load
+        self._loaded_offsets = None if offsets is None else np.array(offsets, dtype=np.int64)
+
+    def info(self):
+        n, total, k = _i64(0), _i64(0), _i64(0)
+        self._check(self.lib.pasio_contig_info(self.ctx, ctypes.byref(n), ctypes.byref(total), ctypes.byref(k)))
+        return n.value, total.value, k.value
+
+    # -- candidates --------------------------------------------------------------------------
+    def set_candidates(self, cands):
+        """cands: None (all positions) or an int64 array; cached by array identity."""
+        if cands is None:
+            self._check(self.lib.pasio_candidates_set(self.ctx, None, 0))
+            self._cands_obj = None
+            return
+        if self._cands_obj is cands:
+            return
+        c = np.ascontiguousarray(cands, dtype=np.int64)
+        self._cands_obj = None
+        self._check(self.lib.pasio_candidates_set(self.ctx, _ptr(c, ctypes.c_int64), len(c)))
+        self._cands_obj = cands
+
+    def candidates(self):
+        m = _i64(0)
+        self._check(self.lib.pasio_candidates_count(self.ctx, ctypes.byref(m)))
+        out = np.empty(m.value, dtype=np.int64)
+        self._check(self.lib.pasio_candidates_download(self.ctx, _ptr(out, ctypes.c_int64), len(out), None))
+        self._cands_obj = out
+        return out
+
+    def candidate_count(self):
+        m = _i64(0)
+        self._check(self.lib.pasio_candidates_count(self.ctx, ctypes.byref(m)))
+        return m.value
+
+    # -- kernels -----------------------------------------------------------------------------
+    def round(self, window_size, window_shift, constraint):
+        n_in, n_out, cells = _i64(0), _i64(0), _i64(0)
+        self._cands_obj = None
+        self._retry(lambda: self.lib.pasio_round(self.ctx, window_size, window_shift, CONSTRAINTS[constraint],
+                                                 ctypes.byref(n_in), ctypes.byref(n_out), ctypes.byref(cells)))
+        return n_in.value, n_out.value, cells.value
+
+    def rounds(self, window_size, window_shift, constraint, num_rounds=None):
+        """RoundReducer loop on the device.  Returns (sizes before each round run, final count, cells)."""
+        n, _, _ = self.info()
+        limit = max(1, n if num_rounds is None else num_rounds)   # round_reducer.py:11-15
+        self._cands_obj = None
+        sizes, cells_total = [], 0
+        while limit > 0:
+            done, n_out, cells = _i64(0), _i64(0), _i64(0)
+            buf = np.zeros(64, dtype=np.int64)
+            step = min(limit, 64)
+            rc = self.lib.pasio_rounds(self.ctx, window_size, window_shift, CONSTRAINTS[constraint], step,
+                                       ctypes.byref(done), ctypes.byref(n_out), ctypes.byref(cells),
+                                       _ptr(buf, ctypes.c_int64), len(buf))
+            sizes.extend(buf[:done.value].tolist())
+            cells_total += cells.value
+            limit -= done.value
+            if rc == E_TABLE_TOO_SHORT:
+                self._grow_tables()
+                continue
+            self._check(rc)
+            if done.value < step or (done.value > 0 and sizes[-1] == n_out.value):
+                break       # fixed point reached inside the library
+        return sizes, self.candidate_count(), cells_total
+
+    def square_split(self, want_arrays=False):
+        """Exact DP over the current candidates; they are replaced by the splits."""
+        m = self.candidate_count()
+        splits = np.empty(m, dtype=np.int64)
+        n_splits, score = _i64(0), ctypes.c_double(0.0)
+        P = np.empty(m) if want_arrays else None
+        prev = np.empty(m, dtype=np.int64) if want_arrays else None
+        self._cands_obj = None
+        self._retry(lambda: self.lib.pasio_square_split(
+            self.ctx, _ptr(splits, ctypes.c_int64), m, ctypes.byref(n_splits), ctypes.byref(score),
+            _ptr(P, ctypes.c_double) if want_arrays else None,
+            _ptr(prev, ctypes.c_int64) if want_arrays else None))
+        out = splits[:n_splits.value].copy()
+        self._cands_obj = out
+        if want_arrays:
+            return np.float64(score.value), out, P, prev
+        return np.float64(score.value), out
+
+    def suffix_scores(self, stop):
+        out = np.empty(stop)
+        if stop > 0:
+            self._retry(lambda: self.lib.pasio_suffix_scores(self.ctx, stop, _ptr(out, ctypes.c_double)))
+        return out
+
+    def cumsum_at_candidates(self):
+        m = self.candidate_count()
+        out = np.empty(m, dtype=np.int64)
+        self._check(self.lib.pasio_cumsum_at(self.ctx, None, m, _ptr(out, ctypes.c_int64)))
+        return out
+
+    def segment_scores(self, scores=True, counts=False, means=False, logfac=False):
+        m = self.candidate_count()
+        nseg = m - 1
+        s = np.empty(nseg) if scores else None
+        c = np.empty(nseg, dtype=np.int64) if counts else None
+        mu = np.empty(nseg) if means else None
+        lf = np.empty(m) if logfac else None
+        nout = _i64(0)
+        self._retry(lambda: self.lib.pasio_segment_scores(
+            self.ctx, _ptr(s, ctypes.c_double) if scores else None, _ptr(c, ctypes.c_int64) if counts else None,
+            _ptr(mu, ctypes.c_double) if means else None, _ptr(lf, ctypes.c_double) if logfac else None,
+            max(nseg, m if logfac else 0), ctypes.byref(nout)))
+        return s, c, mu, lf
+
+    # -- timing ------------------------------------------------------------------------------
+    def timing_reset(self, enable=True):
+        self._check(self.lib.pasio_timing_reset(self.ctx, int(enable)))
+
+    def timing(self):
+        out = {}
+        for k, name in enumerate(TIMING_FAMILIES):
+            ms, n = ctypes.c_double(0), _i64(0)
+            self._check(self.lib.pasio_timing_get(self.ctx, k, ctypes.byref(ms), ctypes.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
+
+_engine = None
+_engine_lock = threading.Lock()
+
+
+def default_device():
+    if 'PASIO_B200_DEVICE' in os.environ:
+        return int(os.environ['PASIO_B200_DEVICE'])
+    if 'LOCAL_RANK' in os.environ:
+        return int(os.environ['LOCAL_RANK'])
+    return 0
+
+
+def engine():
+    """The process-wide Engine (one process per GPU).  Raises if there is no usable device."""
+    global _engine
+    with _engine_lock:
+        if _engine is None:
+            _engine = Engine(default_device())
+    return _engine
+
+
+def reset_engine():
+    global _engine
+    with _engine_lock:
+        if _engine is not None:
+            _engine.close()
+        _engine = None

@@ -1,0 +1,622 @@
+// C-ABI entry points of libpasio_b200.so (declared in include/pasio_b200.h).
+// Host-side orchestration only: buffer management, table bookkeeping, the per-round loop.
+// All arithmetic of the hot path happens in the kernels; nothing here computes on the CPU.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+// ---- small infrastructure ---------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+int pasio_fail(pasio_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+int pasio_reserve(pasio_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.bytes && b.p) return PASIO_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return pasio_fail(ctx, PASIO_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return PASIO_OK;
+}
+
+static cudaEvent_t take_event(pasio_ctx *ctx)
+{
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+TimingScope::TimingScope(pasio_ctx *c, int family, i64 launches) : ctx(c), idx(-1)
+{
+    ctx->fam_launches[family] += launches;
+    if (!ctx->timing) return;
+    TimedSpan s;
+    s.family = family;
+    s.a = take_event(ctx);
+    s.b = take_event(ctx);
+    cudaEventRecord(s.a, ctx->stream);
+    ctx->spans.push_back(s);
+    idx = (int)ctx->spans.size() - 1;
+}
+TimingScope::~TimingScope()
+{
+    if (idx >= 0) cudaEventRecord(ctx->spans[idx].b, ctx->stream);
+}
+
+static int resolve_spans(pasio_ctx *ctx)
+{
+    if (ctx->spans.empty()) return PASIO_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &s : ctx->spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        ctx->fam_ms[s.family] += ms;
+        ctx->event_pool.push_back(s.a);
+        ctx->event_pool.push_back(s.b);
+    }
+    ctx->spans.clear();
+    return PASIO_OK;
+}
+
+static int h2d(pasio_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    TimingScope ts(ctx, TF_H2D);
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PASIO_OK;
+}
+static int d2h(pasio_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    {
+        TimingScope ts(ctx, TF_D2H);
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PASIO_OK;
+}
+
+#define NEED_CTX(ctx) do { if (!(ctx)) return PASIO_E_ARG; cudaSetDevice((ctx)->device); } while (0)
+
+// ---- context ------------------------------------------------------------------------------------
+extern "C" int pasio_abi_version(void) { return PASIO_ABI_VERSION; }
+
+extern "C" const char *pasio_last_error(const pasio_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
+{
+    if (!out) return pasio_fail(nullptr, PASIO_E_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return pasio_fail(nullptr, PASIO_E_CUDA, "no CUDA device: %s (pasio_b200 has no CPU fallback)",
+                          e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return pasio_fail(nullptr, PASIO_E_ARG, "device %d out of range (have %d)", device, count);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return pasio_fail(nullptr, PASIO_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return pasio_fail(nullptr, PASIO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                          device, prop.major, prop.minor);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return pasio_fail(nullptr, PASIO_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    pasio_ctx *ctx = new pasio_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void **)&ctx->h_scalars, 16 * sizeof(i64)) != cudaSuccess ||
+        pasio_reserve(ctx, ctx->scalars, 16 * sizeof(i64)) != PASIO_OK) {
+        g_create_error = "context allocation failed: " + ctx->err;
+        delete ctx;
+        return PASIO_E_CUDA;
+    }
+    memset(ctx->h_scalars, 0, 16 * sizeof(i64));
+    *out = ctx;
+    return PASIO_OK;
+}
+
+extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
+{
+    if (!ctx) return PASIO_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->tab[0], &ctx->tab[1], &ctx->tab[2], &ctx->counts, &ctx->cg, &ctx->cpbits, &ctx->keepbits,
+                      &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en,
+                      &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
+                      &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PASIO_OK;
+}
+
+// ---- parameters and tables ----------------------------------------------------------------------
+extern "C" int pasio_set_params(pasio_ctx *ctx, int alpha_is_int, double alpha, double beta, double pen)
+{
+    NEED_CTX(ctx);
+    if (!(alpha >= 0) || !(beta >= 0)) return pasio_fail(ctx, PASIO_E_ARG, "alpha and beta must be >= 0");
+    if (alpha_is_int && (alpha != (double)(i64)alpha || alpha > 1e9))
+        return pasio_fail(ctx, PASIO_E_ARG, "alpha_is_int set but alpha=%g is not a small integer", alpha);
+    ctx->alpha_is_int = alpha_is_int ? 1 : 0;
+    ctx->alpha = alpha;
+    ctx->alpha_int = alpha_is_int ? (i64)alpha : 0;
+    ctx->beta = beta;
+    ctx->pen = pen;
+    ctx->have_params = true;
+    return PASIO_OK;
+}
+
+extern "C" int pasio_table_upload(pasio_ctx *ctx, int id, const double *values, int64_t n)
+{
+    NEED_CTX(ctx);
+    if (id < 0 || id > 2 || !values || n < 1) return pasio_fail(ctx, PASIO_E_ARG, "bad table upload (id=%d n=%lld)", id, (long long)n);
+    PASIO_TRY(pasio_reserve(ctx, ctx->tab[id], (size_t)n * 8));
+    PASIO_TRY(h2d(ctx, ctx->tab[id].p, values, (size_t)n * 8));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ntab[id] = n;
+    return PASIO_OK;
+}
+
+extern "C" int pasio_table_need(const pasio_ctx *ctx, int64_t *n_log, int64_t *n_lgamma, int64_t *n_lgamma_alpha)
+{
+    if (!ctx) return PASIO_E_ARG;
+    if (n_log) *n_log = ctx->need[PASIO_TAB_LOG];
+    if (n_lgamma) *n_lgamma = ctx->need[PASIO_TAB_LGAMMA];
+    if (n_lgamma_alpha) *n_lgamma_alpha = ctx->need[PASIO_TAB_LGAMMA_ALPHA];
+    return PASIO_OK;
+}
+
+// DP tables must cover span (log) and count (+alpha for integer alpha)
+static int check_dp_tables(pasio_ctx *ctx, i64 max_span, i64 max_cnt)
+{
+    if (!ctx->have_params) return pasio_fail(ctx, PASIO_E_STATE, "pasio_set_params has not been called");
+    if (max_cnt + ctx->alpha_int >= 2147483647LL)
+        return pasio_fail(ctx, PASIO_E_TOO_LARGE, "count %lld does not fit the 32-bit DP index", (long long)max_cnt);
+    const i64 need_log = max_span + 1;
+    const int gid = ctx->alpha_is_int ? PASIO_TAB_LGAMMA : PASIO_TAB_LGAMMA_ALPHA;
+    const i64 need_g = max_cnt + ctx->alpha_int + 1;
+    bool bad = false;
+    if (ctx->ntab[PASIO_TAB_LOG] < need_log) { ctx->need[PASIO_TAB_LOG] = need_log; bad = true; }
+    if (ctx->ntab[gid] < need_g) { ctx->need[gid] = need_g; bad = true; }
+    if (bad)
+        return pasio_fail(ctx, PASIO_E_TABLE_TOO_SHORT, "tables too short: need log>=%lld, lgamma[%d]>=%lld (have %lld, %lld)",
+                          (long long)need_log, gid, (long long)need_g, (long long)ctx->ntab[PASIO_TAB_LOG],
+                          (long long)ctx->ntab[gid]);
+    return PASIO_OK;
+}
+
+// ---- contig -------------------------------------------------------------------------------------
+static int finish_load(pasio_ctx *ctx, const int64_t *offsets, int64_t n_contigs)
+{
+    const i64 n = ctx->n;
+    ctx->h_bounds.resize((size_t)n_contigs + 1);
+    if (offsets) {
+        for (i64 c = 0; c <= n_contigs; ++c) {
+            if (offsets[c] < 0 || offsets[c] > n || (c > 0 && offsets[c] <= offsets[c - 1]))
+                return pasio_fail(ctx, PASIO_E_ARG, "contig offsets must be strictly ascending within [0, n] (empty contigs are not allowed)");
+            ctx->h_bounds[(size_t)c] = (int32_t)offsets[c];
+        }
+        if (offsets[0] != 0 || offsets[n_contigs] != n)
+            return pasio_fail(ctx, PASIO_E_ARG, "offsets[0] must be 0 and offsets[n_contigs] must be n");
+    } else {
+        ctx->h_bounds[0] = 0;
+        ctx->h_bounds[1] = (int32_t)n;
+    }
+    ctx->n_contigs = n_contigs;
+    const size_t bit_bytes = (size_t)((n + 1 + 31) / 32 + 2) * 4;
+    PASIO_TRY(pasio_reserve(ctx, ctx->cg, (size_t)(n + 1) * 8));
+    PASIO_TRY(pasio_reserve(ctx, ctx->cpbits, bit_bytes));
+    PASIO_TRY(pasio_reserve(ctx, ctx->keepbits, bit_bytes));
+    PASIO_TRY(pasio_reserve(ctx, ctx->bounds, (size_t)(n_contigs + 1) * 4));
+    PASIO_TRY(pasio_reserve(ctx, ctx->brank, (size_t)(n_contigs + 1) * 4));
+    PASIO_TRY(h2d(ctx, ctx->bounds.p, ctx->h_bounds.data(), (size_t)(n_contigs + 1) * 4));
+    PASIO_TRY(launch_scan_counts(ctx));
+    PASIO_TRY(d2h(ctx, ctx->h_scalars, ctx->scalars.p, 2 * sizeof(i64)));
+    if (ctx->h_scalars[1]) return pasio_fail(ctx, PASIO_E_COUNTS, "counts must be >= 0");
+    ctx->total = ctx->h_scalars[0];
+    ctx->have_contig = true;
+    ctx->implicit_all = true;
+    ctx->m = n + 1;
+    ctx->cur = 0;
+    PASIO_TRY(launch_boundary_ranks(ctx));
+    ctx->h_brank = ctx->h_bounds;
+    return PASIO_OK;
+}
+
+static int check_load_args(pasio_ctx *ctx, int64_t n, const int64_t *offsets, int64_t n_contigs)
+{
+    ctx->have_contig = false;
+    if (n < 1) return pasio_fail(ctx, PASIO_E_COUNTS, "contig is empty");            // len(counts) > 0
+    if (n > 2147483645LL) return pasio_fail(ctx, PASIO_E_TOO_LARGE, "contig of %lld nt exceeds 2^31-3", (long long)n);
+    if (n_contigs < 1 || (n_contigs > 1 && !offsets)) return pasio_fail(ctx, PASIO_E_ARG, "bad n_contigs/offsets");
+    return PASIO_OK;
+}
+
+extern "C" int pasio_contig_load(pasio_ctx *ctx, const int64_t *counts, int64_t n, const int64_t *offsets,
+                                 int64_t n_contigs)
+{
+    NEED_CTX(ctx);
+    if (!counts) return pasio_fail(ctx, PASIO_E_ARG, "counts is NULL");
+    PASIO_TRY(check_load_args(ctx, n, offsets, n_contigs));
+    ctx->n = n;
+    PASIO_TRY(pasio_reserve(ctx, ctx->counts, (size_t)n * 8 + 16));
+    PASIO_TRY(h2d(ctx, ctx->counts.p, counts, (size_t)n * 8));
+    return finish_load(ctx, offsets, n_contigs);
+}
+
+extern "C" int pasio_contig_load_rle(pasio_ctx *ctx, const int64_t *starts, const int64_t *values, int64_t n_runs,
+                                     const int64_t *offsets, int64_t n_contigs)
+{
+    NEED_CTX(ctx);
+    if (!starts || !values || n_runs < 1) return pasio_fail(ctx, PASIO_E_ARG, "bad run-length input");
+    if (starts[0] != 0) return pasio_fail(ctx, PASIO_E_ARG, "starts[0] must be 0");
+    const i64 n = starts[n_runs];
+    PASIO_TRY(check_load_args(ctx, n, offsets, n_contigs));
+    ctx->n = n;
+    PASIO_TRY(pasio_reserve(ctx, ctx->counts, (size_t)n * 8 + 16));
+    // stage the runs in scratch buffers (dpP / dpJump are free while a contig is being loaded)
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)(n_runs + 1) * 8));
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpJump, (size_t)n_runs * 8));
+    PASIO_TRY(h2d(ctx, ctx->dpP.p, starts, (size_t)(n_runs + 1) * 8));
+    PASIO_TRY(h2d(ctx, ctx->dpJump.p, values, (size_t)n_runs * 8));
+    PASIO_TRY(launch_expand_rle(ctx, ctx->dpP.as<i64>(), ctx->dpJump.as<i64>(), n_runs));
+    return finish_load(ctx, offsets, n_contigs);
+}
+
+extern "C" int pasio_contig_info(const pasio_ctx *ctx, int64_t *n, int64_t *total_count, int64_t *n_contigs)
+{
+    if (!ctx || !ctx->have_contig) return PASIO_E_STATE;
+    if (n) *n = ctx->n;
+    if (total_count) *total_count = ctx->total;
+    if (n_contigs) *n_contigs = ctx->n_contigs;
+    return PASIO_OK;
+}
+
+extern "C" int pasio_cumsum_at(pasio_ctx *ctx, const int64_t *positions, int64_t m, int64_t *out)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (m < 0 || !out) return pasio_fail(ctx, PASIO_E_ARG, "bad arguments");
+    if (m == 0) return PASIO_OK;
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)m * 8));
+    if (positions) {
+        for (i64 k = 0; k < m; ++k)
+            if (positions[k] < 0 || positions[k] > ctx->n) return pasio_fail(ctx, PASIO_E_ARG, "position out of range");
+        PASIO_TRY(pasio_reserve(ctx, ctx->dpJump, (size_t)m * 8));
+        PASIO_TRY(h2d(ctx, ctx->dpJump.p, positions, (size_t)m * 8));
+        PASIO_TRY(launch_gather_i64(ctx, ctx->cg.as<i64>(), nullptr, ctx->dpJump.as<i64>(), m, ctx->dpP.as<i64>()));
+    } else {   // at the current candidates
+        if (m != ctx->m) return pasio_fail(ctx, PASIO_E_ARG, "m must equal the candidate count");
+        PASIO_TRY(launch_gather_i64(ctx, ctx->cg.as<i64>(), cur_cand(ctx), nullptr, m, ctx->dpP.as<i64>()));
+    }
+    return d2h(ctx, out, ctx->dpP.p, (size_t)m * 8);
+}
+
+// ---- candidates ---------------------------------------------------------------------------------
+__global__ void narrow_candidates_kernel(const i64 *__restrict__ in, i64 m, i64 n, int32_t *__restrict__ out, i64 *bad)
+{
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (i64)gridDim.x * blockDim.x) {
+        i64 v = in[k];
+        if (v < 0 || v > n) { *bad = 1; v = 0; }
+        out[k] = (int32_t)v;
+    }
+}
+
+static int refresh_boundary_ranks(pasio_ctx *ctx)
+{
+    PASIO_TRY(launch_boundary_ranks(ctx));
+    if (ctx->n_contigs > 1) {
+        ctx->h_brank.resize((size_t)ctx->n_contigs + 1);
+        PASIO_TRY(d2h(ctx, ctx->h_brank.data(), ctx->brank.p, (size_t)(ctx->n_contigs + 1) * 4));
+    }
+    return PASIO_OK;
+}
+
+extern "C" int pasio_candidates_set(pasio_ctx *ctx, const int64_t *cands, int64_t m)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (!cands) {
+        ctx->implicit_all = true;
+        ctx->m = ctx->n + 1;
+        return refresh_boundary_ranks(ctx);
+    }
+    if (m < 2 || m > ctx->n + 1) return pasio_fail(ctx, PASIO_E_CANDIDATES, "need 2 <= len(candidates) <= n+1");
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpJump, (size_t)m * 8));
+    PASIO_TRY(pasio_reserve(ctx, ctx->cand[ctx->cur], (size_t)m * 4));
+    PASIO_TRY(h2d(ctx, ctx->dpJump.p, cands, (size_t)m * 8));
+    i64 *d_bad = ctx->scalars.as<i64>() + 5;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, 8, ctx->stream));
+    narrow_candidates_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->dpJump.as<i64>(), m, ctx->n,
+                                                                        ctx->cand[ctx->cur].as<int32_t>(), d_bad);
+    CUDA_TRY(ctx, cudaGetLastError());
+    PASIO_TRY(d2h(ctx, ctx->h_scalars + 5, d_bad, 8));
+    if (ctx->h_scalars[5]) { ctx->implicit_all = true; ctx->m = ctx->n + 1; return pasio_fail(ctx, PASIO_E_CANDIDATES, "candidate out of range"); }
+    ctx->implicit_all = false;
+    ctx->m = m;
+    PASIO_TRY(refresh_boundary_ranks(ctx));
+    i64 bad = 0;
+    PASIO_TRY(launch_validate_candidates(ctx, &bad));
+    if (bad) {
+        ctx->implicit_all = true;
+        ctx->m = ctx->n + 1;
+        refresh_boundary_ranks(ctx);
+        return pasio_fail(ctx, PASIO_E_CANDIDATES,
+                          "candidates must start at 0, end at len(counts), ascend strictly and contain every contig boundary");
+    }
+    return PASIO_OK;
+}
+
+extern "C" int pasio_candidates_count(const pasio_ctx *ctx, int64_t *m)
+{
+    if (!ctx || !ctx->have_contig || !m) return PASIO_E_STATE;
+    *m = ctx->m;
+    return PASIO_OK;
+}
+
+__global__ void widen_candidates_kernel(const int32_t *__restrict__ in, i64 m, i64 *__restrict__ out)
+{
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (i64)gridDim.x * blockDim.x)
+        out[k] = in ? (i64)in[k] : k;
+}
+
+extern "C" int pasio_candidates_download(pasio_ctx *ctx, int64_t *out, int64_t capacity, int64_t *m)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (m) *m = ctx->m;
+    if (!out) return PASIO_OK;
+    if (capacity < ctx->m) return pasio_fail(ctx, PASIO_E_ARG, "capacity %lld < %lld candidates", (long long)capacity, (long long)ctx->m);
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpJump, (size_t)ctx->m * 8));
+    widen_candidates_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(cur_cand(ctx), ctx->m, ctx->dpJump.as<i64>());
+    CUDA_TRY(ctx, cudaGetLastError());
+    return d2h(ctx, out, ctx->dpJump.p, (size_t)ctx->m * 8);
+}
+
+// ---- rounds -------------------------------------------------------------------------------------
+// Window table of a batch: windows are generated per contig over that contig's slice of the
+// candidate list (dto/sliding_window.py:9-15 applied per contig).
+static int build_window_table(pasio_ctx *ctx, i64 wsize, i64 wshift, i64 *nwin_out)
+{
+    if (ctx->n_contigs == 1) {
+        *nwin_out = (ctx->m - 1 + wshift - 1) / wshift;        // len(range(0, m-1, shift))
+        return PASIO_OK;
+    }
+    ctx->h_win_st.clear();
+    ctx->h_win_en.clear();
+    for (i64 c = 0; c < ctx->n_contigs; ++c) {
+        const i64 b0 = ctx->h_brank[(size_t)c], b1 = ctx->h_brank[(size_t)c + 1];
+        const i64 mc = b1 - b0 + 1;
+        for (i64 st = 0; st < mc - 1; st += wshift) {
+            i64 en = st + wsize + 1;
+            if (en > mc) en = mc;
+            ctx->h_win_st.push_back((int32_t)(b0 + st));
+            ctx->h_win_en.push_back((int32_t)(b0 + en));
+        }
+    }
+    const size_t nw = ctx->h_win_st.size();
+    PASIO_TRY(pasio_reserve(ctx, ctx->win_st, nw * 4));
+    PASIO_TRY(pasio_reserve(ctx, ctx->win_en, nw * 4));
+    PASIO_TRY(h2d(ctx, ctx->win_st.p, ctx->h_win_st.data(), nw * 4));
+    PASIO_TRY(h2d(ctx, ctx->win_en.p, ctx->h_win_en.data(), nw * 4));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors are reused next round
+    *nwin_out = (i64)nw;
+    return PASIO_OK;
+}
+
+extern "C" int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int constraint,
+                           int64_t *n_in, int64_t *n_out, int64_t *cells)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (window_size < 1 || window_shift < 1 || window_size > 2147483000LL || window_shift > 2147483000LL)
+        return pasio_fail(ctx, PASIO_E_ARG, "window_size and window_shift must be positive");
+    if (constraint < 0 || constraint > 2) return pasio_fail(ctx, PASIO_E_ARG, "unknown constraint %d", constraint);
+    if (n_in) *n_in = ctx->m;
+    if (n_out) *n_out = ctx->m;
+    if (cells) *cells = 0;
+    i64 nwin = 0;
+    PASIO_TRY(build_window_table(ctx, window_size, window_shift, &nwin));
+    i64 max_span = 0, max_cnt = 0;
+    PASIO_TRY(launch_window_prepass(ctx, nwin, (int)window_size, (int)window_shift, &max_span, &max_cnt));
+    PASIO_TRY(check_dp_tables(ctx, max_span, max_cnt));
+
+    const size_t bit_bytes = (size_t)((ctx->n + 1 + 31) / 32 + 2) * 4;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->keepbits.p, 0, bit_bytes, ctx->stream));
+    PASIO_TRY(launch_window_dp(ctx, nwin, (int)window_size, (int)window_shift, constraint));
+
+    // survivors: at most the current count (the new list is a subset, round_reducer.py:25)
+    const int nxt = 1 - ctx->cur;
+    PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)ctx->m * 4));
+    i64 m_new = 0;
+    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    PASIO_TRY(d2h(ctx, ctx->h_scalars + 10, ctx->scalars.as<i64>() + 10, 8));
+    if (cells) *cells = ctx->h_scalars[10];
+    ctx->cur = nxt;
+    ctx->implicit_all = false;
+    ctx->m = m_new;
+    if (n_out) *n_out = m_new;
+    return refresh_boundary_ranks(ctx);
+}
+
+extern "C" int pasio_rounds(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int constraint,
+                            int64_t max_rounds, int64_t *rounds_done, int64_t *n_out, int64_t *cells,
+                            int64_t *sizes, int64_t sizes_cap)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    // round_reducer.py:11-15: None -> len(counts); at least one round
+    i64 limit = max_rounds <= 0 ? ctx->n : max_rounds;
+    if (limit < 1) limit = 1;
+    i64 done = 0, total_cells = 0;
+    int rc = PASIO_OK;
+    while (done < limit) {
+        int64_t a = 0, b = 0, c = 0;
+        rc = pasio_round(ctx, window_size, window_shift, constraint, &a, &b, &c);
+        if (rc != PASIO_OK) break;
+        if (sizes && done < sizes_cap) sizes[done] = a;
+        ++done;
+        total_cells += c;
+        if (a == b) break;               // np.array_equal(new, old): fixed point (round_reducer.py:21)
+    }
+    if (rounds_done) *rounds_done = done;
+    if (n_out) *n_out = ctx->m;
+    if (cells) *cells = total_cells;
+    return rc;
+}
+
+// ---- exact DP -----------------------------------------------------------------------------------
+extern "C" int pasio_square_split(pasio_ctx *ctx, int64_t *out_splits, int64_t cap, int64_t *n_splits,
+                                  double *score, double *prefix_scores, int64_t *previous_splits)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (ctx->n_contigs != 1) return pasio_fail(ctx, PASIO_E_STATE, "pasio_square_split works on a single-contig context");
+    const i64 N = ctx->m;
+    // candidates span the whole contig: first = 0, last = n
+    PASIO_TRY(check_dp_tables(ctx, ctx->n, ctx->total));
+    PASIO_TRY(launch_gather_candidates(ctx));
+    PASIO_TRY(launch_exact_dp(ctx, N));
+    if (score) PASIO_TRY(d2h(ctx, score, ctx->dpP.as<double>() + (N - 1), 8));
+    if (prefix_scores) PASIO_TRY(d2h(ctx, prefix_scores, ctx->dpP.p, (size_t)N * 8));
+    if (previous_splits) {
+        std::vector<int> tmp((size_t)N);
+        PASIO_TRY(d2h(ctx, tmp.data(), ctx->dpPrev.p, (size_t)N * 4));
+        for (i64 k = 0; k < N; ++k) previous_splits[k] = tmp[(size_t)k];
+    }
+    PASIO_TRY(launch_backtrace_mark(ctx, N));
+    const int nxt = 1 - ctx->cur;
+    PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)N * 4));
+    i64 m_new = 0;
+    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    ctx->cur = nxt;
+    ctx->implicit_all = false;
+    ctx->m = m_new;
+    PASIO_TRY(refresh_boundary_ranks(ctx));
+    if (n_splits) *n_splits = m_new;
+    if (out_splits) {
+        if (cap < m_new) return pasio_fail(ctx, PASIO_E_ARG, "capacity %lld < %lld splits", (long long)cap, (long long)m_new);
+        return pasio_candidates_download(ctx, out_splits, cap, nullptr);
+    }
+    return PASIO_OK;
+}
+
+extern "C" int pasio_suffix_scores(pasio_ctx *ctx, int64_t stop, double *out)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (stop < 0 || stop >= ctx->m || !out) return pasio_fail(ctx, PASIO_E_ARG, "stop out of range");
+    if (stop == 0) return PASIO_OK;
+    // arguments are bounded by the span / count between candidate 0 and candidate `stop`
+    i64 ends[2] = {0, stop};
+    i64 pos[2] = {0, stop};
+    if (!ctx->implicit_all) {
+        int32_t p32[2];
+        PASIO_TRY(d2h(ctx, &p32[0], ctx->cand[ctx->cur].as<int32_t>() + ends[0], 4));
+        PASIO_TRY(d2h(ctx, &p32[1], ctx->cand[ctx->cur].as<int32_t>() + ends[1], 4));
+        pos[0] = p32[0];
+        pos[1] = p32[1];
+    }
+    i64 c[2];
+    PASIO_TRY(d2h(ctx, &c[0], ctx->cg.as<i64>() + pos[0], 8));
+    PASIO_TRY(d2h(ctx, &c[1], ctx->cg.as<i64>() + pos[1], 8));
+    PASIO_TRY(check_dp_tables(ctx, pos[1] - pos[0], c[1] - c[0]));
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)stop * 8));
+    PASIO_TRY(launch_suffix_row(ctx, stop, ctx->dpP.as<double>()));
+    return d2h(ctx, out, ctx->dpP.p, (size_t)stop * 8);
+}
+
+// ---- per-segment outputs ------------------------------------------------------------------------
+extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *segment_counts, double *mean_counts,
+                                    double *logfac_cumsum, int64_t capacity, int64_t *n_segments)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (!ctx->have_params) return pasio_fail(ctx, PASIO_E_STATE, "pasio_set_params has not been called");
+    const i64 nseg = ctx->m - 1;
+    if (n_segments) *n_segments = nseg;
+    if (capacity < nseg && (scores || segment_counts || mean_counts))
+        return pasio_fail(ctx, PASIO_E_ARG, "capacity %lld < %lld segments", (long long)capacity, (long long)nseg);
+    if (scores || segment_counts || mean_counts) {
+        // largest segment length / count decide the table lengths (windows of 2 candidates, shift 1)
+        const i64 saved_contigs = ctx->n_contigs;
+        ctx->n_contigs = 1;   // closed-form geometry over the whole list; segments never cross boundaries
+        i64 max_len = 0, max_cnt = 0;
+        int rc = launch_window_prepass(ctx, nseg, 1, 1, &max_len, &max_cnt);
+        ctx->n_contigs = saved_contigs;
+        PASIO_TRY(rc);
+        bool bad = false;
+        if (ctx->ntab[PASIO_TAB_LOG] < max_len + 1) { ctx->need[PASIO_TAB_LOG] = max_len + 1; bad = true; }
+        if (ctx->ntab[PASIO_TAB_LGAMMA_ALPHA] < max_cnt + 1) { ctx->need[PASIO_TAB_LGAMMA_ALPHA] = max_cnt + 1; bad = true; }
+        if (bad) return pasio_fail(ctx, PASIO_E_TABLE_TOO_SHORT, "tables too short for segment scores: need log>=%lld, lgamma_alpha>=%lld",
+                                   (long long)(max_len + 1), (long long)(max_cnt + 1));
+        PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)nseg * 8));
+        PASIO_TRY(pasio_reserve(ctx, ctx->dpJump, (size_t)nseg * 8));
+        PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)nseg * 8));
+        PASIO_TRY(launch_segment_scores(ctx, ctx->dpP.as<double>(), ctx->dpJump.as<i64>(), ctx->dpPart.as<double>()));
+        if (scores) PASIO_TRY(d2h(ctx, scores, ctx->dpP.p, (size_t)nseg * 8));
+        if (segment_counts) PASIO_TRY(d2h(ctx, segment_counts, ctx->dpJump.p, (size_t)nseg * 8));
+        if (mean_counts) PASIO_TRY(d2h(ctx, mean_counts, ctx->dpPart.p, (size_t)nseg * 8));
+    }
+    if (logfac_cumsum) {
+        if (capacity < nseg) return pasio_fail(ctx, PASIO_E_ARG, "capacity too small");
+        DevBuf full;   // n+1 doubles; transient
+        PASIO_TRY(pasio_reserve(ctx, full, (size_t)(ctx->n + 1) * 8));
+        int rc = launch_logfac_scan(ctx, full.as<double>());
+        if (rc == PASIO_OK) rc = pasio_reserve(ctx, ctx->dpP, (size_t)ctx->m * 8);
+        if (rc == PASIO_OK) rc = launch_gather_f64_at_cands(ctx, full.as<double>(), ctx->dpP.as<double>());
+        if (rc == PASIO_OK) rc = d2h(ctx, logfac_cumsum, ctx->dpP.p, (size_t)ctx->m * 8);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(full.p);
+        PASIO_TRY(rc);
+    }
+    return PASIO_OK;
+}
+
+// ---- measurement hooks --------------------------------------------------------------------------
+extern "C" int pasio_timing_reset(pasio_ctx *ctx, int enable)
+{
+    NEED_CTX(ctx);
+    PASIO_TRY(resolve_spans(ctx));
+    for (int f = 0; f < TF_COUNT; ++f) { ctx->fam_ms[f] = 0; ctx->fam_launches[f] = 0; }
+    ctx->timing = enable != 0;
+    return PASIO_OK;
+}
+
+extern "C" int pasio_timing_get(pasio_ctx *ctx, int family, double *ms, int64_t *launches)
+{
+    NEED_CTX(ctx);
+    if (family < 0 || family >= TF_COUNT) return pasio_fail(ctx, PASIO_E_ARG, "unknown timing family");
+    PASIO_TRY(resolve_spans(ctx));
+    if (ms) *ms = ctx->fam_ms[family];
+    if (launches) *launches = ctx->fam_launches[family];
+    return PASIO_OK;
+}

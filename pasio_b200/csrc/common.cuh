@@ -1,0 +1,168 @@
+// Internal declarations shared by the CUDA translation units of libpasio_b200.so.
+// sm_100a only; no other architecture is targeted.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pasio_b200.h"
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define PASIO_ABI_VERSION 1
+
+// Grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum TimingFamily { TF_SCAN = 0, TF_WINDOW_DP = 1, TF_COMPACT = 2, TF_EXACT_DP = 3, TF_SCORE = 4,
+                    TF_H2D = 5, TF_D2H = 6, TF_COUNT = 7 };
+
+struct TimedSpan { int family; cudaEvent_t a, b; };
+
+struct pasio_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;          // max dynamic shared memory per block (opt-in)
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // scorer parameters (log_marginal_likelyhood.py:6-16,62)
+    bool have_params = false;
+    int alpha_is_int = 1;
+    i64 alpha_int = 1;
+    double alpha = 1.0, beta = 1.0, pen = 0.0;
+
+    // look-up tables (cached_log.py), device copies
+    DevBuf tab[3];
+    i64 ntab[3] = {0, 0, 0};
+    i64 need[3] = {0, 0, 0};
+
+    // loaded batch ("super-contig": contigs concatenated, boundaries forced)
+    bool have_contig = false;
+    i64 n = 0;                   // total nt
+    i64 total = 0;               // total count
+    i64 n_contigs = 0;
+    std::vector<int32_t> h_bounds;   // n_contigs+1 boundary positions (host copy)
+    DevBuf counts;               // int64[n]
+    DevBuf cg;                   // int64[n+1] exclusive prefix sums, cg[0]=0
+    DevBuf cpbits;               // uint32 bitmap over positions 0..n : counts[p-1]!=counts[p]
+    DevBuf keepbits;             // uint32 bitmap over positions 0..n : survivors of a round
+    DevBuf bounds;               // int32[n_contigs+1]
+    DevBuf brank;                // int32[n_contigs+1] index of each boundary in the candidate list
+
+    // candidates (positions, int32, ascending); implicit_all: cand[q] == q
+    bool implicit_all = true;
+    DevBuf cand[2];
+    int cur = 0;
+    i64 m = 0;
+
+    // per-round window table for batches (n_contigs > 1)
+    DevBuf win_st, win_en;
+    std::vector<int32_t> h_win_st, h_win_en, h_brank;
+
+    // scratch
+    DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan;
+    i64 *h_scalars = nullptr;    // pinned, 16 entries
+
+    // timing
+    bool timing = false;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double fam_ms[TF_COUNT] = {0};
+    i64 fam_launches[TF_COUNT] = {0};
+};
+
+int pasio_fail(pasio_ctx *ctx, int code, const char *fmt, ...);
+int pasio_reserve(pasio_ctx *ctx, DevBuf &b, size_t bytes);   // grow-only; returns status
+
+#define CUDA_TRY(ctx, call)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return pasio_fail((ctx), PASIO_E_CUDA, "%s failed: %s (%s:%d)", #call,              \
+                              cudaGetErrorString(e__), __FILE__, __LINE__);                     \
+    } while (0)
+
+#define PASIO_TRY(call)                    \
+    do {                                   \
+        int rc__ = (call);                 \
+        if (rc__ != PASIO_OK) return rc__; \
+    } while (0)
+
+// RAII-less timing helpers: record an event pair around a family of launches.
+struct TimingScope {
+    pasio_ctx *ctx;
+    int idx;
+    TimingScope(pasio_ctx *c, int family, i64 launches = 1);
+    ~TimingScope();
+};
+
+// ---- launchers implemented in the kernel translation units (all asynchronous on ctx->stream) ----
+
+// scan.cu
+int launch_scan_counts(pasio_ctx *ctx);                       // counts -> cg, cpbits, validation, total
+int launch_expand_rle(pasio_ctx *ctx, const i64 *d_starts, const i64 *d_values, i64 n_runs);
+int launch_logfac_scan(pasio_ctx *ctx, double *d_out);        // float64 prefix sums of G[counts+1], n+1 entries
+
+// compact.cu
+int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count);  // keepbits -> sorted positions; syncs
+int launch_boundary_ranks(pasio_ctx *ctx);                    // brank from current candidates
+int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt);  // syncs
+int launch_validate_candidates(pasio_ctx *ctx, i64 *h_bad);   // syncs
+
+// window_dp.cu
+int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constraint);
+int window_dp_max_candidates(pasio_ctx *ctx);
+
+// exact_dp.cu
+int launch_exact_dp(pasio_ctx *ctx, i64 N);                   // over ctx->dpL/dpC -> dpP/dpPrev
+int launch_gather_candidates(pasio_ctx *ctx);                 // current candidates -> dpL/dpC (rebased)
+int launch_backtrace_mark(pasio_ctx *ctx, i64 N);             // dpPrev -> keepbits (positions on the optimal path)
+int launch_suffix_row(pasio_ctx *ctx, i64 stop, double *d_out);
+
+// score.cu
+int launch_segment_scores(pasio_ctx *ctx, double *d_scores, i64 *d_segcounts, double *d_means);
+int launch_gather_i64(pasio_ctx *ctx, const i64 *d_src, const int32_t *d_idx32, const i64 *d_idx64, i64 m, i64 *d_out);
+int launch_gather_f64_at_cands(pasio_ctx *ctx, const double *d_src, double *d_out);
+
+static inline const int32_t *cur_cand(const pasio_ctx *ctx) {
+    return ctx->implicit_all ? nullptr : ctx->cand[ctx->cur].as<int32_t>();
+}
+
+// Window geometry of dto/sliding_window.py:9-15 over candidate indices: either the closed form
+// for one contig or a host-built table for a batch (windows never span contigs).
+struct WinGeom {
+    const int32_t *st_tab;
+    const int32_t *en_tab;
+    i64 m;
+    int wsize, wshift;
+};
+WinGeom make_geom(const pasio_ctx *ctx, int wsize, int wshift);
+
+// ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void window_range(const WinGeom &g, i64 w, i64 &st, i64 &en) {
+    if (g.st_tab) {
+        st = __ldg(g.st_tab + w);
+        en = __ldg(g.en_tab + w);
+    } else {
+        st = w * g.wshift;                       // range(0, len-1, shift)
+        en = min(st + (i64)g.wsize + 1, g.m);    // stop = min(start + size + 1, len)
+    }
+}
+// Exact int32 (0 <= v < 2^31) -> double with one DADD on the FP64 pipe instead of a
+// quarter-rate I2F conversion: 2^52 + v is representable, so the subtraction is exact.
+__device__ __forceinline__ double u32_to_double(int v) {
+    return __dsub_rn(__hiloint2double(0x43300000, v), 4503599627370496.0);
+}
+__device__ __forceinline__ bool bit_test(const uint32_t *__restrict__ bits, i64 p) {
+    return (__ldg(bits + (p >> 5)) >> (p & 31)) & 1u;
+}
+#endif

@@ -1,0 +1,242 @@
+// K2: survivor bitmap -> sorted candidate list (stream compaction), plus the small per-round
+// helpers around it: boundary ranks, window requirements, candidate validation.
+//
+// Replaces the set-union + sort of SlidingWindowReducer.reduce_candidate_list
+// (/root/reference/src/pasio/splitters/sliding_window_reducer.py:22-29): windows scatter
+// survivor bits into a position bitmap, and one ordered compaction of the bitmap yields the
+// next round's ascending candidate array.  HBM-trivial: (n+1)/8 bytes read, 4 B per survivor.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CP_THREADS = 256;
+constexpr int CP_WORDS = 4;                       // words per thread
+constexpr int CP_TILE = CP_THREADS * CP_WORDS;    // words per block
+
+__global__ void __launch_bounds__(CP_THREADS)
+popc_block_sums(const uint32_t *__restrict__ bits, i64 nwords, int *__restrict__ blocksum)
+{
+    __shared__ int s_warp[CP_THREADS / 32];
+    const i64 base = (i64)blockIdx.x * CP_TILE + (i64)threadIdx.x * CP_WORDS;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < CP_WORDS; ++k)
+        if (base + k < nwords) c += __popc(__ldg(bits + base + k));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < CP_THREADS / 32; ++w) t += s_warp[w];
+        blocksum[blockIdx.x] = t;
+    }
+}
+
+__device__ __forceinline__ int block_excl_scan_int(int x, int *s_warp, int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w) {
+        int t = s_warp[w];
+        if (w < warp) off += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + incl - x;
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+scan_block_sums(int *blocksum, i64 nblocks, i64 *total_out)
+{
+    __shared__ int s_warp[CP_THREADS / 32];
+    int carry = 0;
+    for (i64 base = 0; base < nblocks; base += CP_THREADS) {
+        i64 i = base + threadIdx.x;
+        int x = (i < nblocks) ? blocksum[i] : 0;
+        int tot;
+        int ex = block_excl_scan_int(x, s_warp, &tot);
+        if (i < nblocks) blocksum[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+scatter_bits(const uint32_t *__restrict__ bits, i64 nwords, const int *__restrict__ blockprefix,
+             int32_t *__restrict__ out)
+{
+    __shared__ int s_warp[CP_THREADS / 32];
+    const i64 base = (i64)blockIdx.x * CP_TILE + (i64)threadIdx.x * CP_WORDS;
+    uint32_t w[CP_WORDS];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < CP_WORDS; ++k) {
+        w[k] = (base + k < nwords) ? __ldg(bits + base + k) : 0u;
+        c += __popc(w[k]);
+    }
+    int tot;
+    int off = blockprefix[blockIdx.x] + block_excl_scan_int(c, s_warp, &tot);
+#pragma unroll
+    for (int k = 0; k < CP_WORDS; ++k) {
+        uint32_t x = w[k];
+        const int32_t pos0 = (int32_t)((base + k) << 5);
+        while (x) {
+            int b = __ffs(x) - 1;
+            out[off++] = pos0 + b;
+            x &= x - 1;
+        }
+    }
+}
+
+// index of every contig boundary in the (sorted) candidate list
+__global__ void boundary_ranks_kernel(const int32_t *__restrict__ cand, i64 m,
+                                      const int32_t *__restrict__ bounds, i64 nb, int32_t *__restrict__ brank)
+{
+    i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nb) return;
+    int32_t b = bounds[c];
+    if (!cand) { brank[c] = b; return; }
+    i64 lo = 0, hi = m;               // lower_bound
+    while (lo < hi) {
+        i64 mid = (lo + hi) >> 1;
+        if (__ldg(cand + mid) < b) lo = mid + 1; else hi = mid;
+    }
+    brank[c] = (int32_t)lo;
+}
+
+// largest window span (nt) and window count: the table lengths a round needs
+__global__ void window_prepass_kernel(WinGeom g, i64 nwin, const int32_t *__restrict__ cand,
+                                      const i64 *__restrict__ cg, u64 *out /* [0]=span, [1]=count */)
+{
+    i64 span = 0, cnt = 0;
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < nwin; w += (i64)gridDim.x * blockDim.x) {
+        i64 st, en;
+        window_range(g, w, st, en);
+        i64 a = cand ? __ldg(cand + st) : st;
+        i64 b = cand ? __ldg(cand + en - 1) : en - 1;
+        span = max(span, b - a);
+        cnt = max(cnt, __ldg(cg + b) - __ldg(cg + a));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        span = max(span, __shfl_xor_sync(0xffffffffu, span, d));
+        cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out + 0, (u64)span);
+        atomicMax(out + 1, (u64)cnt);
+    }
+}
+
+// assert_correct_split_candidates (log_marginal_likelyhood.py:36-40) + boundaries present
+__global__ void validate_candidates_kernel(const int32_t *__restrict__ cand, i64 m, i64 n,
+                                           const int32_t *__restrict__ bounds, const int32_t *__restrict__ brank,
+                                           i64 nb, i64 *bad)
+{
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool b = false;
+    for (i64 i = t; i < m; i += stride) {
+        int32_t v = __ldg(cand + i);
+        if (i == 0 && v != 0) b = true;
+        if (i == m - 1 && v != n) b = true;
+        if (i > 0 && __ldg(cand + i - 1) >= v) b = true;
+    }
+    for (i64 c = t; c < nb; c += stride) {
+        int32_t r = brank[c];
+        if (r < 0 || r >= m || __ldg(cand + r) != bounds[c]) b = true;
+    }
+    if (b) *bad = 1;
+}
+
+}  // namespace
+
+WinGeom make_geom(const pasio_ctx *ctx, int wsize, int wshift)
+{
+    WinGeom g;
+    if (ctx->n_contigs > 1) {
+        g.st_tab = ctx->win_st.as<int32_t>();
+        g.en_tab = ctx->win_en.as<int32_t>();
+    } else {
+        g.st_tab = nullptr;
+        g.en_tab = nullptr;
+    }
+    g.m = ctx->m;
+    g.wsize = wsize;
+    g.wshift = wshift;
+    return g;
+}
+
+int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count)
+{
+    const i64 nwords = (ctx->n + 1 + 31) / 32;
+    const i64 nblocks = (nwords + CP_TILE - 1) / CP_TILE;
+    PASIO_TRY(pasio_reserve(ctx, ctx->blocksum, (size_t)nblocks * sizeof(int)));
+    const uint32_t *bits = ctx->keepbits.as<uint32_t>();
+    int *bs = ctx->blocksum.as<int>();
+    i64 *d_total = ctx->scalars.as<i64>() + 4;
+    {
+        TimingScope ts(ctx, TF_COMPACT, 3);
+        popc_block_sums<<<(unsigned)nblocks, CP_THREADS, 0, ctx->stream>>>(bits, nwords, bs);
+        scan_block_sums<<<1, CP_THREADS, 0, ctx->stream>>>(bs, nblocks, d_total);
+        scatter_bits<<<(unsigned)nblocks, CP_THREADS, 0, ctx->stream>>>(bits, nwords, bs, d_out);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *h_count = ctx->h_scalars[4];
+    return PASIO_OK;
+}
+
+int launch_boundary_ranks(pasio_ctx *ctx)
+{
+    const i64 nb = ctx->n_contigs + 1;
+    boundary_ranks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(
+        cur_cand(ctx), ctx->m, ctx->bounds.as<int32_t>(), nb, ctx->brank.as<int32_t>());
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}
+
+int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt)
+{
+    u64 *d_out = ctx->scalars.as<u64>() + 6;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, 16, ctx->stream));
+    unsigned blocks = (unsigned)((nwin + 255) / 256);
+    if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    if (blocks == 0) blocks = 1;
+    {
+        TimingScope ts(ctx, TF_COMPACT);
+        window_prepass_kernel<<<blocks, 256, 0, ctx->stream>>>(make_geom(ctx, wsize, wshift), nwin, cur_cand(ctx),
+                                                              ctx->cg.as<i64>(), d_out);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 6, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *h_max_span = ctx->h_scalars[6];
+    *h_max_cnt = ctx->h_scalars[7];
+    return PASIO_OK;
+}
+
+int launch_validate_candidates(pasio_ctx *ctx, i64 *h_bad)
+{
+    i64 *d_bad = ctx->scalars.as<i64>() + 5;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, 8, ctx->stream));
+    validate_candidates_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+        ctx->cand[ctx->cur].as<int32_t>(), ctx->m, ctx->n, ctx->bounds.as<int32_t>(),
+        ctx->brank.as<int32_t>(), ctx->n_contigs + 1, d_bad);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 5, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *h_bad = ctx->h_scalars[5];
+    return PASIO_OK;
+}

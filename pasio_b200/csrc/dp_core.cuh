@@ -1,0 +1,153 @@
+// The DP cell and the in-CTA block step shared by the batched window kernel (K4) and the
+// diagonal step of the exact kernel (K3).
+//
+// One cell restates, in the reference's operation order,
+//   LogMarginalLikelyhood{Int,Real}AlphaComputer.all_suffixes_self_score
+//     /root/reference/src/pasio/log_marginal_likelyhood.py:105-115 (int alpha), :121-132 (real alpha)
+//   + the row update of SquareSplitter.split_without_normalizations
+//     /root/reference/src/pasio/splitters/square_splitter.py:84-94
+//       s    = (alpha + C_j) - C_i
+//       self = G[s] - s * Lg[L_j - L_i]          (un-fused DMUL then DADD, like numpy's two ufunc loops)
+//       t    = self + P_i
+//       P_j  = max_i t  + segment_creation_cost,  prev_j = first index of the maximum (np.argmax)
+// G and Lg are host-built tables (numpy/scipy values), so the device does no transcendental math.
+#pragma once
+#include "common.cuh"
+
+// Per-row constants.  AI = integer alpha (table index includes alpha, s is that integer);
+// real alpha: table index is the raw count, s = (alpha + C_j) - C_i in float64 with the
+// reference's two roundings.
+template <bool AI>
+struct RowConst {
+    int cjx;      // AI: C_j + alpha ; else C_j
+    int lj;       // L_j
+    double aj;    // !AI: fl(alpha + C_j)
+};
+
+template <bool AI>
+__device__ __forceinline__ RowConst<AI> make_row(int cj, int lj, int alpha_int, double alpha)
+{
+    RowConst<AI> r;
+    r.lj = lj;
+    if (AI) {
+        r.cjx = cj + alpha_int;
+        r.aj = 0.0;
+    } else {
+        r.cjx = cj;
+        r.aj = __dadd_rn(alpha, u32_to_double(cj));
+    }
+    return r;
+}
+
+// self score of segment [i, j): G[s] - s * Lg[len]
+template <bool AI>
+__device__ __forceinline__ double self_score(int ci, int li, const RowConst<AI> &r,
+                                             const double *__restrict__ gtab, const double *__restrict__ ltab)
+{
+    const int idx = r.cjx - ci;
+    const int len = r.lj - li;
+    const double g = __ldg(gtab + idx);
+    const double lg = __ldg(ltab + len);
+    const double s = AI ? u32_to_double(idx) : __dsub_rn(r.aj, u32_to_double(ci));
+    return __dsub_rn(g, __dmul_rn(s, lg));
+}
+
+// Sweep columns [i0, i1) for this lane's row; strict '>' keeps the first maximum.
+// sLC[i] = (L_i, C_i), sP[i] = P_i (shared memory, broadcast reads).
+template <bool AI>
+__device__ __forceinline__ void sweep_columns(int i0, int i1, const int2 *sLC, const double *sP,
+                                              const RowConst<AI> &r, const double *__restrict__ gtab,
+                                              const double *__restrict__ ltab, double &best, int &arg)
+{
+    int i = i0;
+    for (; i + 4 <= i1; i += 4) {
+        int2 a0 = sLC[i], a1 = sLC[i + 1], a2 = sLC[i + 2], a3 = sLC[i + 3];
+        double t0 = self_score<AI>(a0.y, a0.x, r, gtab, ltab);
+        double t1 = self_score<AI>(a1.y, a1.x, r, gtab, ltab);
+        double t2 = self_score<AI>(a2.y, a2.x, r, gtab, ltab);
+        double t3 = self_score<AI>(a3.y, a3.x, r, gtab, ltab);
+        t0 = __dadd_rn(t0, sP[i]);
+        t1 = __dadd_rn(t1, sP[i + 1]);
+        t2 = __dadd_rn(t2, sP[i + 2]);
+        t3 = __dadd_rn(t3, sP[i + 3]);
+        if (t0 > best) { best = t0; arg = i; }
+        if (t1 > best) { best = t1; arg = i + 1; }
+        if (t2 > best) { best = t2; arg = i + 2; }
+        if (t3 > best) { best = t3; arg = i + 3; }
+    }
+    for (; i < i1; ++i) {
+        int2 a = sLC[i];
+        double t = __dadd_rn(self_score<AI>(a.y, a.x, r, gtab, ltab), sP[i]);
+        if (t > best) { best = t; arg = i; }
+    }
+}
+
+constexpr int DP_JB = 32;   // rows resolved per block step (one per lane)
+
+// One block step over rows [jb, jb+32) of a candidate list held in shared memory.
+//   rectangle: columns [col0, jb) split across the CTA's warps (lane = row);
+//   triangle : columns [jb, j) -- the 32x32 self scores are computed by all warps, then warp 0
+//              resolves the 32 rows in order, broadcasting each finished P by shuffle.
+// init_best/init_arg (warp 0 only, per lane) seed the running maximum with what earlier columns
+// (outside [col0, jb)) contributed; pass -inf / 0 when there are none.
+// Requires col0 <= jb, blockDim.x == NW*32.  Ends with a __syncthreads().
+template <bool AI, int NW>
+__device__ __forceinline__ void dp_block_step(int jb, int N, int col0, const int2 *sLC, double *sP,
+                                              unsigned short *sPrev16, int *sPrev32,
+                                              double *sPartV, int *sPartA, double *sTri,
+                                              const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                              int alpha_int, double alpha, double pen,
+                                              double init_best, int init_arg, int arg_offset)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = min(jb + lane, N - 1);
+    const int2 lc = sLC[j];
+    const RowConst<AI> r = make_row<AI>(lc.y, lc.x, alpha_int, alpha);
+
+    // rectangle
+    const int ncol = jb - col0;
+    const int chunk = (ncol + NW - 1) / NW;
+    const int i0 = col0 + warp * chunk;
+    const int i1 = min(i0 + chunk, jb);
+    double best = -INFINITY;
+    int arg = i0;
+    sweep_columns<AI>(i0, i1, sLC, sP, r, gtab, ltab, best, arg);
+    sPartV[warp * 32 + lane] = best;
+    sPartA[warp * 32 + lane] = arg;
+
+    // triangle self scores: pair (k, l), column jb+k, row jb+l, k < l
+    for (int k = warp; k < DP_JB; k += NW) {
+        if (k < lane && jb + lane < N) {
+            const int2 a = sLC[jb + k];
+            sTri[k * DP_JB + lane] = self_score<AI>(a.y, a.x, r, gtab, ltab);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        best = init_best;
+        arg = init_arg;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            double v = sPartV[w * 32 + lane];
+            if (v > best) { best = v; arg = sPartA[w * 32 + lane] + arg_offset; }
+        }
+        double mine = 0.0;
+        const int rows = min(DP_JB, N - jb);
+        for (int k = 0; k < rows; ++k) {
+            const double pf = __dadd_rn(best, pen);          // prefix_scores[j] = max + segment_creation_cost
+            const double pk = __shfl_sync(0xffffffffu, pf, k);
+            if (lane == k) mine = pf;
+            if (lane > k) {
+                const double t = __dadd_rn(sTri[k * DP_JB + lane], pk);
+                if (t > best) { best = t; arg = jb + k + arg_offset; }
+            }
+        }
+        if (jb + lane < N) {
+            sP[jb + lane] = mine;
+            if (sPrev16) sPrev16[jb + lane] = (unsigned short)arg;
+            else sPrev32[jb + lane] = arg;
+        }
+    }
+    __syncthreads();
+}

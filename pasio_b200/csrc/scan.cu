@@ -1,0 +1,306 @@
+// K1: per-contig coverage prefix sums as a single-pass decoupled-look-back scan, fused with
+// the change-point bitmap of NotConstantReducer and the counts >= 0 validation.
+//
+// Replaces np.cumsum(counts) in LogMarginalLikelyhoodComputer.__init__
+// (/root/reference/src/pasio/log_marginal_likelyhood.py:57), which the reference re-runs for
+// every window, and the counts[:-1] != counts[1:] test of NotConstantReducer
+// (splitters/constants_reducer.py:16-17).  HBM-bound: 8 B read + 8 B written per nt.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// tile status word: top 2 bits = flag (0 invalid, 1 aggregate, 2 inclusive prefix), low 62 = value
+__device__ __forceinline__ u64 pack_state(u64 flag, i64 v) { return (flag << 62) | (u64)v; }
+__device__ __forceinline__ u64 ld_state(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
+__device__ __forceinline__ void st_state(u64 *p, u64 v) { *reinterpret_cast<volatile u64 *>(p) = v; }
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
+                   uint8_t *__restrict__ cpbytes, u64 *tile_state, unsigned *tile_counter,
+                   i64 *scalars /* [0]=total, [1]=negative seen */)
+{
+    __shared__ unsigned s_tile;
+    __shared__ i64 s_warp[SCAN_THREADS / 32];
+    __shared__ i64 s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);   // tiles start in issue order: look-back never waits on an unscheduled tile
+    __syncthreads();
+    const i64 tile = s_tile;
+    const i64 base = tile * SCAN_TILE + (i64)tid * SCAN_ITEMS;
+
+    i64 v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n) {
+        const longlong2 *src = reinterpret_cast<const longlong2 *>(counts + base);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 2; ++k) {
+            longlong2 t = __ldg(src + k);
+            v[2 * k] = t.x;
+            v[2 * k + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < n) ? __ldg(counts + base + k) : 0;
+    }
+
+    // change-point byte for positions base..base+7 (flag at p: counts[p-1] != counts[p], 1 <= p <= n-1)
+    if (base < n) {
+        i64 before = (base > 0) ? __ldg(counts + base - 1) : v[0];
+        unsigned byte = 0;
+        bool neg = false;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            i64 p = base + k;
+            if (p >= 1 && p <= n - 1 && v[k] != before) byte |= 1u << k;
+            before = v[k];
+            neg |= (p < n) && (v[k] < 0);
+        }
+        cpbytes[base >> 3] = (uint8_t)byte;
+        if (neg) scalars[1] = 1;
+    }
+
+    // thread-local inclusive sums, then block scan of thread totals
+#pragma unroll
+    for (int k = 1; k < SCAN_ITEMS; ++k) v[k] += v[k - 1];
+    i64 incl = v[SCAN_ITEMS - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        i64 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    i64 warp_off = 0, aggregate = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        i64 t = s_warp[w];
+        if (w < warp) warp_off += t;
+        aggregate += t;
+    }
+    const i64 thread_excl = warp_off + incl - v[SCAN_ITEMS - 1];
+
+    // decoupled look-back over predecessor tiles (warp 0)
+    if (warp == 0) {
+        i64 running = 0;
+        if (tile > 0) {
+            if (lane == 0) st_state(tile_state + tile, pack_state(1, aggregate));
+            i64 look = tile - 1;
+            while (true) {
+                i64 idx = look - lane;
+                u64 st;
+                do {
+                    st = (idx >= 0) ? ld_state(tile_state + idx) : pack_state(2, 0);
+                } while (__any_sync(0xffffffffu, (st >> 62) == 0));
+                unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+                i64 val = (lane <= stop) ? (i64)(st & 0x3fffffffffffffffull) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                running += val;
+                if (has_prefix) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_state(tile_state + tile, pack_state(2, running + aggregate));
+            s_prefix = running;
+        }
+    }
+    __syncthreads();
+    const i64 off = s_prefix + thread_excl;
+
+    if (tile == 0 && tid == 0) cg[0] = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        i64 p = base + k;
+        if (p < n) {
+            i64 c = off + v[k];
+            cg[p + 1] = c;
+            if (p == n - 1) scalars[0] = c;
+        }
+    }
+}
+
+// Expand run-length intervals (bedgraph form) to the dense int64 profile.
+__global__ void expand_rle_kernel(const i64 *__restrict__ starts, const i64 *__restrict__ values,
+                                  i64 n_runs, i64 n, i64 *__restrict__ counts)
+{
+    const i64 base = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (base >= n) return;
+    // last run with starts[r] <= base
+    i64 lo = 0, hi = n_runs - 1;
+    while (lo < hi) {
+        i64 mid = (lo + hi + 1) >> 1;
+        if (__ldg(starts + mid) <= base) lo = mid; else hi = mid - 1;
+    }
+    i64 r = lo;
+    i64 next = __ldg(starts + r + 1);
+    i64 val = __ldg(values + r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        i64 p = base + k;
+        if (p >= n) break;
+        while (p >= next) {
+            ++r;
+            next = __ldg(starts + r + 1);
+            val = __ldg(values + r);
+        }
+        counts[p] = val;
+    }
+}
+
+// ---- deterministic float64 prefix sums of lgamma(counts+1) (logfac_cumsum) ------------------
+// Replaces np.cumsum(gammaln(counts + 1)) (log_marginal_likelyhood.py:59-60).  The reference sums
+// sequentially; a parallel scan rounds differently, so this column is tolerance-only.
+// Three fixed-shape passes so the result is reproducible run to run.
+constexpr int FS_THREADS = 256;
+constexpr int FS_ITEMS = 8;
+constexpr int FS_TILE = FS_THREADS * FS_ITEMS;
+
+__device__ __forceinline__ double block_excl_scan(double x, double *s_warp, double *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    double off = 0, tot = 0;
+    for (int w = 0; w < FS_THREADS / 32; ++w) {
+        double t = s_warp[w];
+        if (w < warp) off += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + incl - x;
+}
+
+__global__ void __launch_bounds__(FS_THREADS)
+logfac_tile_sums(const i64 *__restrict__ counts, i64 n, const double *__restrict__ gtab, double *tile_sum)
+{
+    __shared__ double s_warp[FS_THREADS / 32];
+    const i64 base = (i64)blockIdx.x * FS_TILE + (i64)threadIdx.x * FS_ITEMS;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < FS_ITEMS; ++k)
+        if (base + k < n) s += __ldg(gtab + __ldg(counts + base + k) + 1);
+    double tot;
+    block_excl_scan(s, s_warp, &tot);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(FS_THREADS)
+logfac_scan_tile_sums(double *tile_sum, i64 n_tiles)
+{
+    __shared__ double s_warp[FS_THREADS / 32];
+    double carry = 0;
+    for (i64 base = 0; base < n_tiles; base += FS_THREADS) {
+        i64 i = base + threadIdx.x;
+        double x = (i < n_tiles) ? tile_sum[i] : 0.0;
+        double tot;
+        double ex = block_excl_scan(x, s_warp, &tot);
+        if (i < n_tiles) tile_sum[i] = carry + ex;
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(FS_THREADS)
+logfac_scan_apply(const i64 *__restrict__ counts, i64 n, const double *__restrict__ gtab,
+                  const double *__restrict__ tile_prefix, double *__restrict__ out)
+{
+    __shared__ double s_warp[FS_THREADS / 32];
+    const i64 base = (i64)blockIdx.x * FS_TILE + (i64)threadIdx.x * FS_ITEMS;
+    double v[FS_ITEMS];
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < FS_ITEMS; ++k) {
+        double x = (base + k < n) ? __ldg(gtab + __ldg(counts + base + k) + 1) : 0.0;
+        s += x;
+        v[k] = s;
+    }
+    double tot;
+    double off = tile_prefix[blockIdx.x] + block_excl_scan(s, s_warp, &tot);
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < FS_ITEMS; ++k)
+        if (base + k < n) out[base + k + 1] = off + v[k];
+}
+
+__global__ void max_count_kernel(const i64 *__restrict__ counts, i64 n, u64 *out)
+{
+    i64 mx = 0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        mx = max(mx, __ldg(counts + i));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (u64)mx);
+}
+
+}  // namespace
+
+int launch_scan_counts(pasio_ctx *ctx)
+{
+    const i64 n = ctx->n;
+    const i64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    PASIO_TRY(pasio_reserve(ctx, ctx->tilestate, (size_t)(tiles + 1) * 8 + 16));
+    u64 *state = ctx->tilestate.as<u64>() + 2;
+    unsigned *counter = ctx->tilestate.as<unsigned>();
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->tilestate.p, 0, (size_t)(tiles + 1) * 8 + 16, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(i64), ctx->stream));
+    const size_t bit_bytes = (size_t)((n + 1 + 31) / 32 + 2) * 4;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->cpbits.p, 0, bit_bytes, ctx->stream));
+    {
+        TimingScope ts(ctx, TF_SCAN);
+        scan_counts_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(
+            ctx->counts.as<i64>(), n, ctx->cg.as<i64>(), ctx->cpbits.as<uint8_t>(), state, counter,
+            ctx->scalars.as<i64>());
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}
+
+int launch_expand_rle(pasio_ctx *ctx, const i64 *d_starts, const i64 *d_values, i64 n_runs)
+{
+    const i64 n = ctx->n;
+    const i64 threads = (n + 7) / 8;
+    TimingScope ts(ctx, TF_SCAN);
+    expand_rle_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(
+        d_starts, d_values, n_runs, n, ctx->counts.as<i64>());
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}
+
+int launch_logfac_scan(pasio_ctx *ctx, double *d_out)
+{
+    const i64 n = ctx->n;
+    // the lgamma table must cover max(counts)+1
+    u64 *d_max = ctx->scalars.as<u64>() + 8;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, 8, ctx->stream));
+    max_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, d_max);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 8, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const i64 max_count = ctx->h_scalars[8];
+    if (max_count + 2 > ctx->ntab[PASIO_TAB_LGAMMA]) {
+        ctx->need[PASIO_TAB_LGAMMA] = max_count + 2;
+        return pasio_fail(ctx, PASIO_E_TABLE_TOO_SHORT, "lgamma table has %lld entries, logfac needs %lld",
+                          (long long)ctx->ntab[PASIO_TAB_LGAMMA], (long long)(max_count + 2));
+    }
+    const i64 tiles = (n + FS_TILE - 1) / FS_TILE;
+    PASIO_TRY(pasio_reserve(ctx, ctx->fscan, (size_t)tiles * 8));
+    const double *gtab = ctx->tab[PASIO_TAB_LGAMMA].as<double>();
+    TimingScope ts(ctx, TF_SCORE, 3);
+    logfac_tile_sums<<<(unsigned)tiles, FS_THREADS, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, gtab,
+                                                                     ctx->fscan.as<double>());
+    logfac_scan_tile_sums<<<1, FS_THREADS, 0, ctx->stream>>>(ctx->fscan.as<double>(), tiles);
+    logfac_scan_apply<<<(unsigned)tiles, FS_THREADS, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, gtab,
+                                                                      ctx->fscan.as<double>(), d_out);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}

@@ -1,0 +1,72 @@
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a B200 (run with -m gpu on the GPU box)')
+
+
+def host_tables_sha1():
+    import scipy.special
+    k = np.arange(1 << 20)
+    h = hashlib.sha1()
+    h.update(np.log(k + 1.0).tobytes())
+    h.update(scipy.special.gammaln(k + 0).tobytes())
+    return h.hexdigest()
+
+
+_HOST_SHA = None
+
+
+class Golden(object):
+    """Fixture file made by oracle/make_golden.py from the unmodified reference."""
+
+    def __init__(self, name):
+        self.d = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+        global _HOST_SHA
+        if _HOST_SHA is None:
+            _HOST_SHA = host_tables_sha1()
+        # bit-level comparison with the fixtures is meaningful only if this host's np.log /
+        # gammaln produce the table bits the fixtures were generated with
+        self.same_tables = ('tables_sha1' not in self.d.files) or (str(self.d['tables_sha1']) == _HOST_SHA)
+
+    def __getitem__(self, key):
+        return self.d[key]
+
+    def has(self, key):
+        return key in self.d.files
+
+    def counts(self, name):
+        from pasio_b200 import synth
+        if self.has(name + '.counts'):
+            return self.d[name + '.counts'].astype(np.int64)
+        c = eval(str(self.d[name + '.gen']), {k: getattr(synth, k) for k in dir(synth)})
+        assert hashlib.sha1(c.tobytes()).hexdigest() == str(self.d[name + '.counts_sha1'])
+        return c
+
+    def check_splits(self, got, want, score_got, score_want, what=''):
+        """bit-exact on a host with the fixture's tables; otherwise score-only with 1e-9 relative"""
+        assert abs(float(score_got) - float(score_want)) <= 1e-9 * abs(float(score_want)), what
+        if self.same_tables:
+            assert np.array_equal(got, want), what
+            assert float(score_got) == float(score_want), what
+
+
+@pytest.fixture(scope='session')
+def golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Golden(name)
+        return cache[name]
+    return get

@@ -1,0 +1,123 @@
+"""The oracle (oracle/pasio_oracle.py numpy restatement, oracle/dp_oracle.c) pinned against
+fixtures generated from the unmodified reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import pasio_oracle as po
+from oracle import c_oracle
+from pasio_b200 import synth
+
+EXACT_CASES = ['pp2000_a1b1', 'pp2000_a3b5', 'pp2000_a2.5b3', 'pp2000_a1b0.5', 'sparse3000_a1b1',
+               'sparse3000_a0.5b1', 'bench1001_a1b1', 'wide1502_a1b1', 'wide1502_a2.5b3',
+               'one_nt', 'two_nt', 'zeros500', 'const500']
+
+
+def _tables(ab):
+    alpha, beta = float(ab[0]), float(ab[1])
+    return po.Tables(po.normalise_alpha(alpha), beta), alpha, beta
+
+
+@pytest.mark.parametrize('name', EXACT_CASES)
+def test_exact_dp_numpy_oracle(golden, name):
+    g = golden('exact.npz')
+    counts, cands = g.counts(name), g[name + '.cands']
+    t, _, _ = _tables(g[name + '.ab'])
+    score, splits, _, _ = po.square_split(counts, cands, t)
+    g.check_splits(splits, g[name + '.splits'], score, g[name + '.score'], name)
+
+
+@pytest.mark.parametrize('name', EXACT_CASES)
+def test_exact_dp_c_oracle(golden, name):
+    g = golden('exact.npz')
+    counts, cands = g.counts(name), g[name + '.cands']
+    _, alpha, beta = _tables(g[name + '.ab'])
+    score, splits, _, _ = c_oracle.FlatOracle(counts, alpha, beta).square_split(cands)
+    g.check_splits(splits, g[name + '.splits'], score, g[name + '.score'], name)
+
+
+def test_reducers(golden):
+    g = golden('reducers.npz')
+    for k in range(6):
+        c, cands = g['r%d.counts' % k], g['r%d.cands' % k]
+        assert np.array_equal(po.not_zero(c, cands), g['r%d.notzero' % k])
+        assert np.array_equal(po.not_constant(c, cands), g['r%d.notconstant' % k])
+
+
+ROUND_CASES = ['dn60k_c', 'dn60k_z', 'dn20k_n', 'dn60k_real', 'pp30k_c', 'tail_c', 'odd_shift']
+
+
+@pytest.mark.parametrize('name', ROUND_CASES)
+def test_rounds_numpy_and_c_oracle(golden, name):
+    g = golden('rounds.npz')
+    counts = g[name + '.counts'].astype(np.int64)
+    wsize, wshift, alpha, beta = g[name + '.params']
+    wsize, wshift = int(wsize), int(wshift)
+    constraint = str(g[name + '.constraint'])
+    t = po.Tables(po.normalise_alpha(float(alpha)), float(beta))
+    fo = c_oracle.FlatOracle(counts, float(alpha), float(beta))
+    cands = np.arange(len(counts) + 1)
+    for r in range(int(g[name + '.nrounds'])):
+        want = g[name + '.round%d' % r]
+        flat, _ = fo.round(cands, wsize, wshift, constraint)
+        if r < 2:       # the object-faithful numpy loop is slow; two rounds pin it
+            obj = po.sliding_window_round(counts, cands, t, wsize, wshift, constraint)
+            assert np.array_equal(obj, flat)
+        if g.same_tables:
+            assert np.array_equal(flat, want), (name, r)
+        cands = flat
+    score, splits = po.nop_split(counts, cands, t)
+    g.check_splits(splits, g[name + '.splits'], score, g[name + '.score'], name)
+
+
+def test_default_pipeline_oracle(golden):
+    g = golden('pipeline.npz')
+    name = 'rounds2'
+    counts = g[name + '.counts'].astype(np.int64)
+    t = po.Tables(1, 1.0)
+    out = po.default_pipeline(counts, t, window_size=1000, window_shift=500, num_rounds=2)
+    if g.same_tables:
+        assert np.array_equal(out['splits'][:-1], g[name + '.starts'])
+        assert np.array_equal(out['splits'][1:], g[name + '.stops'])
+        assert np.array_equal(out['mean_counts'], g[name + '.mean'])
+        assert np.array_equal(out['lmm'], g[name + '.lmm'])
+        assert out['score'] == g[name + '.score']
+
+
+def test_flat_rounds_match_pipeline_fixture(golden):
+    g = golden('pipeline.npz')
+    for name, kw in [('default300k', dict(w=2500, s=1250, c='constants', a=1.0, b=1.0)),
+                     ('zeros100k', dict(w=600, s=300, c='zeros', a=1.0, b=1.0)),
+                     ('real100k', dict(w=1000, s=500, c='constants', a=0.7, b=2.0))]:
+        counts = g[name + '.counts'].astype(np.int64)
+        fo = c_oracle.FlatOracle(counts, kw['a'], kw['b'])
+        cands, sizes, cells = fo.rounds(kw['w'], kw['s'], kw['c'])
+        if g.same_tables:
+            assert np.array_equal(cands[:-1], g[name + '.starts']), name
+            assert np.array_equal(cands[1:], g[name + '.stops']), name
+
+
+def test_known_answer_log_marginal_likelyhood():
+    """reference tests/test_pasio.py:45-65 restated (np.math is gone in numpy 2)."""
+    import math
+
+    def exact(counts, alpha, beta):
+        fac = 1
+        for c in counts:
+            fac *= math.factorial(int(c))
+        cs, ns = int(sum(counts)), len(counts)
+        return np.log((beta ** alpha) * math.gamma(cs + alpha) / (math.gamma(alpha) * fac * ((ns + beta) ** (cs + alpha))))
+
+    for counts, alpha, beta in [([0], 3, 5), ([0, 1], 3, 5), ([4, 0, 1, 3], 5, 2), ([4, 0, 1, 3], 1, 1)]:
+        counts = np.array(counts)
+        sc = po.Scorer(counts, np.array([0, len(counts)]), po.Tables(alpha, beta))
+        assert np.allclose(sc.log_marginal_likelyhoods(), exact(counts, alpha, beta))
+
+
+def test_config1_fixture_is_consistent(golden):
+    """BASELINE config 1 (N=100 001): the fixture's optimal score equals the sum of its segment scores."""
+    g = golden('config1.npz')
+    counts = g.counts('config1')
+    splits = g['config1.splits']
+    assert len(splits) == 5123 and counts.sum() == 954615
+    sc = po.Scorer(counts, splits, po.Tables(1, 1.0))
+    assert abs(np.sum(sc.scores()) - float(g['config1.score'])) <= 1e-9 * abs(float(g['config1.score']))
