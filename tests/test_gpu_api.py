@@ -1,0 +1,235 @@
+"""The reference's own LogML tests (/root/reference/tests/test_pasio.py, test_bench_pasio.py) restated
+against pasio_b200's drop-in classes, plus whole-pipeline parity with fixtures generated from the
+unmodified reference.  Everything here computes on the GPU."""
+import io
+import math
+
+import numpy as np
+import pytest
+
+import pasio_b200
+from pasio_b200.log_marginal_likelyhood import (LogMarginalLikelyhoodIntAlphaComputer,
+                                                LogMarginalLikelyhoodRealAlphaComputer, ScorerFactory)
+from pasio_b200.splitters import (SquareSplitter, SlidingWindowReducer, RoundReducer, NotZeroReducer,
+                                  NotConstantReducer, ReducerCombiner, NopSplitter, configure_splitter)
+from pasio_b200.dto.sliding_window import SlidingWindow
+from pasio_b200.process_bedgraph import split_bedgraph_stream
+from pasio_b200 import synth
+from oracle import pasio_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stat_split_into_segments_square():
+    # reference tests/test_pasio.py:12-43
+    def split_on_two_segments_or_not(counts, scorer_factory):
+        scorer = scorer_factory(counts, np.arange(len(counts) + 1))
+        best_score = scorer.score(0, len(counts))
+        split_point = 0
+        for i in range(len(counts)):
+            current_score = scorer.score(0, i) + scorer.score(i, len(counts))
+            if current_score > best_score:
+                split_point = i
+                best_score = current_score
+        return best_score, split_point
+
+    np.random.seed(4)
+    scorer_factory = lambda counts, split_candidates: LogMarginalLikelyhoodIntAlphaComputer(counts, 1, 1, split_candidates)
+    for repeat in range(5):
+        counts = np.concatenate([np.random.poisson(15, 100), np.random.poisson(20, 100)])
+        optimal_score, optimal_split = SquareSplitter(scorer_factory).split(counts, np.arange(len(counts) + 1))
+        two_split_score, two_split_point = split_on_two_segments_or_not(counts, scorer_factory)
+        assert optimal_score >= two_split_score
+        assert two_split_point in optimal_split
+        scorer = scorer_factory(counts, optimal_split)
+        assert np.allclose(optimal_score, np.sum(scorer.scores()))
+        assert abs(two_split_point - 100) < 10
+
+
+def test_log_marginal_likelyhood_exact():
+    # reference tests/test_pasio.py:45-65 (math.factorial instead of the removed np.math)
+    def exact_function(counts, alpha, beta):
+        fac = 1
+        for c in counts:
+            fac *= math.factorial(int(c))
+        cs, ns = int(sum(counts)), len(counts)
+        return np.log((beta ** alpha) * math.gamma(cs + alpha) / (math.gamma(alpha) * fac * ((ns + beta) ** (cs + alpha))))
+    for counts, alpha, beta in [([0], 3, 5), ([0, 1], 3, 5), ([4, 0, 1, 3], 5, 2), ([4, 0, 1, 3], 1, 1)]:
+        counts = np.array(counts)
+        scorer = LogMarginalLikelyhoodIntAlphaComputer(counts, alpha, beta, split_candidates=np.array([0, len(counts)]))
+        assert np.allclose(scorer.log_marginal_likelyhoods(), exact_function(counts, alpha, beta))
+
+
+def test_suffixes_scores():
+    # reference tests/test_pasio.py:193-204
+    np.random.seed(2)
+    counts = np.concatenate([np.random.poisson(15, 100), np.random.poisson(20, 100)])
+    scorer = LogMarginalLikelyhoodIntAlphaComputer(counts, 1, 1, np.arange(len(counts) + 1))
+    assert np.allclose(scorer.all_suffixes_self_score(150), np.array([scorer.self_score(i, 150) for i in range(150)]))
+    counts = np.array([0, 0, 1, 0, 0, 2, 2, 2, 10, 11, 100, 1, 0, 0, 1, 0], dtype='int64')
+    scorer = LogMarginalLikelyhoodIntAlphaComputer(counts, 1, 1, np.arange(len(counts) + 1))
+    want = [scorer.self_score(i, len(counts) - 1) for i in range(len(counts) - 1)]
+    assert np.allclose(scorer.all_suffixes_self_score(len(counts) - 1), np.array(want))
+
+
+def test_suffixes_scores_with_candidates():
+    # reference tests/test_pasio.py:206-224
+    np.random.seed(2)
+    counts = np.arange(1, 10)
+    scorer = LogMarginalLikelyhoodIntAlphaComputer(counts, 1, 1, np.arange(len(counts) + 1))
+    candidates = np.array([0, 1, 3, 4, 5, 6, 7, 8, 9])
+    scorer_with_candidates = LogMarginalLikelyhoodIntAlphaComputer(counts, 1, 1, candidates)
+    assert np.allclose(scorer.all_suffixes_self_score(9)[candidates[:-1]],
+                       scorer_with_candidates.all_suffixes_self_score(8))
+    counts = np.concatenate([np.random.poisson(15, 100), np.random.poisson(20, 100)])
+    scorer = LogMarginalLikelyhoodIntAlphaComputer(counts, 1, 1, np.arange(len(counts) + 1))
+    candidates = np.array([0, 1, 10, 20, 21, 30, 40, 149, 200])
+    scorer_with_candidates = LogMarginalLikelyhoodIntAlphaComputer(counts, 1, 1, candidates)
+    assert np.allclose(scorer.all_suffixes_self_score(200)[candidates[:-1]],
+                       scorer_with_candidates.all_suffixes_self_score(len(candidates) - 1))
+
+
+def test_scorer_attributes_match_oracle():
+    counts = synth.piecewise_poisson(3000, 8)
+    cands = synth.random_candidates(3000, 200, 8)
+    for alpha, beta, cls in [(1, 1, LogMarginalLikelyhoodIntAlphaComputer), (2.5, 0.5, LogMarginalLikelyhoodRealAlphaComputer)]:
+        sc = cls(counts, alpha, beta, cands)
+        ref = po.Scorer(counts, cands, po.Tables(alpha, beta))
+        assert np.array_equal(sc.cumsum, ref.cumsum)
+        assert sc.segment_creation_cost == ref.pen
+        assert np.array_equal(sc.scores(), ref.scores())
+        assert np.array_equal(sc.mean_counts(), ref.mean_counts())
+        assert np.allclose(sc.logfac_cumsum, ref.logfac_cumsum, rtol=1e-12, atol=1e-9)
+        assert np.allclose(sc.log_marginal_likelyhoods(), ref.log_marginal_likelyhoods(), rtol=1e-9, atol=1e-9)
+        assert abs(sc.total_sum_logfac() - ref.total_sum_logfac()) <= 1e-9 * abs(ref.total_sum_logfac())
+        assert sc.score(3, 17) == ref.row(17)[3] + ref.pen
+        assert sc.score_no_splits() == ref.row(len(cands) - 1)[0] + ref.pen
+
+
+def test_scorer_asserts():
+    with pytest.raises(AssertionError):
+        LogMarginalLikelyhoodIntAlphaComputer(np.array([1, -2, 3]), 1, 1, np.array([0, 3]))
+    with pytest.raises(AssertionError):
+        LogMarginalLikelyhoodIntAlphaComputer(np.array([1.0, 2.0]), 1, 1, np.array([0, 2]))
+    with pytest.raises(AssertionError):
+        LogMarginalLikelyhoodIntAlphaComputer(np.array([1, 2, 3]), 1, 1, np.array([0, 2]))
+    with pytest.raises(AssertionError):
+        LogMarginalLikelyhoodIntAlphaComputer(np.array([1, 2, 3]), 1, 1, np.array([0, 2, 2, 3]))
+    with pytest.raises(AssertionError):
+        LogMarginalLikelyhoodIntAlphaComputer([1, 2, 3], 1, 1, np.array([0, 3]))
+    with pytest.raises(AssertionError):
+        ScorerFactory(-1, 1)
+
+
+def test_benchmark_shapes():
+    # reference tests/test_bench_pasio.py:19-48 shapes (results vs the oracle)
+    f = lambda c, s: LogMarginalLikelyhoodIntAlphaComputer(c, 1, 1, s)
+    t = po.Tables(1, 1)
+    for half in [50, 500]:
+        np.random.seed(2)
+        counts = np.concatenate([np.random.poisson(15, half), np.random.poisson(20, half)])
+        score, splits = SquareSplitter(f).split(counts, np.arange(len(counts) + 1))
+        o = po.square_split(counts, np.arange(len(counts) + 1), t)
+        assert score == o[0] and np.array_equal(splits, o[1])
+    np.random.seed(2)
+    counts = np.concatenate([np.random.poisson(15, 50000), np.random.poisson(20, 50000)])
+    cands = np.hstack([np.arange(0, len(counts), 100), 100000])
+    score, splits = SquareSplitter(f).split(counts, cands)
+    o = po.square_split(counts, cands, t)
+    assert score == o[0] and np.array_equal(splits, o[1])
+
+
+def test_object_route_equals_fused_route():
+    """lambda factories are not fused: windows go one by one through the objects (and still run the DP
+    on the GPU); the result must equal the fused one-launch-per-round path."""
+    counts = synth.dnase_like(12000, 21, hotspot_share=0.5)
+    cands = np.arange(len(counts) + 1)
+    lam = lambda c, s: LogMarginalLikelyhoodIntAlphaComputer(c, 1, 1, s)
+    fused_f = ScorerFactory(1.0, 1.0)
+    for head in [NotConstantReducer, NotZeroReducer, None]:
+        def graph(fac):
+            sq = SquareSplitter(fac)
+            base = ReducerCombiner(head(), sq) if head else sq
+            return RoundReducer(SlidingWindowReducer(SlidingWindow(200, 100), base))
+        slow = graph(lam).reduce_candidate_list(counts, cands)
+        fast = graph(fused_f).reduce_candidate_list(counts, cands)
+        assert np.array_equal(slow, fast)
+        one = SlidingWindowReducer(SlidingWindow(200, 100), SquareSplitter(fused_f)).reduce_candidate_list(counts, cands)
+        assert one[0] == 0 and one[-1] == len(counts)
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('default300k', dict()),
+    ('exact4k', dict(algorithm='exact')),
+    ('zeros100k', dict(split_constraints='zeros', window_size=600, window_shift=300)),
+    ('real100k', dict(alpha=0.7, beta=2.0, window_size=1000, window_shift=500)),
+    ('rounds2', dict(num_rounds=2, window_size=1000, window_shift=500)),
+])
+def test_segments_with_scores_vs_reference_fixture(golden, name, kwargs):
+    g = golden('pipeline.npz')
+    counts = g[name + '.counts'].astype(np.int64)
+    splitter = configure_splitter(**kwargs)
+    segs = list(pasio_b200.segments_with_scores(counts, splitter))
+    starts = np.array([s.start for s in segs])
+    stops = np.array([s.stop for s in segs])
+    means = np.array([s.mean_count for s in segs])
+    lmm = np.array([s.log_marginal_likelyhood for s in segs])
+    score, splits = splitter.split(counts, np.arange(len(counts) + 1))
+    g.check_splits(np.concatenate([starts, stops[-1:]]), np.concatenate([g[name + '.starts'], g[name + '.stops'][-1:]]),
+                   score, g[name + '.score'], name)
+    assert np.array_equal(splits[:-1], starts)
+    if g.same_tables:
+        assert np.array_equal(means, g[name + '.mean'])
+        # logfac_cumsum is a parallel scan here and a sequential sum in the reference: tolerance only
+        assert np.allclose(lmm, g[name + '.lmm'], rtol=1e-9, atol=1e-7)
+
+
+def test_split_bedgraph_text_vs_reference_fixture(golden):
+    g = golden('pipeline.npz')
+    text = str(g['bg.input'])
+    for mode in ['bedgraph', 'bed', 'bedgraph+length+LMM']:
+        for gaps in [False, True]:
+            out = io.StringIO()
+            split_bedgraph_stream(io.StringIO(text), out, configure_splitter(window_size=500, window_shift=250),
+                                  split_at_gaps=gaps, output_mode=mode)
+            want = str(g['bg.%s.%d' % (mode, int(gaps))])
+            if not g.same_tables:
+                continue
+            if mode != 'bedgraph+length+LMM':
+                assert out.getvalue() == want, (mode, gaps)
+            else:
+                a = [ln.split('\t') for ln in out.getvalue().splitlines()]
+                b = [ln.split('\t') for ln in want.splitlines()]
+                assert len(a) == len(b)
+                for x, y in zip(a, b):
+                    assert x[:5] == y[:5]
+                    assert abs(float(x[5]) - float(y[5])) <= 2e-6 + 1e-9 * abs(float(y[5]))
+
+
+def test_slidingwindow_algorithm_graph():
+    # the reference crashes for algorithm='slidingwindow' (NameError); the intended graph is
+    # ReducerCombiner(SlidingWindowReducer, SquareSplitter) -- checked against the oracle
+    counts = synth.dnase_like(20000, 3, hotspot_share=0.5)
+    splitter = configure_splitter(algorithm='slidingwindow', window_size=300, window_shift=150)
+    score, splits = splitter.split(counts, np.arange(len(counts) + 1))
+    t = po.Tables(1, 1.0)
+    reduced = po.sliding_window_round(counts, np.arange(len(counts) + 1), t, 300, 150, 'constants')
+    o = po.square_split(counts, reduced, t)
+    assert score == o[0] and np.array_equal(splits, o[1])
+    segs = list(pasio_b200.segments_with_scores(counts, splitter))
+    assert np.array_equal([s.start for s in segs], o[1][:-1])
+
+
+def test_regularized_split_uses_device_rows():
+    """regularisation callables are Python: the recurrence is host-driven, rows come from the GPU"""
+    counts = synth.piecewise_poisson(400, 4)
+    cands = np.arange(401)
+    sp = SquareSplitter(ScorerFactory(1.0, 1.0), split_number_regularization_multiplier=3.0)
+    score, splits = sp.split(counts, cands)
+    o = po.square_split_regularized(counts, cands, po.Tables(1, 1.0), num_mult=3.0)
+    assert score == o[0] and np.array_equal(splits, o[1])
+    sp = SquareSplitter(ScorerFactory(1.0, 1.0), length_regularization_multiplier=1.5,
+                        length_regularization_function=lambda x: 1 / np.log(1 + x))
+    score, splits = sp.split(counts, cands)
+    o = po.square_split_regularized(counts, cands, po.Tables(1, 1.0), len_mult=1.5, len_fn=lambda x: 1 / np.log(1 + x))
+    assert score == o[0] and np.array_equal(splits, o[1])

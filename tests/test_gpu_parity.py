@@ -1,0 +1,270 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via pasio_b200._native.Engine) against the
+oracle and against fixtures generated from the unmodified reference.  Bit-exact for splits,
+prefix scores and arg-max indices; 1e-9 relative for summed scores."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+from oracle import pasio_oracle as po
+from oracle import c_oracle
+from pasio_b200 import synth, _native
+from pasio_b200.log_marginal_likelyhood import ScorerFactory
+
+pytestmark = pytest.mark.gpu
+
+_factories = {}
+
+
+def factory(alpha, beta):
+    key = (alpha, beta)
+    if key not in _factories:
+        _factories[key] = ScorerFactory(alpha, beta)
+    return _factories[key]
+
+
+@pytest.fixture(scope='module')
+def eng():
+    return _native.engine()
+
+
+def gpu_exact(eng, counts, cands, alpha, beta, arrays=True):
+    eng.use_scorer(factory(alpha, beta))
+    eng.load(counts)
+    all_pos = len(cands) == len(counts) + 1
+    eng.set_candidates(None if all_pos else cands)
+    return eng.square_split(want_arrays=arrays)
+
+
+EXACT_CASES = ['pp2000_a1b1', 'pp2000_a3b5', 'pp2000_a2.5b3', 'pp2000_a1b0.5', 'sparse3000_a1b1',
+               'sparse3000_a0.5b1', 'bench1001_a1b1', 'wide1502_a1b1', 'wide1502_a2.5b3',
+               'one_nt', 'two_nt', 'zeros500', 'const500']
+
+
+@pytest.mark.parametrize('name', EXACT_CASES)
+def test_exact_dp_vs_reference_fixture(eng, golden, name):
+    g = golden('exact.npz')
+    counts, cands = g.counts(name), g[name + '.cands'].astype(np.int64)
+    alpha, beta = [float(x) for x in g[name + '.ab']]
+    score, splits, P, prev = gpu_exact(eng, counts, cands, alpha, beta)
+    g.check_splits(splits, g[name + '.splits'], score, g[name + '.score'], name)
+    # and bit for bit against the oracle's DP arrays on this host
+    o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, alpha, beta).square_split(cands)
+    assert np.array_equal(P, o_P) and np.array_equal(prev, o_prev)
+    assert score == o_score and np.array_equal(splits, o_splits)
+
+
+@pytest.mark.parametrize('n', [1, 2, 31, 32, 33, 34, 63, 64, 65, 127, 128, 129, 130, 255, 256, 257, 258, 300, 1000, 4100])
+@pytest.mark.parametrize('ab', [(1.0, 1.0), (2.5, 3.0)])
+def test_exact_dp_block_edges(eng, n, ab):
+    """candidate counts around the 32-row / 128-row / 256-column tile edges"""
+    rs = np.random.RandomState(n)
+    counts = (rs.poisson(3, n) * (rs.random_sample(n) < 0.6)).astype(np.int64)
+    cands = np.arange(n + 1, dtype=np.int64)
+    score, splits, P, prev = gpu_exact(eng, counts, cands, *ab)
+    o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, *ab).square_split(cands)
+    assert np.array_equal(P, o_P)
+    assert np.array_equal(prev, o_prev)
+    assert np.array_equal(splits, o_splits) and score == o_score
+
+
+def test_exact_dp_sparse_candidates_and_ties(eng):
+    counts = synth.dnase_like(200000, 77, hotspot_share=0.3)
+    cands = synth.random_candidates(len(counts), 3000, 78)
+    for ab in [(1.0, 1.0), (0.5, 2.0), (4.0, 0.25)]:
+        score, splits, P, prev = gpu_exact(eng, counts, cands, *ab)
+        o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, *ab).square_split(cands)
+        assert np.array_equal(P, o_P) and np.array_equal(prev, o_prev)
+        assert np.array_equal(splits, o_splits)
+
+
+def test_suffix_rows_vs_numpy_oracle(eng):
+    counts = synth.piecewise_poisson(5000, 3)
+    for alpha, beta, cands in [(1.0, 1.0, np.arange(5001)), (2.5, 3.0, synth.random_candidates(5000, 400, 1))]:
+        f = factory(alpha, beta)
+        eng.use_scorer(f)
+        eng.load(counts)
+        eng.set_candidates(None if len(cands) == 5001 else cands)
+        sc = po.Scorer(counts, cands, po.Tables(po.normalise_alpha(alpha), beta))
+        for stop in [1, 2, 33, len(cands) // 2, len(cands) - 1]:
+            assert np.array_equal(eng.suffix_scores(stop), sc.row(stop)), (alpha, stop)
+        assert np.array_equal(eng.cumsum_at_candidates(), sc.cumsum)
+
+
+ROUND_CASES = ['dn60k_c', 'dn60k_z', 'dn20k_n', 'dn60k_real', 'pp30k_c', 'tail_c', 'odd_shift']
+
+
+@pytest.mark.parametrize('name', ROUND_CASES)
+def test_rounds_vs_reference_fixture(eng, golden, name):
+    g = golden('rounds.npz')
+    counts = g[name + '.counts'].astype(np.int64)
+    wsize, wshift, alpha, beta = g[name + '.params']
+    wsize, wshift, alpha, beta = int(wsize), int(wshift), float(alpha), float(beta)
+    constraint = str(g[name + '.constraint'])
+    fo = c_oracle.FlatOracle(counts, alpha, beta)
+    eng.use_scorer(factory(alpha, beta))
+    eng.load(counts)
+    eng.set_candidates(None)
+    cands = np.arange(len(counts) + 1, dtype=np.int64)
+    nrounds = int(g[name + '.nrounds'])
+    for r in range(nrounds):
+        n_in, n_out, cells = eng.round(wsize, wshift, constraint)
+        got = eng.candidates()
+        want, o_cells = fo.round(cands, wsize, wshift, constraint)
+        assert np.array_equal(got, want), (name, r)
+        assert (n_in, n_out, cells) == (len(cands), len(want), o_cells)
+        if g.same_tables:
+            assert np.array_equal(got, g[name + '.round%d' % r]), (name, r)
+        cands = got
+    # the whole loop in one call
+    eng.set_candidates(None)
+    sizes, final, _ = eng.rounds(wsize, wshift, constraint)
+    assert len(sizes) == nrounds and final == len(cands)
+    assert np.array_equal(eng.candidates(), cands)
+    # explicit starting candidates (round 2 input) give round 2 output
+    if nrounds >= 2:
+        start = fo.round(np.arange(len(counts) + 1), wsize, wshift, constraint)[0]
+        eng.set_candidates(start)
+        eng.round(wsize, wshift, constraint)
+        assert np.array_equal(eng.candidates(), fo.round(start, wsize, wshift, constraint)[0])
+    # final scoring (NopSplitter) against the fixture
+    scores, segc, means, logfac = eng.segment_scores(scores=True, counts=True, means=True, logfac=True)
+    sc = po.Scorer(counts, cands, po.Tables(po.normalise_alpha(alpha), beta))
+    assert np.array_equal(scores, sc.scores())
+    assert np.array_equal(means, sc.mean_counts())
+    assert np.array_equal(segc, np.diff(sc.cumsum))
+    assert np.allclose(logfac, sc.logfac_cumsum, rtol=1e-12, atol=1e-9)
+    g.check_splits(cands, g[name + '.splits'], np.sum(scores), g[name + '.score'], name)
+
+
+def test_max_rounds_and_resume(eng):
+    counts = synth.dnase_like(60000, 13, hotspot_share=0.3)
+    fo = c_oracle.FlatOracle(counts, 1.0, 1.0)
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.load(counts)
+    for limit in [1, 2, 3]:
+        eng.set_candidates(None)
+        sizes, final, _ = eng.rounds(400, 200, 'constants', num_rounds=limit)
+        want, o_sizes, _ = fo.rounds(400, 200, 'constants', num_rounds=limit)
+        assert np.array_equal(eng.candidates(), want) and len(sizes) == limit
+
+
+def test_batch_equals_per_contig(eng):
+    lens = [1, 2, 700, 5000, 1249, 1251, 2501, 20000, 3]
+    parts = [synth.dnase_like(n, 100 + k, hotspot_share=0.5) for k, n in enumerate(lens)]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    counts = np.concatenate(parts)
+    eng.use_scorer(factory(1.0, 1.0))
+    for constraint in ['constants', 'zeros', 'none']:
+        eng.load(counts, offsets=offsets)
+        eng.set_candidates(None)
+        eng.rounds(300, 150, constraint)
+        got = eng.candidates()
+        want = []
+        for k, part in enumerate(parts):
+            c, _, _ = c_oracle.FlatOracle(part, 1.0, 1.0).rounds(300, 150, constraint)
+            want.append(c + offsets[k])
+        want = np.unique(np.concatenate(want))
+        assert np.array_equal(got, want), constraint
+    eng.load(counts)        # leave the engine in single-contig mode
+
+
+def test_rle_load_equals_dense(eng):
+    counts = synth.dnase_like(300000, 5, hotspot_share=0.2)
+    change = np.flatnonzero(counts[1:] != counts[:-1]) + 1
+    starts = np.concatenate([[0], change, [len(counts)]]).astype(np.int64)
+    values = counts[starts[:-1]]
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.load_rle(starts, values)
+    assert eng.info()[:2] == (len(counts), int(counts.sum()))
+    eng.rounds(500, 250, 'constants')
+    a = eng.candidates()
+    eng.load(counts)
+    eng.set_candidates(None)
+    eng.rounds(500, 250, 'constants')
+    assert np.array_equal(a, eng.candidates())
+
+
+def test_error_behaviour(eng):
+    eng.use_scorer(factory(1.0, 1.0))
+    bad = np.array([1, 2, -1, 4], dtype=np.int64)
+    with pytest.raises(AssertionError):
+        eng.load(bad)
+    good = np.array([1, 2, 0, 4, 4, 4], dtype=np.int64)
+    eng.load(good)
+    for cands in [[1, 3, 6], [0, 3, 5], [0, 3, 3, 6], [0, 4, 2, 6]]:
+        with pytest.raises(AssertionError):
+            eng.set_candidates(np.array(cands, dtype=np.int64))
+    eng.set_candidates(np.array([0, 3, 6], dtype=np.int64))
+    assert eng.candidate_count() == 3
+    # a window that cannot fit one CTA's shared memory is refused, not silently mis-computed
+    big = synth.piecewise_poisson(40000, 1) + 1
+    eng.load(big)
+    eng.set_candidates(None)
+    with pytest.raises(_native.PasioDeviceError):
+        eng.round(30000, 15000, 'none')
+
+
+def test_config1_full_vs_reference_fixture(eng, golden):
+    """BASELINE config 1 in full: n=100 000 nt, all positions candidates (5.0e9 cells)."""
+    g = golden('config1.npz')
+    counts = g.counts('config1')
+    score, splits = gpu_exact(eng, counts, np.arange(len(counts) + 1), 1.0, 1.0, arrays=False)
+    g.check_splits(splits, g['config1.splits'], score, g['config1.score'], 'config1')
+    # size-independent properties: the optimum equals the sum of its segment scores, and is a fixed point
+    eng.set_candidates(splits)
+    scores = eng.segment_scores(scores=True)[0]
+    assert abs(np.sum(scores) - score) <= 1e-9 * abs(score)
+    score2, splits2 = eng.square_split()
+    assert np.array_equal(splits2, splits)
+
+
+def test_config3_prefix_property(eng):
+    """BASELINE config 3: N=200 000 candidates over 2 Mb.  The first K rows of the DP depend only on
+    the first K candidates, so the oracle pins a prefix of the full-size run bit for bit."""
+    counts = synth.piecewise_poisson(2000000, 1)
+    cands = synth.random_candidates(len(counts), 200000, 1)
+    score, splits, P, prev = gpu_exact(eng, counts, cands, 1.0, 1.0)
+    K = 20000
+    sub_counts = counts[:cands[K - 1]]
+    _, _, o_P, o_prev = c_oracle.FlatOracle(sub_counts, 1.0, 1.0).square_split(cands[:K])
+    assert np.array_equal(P[:K], o_P) and np.array_equal(prev[:K], o_prev)
+    assert splits[0] == 0 and splits[-1] == len(counts) and np.all(np.diff(splits) > 0)
+    assert np.all(np.isin(splits, cands))
+    eng.set_candidates(splits)
+    scores = eng.segment_scores(scores=True)[0]
+    assert abs(np.sum(scores) - score) <= 1e-9 * abs(score)
+
+
+def test_default_pipeline_5mb_vs_oracle(eng):
+    """default flags (2500/1250, constants) on a 5 Mb DNase-like contig, every round checked"""
+    counts = synth.dnase_like(5000000, 0)
+    fo = c_oracle.FlatOracle(counts, 1.0, 1.0)
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.load(counts)
+    eng.set_candidates(None)
+    cands = np.arange(len(counts) + 1, dtype=np.int64)
+    for r in range(20):
+        n_in, n_out, cells = eng.round(2500, 1250, 'constants')
+        want, o_cells = fo.round(cands, 2500, 1250, 'constants')
+        got = eng.candidates()
+        assert np.array_equal(got, want), r
+        assert cells == o_cells
+        if len(want) == len(cands):
+            break
+        cands = want
+    assert r >= 2
+
+
+def test_timing_hooks(eng):
+    counts = synth.dnase_like(100000, 9, hotspot_share=0.3)
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.timing_reset(True)
+    eng.load(counts)
+    eng.set_candidates(None)
+    eng.rounds(500, 250, 'constants')
+    t = eng.timing()
+    eng.timing_reset(False)
+    assert t['scan'][1] == 1 and t['scan'][0] > 0
+    assert t['window_dp'][1] >= 2 and t['window_dp'][0] > 0

@@ -1,0 +1,260 @@
+"""Host-side logic that needs no GPU: the reference's fake-scorer tests
+(/root/reference/tests/test_pasio.py:68-175, :230-325; tests/test_slice_when.py) restated against
+pasio_b200, option validation, fusion-plan recognition, table builders, LPT sharding."""
+import numpy as np
+import pytest
+
+from pasio_b200.splitters import (SquareSplitter, SlidingWindowReducer, RoundReducer, NotZeroReducer,
+                                  NotConstantReducer, ReducerCombiner, NopSplitter, configure_splitter)
+from pasio_b200.splitters import _fusion
+from pasio_b200.dto.sliding_window import SlidingWindow
+from pasio_b200.process_bedgraph import parse_bedgraph, parse_bedgraph_stream
+from pasio_b200.utils.slice_when import slice_when
+from pasio_b200.cached_log import LogComputer, LogGammaComputer
+from pasio_b200 import sharding
+
+
+class SimpleScorer:
+    # user-defined scorer object (reference tests/test_pasio.py:68-87): not LogML, cannot run on a device
+    def __init__(self, sequence, split_candidates):
+        self.sequence = sequence
+        self.split_candidates = split_candidates
+        self.segment_creation_cost = 0
+
+    def score(self, start, stop):
+        return self.self_score(start, stop)
+
+    def self_score(self, start, stop):
+        start = self.split_candidates[start]
+        stop = self.split_candidates[stop]
+        if len(set(self.sequence[start:stop])) == 1:
+            return (stop - start) ** 2
+        return stop - start
+
+    def all_suffixes_self_score(self, stop):
+        return np.array([self.self_score(i, stop) for i in range(stop)], dtype='float64')
+
+
+class SimpleGreedyScorer(SimpleScorer):
+    def self_score(self, start, stop):
+        return (self.split_candidates[stop] - self.split_candidates[start]) ** 0.5
+
+
+simple = lambda counts, cands: SimpleScorer(counts, cands)
+greedy = lambda counts, cands: SimpleGreedyScorer(counts, cands)
+
+
+@pytest.mark.parametrize('seq,cands,splits,score', [
+    ('A', None, [0, 1], 1), ('AAA', None, [0, 3], 9), ('AAABBB', None, [0, 3, 6], 18),
+    ('AAABBBC', None, [0, 3, 6, 7], 19), ('ABBBC', None, [0, 1, 4, 5], 11),
+    ('AAABBB', [0, 1, 2, 3, 5, 6], [0, 3, 6], 18), ('AAABBB', [0, 3, 5, 6], [0, 3, 6], 18),
+    ('AAABBBC', [0, 3, 7], [0, 3, 7], 13), ('AAAAAA', [0, 3, 6], [0, 6], 36)])
+def test_square_splitter_with_user_scorer(seq, cands, splits, score):
+    cands = np.arange(len(seq) + 1) if cands is None else np.array(cands)
+    got_score, got = SquareSplitter(simple).split(seq, cands)
+    assert np.array_equal(got, splits) and got_score == score
+
+
+def test_split_number_regularization():
+    sp = SquareSplitter(SimpleScorer, split_number_regularization_multiplier=3,
+                        split_number_regularization_function=lambda x: x)
+    score, splits = sp.split('AAABAA', np.arange(7))
+    assert np.array_equal(splits, [0, 3, 6]) and score == 9
+
+
+def test_length_regularization():
+    fn = lambda x: 1 / np.log(1 + x)
+    sp = SquareSplitter(SimpleScorer, length_regularization_multiplier=1.5, length_regularization_function=fn)
+    score, splits = sp.split('AAABAA', np.arange(7))
+    assert np.array_equal(splits, [0, 3, 6])
+    assert score == 9 + 3 - 1.5 * (1 / np.log(3 + 1) + 1 / np.log(3 + 1))
+    score, splits = sp.split('AAABAA', np.array([0, 4, 5, 6]))
+    assert np.array_equal(splits, [0, 4, 6])
+    assert score == 4 + 4 - 1.5 * (1 / np.log(4 + 1) + 1 / np.log(2 + 1))
+
+
+def test_collect_split_points():
+    f = SquareSplitter.collect_split_points
+    assert f([0, 0, 0]) == [0, 2]
+    assert f([0, 0, 1, 2, 3, 4]) == [0, 1, 2, 3, 4, 5]
+    assert f([0, 0, 0, 0, 0, 2, 3, 4]) == [0, 4, 7]
+    assert f([0, 0, 0, 2, 1, 4]) == [0, 1, 4, 5]
+    assert f([0, 0, 0, 2, 1, 3]) == [0, 2, 3, 5]
+
+
+def test_sliding_window_with_user_scorer():
+    A, B = 'A' * 16, 'B' * 17
+    seq = A + B
+    window = SlidingWindow(window_size=10, window_shift=5)
+    base = SquareSplitter(simple)
+    score, splits = ReducerCombiner(SlidingWindowReducer(window, base_reducer=base), base).split(seq, np.arange(len(seq) + 1))
+    assert np.array_equal(splits, [0, len(A), len(seq)]) and score == len(A) ** 2 + len(B) ** 2
+    base = SquareSplitter(simple, split_number_regularization_multiplier=2)
+    score, splits = ReducerCombiner(SlidingWindowReducer(window, base_reducer=base), base).split(seq, np.arange(len(seq) + 1))
+    assert np.array_equal(splits, [0, len(A), len(seq)]) and score == len(A) ** 2 + len(B) ** 2 - 2
+
+
+def test_round_reducer_with_user_scorer():
+    seq = 'A' * 40 + 'B' * 33 + 'C' * 50
+    window = SlidingWindow(window_size=12, window_shift=6)
+    base = SquareSplitter(simple)
+    reducer = RoundReducer(SlidingWindowReducer(window, base))
+    got = reducer.reduce_candidate_list(seq, np.arange(len(seq) + 1))
+    once = SlidingWindowReducer(window, base).reduce_candidate_list(seq, got)
+    assert np.array_equal(once, got)                       # fixed point
+    assert 40 in got and 73 in got and got[0] == 0 and got[-1] == len(seq)
+    one_round = RoundReducer(SlidingWindowReducer(window, base), num_rounds=1).reduce_candidate_list(seq, np.arange(len(seq) + 1))
+    assert np.array_equal(one_round, SlidingWindowReducer(window, base).reduce_candidate_list(seq, np.arange(len(seq) + 1)))
+
+
+def test_not_constant_and_not_zero():
+    seq = np.array([1, 1, 1, 2, 2, 2, 2])
+    allp = np.arange(len(seq) + 1)
+    assert np.array_equal(ReducerCombiner(NotZeroReducer(), SquareSplitter(simple)).split(seq, allp)[1], [0, 3, 7])
+    assert np.array_equal(ReducerCombiner(NotZeroReducer(), SquareSplitter(greedy)).split(seq, allp)[1], list(range(8)))
+    assert np.array_equal(ReducerCombiner(NotConstantReducer(), SquareSplitter(greedy)).split(seq, allp)[1], [0, 3, 7])
+    assert np.array_equal(ReducerCombiner(NotConstantReducer(), SquareSplitter(greedy)).split(seq, np.array([0, 1, 2, 3, 4, 5, 7]))[1], [0, 3, 7])
+    nc = NotConstantReducer()
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.array([0, 3, 7])), [0, 3, 7])
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.arange(8)), [0, 3, 7])
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.array([0, 3, 5, 7])), [0, 3, 7])
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.array([0, 5, 7])), [0, 7])
+    assert np.array_equal(NotZeroReducer().reduce_candidate_list(np.zeros(5, dtype=int), np.arange(6)), [0, 5])
+    assert np.array_equal(NotZeroReducer().reduce_candidate_list(seq, np.array([0, 5, 7])), [0, 5, 7])
+
+
+def test_reducers_vs_reference_fixture(golden):
+    g = golden('reducers.npz')
+    for k in range(6):
+        c, cands = g['r%d.counts' % k], g['r%d.cands' % k]
+        assert np.array_equal(NotZeroReducer().reduce_candidate_list(c, cands), g['r%d.notzero' % k])
+        assert np.array_equal(NotConstantReducer().reduce_candidate_list(c, cands), g['r%d.notconstant' % k])
+
+
+def test_reducer_combiner_without_splitter():
+    rc = ReducerCombiner(NotZeroReducer())
+    with pytest.raises(Exception):
+        rc.split(np.array([1]), np.array([0, 1]))
+    with pytest.raises(Exception):
+        rc.scorer(np.array([1]), np.array([0, 1]))
+
+
+def test_sliding_window_geometry():
+    # dto/sliding_window.py:9-15; trailing windows are subsets of earlier ones
+    sizes = [len(w) for w, _ in SlidingWindow(100, 50).windows(np.arange(202))]
+    assert sizes == [101, 101, 101, 52, 2]
+    w = SlidingWindow(10, 5)
+    assert w.ranges(2) == [(0, 2)]
+    assert w.ranges(11) == [(0, 11), (5, 11)]
+    assert [c for _, c in w.windows(np.arange(11))] == [1.0, 1.0]
+
+
+def test_configure_splitter_validation_and_plans():
+    with pytest.raises(ValueError):
+        configure_splitter(algorithm='bogus')
+    with pytest.raises(ValueError):
+        configure_splitter(window_shift=None)
+    with pytest.raises(ValueError):
+        configure_splitter(window_size=None)
+    with pytest.raises(ValueError):
+        configure_splitter(length_regularization=1.0)
+    with pytest.raises(ValueError):
+        configure_splitter(length_regularization_function='revlog')
+    with pytest.raises(ValueError):
+        configure_splitter(split_constraints='bogus')
+    s = configure_splitter(some_unknown_flag=1)
+    plan = _fusion.pipeline_plan(s)
+    assert plan['final'] == 'nop' and plan['steps'][0][0] == 'rounds' and plan['steps'][0][2:] == (2500, 1250, 'constants', None)
+    assert _fusion.pipeline_plan(configure_splitter(algorithm='exact'))['final'] == 'exact'
+    plan = _fusion.pipeline_plan(configure_splitter(algorithm='slidingwindow', split_constraints='zeros'))
+    assert plan['final'] == 'exact' and plan['steps'][0][0] == 'window' and plan['steps'][0][4] == 'zeros'
+    # regularised or user-scorer graphs are never fused
+    assert _fusion.pipeline_plan(configure_splitter(split_number_regularization=1.0)) is None
+    assert _fusion.pipeline_plan(SquareSplitter(simple)) is None
+    s = configure_splitter(length_regularization=2.0, length_regularization_function='revlog', algorithm='exact')
+    assert s.length_regularization_function(np.array([1.0])) == 1 / np.log(2.0)
+
+
+def test_table_builders_extend_bit_identically():
+    import scipy.special
+    lc = LogComputer(shift=1.0, cache_size=4096)
+    lg = LogGammaComputer(shift=2.5, cache_size=4096)
+    n = 3 * (1 << 20) + 17            # crosses the chunked multi-thread build
+    assert np.array_equal(lc.table(n)[:n], np.log(np.arange(n) + 1.0))
+    assert np.array_equal(lg.table(n)[:n], scipy.special.gammaln(np.arange(n) + 2.5))
+    x = np.array([0, 5, 4095, 4096, 100000, n - 1])
+    assert np.array_equal(lc.compute_for_array_unbound(x), np.log(x + 1.0))
+    assert np.array_equal(lg.compute_for_array(x, max_value=n), scipy.special.gammaln(x + 2.5))
+    assert lc.compute_for_number(7) == np.log(8.0) and lc.compute_for_number(10 ** 7) == np.log(10 ** 7 + 1.0)
+
+
+def test_approximate_log_gamma():
+    # reference tests/test_pasio.py:178-190
+    c = LogGammaComputer()
+    tol = 1e-8
+    for k in [256, 4095, 4096, 4097, 10000]:
+        assert np.abs(np.log(np.arange(1, k + 1)).sum() - c.compute_for_number(k + 1)) < tol
+    arr = np.array([0, 1, 20, 1024, 10000])
+    want = np.array([np.log(np.arange(1, x + 1)).sum() for x in arr])
+    assert np.allclose(c.compute_for_array_unbound(arr + 1), want, atol=tol)
+
+
+def test_bedgraph_reader(tmp_path):
+    # reference tests/test_pasio.py:237-260
+    p = tmp_path / 'test.bedgraph'
+    p.write_text('''chr1 0 10 0
+        chr1 10 22 21
+        chr1 22 23 30
+        chr1 23 50 0
+        chr2 0 15 0
+        chr2 15 50 2
+        chr2 50 60 0
+        ''')
+    chroms = {k: v for (k, v, l) in parse_bedgraph(str(p))}
+    assert len(chroms) == 2 and len(chroms['chr1']) == 50 and len(chroms['chr2']) == 60
+    assert np.all(chroms['chr1'][0:10] == 0) and np.all(chroms['chr1'][10:22] == 21)
+    assert chroms['chr1'][22] == 30 and np.all(chroms['chr1'][23:50] == 0)
+    assert np.all(chroms['chr2'][0:15] == 0) and np.all(chroms['chr2'][15:50] == 2) and np.all(chroms['chr2'][50:60] == 0)
+    assert chroms['chr1'].dtype == int
+
+
+def test_bedgraph_gaps(golden):
+    import io
+    text = 'c1\t5\t8\t2\nc1\t10\t12\t7.0\nc2\t0\t1\t4\n'
+    filled = list(parse_bedgraph_stream(io.StringIO(text)))
+    assert [(c, s) for c, _, s in filled] == [('c1', 5), ('c2', 0)]
+    assert filled[0][1].tolist() == [2, 2, 2, 0, 0, 7, 7]
+    cut = list(parse_bedgraph_stream(io.StringIO(text), split_at_gaps=True))
+    assert [(c, p.tolist(), s) for c, p, s in cut] == [('c1', [2, 2, 2], 5), ('c1', [7, 7], 10), ('c2', [4], 0)]
+
+
+def test_slice_when():
+    # reference tests/test_slice_when.py
+    neq = lambda a, b: a != b
+    groups = lambda xs: [list(g) for g in slice_when(xs, neq)]
+    assert groups([]) == []
+    assert groups([1]) == [[1]]
+    assert groups([1, 1, 2, 3, 3, 3]) == [[1, 1], [2], [3, 3, 3]]
+    assert groups(iter([1, 2, 2])) == [[1], [2, 2]]
+    it = slice_when([1, 1, 2, 2, 3], neq)
+    first = next(it)
+    assert next(first) == 1
+    second = next(it)              # unfinished first group is drained
+    assert list(second) == [2, 2]
+    assert list(next(it)) == [3]
+    with pytest.raises(StopIteration):
+        next(it)
+
+
+def test_lpt_assignment():
+    lens = [248, 242, 198, 190, 181, 170, 159, 145, 138, 133, 135, 133, 114, 107, 101, 90, 83, 80, 58, 64, 46, 50, 156, 57]
+    for world in [1, 2, 4, 8]:
+        rank_of = sharding.lpt_assign(lens, world)
+        loads = [sum(l for l, r in zip(lens, rank_of) if r == k) for k in range(world)]
+        assert sum(loads) == sum(lens)
+        assert max(loads) <= sum(lens) / world + max(lens)        # LPT bound
+        assert max(loads) / (sum(lens) / world) < 1.1 or world == 8
+    # deterministic and order-independent of ties
+    assert np.array_equal(sharding.lpt_assign(lens, 4), sharding.lpt_assign(list(lens), 4))
+    res = sharding.segment_contigs([('a', np.zeros(3), 0), ('b', np.zeros(9), 0)], lambda n, c, s: n + str(len(c)))
+    assert res == ['a3', 'b9']
