@@ -129,6 +129,7 @@ def test_rounds_vs_reference_fixture(eng, golden, name):
         eng.round(wsize, wshift, constraint)
         assert np.array_equal(eng.candidates(), fo.round(start, wsize, wshift, constraint)[0])
     # final scoring (NopSplitter) against the fixture
+    eng.set_candidates(cands)
     scores, segc, means, logfac = eng.segment_scores(scores=True, counts=True, means=True, logfac=True)
     sc = po.Scorer(counts, cands, po.Tables(po.normalise_alpha(alpha), beta))
     assert np.array_equal(scores, sc.scores())
