@@ -81,6 +81,10 @@ int pasio_contig_load(pasio_ctx *ctx, const int64_t *counts, int64_t n,
  * run r covers [starts[r], starts[r+1]) with value values[r]; starts has n_runs+1 entries. */
 int pasio_contig_load_rle(pasio_ctx *ctx, const int64_t *starts, const int64_t *values,
                           int64_t n_runs, const int64_t *offsets, int64_t n_contigs);
+/* Same as pasio_contig_load with the counts already resident in device memory (no copy is made;
+ * the caller keeps d_counts alive and unmodified until the next load). */
+int pasio_contig_load_device(pasio_ctx *ctx, const int64_t *d_counts_device, int64_t n,
+                             const int64_t *offsets, int64_t n_contigs);
 int pasio_contig_info(const pasio_ctx *ctx, int64_t *n, int64_t *total_count, int64_t *n_contigs);
 /* cumsum[candidates] as the reference scorer exposes it (log_marginal_likelyhood.py:57). */
 int pasio_cumsum_at(pasio_ctx *ctx, const int64_t *positions, int64_t m, int64_t *out);
@@ -138,6 +142,11 @@ int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *segment_counts
  * kernel family since the last reset: 0 scan, 1 window DP, 2 compaction+prepass,
  * 3 exact DP, 4 scoring, 5 H2D, 6 D2H. */
 int pasio_timing_reset(pasio_ctx *ctx, int enable);
+/* The context's cudaStream_t (as void*), so a caller can bracket calls with its own CUDA events. */
+void *pasio_stream(pasio_ctx *ctx);
+/* FP64-pipe micro-benchmark (independent DFMA chains on every SM): measured FP64 instructions/s,
+ * the denominator of the DP roofline (MEASURED_PEAKS.json has no FP64 entry). */
+int pasio_fp64_peak(pasio_ctx *ctx, double *instr_per_sec);
 int pasio_timing_get(pasio_ctx *ctx, int family, double *ms, int64_t *launches);
 
 #ifdef __cplusplus

@@ -35,6 +35,7 @@ SIGNATURES = {
     'pasio_table_need': (ctypes.c_int, [_vp, _i64p, _i64p, _i64p]),
     'pasio_contig_load': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _i64]),
     'pasio_contig_load_rle': (ctypes.c_int, [_vp, _i64p, _i64p, _i64, _i64p, _i64]),
+    'pasio_contig_load_device': (ctypes.c_int, [_vp, _vp, _i64, _i64p, _i64]),
     'pasio_contig_info': (ctypes.c_int, [_vp, _i64p, _i64p, _i64p]),
     'pasio_cumsum_at': (ctypes.c_int, [_vp, _i64p, _i64, _i64p]),
     'pasio_candidates_set': (ctypes.c_int, [_vp, _i64p, _i64]),
@@ -47,6 +48,8 @@ SIGNATURES = {
     'pasio_segment_scores': (ctypes.c_int, [_vp, _f64p, _i64p, _f64p, _f64p, _i64, _i64p]),
     'pasio_timing_reset': (ctypes.c_int, [_vp, ctypes.c_int]),
     'pasio_timing_get': (ctypes.c_int, [_vp, ctypes.c_int, _f64p, _i64p]),
+    'pasio_stream': (_vp, [_vp]),
+    'pasio_fp64_peak': (ctypes.c_int, [_vp, _f64p]),
 }
 
 _lib = None
@@ -175,6 +178,32 @@ class Engine(object):
         self._check(rc)
         self._loaded = counts
         self._loaded_offsets = None if offsets is None else np.array(offsets, dtype=np.int64)
+
+    def load_device(self, device_ptr, n, owner=None, offsets=None):
+        """counts already in HBM (int64[n] at device_ptr, e.g. a torch tensor's data_ptr()); no copy."""
+        self._loaded = None
+        self._cands_obj = None
+        if offsets is None:
+            rc = self.lib.pasio_contig_load_device(self.ctx, _vp(device_ptr), n, None, 1)
+        else:
+            off = np.ascontiguousarray(offsets, dtype=np.int64)
+            rc = self.lib.pasio_contig_load_device(self.ctx, _vp(device_ptr), n, _ptr(off, ctypes.c_int64), len(off) - 1)
+        self._check(rc)
+        self._loaded = owner if owner is not None else object()   # keeps the device buffer alive
+        self._loaded_offsets = None if offsets is None else np.array(offsets, dtype=np.int64)
+
+    def invalidate(self):
+        """Forget the identity caches (the next load / set_candidates re-uploads)."""
+        self._loaded = None
+        self._cands_obj = None
+
+    def stream_handle(self):
+        return self.lib.pasio_stream(self.ctx)
+
+    def fp64_peak(self):
+        v = ctypes.c_double(0)
+        self._check(self.lib.pasio_fp64_peak(self.ctx, ctypes.byref(v)))
+        return v.value
 
     def load_rle(self, starts, values, offsets=None):
         starts = np.ascontiguousarray(starts, dtype=np.int64)

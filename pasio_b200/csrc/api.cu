@@ -95,6 +95,11 @@ static int d2h(pasio_ctx *ctx, void *dst, const void *src, size_t bytes)
     return PASIO_OK;
 }
 
+static void drop_borrowed_counts(pasio_ctx *ctx)
+{
+    if (ctx->counts_borrowed) { ctx->counts.p = nullptr; ctx->counts.bytes = 0; ctx->counts_borrowed = false; }
+}
+
 #define NEED_CTX(ctx) do { if (!(ctx)) return PASIO_E_ARG; cudaSetDevice((ctx)->device); } while (0)
 
 // ---- context ------------------------------------------------------------------------------------
@@ -145,6 +150,7 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     if (!ctx) return PASIO_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    drop_borrowed_counts(ctx);
     DevBuf *bufs[] = {&ctx->tab[0], &ctx->tab[1], &ctx->tab[2], &ctx->counts, &ctx->cg, &ctx->cpbits, &ctx->keepbits,
                       &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
@@ -267,8 +273,23 @@ extern "C" int pasio_contig_load(pasio_ctx *ctx, const int64_t *counts, int64_t 
     if (!counts) return pasio_fail(ctx, PASIO_E_ARG, "counts is NULL");
     PASIO_TRY(check_load_args(ctx, n, offsets, n_contigs));
     ctx->n = n;
+    drop_borrowed_counts(ctx);
     PASIO_TRY(pasio_reserve(ctx, ctx->counts, (size_t)n * 8 + 16));
     PASIO_TRY(h2d(ctx, ctx->counts.p, counts, (size_t)n * 8));
+    return finish_load(ctx, offsets, n_contigs);
+}
+
+extern "C" int pasio_contig_load_device(pasio_ctx *ctx, const int64_t *d_counts, int64_t n, const int64_t *offsets,
+                                        int64_t n_contigs)
+{
+    NEED_CTX(ctx);
+    if (!d_counts) return pasio_fail(ctx, PASIO_E_ARG, "d_counts is NULL");
+    PASIO_TRY(check_load_args(ctx, n, offsets, n_contigs));
+    ctx->n = n;
+    if (ctx->counts.p && !ctx->counts_borrowed) cudaFree(ctx->counts.p);
+    ctx->counts.p = const_cast<int64_t *>(d_counts);
+    ctx->counts.bytes = (size_t)n * 8;
+    ctx->counts_borrowed = true;
     return finish_load(ctx, offsets, n_contigs);
 }
 
@@ -281,6 +302,7 @@ extern "C" int pasio_contig_load_rle(pasio_ctx *ctx, const int64_t *starts, cons
     const i64 n = starts[n_runs];
     PASIO_TRY(check_load_args(ctx, n, offsets, n_contigs));
     ctx->n = n;
+    drop_borrowed_counts(ctx);
     PASIO_TRY(pasio_reserve(ctx, ctx->counts, (size_t)n * 8 + 16));
     // stage the runs in scratch buffers (dpP / dpJump are free while a contig is being loaded)
     PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)(n_runs + 1) * 8));
@@ -602,6 +624,45 @@ extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *seg
 }
 
 // ---- measurement hooks --------------------------------------------------------------------------
+extern "C" void *pasio_stream(pasio_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int pasio_fp64_peak(pasio_ctx *ctx, double *instr_per_sec)
+{
+    NEED_CTX(ctx);
+    if (!instr_per_sec) return pasio_fail(ctx, PASIO_E_ARG, "NULL output");
+    const int blocks = ctx->sm_count * 8, iters = 1 << 15;
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)blocks * 256 * 8));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        fp64_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->dpPart.as<double>(), iters, 0.999999, 1e-9);
+        cudaEventRecord(b, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return pasio_fail(ctx, PASIO_E_CUDA, "fp64 peak kernel: %s", cudaGetErrorString(e));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double rate = (double)blocks * 256 * 8.0 * iters / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *instr_per_sec = best;
+    return PASIO_OK;
+}
+
 extern "C" int pasio_timing_reset(pasio_ctx *ctx, int enable)
 {
     NEED_CTX(ctx);

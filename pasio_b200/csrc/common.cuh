@@ -51,6 +51,7 @@ struct pasio_ctx {
     i64 n_contigs = 0;
     std::vector<int32_t> h_bounds;   // n_contigs+1 boundary positions (host copy)
     DevBuf counts;               // int64[n]
+    bool counts_borrowed = false; // counts.p belongs to the caller (pasio_contig_load_device)
     DevBuf cg;                   // int64[n+1] exclusive prefix sums, cg[0]=0
     DevBuf cpbits;               // uint32 bitmap over positions 0..n : counts[p-1]!=counts[p]
     DevBuf keepbits;             // uint32 bitmap over positions 0..n : survivors of a round
