@@ -54,30 +54,35 @@ __device__ __forceinline__ double self_score(int ci, int li, const RowConst<AI> 
 
 // Sweep columns [i0, i1) for this lane's row; strict '>' keeps the first maximum.
 // sLC[i] = (L_i, C_i), sP[i] = P_i (shared memory, broadcast reads).
-template <bool AI>
+// The table gathers are the long-latency part: each batch of U cells first issues all 2*U
+// gathers, then does the arithmetic, so a warp keeps 2*U loads in flight.
+template <bool AI, int U>
 __device__ __forceinline__ void sweep_columns(int i0, int i1, const int2 *sLC, const double *sP,
                                               const RowConst<AI> &r, const double *__restrict__ gtab,
                                               const double *__restrict__ ltab, double &best, int &arg)
 {
     int i = i0;
-    for (; i + 4 <= i1; i += 4) {
-        int2 a0 = sLC[i], a1 = sLC[i + 1], a2 = sLC[i + 2], a3 = sLC[i + 3];
-        double t0 = self_score<AI>(a0.y, a0.x, r, gtab, ltab);
-        double t1 = self_score<AI>(a1.y, a1.x, r, gtab, ltab);
-        double t2 = self_score<AI>(a2.y, a2.x, r, gtab, ltab);
-        double t3 = self_score<AI>(a3.y, a3.x, r, gtab, ltab);
-        t0 = __dadd_rn(t0, sP[i]);
-        t1 = __dadd_rn(t1, sP[i + 1]);
-        t2 = __dadd_rn(t2, sP[i + 2]);
-        t3 = __dadd_rn(t3, sP[i + 3]);
-        if (t0 > best) { best = t0; arg = i; }
-        if (t1 > best) { best = t1; arg = i + 1; }
-        if (t2 > best) { best = t2; arg = i + 2; }
-        if (t3 > best) { best = t3; arg = i + 3; }
+    for (; i + U <= i1; i += U) {
+        double g[U], lg[U];
+        int sx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int2 a = sLC[i + u];
+            const int idx = r.cjx - a.y;
+            g[u] = __ldg(gtab + idx);
+            lg[u] = __ldg(ltab + (r.lj - a.x));
+            sx[u] = AI ? idx : a.y;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double s = AI ? u32_to_double(sx[u]) : __dsub_rn(r.aj, u32_to_double(sx[u]));
+            const double t = __dadd_rn(__dsub_rn(g[u], __dmul_rn(s, lg[u])), sP[i + u]);
+            if (t > best) { best = t; arg = i + u; }
+        }
     }
     for (; i < i1; ++i) {
-        int2 a = sLC[i];
-        double t = __dadd_rn(self_score<AI>(a.y, a.x, r, gtab, ltab), sP[i]);
+        const int2 a = sLC[i];
+        const double t = __dadd_rn(self_score<AI>(a.y, a.x, r, gtab, ltab), sP[i]);
         if (t > best) { best = t; arg = i; }
     }
 }
@@ -91,7 +96,7 @@ constexpr int DP_JB = 32;   // rows resolved per block step (one per lane)
 // init_best/init_arg (warp 0 only, per lane) seed the running maximum with what earlier columns
 // (outside [col0, jb)) contributed; pass -inf / 0 when there are none.
 // Requires col0 <= jb, blockDim.x == NW*32.  Ends with a __syncthreads().
-template <bool AI, int NW>
+template <bool AI, int NW, int U>
 __device__ __forceinline__ void dp_block_step(int jb, int N, int col0, const int2 *sLC, double *sP,
                                               unsigned short *sPrev16, int *sPrev32,
                                               double *sPartV, int *sPartA, double *sTri,
@@ -111,7 +116,7 @@ __device__ __forceinline__ void dp_block_step(int jb, int N, int col0, const int
     const int i1 = min(i0 + chunk, jb);
     double best = -INFINITY;
     int arg = i0;
-    sweep_columns<AI>(i0, i1, sLC, sP, r, gtab, ltab, best, arg);
+    sweep_columns<AI, U>(i0, i1, sLC, sP, r, gtab, ltab, best, arg);
     sPartV[warp * 32 + lane] = best;
     sPartA[warp * 32 + lane] = arg;
 

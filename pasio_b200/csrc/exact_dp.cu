@@ -62,7 +62,7 @@ exact_rect_kernel(int jb, int N, int ncols, const int32_t *__restrict__ L, const
     const int i0 = half ? mid : 0, i1 = half ? nloc : mid;
     double best = -INFINITY;
     int arg = i0;
-    sweep_columns<AI>(i0, i1, sLC, sP, r, gtab, ltab, best, arg);
+    sweep_columns<AI, 8>(i0, i1, sLC, sP, r, gtab, ltab, best, arg);
     if (half == 0) { sV[rs * 32 + lane] = best; sA[rs * 32 + lane] = arg; }
     __syncthreads();
     if (half == 1) {
@@ -117,7 +117,7 @@ exact_diag_kernel(int jb, int N, int nparts, const int32_t *__restrict__ L, cons
             const double v1 = sInitV[1][sb + lane];
             if (v1 > ib) { ib = v1; ia = sInitA[1][sb + lane]; }
         }
-        dp_block_step<AI, XD_WARPS>(sb, nrows, 0, sLC, sP, nullptr, sPrev, sPartV, sPartA, sTri, gtab, ltab,
+        dp_block_step<AI, XD_WARPS, 4>(sb, nrows, 0, sLC, sP, nullptr, sPrev, sPartV, sPartA, sTri, gtab, ltab,
                                     alpha_int, alpha, pen, ib, ia, jb);
     }
     if (tid < nrows) {

@@ -15,6 +15,7 @@
 // doubling and an atomicOr scatter of the survivors into the position bitmap.
 // CTAs are persistent and pull windows from an atomic counter (window cost varies as N^2).
 #include "dp_core.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -51,8 +52,8 @@ __host__ __device__ inline size_t window_smem_bytes(int cap)
            + capr * 2;              // sPrev
 }
 
-template <bool AI>
-__global__ void __launch_bounds__(WD_THREADS)
+template <bool AI, int U>
+__global__ void __launch_bounds__(WD_THREADS, 3)
 window_dp_kernel(WinDpParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -119,7 +120,7 @@ window_dp_kernel(WinDpParams p)
         if (tid == 0) { sP[0] = 0.0; sPrev[0] = 0; }
         __syncthreads();
         for (int jb = 1; jb < N; jb += DP_JB)
-            dp_block_step<AI, WD_WARPS>(jb, N, 0, sLC, sP, sPrev, nullptr, sPartV, sPartA, sTri,
+            dp_block_step<AI, WD_WARPS, U>(jb, N, 0, sLC, sP, sPrev, nullptr, sPartV, sPartA, sTri,
                                         p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
 
         // ---- (C) back-trace by pointer doubling, scatter survivors ----------------------------
@@ -183,7 +184,9 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 10, 0, 16, ctx->stream));
 
     const size_t smem = window_smem_bytes(p.cap);
-    auto kern = ctx->alpha_is_int ? window_dp_kernel<true> : window_dp_kernel<false>;
+    static const int unroll = getenv("PASIO_WD_UNROLL") ? atoi(getenv("PASIO_WD_UNROLL")) : 8;
+    auto kern = ctx->alpha_is_int ? (unroll == 4 ? window_dp_kernel<true, 4> : window_dp_kernel<true, 8>)
+                                  : (unroll == 4 ? window_dp_kernel<false, 4> : window_dp_kernel<false, 8>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_THREADS, smem));
