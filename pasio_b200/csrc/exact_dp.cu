@@ -5,19 +5,14 @@
 // (/root/reference/src/pasio/splitters/square_splitter.py:67-109) driven by
 // all_suffixes_self_score (/root/reference/src/pasio/log_marginal_likelyhood.py:105-132).
 //
-// Rows are resolved in blocks of XD_ROWS.  For the block starting at row jb:
-//   rectangle kernel : columns [0, jb) are final; they are cut into chunks, one CTA per chunk,
-//                      lane = row, and each CTA emits a per-row partial (max, first arg-max);
-//   diagonal kernel  : one CTA merges the partials in column order (strict '>' keeps the first
-//                      maximum, like np.argmax) and resolves the XD_ROWS x XD_ROWS triangle with
-//                      the same 32-row block step the window kernel uses (dp_core.cuh).
-// Launches are stream-ordered, so there is no inter-CTA spinning.  Back-trace is pointer doubling.
+// One persistent, cooperatively launched kernel: a diagonal CTA resolves the dependent chain of rows
+// while worker CTAs fold the finished columns into the rows ahead of it (blocked wave-front with
+// look-ahead; details above exact_pipeline_kernel).  Back-trace is pointer doubling.
 #include "dp_core.cuh"
 
 namespace {
 
 constexpr int XD_ROWS = 128;           // rows per block step (4 sub-blocks of 32)
-constexpr int XD_COLS = 256;           // columns per rectangle CTA
 constexpr int XD_THREADS = 256;
 constexpr int XD_WARPS = XD_THREADS / 32;
 
@@ -33,96 +28,191 @@ __global__ void gather_candidates_kernel(const int32_t *__restrict__ cand, i64 m
     }
 }
 
-// Rectangle: rows [jb, jb+XD_ROWS) x columns chunk [c0, c1) of final columns.
-// warp w: row sub-block (w & 3), column half (w >> 2) of the chunk.
-template <bool AI>
-__global__ void __launch_bounds__(XD_THREADS)
-exact_rect_kernel(int jb, int N, int ncols, const int32_t *__restrict__ L, const int32_t *__restrict__ C,
-                  const double *P, const double *__restrict__ gtab, const double *__restrict__ ltab,
-                  int alpha_int, double alpha, double *part_val, int *part_arg)
+// ---- persistent pipeline ---------------------------------------------------------------------
+// Row-blocks of XR rows; block b = rows [1 + XR*b, 1 + XR*(b+1)).  Row 0 is the base (P[0] = 0).
+// Column block c = the same rows used as columns once final (block 0 also carries column 0).
+//   CTA 0 (diagonal): for b = 0, 1, ...: waits for the owner's partial of block b, adds the tile
+//       (column block b-1) x (row block b) from shared memory, resolves the XR x XR triangle with
+//       the 32-row block step, publishes P / prev and bumps `done_block`.
+//   CTAs 1..W (workers): worker w owns row blocks b == w (mod W).  It walks the column blocks in
+//       order as they become final and folds tile (c, b) into a running (max, first arg-max) for
+//       every owned block b >= c + 2; after column b-2 the partial of block b is complete and its
+//       `ready` flag is raised.  Columns are folded in ascending order with strict '>', so the first
+//       maximum wins exactly as in np.argmax.
+// All CTAs are co-resident (cooperative launch), so the flag waits cannot deadlock: the diagonal
+// waits only for work that depends on blocks it has already published.
+struct XdParams {
+    int N, nB, W;
+    const int32_t *L;
+    const int32_t *C;
+    double *P;
+    int *prev;
+    double *run_val;      // per row: running max over the worker-owned columns
+    int *run_arg;
+    int *ready;           // per row block: worker partial complete
+    int *done_block;      // number of row blocks the diagonal has finished
+    const double *gtab;
+    const double *ltab;
+    int alpha_int;
+    double alpha, pen;
+};
+
+__device__ __forceinline__ int ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_flag(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+
+__device__ __forceinline__ void wait_at_least(const int *flag, int target)
 {
-    __shared__ int2 sLC[XD_COLS];
-    __shared__ double sP[XD_COLS];
-    __shared__ double sV[XD_ROWS];
-    __shared__ int sA[XD_ROWS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = blockIdx.x * XD_COLS;
-    const int c1 = min(c0 + XD_COLS, ncols);
-    for (int i = c0 + tid; i < c1; i += XD_THREADS) {
-        sLC[i - c0] = make_int2(__ldg(L + i), __ldg(C + i));
-        sP[i - c0] = P[i];
+    if (threadIdx.x == 0) {
+        while (ld_flag(flag) < target) __nanosleep(40);
+        __threadfence();
     }
     __syncthreads();
+}
+__device__ __forceinline__ void publish(int *flag, int value)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_flag(flag, value);
+    }
+}
+
+// One XR-row x ncol-column tile: warp = (row group rs, column half).  Returns through shared sV/sA
+// the per-row (max, arg local to the tile); valid in the threads of half 1 after the call.
+template <bool AI>
+__device__ __forceinline__ void xd_tile(int row0, int N, int ncol, const int2 *sLC, const double *sP,
+                                        const int32_t *__restrict__ L, const int32_t *__restrict__ C,
+                                        const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                        int alpha_int, double alpha, double *sV, int *sA,
+                                        double &best, int &arg)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rs = warp & 3, half = warp >> 2;
-    const int row = jb + rs * 32 + lane;
+    const int row = row0 + rs * 32 + lane;
     const int j = min(row, N - 1);
     const RowConst<AI> r = make_row<AI>(__ldg(C + j), __ldg(L + j), alpha_int, alpha);
-    const int nloc = c1 - c0;
-    const int mid = (nloc + 1) / 2;
-    const int i0 = half ? mid : 0, i1 = half ? nloc : mid;
-    double best = -INFINITY;
-    int arg = i0;
+    const int mid = (ncol + 1) / 2;
+    const int i0 = half ? mid : 0, i1 = half ? ncol : mid;
+    best = -INFINITY;
+    arg = i0;
     sweep_columns<AI, 8>(i0, i1, sLC, sP, r, gtab, ltab, best, arg);
     if (half == 0) { sV[rs * 32 + lane] = best; sA[rs * 32 + lane] = arg; }
     __syncthreads();
     if (half == 1) {
         const double v0 = sV[rs * 32 + lane];
-        const int a0 = sA[rs * 32 + lane];
-        if (!(best > v0)) { best = v0; arg = a0; }     // earlier columns win ties
-        part_val[(size_t)blockIdx.x * XD_ROWS + rs * 32 + lane] = best;
-        part_arg[(size_t)blockIdx.x * XD_ROWS + rs * 32 + lane] = arg + c0;
+        if (!(best > v0)) { best = v0; arg = sA[rs * 32 + lane]; }    // earlier columns win ties
     }
 }
 
-// Diagonal: merge partials, resolve rows [jb, jb+XD_ROWS) against columns [jb, row).
 template <bool AI>
 __global__ void __launch_bounds__(XD_THREADS)
-exact_diag_kernel(int jb, int N, int nparts, const int32_t *__restrict__ L, const int32_t *__restrict__ C,
-                  double *P, int *prev, const double *__restrict__ gtab, const double *__restrict__ ltab,
-                  int alpha_int, double alpha, double pen, const double *part_val, const int *part_arg)
+exact_pipeline_kernel(XdParams p)
 {
-    __shared__ int2 sLC[XD_ROWS];
-    __shared__ double sP[XD_ROWS];
-    __shared__ int sPrev[XD_ROWS];
-    __shared__ double sInitV[2][XD_ROWS];
-    __shared__ int sInitA[2][XD_ROWS];
+    constexpr int XR = XD_ROWS;
+    __shared__ int2 sLCp[XR + 1];           // previous / column block
+    __shared__ double sPp[XR + 1];
+    __shared__ double sV[2][XR];
+    __shared__ int sA[2][XR];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rs = warp & 3, half = warp >> 2;
+
+    if (blockIdx.x != 0) {
+        // ------------------------------- worker -------------------------------------------------
+        const int w = blockIdx.x - 1;
+        int flip = 0;
+        for (int c = 0; c + 2 < p.nB; ++c) {
+            int bfirst = c + 2;
+            bfirst += ((w - bfirst) % p.W + p.W) % p.W;           // first owned block >= c+2
+            if (bfirst >= p.nB) break;                              // owned set only shrinks with c
+            wait_at_least(p.done_block, c + 1);
+            const int c0 = c == 0 ? 0 : 1 + XR * c;
+            const int c1 = min(1 + XR * (c + 1), p.N);
+            const int ncol = c1 - c0;
+            for (int i = tid; i < ncol; i += XD_THREADS) {
+                sLCp[i] = make_int2(__ldg(p.L + c0 + i), __ldg(p.C + c0 + i));
+                sPp[i] = __ldcg(p.P + c0 + i);
+            }
+            __syncthreads();
+            for (int b = bfirst; b < p.nB; b += p.W) {
+                const int row0 = 1 + XR * b;
+                double best;
+                int arg;
+                xd_tile<AI>(row0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha,
+                            sV[flip], sA[flip], best, arg);
+                flip ^= 1;
+                const int row = row0 + rs * 32 + lane;
+                if (half == 1 && row < p.N) {
+                    bool take = true;
+                    if (c > 0) take = best > __ldcg(p.run_val + row);
+                    if (take) {
+                        __stcg(p.run_val + row, best);
+                        __stcg(p.run_arg + row, arg + c0);
+                    }
+                }
+                if (b == c + 2) publish(p.ready + b, 1);
+            }
+            __syncthreads();                                       // column block buffer is reloaded next
+        }
+        return;
+    }
+
+    // ----------------------------------- diagonal ---------------------------------------------
+    __shared__ int2 sLCc[XR];
+    __shared__ double sPc[XR];
+    __shared__ int sPrevc[XR];
+    __shared__ double sInitV[XR];
+    __shared__ int sInitA[XR];
     __shared__ double sPartV[XD_WARPS * 32];
     __shared__ int sPartA[XD_WARPS * 32];
     __shared__ double sTri[DP_JB * DP_JB];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int nrows = min(XD_ROWS, N - jb);
 
-    if (tid < nrows) sLC[tid] = make_int2(__ldg(L + jb + tid), __ldg(C + jb + tid));
-    {   // two threads per row merge the column-ordered partials
-        const int row = tid & (XD_ROWS - 1), h = tid >> 7;
-        const int mid = (nparts + 1) / 2;
-        const int p0 = h ? mid : 0, p1 = h ? nparts : mid;
-        double best = -INFINITY;
-        int arg = 0;
-        for (int q = p0; q < p1; ++q) {
-            const double v = part_val[(size_t)q * XD_ROWS + row];
-            if (v > best) { best = v; arg = part_arg[(size_t)q * XD_ROWS + row]; }
-        }
-        sInitV[h][row] = best;
-        sInitA[h][row] = arg;
+    if (tid == 0) {
+        sLCp[0] = make_int2(__ldg(p.L), __ldg(p.C));
+        sPp[0] = 0.0;                       // prefix_scores[0] = 0 (square_splitter.py:72)
+        __stcg(p.P, 0.0);
+        __stcg(p.prev, 0);
     }
+    int ncol = 1, col_base = 0;
     __syncthreads();
-
-    for (int sb = 0; sb < nrows; sb += DP_JB) {
-        double ib = -INFINITY;
-        int ia = 0;
-        if (tid < 32 && sb + lane < nrows) {
-            ib = sInitV[0][sb + lane];
-            ia = sInitA[0][sb + lane];
-            const double v1 = sInitV[1][sb + lane];
-            if (v1 > ib) { ib = v1; ia = sInitA[1][sb + lane]; }
+    for (int b = 0; b < p.nB; ++b) {
+        const int r0 = 1 + XR * b;
+        const int nrows = min(XR, p.N - r0);
+        if (tid < nrows) sLCc[tid] = make_int2(__ldg(p.L + r0 + tid), __ldg(p.C + r0 + tid));
+        if (b >= 2) wait_at_least(p.ready + b, 1);
+        // tile (previous block) x (this block), seeded with the worker partial
+        double best;
+        int arg;
+        xd_tile<AI>(r0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, sV[0], sA[0], best, arg);
+        if (half == 1) {
+            const int t = rs * 32 + lane;
+            arg += col_base;
+            if (b >= 2 && t < nrows) {
+                const double rv = __ldcg(p.run_val + r0 + t);
+                if (!(best > rv)) { best = rv; arg = __ldcg(p.run_arg + r0 + t); }   // older columns win ties
+            }
+            sInitV[t] = best;
+            sInitA[t] = arg;
         }
-        dp_block_step<AI, XD_WARPS, 4>(sb, nrows, 0, sLC, sP, nullptr, sPrev, sPartV, sPartA, sTri, gtab, ltab,
-                                    alpha_int, alpha, pen, ib, ia, jb);
-    }
-    if (tid < nrows) {
-        P[jb + tid] = sP[tid];
-        prev[jb + tid] = sPrev[tid];
+        __syncthreads();
+        for (int sb = 0; sb < nrows; sb += DP_JB) {
+            double ib = -INFINITY;
+            int ia = 0;
+            if (tid < 32 && sb + lane < nrows) { ib = sInitV[sb + lane]; ia = sInitA[sb + lane]; }
+            dp_block_step<AI, XD_WARPS, 4>(sb, nrows, 0, sLCc, sPc, nullptr, sPrevc, sPartV, sPartA, sTri,
+                                           p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, ib, ia, r0);
+        }
+        // this block becomes the column block of the next one; block 0 keeps column 0 in front of it
+        const int keep0 = (b == 0) ? 1 : 0;
+        if (tid < nrows) {
+            __stcg(p.P + r0 + tid, sPc[tid]);
+            __stcg(p.prev + r0 + tid, sPrevc[tid]);
+            sLCp[tid + keep0] = sLCc[tid];
+            sPp[tid + keep0] = sPc[tid];
+        }
+        ncol = nrows + keep0;
+        col_base = r0 - keep0;
+        publish(p.done_block, b + 1);
+        __syncthreads();
     }
 }
 
@@ -193,40 +283,47 @@ int launch_gather_candidates(pasio_ctx *ctx)
 template <bool AI>
 static int run_exact_dp(pasio_ctx *ctx, i64 N)
 {
-    const int32_t *L = ctx->dpL.as<int32_t>();
-    const int32_t *C = ctx->dpC.as<int32_t>();
-    double *P = ctx->dpP.as<double>();
-    int *prev = ctx->dpPrev.as<int>();
-    const double *gtab = ctx->tab[AI ? PASIO_TAB_LGAMMA : PASIO_TAB_LGAMMA_ALPHA].as<double>();
-    const double *ltab = ctx->tab[PASIO_TAB_LOG].as<double>();
-    double *pv = ctx->dpPart.as<double>();
-    int *pa = ctx->dpPartArg.as<int>();
-    const int alpha_int = (int)ctx->alpha_int;
-    // row 0: prefix_scores[0] = 0, previous_splits[0] = 0 (square_splitter.py:72,78)
-    CUDA_TRY(ctx, cudaMemsetAsync(P, 0, 8, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(prev, 0, 4, ctx->stream));
-    i64 launches = 0;
-    TimingScope ts(ctx, TF_EXACT_DP, 0);
-    for (i64 jb = 1; jb < N; jb += XD_ROWS) {
-        const int nparts = (int)((jb + XD_COLS - 1) / XD_COLS);
-        exact_rect_kernel<AI><<<nparts, XD_THREADS, 0, ctx->stream>>>((int)jb, (int)N, (int)jb, L, C, P, gtab, ltab,
-                                                                     alpha_int, ctx->alpha, pv, pa);
-        exact_diag_kernel<AI><<<1, XD_THREADS, 0, ctx->stream>>>((int)jb, (int)N, nparts, L, C, P, prev, gtab, ltab,
-                                                                alpha_int, ctx->alpha, ctx->pen, pv, pa);
-        launches += 2;
-    }
-    ctx->fam_launches[TF_EXACT_DP] += launches;
-    CUDA_TRY(ctx, cudaGetLastError());
+    XdParams p;
+    p.N = (int)N;
+    p.nB = (int)((N - 1 + XD_ROWS - 1) / XD_ROWS);
+    p.L = ctx->dpL.as<int32_t>();
+    p.C = ctx->dpC.as<int32_t>();
+    p.P = ctx->dpP.as<double>();
+    p.prev = ctx->dpPrev.as<int>();
+    p.run_val = ctx->dpPart.as<double>();
+    p.run_arg = ctx->dpPartArg.as<int>();
+    p.ready = ctx->dpMark.as<int>();
+    p.done_block = p.ready + p.nB;
+    p.gtab = ctx->tab[AI ? PASIO_TAB_LGAMMA : PASIO_TAB_LGAMMA_ALPHA].as<double>();
+    p.ltab = ctx->tab[PASIO_TAB_LOG].as<double>();
+    p.alpha_int = (int)ctx->alpha_int;
+    p.alpha = ctx->alpha;
+    p.pen = ctx->pen;
+    int per_sm = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exact_pipeline_kernel<AI>, XD_THREADS, 0));
+    if (per_sm < 1) return pasio_fail(ctx, PASIO_E_CUDA, "exact DP kernel cannot be resident");
+    if (per_sm > 3) per_sm = 3;
+    int workers = ctx->sm_count * per_sm - 1;
+    if (workers > p.nB - 2) workers = p.nB - 2;
+    if (workers < 0) workers = 0;
+    p.W = workers > 0 ? workers : 1;
+    CUDA_TRY(ctx, cudaMemsetAsync(p.ready, 0, (size_t)(p.nB + 1) * sizeof(int), ctx->stream));
+    void *args[] = {&p};
+    TimingScope ts(ctx, TF_EXACT_DP);
+    // cooperative launch = all CTAs co-resident, which the flag waits rely on
+    CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)exact_pipeline_kernel<AI>, dim3(1 + workers), dim3(XD_THREADS),
+                                              args, 0, ctx->stream));
     return PASIO_OK;
 }
 
 int launch_exact_dp(pasio_ctx *ctx, i64 N)
 {
+    const i64 nB = (N - 1 + XD_ROWS - 1) / XD_ROWS;
     PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)N * 8));
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPrev, (size_t)N * 4));
-    const i64 max_parts = (N + XD_COLS - 1) / XD_COLS + 1;
-    PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)max_parts * XD_ROWS * 8));
-    PASIO_TRY(pasio_reserve(ctx, ctx->dpPartArg, (size_t)max_parts * XD_ROWS * 4));
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)N * 8));
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpPartArg, (size_t)N * 4));
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpMark, (size_t)(nB + 2) * sizeof(int) > (size_t)N ? (size_t)(nB + 2) * sizeof(int) : (size_t)N));
     return ctx->alpha_is_int ? run_exact_dp<true>(ctx, N) : run_exact_dp<false>(ctx, N);
 }
 
