@@ -206,12 +206,18 @@ def run_b200(args):
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier(dist, torch)
+    eng.timing_reset(True)
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
+    e2e_each = []
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         m_e2e, score_e2e = step_e2e()
+        e2e_each.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_timing = eng.timing()
+    eng.timing_reset(False)
     e2e_s = max_over_ranks(e2e_s, dist, device)
     e2e_value = total_nt / e2e_s
     assert m_e2e == m_final and abs(score_e2e - score) <= 1e-9 * abs(score)
@@ -267,7 +273,9 @@ def run_b200(args):
         'window_dp_cells_per_s_kernel_only': cells / (wd_ms / args.steps * 1e-3),
         'e2e': {'value': e2e_value, 'unit': 'nt/s', 'h2d_bytes_per_step': int(n * 8),
                 'd2h_bytes_per_step': int(final * 8 * 4), 'ms_per_step': e2e_s * 1e3,
-                'api': 'pasio_b200.segmentation.segment_on_device(counts_pinned_host, plan)'},
+                'api': 'pasio_b200.segmentation.segment_on_device(counts_pinned_host, plan)',
+                'device_ms_per_step': {k: e2e_timing[k][0] / e2e_steps for k in e2e_timing},
+                'ms_each_step': e2e_each},
         'gpu_launches': gpu_launches,
         'kernel_ms_per_step': {k: timing[k][0] / args.steps for k in timing},
         'wall_ms_per_step': wall / args.steps * 1e3,

@@ -154,7 +154,7 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     DevBuf *bufs[] = {&ctx->tab[0], &ctx->tab[1], &ctx->tab[2], &ctx->counts, &ctx->cg, &ctx->cpbits, &ctx->keepbits,
                       &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
-                      &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan};
+                      &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -610,15 +610,12 @@ extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *seg
     }
     if (logfac_cumsum) {
         if (capacity < nseg) return pasio_fail(ctx, PASIO_E_ARG, "capacity too small");
-        DevBuf full;   // n+1 doubles; transient
-        PASIO_TRY(pasio_reserve(ctx, full, (size_t)(ctx->n + 1) * 8));
-        int rc = launch_logfac_scan(ctx, full.as<double>());
-        if (rc == PASIO_OK) rc = pasio_reserve(ctx, ctx->dpP, (size_t)ctx->m * 8);
-        if (rc == PASIO_OK) rc = launch_gather_f64_at_cands(ctx, full.as<double>(), ctx->dpP.as<double>());
-        if (rc == PASIO_OK) rc = d2h(ctx, logfac_cumsum, ctx->dpP.p, (size_t)ctx->m * 8);
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(full.p);
-        PASIO_TRY(rc);
+        // n+1 doubles of scratch, kept for the next call (a 2 GB cudaMalloc/cudaFree per contig is not free)
+        PASIO_TRY(pasio_reserve(ctx, ctx->logfac_full, (size_t)(ctx->n + 1) * 8));
+        PASIO_TRY(launch_logfac_scan(ctx, ctx->logfac_full.as<double>()));
+        PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)ctx->m * 8));
+        PASIO_TRY(launch_gather_f64_at_cands(ctx, ctx->logfac_full.as<double>(), ctx->dpP.as<double>()));
+        PASIO_TRY(d2h(ctx, logfac_cumsum, ctx->dpP.p, (size_t)ctx->m * 8));
     }
     return PASIO_OK;
 }

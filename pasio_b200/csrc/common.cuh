@@ -69,7 +69,7 @@ struct pasio_ctx {
     std::vector<int32_t> h_win_st, h_win_en, h_brank;
 
     // scratch
-    DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan;
+    DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan, logfac_full;
     i64 *h_scalars = nullptr;    // pinned, 16 entries
 
     // timing
