@@ -77,31 +77,65 @@ __device__ __forceinline__ void publish(int *flag, int value)
     }
 }
 
-// One XR-row x ncol-column tile: warp = (row group rs, column half).  Returns through shared sV/sA
-// the per-row (max, arg local to the tile); valid in the threads of half 1 after the call.
+// One XR-row x ncol-column tile.  Warp w owns rows [16w, 16w+16) of the tile; a lane holds 4 of
+// them (rows 4k + lane%4, k = 0..3) and sweeps the columns of phase lane/4 (stride 8), so one gather
+// instruction spans 4 rows + 8 columns of candidates (few L1 lines) and every column record read
+// from shared memory feeds 4 cells.  After the sweep the 8 column phases of a row are merged with
+// the first-maximum rule; lanes 0..3 then hold (max, arg local to the tile) for their 4 rows each.
+constexpr int XT_RPL = 4;      // rows per lane
 template <bool AI>
 __device__ __forceinline__ void xd_tile(int row0, int N, int ncol, const int2 *sLC, const double *sP,
                                         const int32_t *__restrict__ L, const int32_t *__restrict__ C,
                                         const double *__restrict__ gtab, const double *__restrict__ ltab,
-                                        int alpha_int, double alpha, double *sV, int *sA,
-                                        double &best, int &arg)
+                                        int alpha_int, double alpha, double (&best)[XT_RPL], int (&arg)[XT_RPL])
 {
+    constexpr int U = 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rs = warp & 3, half = warp >> 2;
-    const int row = row0 + rs * 32 + lane;
-    const int j = min(row, N - 1);
-    const RowConst<AI> r = make_row<AI>(__ldg(C + j), __ldg(L + j), alpha_int, alpha);
-    const int mid = (ncol + 1) / 2;
-    const int i0 = half ? mid : 0, i1 = half ? ncol : mid;
-    best = -INFINITY;
-    arg = i0;
-    sweep_columns<AI, 8>(i0, i1, sLC, sP, r, gtab, ltab, best, arg);
-    if (half == 0) { sV[rs * 32 + lane] = best; sA[rs * 32 + lane] = arg; }
-    __syncthreads();
-    if (half == 1) {
-        const double v0 = sV[rs * 32 + lane];
-        if (!(best > v0)) { best = v0; arg = sA[rs * 32 + lane]; }    // earlier columns win ties
+    const int rr = lane & 3, cc = lane >> 2;
+    RowConst<AI> r[XT_RPL];
+#pragma unroll
+    for (int k = 0; k < XT_RPL; ++k) {
+        const int j = min(row0 + 16 * warp + 4 * k + rr, N - 1);
+        r[k] = make_row<AI>(__ldg(C + j), __ldg(L + j), alpha_int, alpha);
+        best[k] = -INFINITY;
+        arg[k] = cc;
     }
+    int i = cc;
+    for (; i + (U - 1) * 8 < ncol; i += U * 8) {
+        double g[U][XT_RPL], lg[U][XT_RPL], pc[U];
+        int sx[U][XT_RPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int2 a = sLC[i + 8 * u];
+            pc[u] = sP[i + 8 * u];
+#pragma unroll
+            for (int k = 0; k < XT_RPL; ++k) {
+                const int idx = r[k].cjx - a.y;
+                g[u][k] = __ldg(gtab + idx);
+                lg[u][k] = __ldg(ltab + (r[k].lj - a.x));
+                sx[u][k] = AI ? idx : a.y;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < XT_RPL; ++k) {
+                const double s = AI ? u32_to_double(sx[u][k]) : __dsub_rn(r[k].aj, u32_to_double(sx[u][k]));
+                const double t = __dadd_rn(__dsub_rn(g[u][k], __dmul_rn(s, lg[u][k])), pc[u]);
+                if (t > best[k]) { best[k] = t; arg[k] = i + 8 * u; }
+            }
+    }
+    for (; i < ncol; i += 8) {
+        const int2 a = sLC[i];
+        const double pc = sP[i];
+#pragma unroll
+        for (int k = 0; k < XT_RPL; ++k) {
+            const double t = __dadd_rn(self_score<AI>(a.y, a.x, r[k], gtab, ltab), pc);
+            if (t > best[k]) { best[k] = t; arg[k] = i; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < XT_RPL; ++k) merge_column_phases<4>(best[k], arg[k]);
 }
 
 template <bool AI>
@@ -111,15 +145,11 @@ exact_pipeline_kernel(XdParams p)
     constexpr int XR = XD_ROWS;
     __shared__ int2 sLCp[XR + 1];           // previous / column block
     __shared__ double sPp[XR + 1];
-    __shared__ double sV[2][XR];
-    __shared__ int sA[2][XR];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rs = warp & 3, half = warp >> 2;
 
     if (blockIdx.x != 0) {
         // ------------------------------- worker -------------------------------------------------
         const int w = blockIdx.x - 1;
-        int flip = 0;
         for (int c = 0; c + 2 < p.nB; ++c) {
             int bfirst = c + 2;
             bfirst += ((w - bfirst) % p.W + p.W) % p.W;           // first owned block >= c+2
@@ -135,18 +165,21 @@ exact_pipeline_kernel(XdParams p)
             __syncthreads();
             for (int b = bfirst; b < p.nB; b += p.W) {
                 const int row0 = 1 + XR * b;
-                double best;
-                int arg;
-                xd_tile<AI>(row0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha,
-                            sV[flip], sA[flip], best, arg);
-                flip ^= 1;
-                const int row = row0 + rs * 32 + lane;
-                if (half == 1 && row < p.N) {
-                    bool take = true;
-                    if (c > 0) take = best > __ldcg(p.run_val + row);
-                    if (take) {
-                        __stcg(p.run_val + row, best);
-                        __stcg(p.run_arg + row, arg + c0);
+                double best[XT_RPL];
+                int arg[XT_RPL];
+                xd_tile<AI>(row0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, best, arg);
+                if (lane < 4) {
+#pragma unroll
+                    for (int k = 0; k < XT_RPL; ++k) {
+                        const int row = row0 + 16 * warp + 4 * k + lane;
+                        if (row < p.N) {
+                            bool take = true;
+                            if (c > 0) take = best[k] > __ldcg(p.run_val + row);   // later columns must be strictly better
+                            if (take) {
+                                __stcg(p.run_val + row, best[k]);
+                                __stcg(p.run_arg + row, arg[k] + c0);
+                            }
+                        }
                     }
                 }
                 if (b == c + 2) publish(p.ready + b, 1);
@@ -180,25 +213,31 @@ exact_pipeline_kernel(XdParams p)
         if (tid < nrows) sLCc[tid] = make_int2(__ldg(p.L + r0 + tid), __ldg(p.C + r0 + tid));
         if (b >= 2) wait_at_least(p.ready + b, 1);
         // tile (previous block) x (this block), seeded with the worker partial
-        double best;
-        int arg;
-        xd_tile<AI>(r0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, sV[0], sA[0], best, arg);
-        if (half == 1) {
-            const int t = rs * 32 + lane;
-            arg += col_base;
-            if (b >= 2 && t < nrows) {
-                const double rv = __ldcg(p.run_val + r0 + t);
-                if (!(best > rv)) { best = rv; arg = __ldcg(p.run_arg + r0 + t); }   // older columns win ties
+        {
+            double best[XT_RPL];
+            int arg[XT_RPL];
+            xd_tile<AI>(r0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, best, arg);
+            if (lane < 4) {
+#pragma unroll
+                for (int k = 0; k < XT_RPL; ++k) {
+                    const int t = 16 * warp + 4 * k + lane;
+                    double bv = best[k];
+                    int ba = arg[k] + col_base;
+                    if (b >= 2 && t < nrows) {
+                        const double rv = __ldcg(p.run_val + r0 + t);
+                        if (!(bv > rv)) { bv = rv; ba = __ldcg(p.run_arg + r0 + t); }   // older columns win ties
+                    }
+                    sInitV[t] = bv;
+                    sInitA[t] = ba;
+                }
             }
-            sInitV[t] = best;
-            sInitA[t] = arg;
         }
         __syncthreads();
         for (int sb = 0; sb < nrows; sb += DP_JB) {
             double ib = -INFINITY;
             int ia = 0;
             if (tid < 32 && sb + lane < nrows) { ib = sInitV[sb + lane]; ia = sInitA[sb + lane]; }
-            dp_block_step<AI, XD_WARPS, 4>(sb, nrows, 0, sLCc, sPc, nullptr, sPrevc, sPartV, sPartA, sTri,
+            dp_block_step<AI, XD_WARPS, 4, 32>(sb, nrows, 0, sLCc, sPc, nullptr, sPrevc, sPartV, sPartA, sTri,
                                            p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, ib, ia, r0);
         }
         // this block becomes the column block of the next one; block 0 keeps column 0 in front of it

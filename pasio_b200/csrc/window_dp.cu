@@ -52,7 +52,7 @@ __host__ __device__ inline size_t window_smem_bytes(int cap)
            + capr * 2;              // sPrev
 }
 
-template <bool AI, int U>
+template <bool AI, int U, int RPW>
 __global__ void __launch_bounds__(WD_THREADS, 3)
 window_dp_kernel(WinDpParams p)
 {
@@ -120,7 +120,7 @@ window_dp_kernel(WinDpParams p)
         if (tid == 0) { sP[0] = 0.0; sPrev[0] = 0; }
         __syncthreads();
         for (int jb = 1; jb < N; jb += DP_JB)
-            dp_block_step<AI, WD_WARPS, U>(jb, N, 0, sLC, sP, sPrev, nullptr, sPartV, sPartA, sTri,
+            dp_block_step<AI, WD_WARPS, U, RPW>(jb, N, 0, sLC, sP, sPrev, nullptr, sPartV, sPartA, sTri,
                                         p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
 
         // ---- (C) back-trace by pointer doubling, scatter survivors ----------------------------
@@ -184,9 +184,15 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 10, 0, 16, ctx->stream));
 
     const size_t smem = window_smem_bytes(p.cap);
-    static const int unroll = getenv("PASIO_WD_UNROLL") ? atoi(getenv("PASIO_WD_UNROLL")) : 8;
-    auto kern = ctx->alpha_is_int ? (unroll == 4 ? window_dp_kernel<true, 4> : window_dp_kernel<true, 8>)
-                                  : (unroll == 4 ? window_dp_kernel<false, 4> : window_dp_kernel<false, 8>);
+    // rows per warp in the rectangle sweep (see dp_block_step); PASIO_WD_RPW overrides for experiments
+    static const int rpw = getenv("PASIO_WD_RPW") ? atoi(getenv("PASIO_WD_RPW")) : 4;
+    void (*kern)(WinDpParams);
+    if (ctx->alpha_is_int)
+        kern = rpw == 32 ? window_dp_kernel<true, 8, 32> : rpw == 16 ? window_dp_kernel<true, 8, 16>
+             : rpw == 8 ? window_dp_kernel<true, 8, 8> : window_dp_kernel<true, 8, 4>;
+    else
+        kern = rpw == 32 ? window_dp_kernel<false, 8, 32> : rpw == 16 ? window_dp_kernel<false, 8, 16>
+             : rpw == 8 ? window_dp_kernel<false, 8, 8> : window_dp_kernel<false, 8, 4>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_THREADS, smem));
