@@ -52,44 +52,15 @@ __device__ __forceinline__ double self_score(int ci, int li, const RowConst<AI> 
     return __dsub_rn(g, __dmul_rn(s, lg));
 }
 
-// Sweep columns i0+phase, i0+phase+stride, ... < i1 for this lane's row; strict '>' keeps the first
-// maximum among the lane's own (ascending) columns.
-// sLC[i] = (L_i, C_i), sP[i] = P_i (shared memory; lanes of one column phase read one address).
-// The table gathers are the long-latency part: each batch of U cells first issues all 2*U
-// gathers, then does the arithmetic, so a warp keeps 2*U loads in flight.
-template <bool AI, int U>
-__device__ __forceinline__ void sweep_columns(int i0, int i1, int phase, int stride, const int2 *sLC,
-                                              const double *sP, const RowConst<AI> &r,
-                                              const double *__restrict__ gtab, const double *__restrict__ ltab,
-                                              double &best, int &arg)
-{
-    int i = i0 + phase;
-    for (; i + (U - 1) * stride < i1; i += U * stride) {
-        double g[U], lg[U];
-        int sx[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int2 a = sLC[i + u * stride];
-            const int idx = r.cjx - a.y;
-            g[u] = __ldg(gtab + idx);
-            lg[u] = __ldg(ltab + (r.lj - a.x));
-            sx[u] = AI ? idx : a.y;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const double s = AI ? u32_to_double(sx[u]) : __dsub_rn(r.aj, u32_to_double(sx[u]));
-            const double t = __dadd_rn(__dsub_rn(g[u], __dmul_rn(s, lg[u])), sP[i + u * stride]);
-            if (t > best) { best = t; arg = i + u * stride; }
-        }
-    }
-    for (; i < i1; i += stride) {
-        const int2 a = sLC[i];
-        const double t = __dadd_rn(self_score<AI>(a.y, a.x, r, gtab, ltab), sP[i]);
-        if (t > best) { best = t; arg = i; }
-    }
-}
+// One candidate as a column of the DP: position, cumulative count, finished prefix score.
+// 16 bytes so a column is one LDS.128 (the 8 column phases of a warp read 8 x 16 B = one wavefront).
+struct __align__(16) ColRec {
+    int L;
+    int C;
+    double P;
+};
 
-// Combine the (max, arg) of the CPW lanes that swept interleaved column phases of one row:
+// Combine the (max, arg) of the lanes that swept interleaved column phases of one row:
 // larger value wins, equal values keep the smaller column index (np.argmax's first maximum).
 template <int RPW>
 __device__ __forceinline__ void merge_column_phases(double &best, int &arg)
@@ -102,29 +73,77 @@ __device__ __forceinline__ void merge_column_phases(double &best, int &arg)
     }
 }
 
-constexpr int DP_JB = 32;   // rows resolved per block step (one per lane)
+// Sweep columns i0+phase, i0+phase+stride, ... < i1 for the RPL rows of this lane; strict '>' keeps
+// the first maximum among the lane's own (ascending) columns.  Every column record read from shared
+// memory feeds RPL cells.  The table gathers are the long-latency part: a batch of U columns first
+// issues all 2*U*RPL gathers, then does the arithmetic.
+template <bool AI, int U, int RPL>
+__device__ __forceinline__ void sweep_columns(int i0, int i1, int phase, int stride, const ColRec *sCol,
+                                              const RowConst<AI> (&r)[RPL],
+                                              const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                              double (&best)[RPL], int (&arg)[RPL])
+{
+    int i = i0 + phase;
+    for (; i + (U - 1) * stride < i1; i += U * stride) {
+        double g[U][RPL], lg[U][RPL], pc[U];
+        int sx[U][RPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const ColRec a = sCol[i + u * stride];
+            pc[u] = a.P;
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const int idx = r[k].cjx - a.C;
+                g[u][k] = __ldg(gtab + idx);
+                lg[u][k] = __ldg(ltab + (r[k].lj - a.L));
+                sx[u][k] = AI ? idx : a.C;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const double s = AI ? u32_to_double(sx[u][k]) : __dsub_rn(r[k].aj, u32_to_double(sx[u][k]));
+                const double t = __dadd_rn(__dsub_rn(g[u][k], __dmul_rn(s, lg[u][k])), pc[u]);
+                if (t > best[k]) { best[k] = t; arg[k] = i + u * stride; }
+            }
+    }
+    for (; i < i1; i += stride) {
+        const ColRec a = sCol[i];
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const double t = __dadd_rn(self_score<AI>(a.C, a.L, r[k], gtab, ltab), a.P);
+            if (t > best[k]) { best[k] = t; arg[k] = i; }
+        }
+    }
+}
+
+constexpr int DP_JB = 32;   // rows resolved per block step
+constexpr int DP_RPW = 4;   // a warp's gather spans DP_RPW rows x (32/DP_RPW) column phases
 
 // One block step over rows [jb, jb+32) of a candidate list held in shared memory.
-//   rectangle: columns [col0, jb) split across the CTA's warps (lane = row);
+//   rectangle: columns [col0, jb).  A warp covers RPL*4 rows (a lane: RPL rows, 4 apart) x 8
+//              interleaved column phases, so the 32 addresses of one gather span 4 candidates of rows
+//              plus 8 of columns instead of 32 -- that is what sets the number of L1 lines a gather
+//              touches (profiles/r01_window_dp_*).  Warps beyond the row groups split the columns
+//              into chunks.
 //   triangle : columns [jb, j) -- the 32x32 self scores are computed by all warps, then warp 0
 //              resolves the 32 rows in order, broadcasting each finished P by shuffle.
 // init_best/init_arg (warp 0 only, per lane) seed the running maximum with what earlier columns
 // (outside [col0, jb)) contributed; pass -inf / 0 when there are none.
 // Requires col0 <= jb, blockDim.x == NW*32.  Ends with a __syncthreads().
-template <bool AI, int NW, int U, int RPW>
-__device__ __forceinline__ void dp_block_step(int jb, int N, int col0, const int2 *sLC, double *sP,
+template <bool AI, int NW, int U, int RPL>
+__device__ __forceinline__ void dp_block_step(int jb, int N, int col0, ColRec *sCol,
                                               unsigned short *sPrev16, int *sPrev32,
                                               double *sPartV, int *sPartA, double *sTri,
                                               const double *__restrict__ gtab, const double *__restrict__ ltab,
                                               int alpha_int, double alpha, double pen,
                                               double init_best, int init_arg, int arg_offset)
 {
-    // A warp covers RPW rows x CPW interleaved column phases per step: the 32 gather addresses of one
-    // load then span RPW candidates of rows plus CPW candidates of columns instead of 32 candidates,
-    // which is what sets the number of L1 lines a gather touches (profiles/r01_window_dp_v2_*).
-    constexpr int CPW = 32 / RPW;         // column phases per warp
-    constexpr int NG = DP_JB / RPW;       // row groups per 32-row block
-    constexpr int NQ = NW / NG;           // column chunks (warps per row group)
+    constexpr int RPW = DP_RPW;
+    constexpr int CPW = 32 / RPW;               // column phases per warp
+    constexpr int NG = DP_JB / (RPW * RPL);     // row groups per 32-row block
+    constexpr int NQ = NW / NG;                 // column chunks (warps per row group)
     static_assert(NW % NG == 0 && NQ >= 1, "warps must tile the row groups");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = warp % NG, q = warp / NG;
@@ -132,31 +151,41 @@ __device__ __forceinline__ void dp_block_step(int jb, int N, int col0, const int
 
     // rectangle: columns [col0, jb) in NQ chunks
     {
-        const int j = min(jb + grp * RPW + rr, N - 1);
-        const int2 lc = sLC[j];
-        const RowConst<AI> r = make_row<AI>(lc.y, lc.x, alpha_int, alpha);
+        RowConst<AI> r[RPL];
+        double best[RPL];
+        int arg[RPL];
         const int ncol = jb - col0;
         const int chunk = (ncol + NQ - 1) / NQ;
         const int i0 = col0 + q * chunk;
         const int i1 = min(i0 + chunk, jb);
-        double best = -INFINITY;
-        int arg = i0 + cc;
-        sweep_columns<AI, U>(i0, i1, cc, CPW, sLC, sP, r, gtab, ltab, best, arg);
-        merge_column_phases<RPW>(best, arg);
-        if (cc == 0) {
-            sPartV[q * 32 + grp * RPW + rr] = best;
-            sPartA[q * 32 + grp * RPW + rr] = arg;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const int j = min(jb + grp * RPW * RPL + k * RPW + rr, N - 1);
+            const ColRec me = sCol[j];
+            r[k] = make_row<AI>(me.C, me.L, alpha_int, alpha);
+            best[k] = -INFINITY;
+            arg[k] = i0 + cc;
+        }
+        sweep_columns<AI, U, RPL>(i0, i1, cc, CPW, sCol, r, gtab, ltab, best, arg);
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            merge_column_phases<RPW>(best[k], arg[k]);
+            if (cc == 0) {
+                const int row = grp * RPW * RPL + k * RPW + rr;
+                sPartV[q * 32 + row] = best[k];
+                sPartA[q * 32 + row] = arg[k];
+            }
         }
     }
 
     // triangle self scores: pair (k, l), column jb+k, row jb+l, k < l  (lane = row here)
     {
-        const int2 lc = sLC[min(jb + lane, N - 1)];
-        const RowConst<AI> r = make_row<AI>(lc.y, lc.x, alpha_int, alpha);
+        const ColRec me = sCol[min(jb + lane, N - 1)];
+        const RowConst<AI> r = make_row<AI>(me.C, me.L, alpha_int, alpha);
         for (int k = warp; k < DP_JB; k += NW) {
             if (k < lane && jb + lane < N) {
-                const int2 a = sLC[jb + k];
-                sTri[k * DP_JB + lane] = self_score<AI>(a.y, a.x, r, gtab, ltab);
+                const ColRec a = sCol[jb + k];
+                sTri[k * DP_JB + lane] = self_score<AI>(a.C, a.L, r, gtab, ltab);
             }
         }
     }
@@ -182,7 +211,7 @@ __device__ __forceinline__ void dp_block_step(int jb, int N, int col0, const int
             }
         }
         if (jb + lane < N) {
-            sP[jb + lane] = mine;
+            sCol[jb + lane].P = mine;
             if (sPrev16) sPrev16[jb + lane] = (unsigned short)arg;
             else sPrev32[jb + lane] = arg;
         }

@@ -84,12 +84,11 @@ __device__ __forceinline__ void publish(int *flag, int value)
 // the first-maximum rule; lanes 0..3 then hold (max, arg local to the tile) for their 4 rows each.
 constexpr int XT_RPL = 4;      // rows per lane
 template <bool AI>
-__device__ __forceinline__ void xd_tile(int row0, int N, int ncol, const int2 *sLC, const double *sP,
+__device__ __forceinline__ void xd_tile(int row0, int N, int ncol, const ColRec *sCol,
                                         const int32_t *__restrict__ L, const int32_t *__restrict__ C,
                                         const double *__restrict__ gtab, const double *__restrict__ ltab,
                                         int alpha_int, double alpha, double (&best)[XT_RPL], int (&arg)[XT_RPL])
 {
-    constexpr int U = 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rr = lane & 3, cc = lane >> 2;
     RowConst<AI> r[XT_RPL];
@@ -100,40 +99,7 @@ __device__ __forceinline__ void xd_tile(int row0, int N, int ncol, const int2 *s
         best[k] = -INFINITY;
         arg[k] = cc;
     }
-    int i = cc;
-    for (; i + (U - 1) * 8 < ncol; i += U * 8) {
-        double g[U][XT_RPL], lg[U][XT_RPL], pc[U];
-        int sx[U][XT_RPL];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int2 a = sLC[i + 8 * u];
-            pc[u] = sP[i + 8 * u];
-#pragma unroll
-            for (int k = 0; k < XT_RPL; ++k) {
-                const int idx = r[k].cjx - a.y;
-                g[u][k] = __ldg(gtab + idx);
-                lg[u][k] = __ldg(ltab + (r[k].lj - a.x));
-                sx[u][k] = AI ? idx : a.y;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int k = 0; k < XT_RPL; ++k) {
-                const double s = AI ? u32_to_double(sx[u][k]) : __dsub_rn(r[k].aj, u32_to_double(sx[u][k]));
-                const double t = __dadd_rn(__dsub_rn(g[u][k], __dmul_rn(s, lg[u][k])), pc[u]);
-                if (t > best[k]) { best[k] = t; arg[k] = i + 8 * u; }
-            }
-    }
-    for (; i < ncol; i += 8) {
-        const int2 a = sLC[i];
-        const double pc = sP[i];
-#pragma unroll
-        for (int k = 0; k < XT_RPL; ++k) {
-            const double t = __dadd_rn(self_score<AI>(a.y, a.x, r[k], gtab, ltab), pc);
-            if (t > best[k]) { best[k] = t; arg[k] = i; }
-        }
-    }
+    sweep_columns<AI, 2, XT_RPL>(0, ncol, cc, 8, sCol, r, gtab, ltab, best, arg);
 #pragma unroll
     for (int k = 0; k < XT_RPL; ++k) merge_column_phases<4>(best[k], arg[k]);
 }
@@ -143,8 +109,7 @@ __global__ void __launch_bounds__(XD_THREADS)
 exact_pipeline_kernel(XdParams p)
 {
     constexpr int XR = XD_ROWS;
-    __shared__ int2 sLCp[XR + 1];           // previous / column block
-    __shared__ double sPp[XR + 1];
+    __shared__ ColRec sColP[XR + 1];        // previous / column block
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (blockIdx.x != 0) {
@@ -159,15 +124,16 @@ exact_pipeline_kernel(XdParams p)
             const int c1 = min(1 + XR * (c + 1), p.N);
             const int ncol = c1 - c0;
             for (int i = tid; i < ncol; i += XD_THREADS) {
-                sLCp[i] = make_int2(__ldg(p.L + c0 + i), __ldg(p.C + c0 + i));
-                sPp[i] = __ldcg(p.P + c0 + i);
+                sColP[i].L = __ldg(p.L + c0 + i);
+                sColP[i].C = __ldg(p.C + c0 + i);
+                sColP[i].P = __ldcg(p.P + c0 + i);
             }
             __syncthreads();
             for (int b = bfirst; b < p.nB; b += p.W) {
                 const int row0 = 1 + XR * b;
                 double best[XT_RPL];
                 int arg[XT_RPL];
-                xd_tile<AI>(row0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, best, arg);
+                xd_tile<AI>(row0, p.N, ncol, sColP, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, best, arg);
                 if (lane < 4) {
 #pragma unroll
                     for (int k = 0; k < XT_RPL; ++k) {
@@ -190,8 +156,7 @@ exact_pipeline_kernel(XdParams p)
     }
 
     // ----------------------------------- diagonal ---------------------------------------------
-    __shared__ int2 sLCc[XR];
-    __shared__ double sPc[XR];
+    __shared__ ColRec sColC[XR];
     __shared__ int sPrevc[XR];
     __shared__ double sInitV[XR];
     __shared__ int sInitA[XR];
@@ -200,8 +165,9 @@ exact_pipeline_kernel(XdParams p)
     __shared__ double sTri[DP_JB * DP_JB];
 
     if (tid == 0) {
-        sLCp[0] = make_int2(__ldg(p.L), __ldg(p.C));
-        sPp[0] = 0.0;                       // prefix_scores[0] = 0 (square_splitter.py:72)
+        sColP[0].L = __ldg(p.L);
+        sColP[0].C = __ldg(p.C);
+        sColP[0].P = 0.0;                   // prefix_scores[0] = 0 (square_splitter.py:72)
         __stcg(p.P, 0.0);
         __stcg(p.prev, 0);
     }
@@ -210,13 +176,13 @@ exact_pipeline_kernel(XdParams p)
     for (int b = 0; b < p.nB; ++b) {
         const int r0 = 1 + XR * b;
         const int nrows = min(XR, p.N - r0);
-        if (tid < nrows) sLCc[tid] = make_int2(__ldg(p.L + r0 + tid), __ldg(p.C + r0 + tid));
+        if (tid < nrows) { sColC[tid].L = __ldg(p.L + r0 + tid); sColC[tid].C = __ldg(p.C + r0 + tid); }
         if (b >= 2) wait_at_least(p.ready + b, 1);
         // tile (previous block) x (this block), seeded with the worker partial
         {
             double best[XT_RPL];
             int arg[XT_RPL];
-            xd_tile<AI>(r0, p.N, ncol, sLCp, sPp, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, best, arg);
+            xd_tile<AI>(r0, p.N, ncol, sColP, p.L, p.C, p.gtab, p.ltab, p.alpha_int, p.alpha, best, arg);
             if (lane < 4) {
 #pragma unroll
                 for (int k = 0; k < XT_RPL; ++k) {
@@ -237,16 +203,15 @@ exact_pipeline_kernel(XdParams p)
             double ib = -INFINITY;
             int ia = 0;
             if (tid < 32 && sb + lane < nrows) { ib = sInitV[sb + lane]; ia = sInitA[sb + lane]; }
-            dp_block_step<AI, XD_WARPS, 4, 32>(sb, nrows, 0, sLCc, sPc, nullptr, sPrevc, sPartV, sPartA, sTri,
+            dp_block_step<AI, XD_WARPS, 8, 1>(sb, nrows, 0, sColC, nullptr, sPrevc, sPartV, sPartA, sTri,
                                            p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, ib, ia, r0);
         }
         // this block becomes the column block of the next one; block 0 keeps column 0 in front of it
         const int keep0 = (b == 0) ? 1 : 0;
         if (tid < nrows) {
-            __stcg(p.P + r0 + tid, sPc[tid]);
+            __stcg(p.P + r0 + tid, sColC[tid].P);
             __stcg(p.prev + r0 + tid, sPrevc[tid]);
-            sLCp[tid + keep0] = sLCc[tid];
-            sPp[tid + keep0] = sPc[tid];
+            sColP[tid + keep0] = sColC[tid];
         }
         ncol = nrows + keep0;
         col_base = r0 - keep0;

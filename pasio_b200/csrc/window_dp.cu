@@ -43,32 +43,29 @@ struct WinDpParams {
 __host__ __device__ inline size_t window_smem_bytes(int cap)
 {
     const size_t capr = (size_t)((cap + 31) & ~31);
-    return capr * 8                 // sP
+    return capr * 16                // sCol (L, C, P)
            + WD_WARPS * 32 * 8      // sPartV
            + DP_JB * DP_JB * 8      // sTri
-           + capr * 8               // sLC
            + WD_WARPS * 32 * 4      // sPartA
            + 16 * 4                 // sMisc
-           + capr * 2;              // sPrev
+           + capr * 2 * 2           // sPrev, sJump (back-trace ping-pong)
+           + capr;                  // sMark
 }
 
-template <bool AI, int U, int RPW>
+template <bool AI, int U, int RPL>
 __global__ void __launch_bounds__(WD_THREADS, 3)
 window_dp_kernel(WinDpParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int capr = (p.cap + 31) & ~31;
-    double *sP = reinterpret_cast<double *>(smem);
-    double *sPartV = sP + capr;
+    ColRec *sCol = reinterpret_cast<ColRec *>(smem);
+    double *sPartV = reinterpret_cast<double *>(sCol + capr);
     double *sTri = sPartV + WD_WARPS * 32;
-    int2 *sLC = reinterpret_cast<int2 *>(sTri + DP_JB * DP_JB);
-    int *sPartA = reinterpret_cast<int *>(sLC + capr);
+    int *sPartA = reinterpret_cast<int *>(sTri + DP_JB * DP_JB);
     int *sMisc = sPartA + WD_WARPS * 32;
     unsigned short *sPrev = reinterpret_cast<unsigned short *>(sMisc + 16);
-    // after the DP the P array is dead: reuse it for the back-trace
-    unsigned short *sJumpA = reinterpret_cast<unsigned short *>(sP);
-    unsigned short *sJumpB = sJumpA + capr;
-    unsigned char *sMark = reinterpret_cast<unsigned char *>(sJumpB + capr);
+    unsigned short *sJump = sPrev + capr;
+    unsigned char *sMark = reinterpret_cast<unsigned char *>(sJump + capr);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -109,7 +106,8 @@ window_dp_kernel(WinDpParams p)
             }
             if (take) {
                 const int k = count + woff + __popc(bal & ((1u << lane) - 1u));
-                sLC[k] = make_int2((int)(pos - first), (int)(__ldg(p.cg + pos) - cg_first));
+                sCol[k].L = (int)(pos - first);
+                sCol[k].C = (int)(__ldg(p.cg + pos) - cg_first);
             }
             count += tot;
             __syncthreads();
@@ -117,19 +115,16 @@ window_dp_kernel(WinDpParams p)
         const int N = count;
 
         // ---- (B) DP ---------------------------------------------------------------------------
-        if (tid == 0) { sP[0] = 0.0; sPrev[0] = 0; }
+        if (tid == 0) { sCol[0].P = 0.0; sPrev[0] = 0; }
         __syncthreads();
         for (int jb = 1; jb < N; jb += DP_JB)
-            dp_block_step<AI, WD_WARPS, U, RPW>(jb, N, 0, sLC, sP, sPrev, nullptr, sPartV, sPartA, sTri,
-                                        p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
+            dp_block_step<AI, WD_WARPS, U, RPL>(jb, N, 0, sCol, sPrev, nullptr, sPartV, sPartA, sTri,
+                                                p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
 
         // ---- (C) back-trace by pointer doubling, scatter survivors ----------------------------
-        for (int k = tid; k < N; k += WD_THREADS) {
-            sJumpA[k] = sPrev[k];
-            sMark[k] = (k == N - 1);
-        }
+        for (int k = tid; k < N; k += WD_THREADS) sMark[k] = (k == N - 1);
         __syncthreads();
-        unsigned short *ja = sJumpA, *jb2 = sJumpB;
+        unsigned short *ja = sPrev, *jb2 = sJump;
         for (int reach = 1; reach < N; reach <<= 1) {
             // nodes within `reach` hops of the end are marked; ja[k] is the node 'reach' hops before k
             for (int k = tid; k < N; k += WD_THREADS)
@@ -140,7 +135,7 @@ window_dp_kernel(WinDpParams p)
         }
         for (int k = tid; k < N; k += WD_THREADS) {
             if (sMark[k]) {
-                const i64 pos = first + sLC[k].x;
+                const i64 pos = first + sCol[k].L;
                 atomicOr(p.keepbits + (pos >> 5), 1u << (pos & 31));
             }
         }
@@ -184,15 +179,11 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 10, 0, 16, ctx->stream));
 
     const size_t smem = window_smem_bytes(p.cap);
-    // rows per warp in the rectangle sweep (see dp_block_step); PASIO_WD_RPW overrides for experiments
-    static const int rpw = getenv("PASIO_WD_RPW") ? atoi(getenv("PASIO_WD_RPW")) : 4;
+    // rows per lane in the rectangle sweep (see dp_block_step); PASIO_WD_RPL overrides for experiments
+    static const int rpl = getenv("PASIO_WD_RPL") ? atoi(getenv("PASIO_WD_RPL")) : 2;
     void (*kern)(WinDpParams);
-    if (ctx->alpha_is_int)
-        kern = rpw == 32 ? window_dp_kernel<true, 8, 32> : rpw == 16 ? window_dp_kernel<true, 8, 16>
-             : rpw == 8 ? window_dp_kernel<true, 8, 8> : window_dp_kernel<true, 8, 4>;
-    else
-        kern = rpw == 32 ? window_dp_kernel<false, 8, 32> : rpw == 16 ? window_dp_kernel<false, 8, 16>
-             : rpw == 8 ? window_dp_kernel<false, 8, 8> : window_dp_kernel<false, 8, 4>;
+    if (ctx->alpha_is_int) kern = rpl == 1 ? window_dp_kernel<true, 8, 1> : window_dp_kernel<true, 4, 2>;
+    else kern = rpl == 1 ? window_dp_kernel<false, 8, 1> : window_dp_kernel<false, 4, 2>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_THREADS, smem));
