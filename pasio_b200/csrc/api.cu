@@ -237,8 +237,9 @@ static int finish_load(pasio_ctx *ctx, const int64_t *offsets, int64_t n_contigs
         ctx->h_bounds[1] = (int32_t)n;
     }
     ctx->n_contigs = n_contigs;
-    const size_t bit_bytes = (size_t)((n + 1 + 31) / 32 + 2) * 4;
-    PASIO_TRY(pasio_reserve(ctx, ctx->cg, (size_t)(n + 1) * 8));
+    // bitmaps over positions 0..n, padded to whole scan tiles (2048 positions) so the scan writes 64-bit words freely
+    const size_t bit_bytes = (size_t)((n + 1 + 2047) / 2048) * 256 + 16;
+    PASIO_TRY(pasio_reserve(ctx, ctx->cg, (size_t)(n + 2) * 8));
     PASIO_TRY(pasio_reserve(ctx, ctx->cpbits, bit_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->keepbits, bit_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->bounds, (size_t)(n_contigs + 1) * 4));
@@ -284,6 +285,7 @@ extern "C" int pasio_contig_load_device(pasio_ctx *ctx, const int64_t *d_counts,
 {
     NEED_CTX(ctx);
     if (!d_counts) return pasio_fail(ctx, PASIO_E_ARG, "d_counts is NULL");
+    if (reinterpret_cast<uintptr_t>(d_counts) & 15) return pasio_fail(ctx, PASIO_E_ARG, "d_counts must be 16-byte aligned");
     PASIO_TRY(check_load_args(ctx, n, offsets, n_contigs));
     ctx->n = n;
     if (ctx->counts.p && !ctx->counts_borrowed) cudaFree(ctx->counts.p);

@@ -10,17 +10,31 @@
 namespace {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SCAN_TILE = SCAN_THREADS * 8;      // elements per CTA (8 warps x 256)
 
 // tile status word: top 2 bits = flag (0 invalid, 1 aggregate, 2 inclusive prefix), low 62 = value
 __device__ __forceinline__ u64 pack_state(u64 flag, i64 v) { return (flag << 62) | (u64)v; }
 __device__ __forceinline__ u64 ld_state(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
 __device__ __forceinline__ void st_state(u64 *p, u64 v) { *reinterpret_cast<volatile u64 *>(p) = v; }
 
+__device__ __forceinline__ u64 spread_bits(unsigned x)   // bit k of x -> bit 2k
+{
+    u64 v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+// Each warp owns 256 consecutive elements: 4 slabs of 32 lanes x one 16-byte pair, so every load
+// and store instruction of a warp is one fully coalesced 512-byte access.  cg[p] is the EXCLUSIVE
+// prefix at p, which makes the (cg[2m], cg[2m+1]) pair an aligned 16-byte store.  The change-point
+// bits of a slab come from two ballots interleaved into one 64-bit word.
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
-                   uint8_t *__restrict__ cpbytes, u64 *tile_state, unsigned *tile_counter,
+                   u64 *__restrict__ cpwords, u64 *tile_state, unsigned *tile_counter,
                    i64 *scalars /* [0]=total, [1]=negative seen */)
 {
     __shared__ unsigned s_tile;
@@ -30,57 +44,71 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);   // tiles start in issue order: look-back never waits on an unscheduled tile
     __syncthreads();
     const i64 tile = s_tile;
-    const i64 base = tile * SCAN_TILE + (i64)tid * SCAN_ITEMS;
+    const i64 wbase = tile * SCAN_TILE + (i64)warp * 256;     // first element of this warp's chunk
 
-    i64 v[SCAN_ITEMS];
-    if (base + SCAN_ITEMS <= n) {
-        const longlong2 *src = reinterpret_cast<const longlong2 *>(counts + base);
+    i64 v0[4], v1[4];
+    bool neg = false;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS / 2; ++k) {
-            longlong2 t = __ldg(src + k);
-            v[2 * k] = t.x;
-            v[2 * k + 1] = t.y;
+    for (int k = 0; k < 4; ++k) {
+        const i64 e = wbase + 64 * k + 2 * lane;
+        if (e + 1 < n) {
+            const longlong2 t = __ldg(reinterpret_cast<const longlong2 *>(counts + e));
+            v0[k] = t.x;
+            v1[k] = t.y;
+        } else {
+            v0[k] = (e < n) ? __ldg(counts + e) : 0;
+            v1[k] = 0;
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < n) ? __ldg(counts + base + k) : 0;
+        neg |= (v0[k] < 0) | (v1[k] < 0);
     }
+    if (neg) scalars[1] = 1;
 
-    // change-point byte for positions base..base+7 (flag at p: counts[p-1] != counts[p], 1 <= p <= n-1)
-    if (base < n) {
-        i64 before = (base > 0) ? __ldg(counts + base - 1) : v[0];
-        unsigned byte = 0;
-        bool neg = false;
+    // change-point words: position p flagged when counts[p-1] != counts[p], 1 <= p <= n-1
+    {
+        i64 carry = (wbase > 0 && wbase - 1 < n) ? __ldg(counts + wbase - 1) : 0;   // element before the chunk
+        u64 word[4];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            i64 p = base + k;
-            if (p >= 1 && p <= n - 1 && v[k] != before) byte |= 1u << k;
-            before = v[k];
-            neg |= (p < n) && (v[k] < 0);
+        for (int k = 0; k < 4; ++k) {
+            const i64 e = wbase + 64 * k + 2 * lane;
+            i64 before = __shfl_up_sync(0xffffffffu, v1[k], 1);
+            if (lane == 0) before = carry;
+            const bool f0 = (e >= 1) && (e <= n - 1) && (v0[k] != before);
+            const bool f1 = (e + 1 <= n - 1) && (v1[k] != v0[k]);
+            const unsigned b0 = __ballot_sync(0xffffffffu, f0);
+            const unsigned b1 = __ballot_sync(0xffffffffu, f1);
+            word[k] = spread_bits(b0) | (spread_bits(b1) << 1);
+            carry = __shfl_sync(0xffffffffu, v1[k], 31);
         }
-        cpbytes[base >> 3] = (uint8_t)byte;
-        if (neg) scalars[1] = 1;
+        if (lane < 4 && wbase + 64 * lane <= n) {
+            const u64 w = lane == 0 ? word[0] : lane == 1 ? word[1] : lane == 2 ? word[2] : word[3];
+            cpwords[(wbase >> 6) + lane] = w;
+        }
     }
 
-    // thread-local inclusive sums, then block scan of thread totals
+    // warp-level inclusive scans of the pair sums, slab by slab
+    i64 ex[4];
+    i64 run = 0;
 #pragma unroll
-    for (int k = 1; k < SCAN_ITEMS; ++k) v[k] += v[k - 1];
-    i64 incl = v[SCAN_ITEMS - 1];
+    for (int k = 0; k < 4; ++k) {
+        const i64 pair = v0[k] + v1[k];
+        i64 incl = pair;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        i64 o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
+        for (int d = 1; d < 32; d <<= 1) {
+            const i64 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        ex[k] = run + incl - pair;
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_warp[warp] = run;
     __syncthreads();
     i64 warp_off = 0, aggregate = 0;
 #pragma unroll
     for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        i64 t = s_warp[w];
+        const i64 t = s_warp[w];
         if (w < warp) warp_off += t;
         aggregate += t;
     }
-    const i64 thread_excl = warp_off + incl - v[SCAN_ITEMS - 1];
 
     // decoupled look-back over predecessor tiles (warp 0)
     if (warp == 0) {
@@ -89,13 +117,13 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
             if (lane == 0) st_state(tile_state + tile, pack_state(1, aggregate));
             i64 look = tile - 1;
             while (true) {
-                i64 idx = look - lane;
+                const i64 idx = look - lane;
                 u64 st;
                 do {
                     st = (idx >= 0) ? ld_state(tile_state + idx) : pack_state(2, 0);
                 } while (__any_sync(0xffffffffu, (st >> 62) == 0));
-                unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-                int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
                 i64 val = (lane <= stop) ? (i64)(st & 0x3fffffffffffffffull) : 0;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
@@ -110,16 +138,18 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
         }
     }
     __syncthreads();
-    const i64 off = s_prefix + thread_excl;
-
-    if (tile == 0 && tid == 0) cg[0] = 0;
+    const i64 off = s_prefix + warp_off;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        i64 p = base + k;
-        if (p < n) {
-            i64 c = off + v[k];
-            cg[p + 1] = c;
-            if (p == n - 1) scalars[0] = c;
+    for (int k = 0; k < 4; ++k) {
+        const i64 e = wbase + 64 * k + 2 * lane;
+        const i64 c0 = off + ex[k];
+        const i64 c1 = c0 + v0[k];
+        if (e + 1 <= n) {
+            *reinterpret_cast<longlong2 *>(cg + e) = make_longlong2(c0, c1);
+            if (e + 1 == n) scalars[0] = c1;
+        } else if (e <= n) {
+            cg[e] = c0;
+            if (e == n) scalars[0] = c0;
         }
     }
 }
@@ -248,18 +278,16 @@ __global__ void max_count_kernel(const i64 *__restrict__ counts, i64 n, u64 *out
 int launch_scan_counts(pasio_ctx *ctx)
 {
     const i64 n = ctx->n;
-    const i64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const i64 tiles = (n + 1 + SCAN_TILE - 1) / SCAN_TILE;    // positions 0..n
     PASIO_TRY(pasio_reserve(ctx, ctx->tilestate, (size_t)(tiles + 1) * 8 + 16));
     u64 *state = ctx->tilestate.as<u64>() + 2;
     unsigned *counter = ctx->tilestate.as<unsigned>();
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->tilestate.p, 0, (size_t)(tiles + 1) * 8 + 16, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(i64), ctx->stream));
-    const size_t bit_bytes = (size_t)((n + 1 + 31) / 32 + 2) * 4;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->cpbits.p, 0, bit_bytes, ctx->stream));
     {
         TimingScope ts(ctx, TF_SCAN);
         scan_counts_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(
-            ctx->counts.as<i64>(), n, ctx->cg.as<i64>(), ctx->cpbits.as<uint8_t>(), state, counter,
+            ctx->counts.as<i64>(), n, ctx->cg.as<i64>(), ctx->cpbits.as<u64>(), state, counter,
             ctx->scalars.as<i64>());
     }
     CUDA_TRY(ctx, cudaGetLastError());
