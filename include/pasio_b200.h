@@ -107,6 +107,9 @@ int pasio_candidates_download(pasio_ctx *ctx, int64_t *out, int64_t capacity, in
  * cells: DP (i,j) cells evaluated in this round. */
 int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int constraint,
                 int64_t *n_in, int64_t *n_out, int64_t *cells);
+/* Of the most recent pasio_round: algorithmic cells, and how many of them the kernel proved irrelevant
+ * with the exact far-column bound (csrc/window_dp.cu) instead of evaluating them. */
+int pasio_round_stats(const pasio_ctx *ctx, int64_t *cells, int64_t *cells_skipped);
 /* RoundReducer.reduce_candidate_list (round_reducer.py:10-31): rounds until fixed point or
  * max_rounds (<=0: len(counts)).  Stops with PASIO_E_TABLE_TOO_SHORT when tables must grow
  * (state is kept; call again after uploading longer tables).

@@ -42,6 +42,7 @@ SIGNATURES = {
     'pasio_candidates_count': (ctypes.c_int, [_vp, _i64p]),
     'pasio_candidates_download': (ctypes.c_int, [_vp, _i64p, _i64, _i64p]),
     'pasio_round': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64p, _i64p, _i64p]),
+    'pasio_round_stats': (ctypes.c_int, [_vp, _i64p, _i64p]),
     'pasio_rounds': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64, _i64p, _i64p, _i64p, _i64p, _i64]),
     'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
     'pasio_suffix_scores': (ctypes.c_int, [_vp, _i64, _f64p]),
@@ -260,6 +261,12 @@ class Engine(object):
         self._retry(lambda: self.lib.pasio_round(self.ctx, window_size, window_shift, CONSTRAINTS[constraint],
                                                  ctypes.byref(n_in), ctypes.byref(n_out), ctypes.byref(cells)))
         return n_in.value, n_out.value, cells.value
+
+    def round_stats(self):
+        """(algorithmic cells, cells skipped by the exact bound) of the most recent round"""
+        a, b = _i64(0), _i64(0)
+        self._check(self.lib.pasio_round_stats(self.ctx, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def rounds(self, window_size, window_shift, constraint, num_rounds=None):
         """RoundReducer loop on the device.  Returns (sizes before each round run, final count, cells)."""

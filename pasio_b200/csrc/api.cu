@@ -482,8 +482,10 @@ extern "C" int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_s
     PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)ctx->m * 4));
     i64 m_new = 0;
     PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
-    PASIO_TRY(d2h(ctx, ctx->h_scalars + 10, ctx->scalars.as<i64>() + 10, 8));
+    PASIO_TRY(d2h(ctx, ctx->h_scalars + 10, ctx->scalars.as<i64>() + 10, 24));
     if (cells) *cells = ctx->h_scalars[10];
+    ctx->last_cells = ctx->h_scalars[10];
+    ctx->last_cells_skipped = ctx->h_scalars[12];
     ctx->cur = nxt;
     ctx->implicit_all = false;
     ctx->m = m_new;
@@ -515,6 +517,14 @@ extern "C" int pasio_rounds(pasio_ctx *ctx, int64_t window_size, int64_t window_
     if (n_out) *n_out = ctx->m;
     if (cells) *cells = total_cells;
     return rc;
+}
+
+extern "C" int pasio_round_stats(const pasio_ctx *ctx, int64_t *cells, int64_t *cells_skipped)
+{
+    if (!ctx) return PASIO_E_ARG;
+    if (cells) *cells = ctx->last_cells;
+    if (cells_skipped) *cells_skipped = ctx->last_cells_skipped;
+    return PASIO_OK;
 }
 
 // ---- exact DP -----------------------------------------------------------------------------------

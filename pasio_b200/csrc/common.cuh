@@ -72,6 +72,8 @@ struct pasio_ctx {
     DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan, logfac_full;
     i64 *h_scalars = nullptr;    // pinned, 16 entries
 
+    i64 last_cells = 0, last_cells_skipped = 0;   // of the most recent round
+
     // timing
     bool timing = false;
     std::vector<TimedSpan> spans;

@@ -121,24 +121,18 @@ __device__ __forceinline__ void sweep_columns(int i0, int i1, int phase, int str
 constexpr int DP_JB = 32;   // rows resolved per block step
 constexpr int DP_RPW = 4;   // a warp's gather spans DP_RPW rows x (32/DP_RPW) column phases
 
-// One block step over rows [jb, jb+32) of a candidate list held in shared memory.
+// ---- pieces of one block step over rows [jb, jb+32) of a candidate list in shared memory ------
 //   rectangle: columns [col0, jb).  A warp covers RPL*4 rows (a lane: RPL rows, 4 apart) x 8
 //              interleaved column phases, so the 32 addresses of one gather span 4 candidates of rows
 //              plus 8 of columns instead of 32 -- that is what sets the number of L1 lines a gather
 //              touches (profiles/r01_window_dp_*).  Warps beyond the row groups split the columns
-//              into chunks.
-//   triangle : columns [jb, j) -- the 32x32 self scores are computed by all warps, then warp 0
-//              resolves the 32 rows in order, broadcasting each finished P by shuffle.
-// init_best/init_arg (warp 0 only, per lane) seed the running maximum with what earlier columns
-// (outside [col0, jb)) contributed; pass -inf / 0 when there are none.
-// Requires col0 <= jb, blockDim.x == NW*32.  Ends with a __syncthreads().
+//              into chunks; per-chunk (max, first arg-max) go to sPartV / sPartA.
+//   triangle : columns [jb, j) -- the 32x32 self scores (independent of P) go to sTri.
 template <bool AI, int NW, int U, int RPL>
-__device__ __forceinline__ void dp_block_step(int jb, int N, int col0, ColRec *sCol,
-                                              unsigned short *sPrev16, int *sPrev32,
-                                              double *sPartV, int *sPartA, double *sTri,
-                                              const double *__restrict__ gtab, const double *__restrict__ ltab,
-                                              int alpha_int, double alpha, double pen,
-                                              double init_best, int init_arg, int arg_offset)
+__device__ __forceinline__ void block_rect_tri(int jb, int N, int col0, const ColRec *sCol,
+                                               double *sPartV, int *sPartA, double *sTri,
+                                               const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                               int alpha_int, double alpha)
 {
     constexpr int RPW = DP_RPW;
     constexpr int CPW = 32 / RPW;               // column phases per warp
@@ -148,8 +142,6 @@ __device__ __forceinline__ void dp_block_step(int jb, int N, int col0, ColRec *s
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = warp % NG, q = warp / NG;
     const int rr = lane % RPW, cc = lane / RPW;
-
-    // rectangle: columns [col0, jb) in NQ chunks
     {
         RowConst<AI> r[RPL];
         double best[RPL];
@@ -177,9 +169,7 @@ __device__ __forceinline__ void dp_block_step(int jb, int N, int col0, ColRec *s
             }
         }
     }
-
-    // triangle self scores: pair (k, l), column jb+k, row jb+l, k < l  (lane = row here)
-    {
+    {   // lane = row here
         const ColRec me = sCol[min(jb + lane, N - 1)];
         const RowConst<AI> r = make_row<AI>(me.C, me.L, alpha_int, alpha);
         for (int k = warp; k < DP_JB; k += NW) {
@@ -190,31 +180,57 @@ __device__ __forceinline__ void dp_block_step(int jb, int N, int col0, ColRec *s
         }
     }
     __syncthreads();
+}
 
-    if (warp == 0) {
-        double best = init_best;
-        int arg = init_arg;
+// The dependent part, one warp: merge the NQ column-chunk partials (ascending columns, strict '>'),
+// then resolve the 32 rows in order, broadcasting each finished P by shuffle.
+// init_best/init_arg (per lane) seed the maximum with what columns BEFORE the chunks contributed.
+// sLB (optional) receives, per row, the maximum itself (before the creation cost is added).
+template <int NQ>
+__device__ __forceinline__ void block_chain(int jb, int N, ColRec *sCol, unsigned short *sPrev16, int *sPrev32,
+                                            const double *sPartV, const int *sPartA, const double *sTri, double pen,
+                                            double init_best, int init_arg, int arg_offset, double *sLB)
+{
+    const int lane = threadIdx.x & 31;
+    double best = init_best;
+    int arg = init_arg;
 #pragma unroll
-        for (int w = 0; w < NQ; ++w) {
-            double v = sPartV[w * 32 + lane];
-            if (v > best) { best = v; arg = sPartA[w * 32 + lane] + arg_offset; }
-        }
-        double mine = 0.0;
-        const int rows = min(DP_JB, N - jb);
-        for (int k = 0; k < rows; ++k) {
-            const double pf = __dadd_rn(best, pen);          // prefix_scores[j] = max + segment_creation_cost
-            const double pk = __shfl_sync(0xffffffffu, pf, k);
-            if (lane == k) mine = pf;
-            if (lane > k) {
-                const double t = __dadd_rn(sTri[k * DP_JB + lane], pk);
-                if (t > best) { best = t; arg = jb + k + arg_offset; }
-            }
-        }
-        if (jb + lane < N) {
-            sCol[jb + lane].P = mine;
-            if (sPrev16) sPrev16[jb + lane] = (unsigned short)arg;
-            else sPrev32[jb + lane] = arg;
+    for (int w = 0; w < NQ; ++w) {
+        const double v = sPartV[w * 32 + lane];
+        if (v > best) { best = v; arg = sPartA[w * 32 + lane] + arg_offset; }
+    }
+    double mine = 0.0, lb = 0.0;
+    const int rows = min(DP_JB, N - jb);
+    for (int k = 0; k < rows; ++k) {
+        const double pf = __dadd_rn(best, pen);          // prefix_scores[j] = max + segment_creation_cost
+        const double pk = __shfl_sync(0xffffffffu, pf, k);
+        if (lane == k) { mine = pf; lb = best; }
+        if (lane > k) {
+            const double t = __dadd_rn(sTri[k * DP_JB + lane], pk);
+            if (t > best) { best = t; arg = jb + k + arg_offset; }
         }
     }
+    if (jb + lane < N) {
+        sCol[jb + lane].P = mine;
+        if (sPrev16) sPrev16[jb + lane] = (unsigned short)arg;
+        else sPrev32[jb + lane] = arg;
+        if (sLB) sLB[lane] = lb;
+    }
+}
+
+// One full block step: rectangle over [col0, jb), triangle, chain.  Requires col0 <= jb and
+// blockDim.x == NW*32.  Ends with a __syncthreads().
+template <bool AI, int NW, int U, int RPL>
+__device__ __forceinline__ void dp_block_step(int jb, int N, int col0, ColRec *sCol,
+                                              unsigned short *sPrev16, int *sPrev32,
+                                              double *sPartV, int *sPartA, double *sTri,
+                                              const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                              int alpha_int, double alpha, double pen,
+                                              double init_best, int init_arg, int arg_offset)
+{
+    constexpr int NQ = NW / (DP_JB / (DP_RPW * RPL));
+    block_rect_tri<AI, NW, U, RPL>(jb, N, col0, sCol, sPartV, sPartA, sTri, gtab, ltab, alpha_int, alpha);
+    if ((threadIdx.x >> 5) == 0)
+        block_chain<NQ>(jb, N, sCol, sPrev16, sPrev32, sPartV, sPartA, sTri, pen, init_best, init_arg, arg_offset, nullptr);
     __syncthreads();
 }

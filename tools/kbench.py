@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--nt', type=int, default=100000000)
 ap.add_argument('--reps', type=int, default=2)
 ap.add_argument('--exact', type=int, default=0, help='also time the exact DP with this many nt (all positions)')
+ap.add_argument('--config3', type=int, default=0, help='time the exact DP with this many random candidates over 10x as many nt')
 args = ap.parse_args()
 
 eng = _native.engine()
@@ -45,3 +46,19 @@ if args.exact:
         N = args.exact + 1
         print('exact N=%d: wall %.1f ms, exact_dp %.1f ms (%d launches) -> %.4g cells/s, splits %d score %.6f'
               % (N, wall * 1e3, t['exact_dp'][0], t['exact_dp'][1], N * (N - 1) / 2 / (t['exact_dp'][0] * 1e-3), len(splits), score))
+
+if args.config3:
+    N = args.config3
+    c = synth.piecewise_poisson(10 * N, 1)
+    cands = synth.random_candidates(len(c), N, 1)
+    eng.load(c)
+    for rep in range(2):
+        eng.set_candidates(cands)
+        eng._cands_obj = None
+        eng.timing_reset(True)
+        t0 = time.perf_counter()
+        score, splits = eng.square_split()
+        wall = time.perf_counter() - t0
+        t = eng.timing()
+        print('config3 N=%d: wall %.1f ms, exact_dp %.1f ms -> %.4g cells/s, splits %d score %.6f'
+              % (N, wall * 1e3, t['exact_dp'][0], N * (N - 1) / 2 / (t['exact_dp'][0] * 1e-3), len(splits), score))
