@@ -23,6 +23,7 @@ constexpr int WD_THREADS = 256;
 constexpr int WD_WARPS = WD_THREADS / 32;
 constexpr int PR_NEAR = 64;     // pruned path: columns this close to the row block are always evaluated
 constexpr int PR_FB = 8;        // pruned path: far columns are bounded in blocks of 8
+constexpr int PR_LIST = 64;     // pruned path: per-row survivor list capacity (entries = far block numbers)
 
 struct WinDpParams {
     WinGeom geom;
@@ -54,7 +55,8 @@ __host__ __device__ inline size_t window_smem_bytes(int cap)
            + capr * 2 * 2           // sPrev, sJump (back-trace ping-pong)
            + capr                   // sMark
            + (capr / PR_FB) * 8     // sBMax: max P of every 8-column block (pruned path)
-           + 32 * 8 * 2 + 32 * 4    // sLB, sFarV, sFarA
+           + 32 * 8 * 2 + 32 * 4    // sLB (unused), sFarV, sFarA
+           + 32 * PR_LIST * 2       // survivor lists, one per row of the block
            + 4 * 8;                 // sScal
 }
 
@@ -77,88 +79,141 @@ __device__ __forceinline__ void lex_max(double &best, int &arg, double v, int a)
     if (v > best || (v == best && a < arg)) { best = v; arg = a; }
 }
 
-template <bool AI>
+
+// Far columns of one 32-row block.  Warp w owns rows 4w..4w+3.
+//   lower bounds : LB_j = max( best over the near columns (sPartV),  the "split at every candidate"
+//                  path through the block's own rows ) -- both are feasible segmentations; the path
+//                  value is formed with a parallel prefix sum and lowered by delta to stay below the
+//                  sequentially rounded value the chain would produce.
+//   F1 (bounds)  : lane = (row rr, column block cc), 4 x 8 per step, UF steps in flight; surviving
+//                  block numbers are appended to per-row lists in shared memory.
+//   F2 (exact)   : 8-lane group g walks the list of row g: lane l8 evaluates column l8 of every
+//                  surviving block, keeping its own running (max, first arg-max); the 8 lanes are
+//                  merged once at the end.  Lists are flushed whenever they might overflow.
+// Writes sFarV / sFarA for the warp's 4 rows; returns the number of cells skipped.
+template <bool AI, int NQ>
 __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const double *sBMax,
-                                        const double *sLB, double *sFarV, int *sFarA, double delta,
+                                        const double *sPartV, unsigned short *sList, double *sFarV, int *sFarA,
+                                        double delta, double pen,
                                         const double *__restrict__ gtab, const double *__restrict__ ltab,
                                         int alpha_int, double alpha)
 {
+    constexpr int UF = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rr = lane & 3, cc = lane >> 2;              // bound phase: 4 rows x 8 column blocks
-    const int sub = lane >> 3, l8 = lane & 7;             // exact phase: 4 surviving blocks x 8 columns
-    const int r = 4 * warp + rr;
-    const bool row_ok = jb + r < N;
-    const ColRec me = sCol[min(jb + r, N - 1)];
-    const RowConst<AI> rc = make_row<AI>(me.C, me.L, alpha_int, alpha);
-    const double lb = row_ok ? sLB[r] : INFINITY;
-    u64 skipped = 0;
+    const int rr = lane & 3, cc = lane >> 2;              // F1: 4 rows x 8 column blocks
+    const int grp = lane >> 3, l8 = lane & 7;             // F2: row grp, column l8 of a block
+    unsigned short *myList = sList + (warp * 4) * PR_LIST;
 
-    // column 0 is not part of any 8-block: evaluate it exactly and seed the far result with it
-    if (cc == 0 && row_ok) {
-        const ColRec a = sCol[0];
-        sFarV[r] = __dadd_rn(self_score<AI>(a.C, a.L, rc, gtab, ltab), a.P);
-        sFarA[r] = 0;
+    // ---- lower bounds for all 32 rows (every warp computes them; no block-wide sync needed) ----
+    double lb;
+    {
+        const int j = min(jb + lane, N - 1);
+        const ColRec me = sCol[j], before = sCol[j - 1];
+        const RowConst<AI> rj = make_row<AI>(me.C, me.L, alpha_int, alpha);
+        double run = self_score<AI>(before.C, before.L, rj, gtab, ltab) + (lane ? pen : 0.0);   // w(j-1, j) [+ pen of the previous row]
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, run, d);
+            if (lane >= d) run += o;
+        }
+        double path = sCol[jb - 1].P + run - delta;      // P_{jb-1} + sum_{m<=l} w(m-1,m) + l*pen, kept below its rounded value
+        if (!(path == path)) path = -INFINITY;           // inf - inf etc.: no information
+        double nearbest = sPartV[lane];
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) nearbest = fmax(nearbest, sPartV[q * 32 + lane]);
+        lb = fmax(path, nearbest);
     }
-    __syncwarp();
+    const int r1 = 4 * warp + rr;                          // F1 row
+    const bool row1_ok = jb + r1 < N;
+    const double lb1 = __shfl_sync(0xffffffffu, lb, r1);
+    const ColRec me1 = sCol[min(jb + r1, N - 1)];
+    const RowConst<AI> rc1 = make_row<AI>(me1.C, me1.L, alpha_int, alpha);
+    const int r2 = 4 * warp + grp;                         // F2 row
+    const bool row2_ok = jb + r2 < N;
+    const ColRec me2 = sCol[min(jb + r2, N - 1)];
+    const RowConst<AI> rc2 = make_row<AI>(me2.C, me2.L, alpha_int, alpha);
 
-    for (int cb0 = 0; cb0 < nfar; cb0 += 8) {
-        const int b = cb0 + cc;
-        bool surv = false;
-        if (row_ok && b < nfar) {
-            const ColRec a = sCol[1 + PR_FB * b];                  // first column: largest count, longest length
-            const ColRec z = sCol[PR_FB * b + PR_FB];              // last column: smallest count, shortest length
-            const int x_hi = rc.cjx - a.C, x_lo = rc.cjx - z.C;
-            const double lg = __ldg(ltab + (rc.lj - z.L));
-            const double s_hi = AI ? u32_to_double(x_hi) : __dsub_rn(rc.aj, u32_to_double(a.C));
-            const double s_lo = AI ? u32_to_double(x_lo) : __dsub_rn(rc.aj, u32_to_double(z.C));
-            const double f_hi = __dsub_rn(__ldg(gtab + x_hi), __dmul_rn(s_hi, lg));
-            const double f_lo = __dsub_rn(__ldg(gtab + x_lo), __dmul_rn(s_lo, lg));
-            const double ub = fmax(f_hi, f_lo) + sBMax[b] + delta;
-            surv = !(ub < lb);                                      // NaN keeps the block
-            if (!surv) skipped += PR_FB;
+    // running far result of this lane (F2 role): column 0 is in no 8-block, lane l8 == 0 takes it
+    double best = -INFINITY;
+    int arg = 0x7fffffff;
+    if (l8 == 0 && row2_ok) {
+        const ColRec a = sCol[0];
+        best = __dadd_rn(self_score<AI>(a.C, a.L, rc2, gtab, ltab), a.P);
+        arg = 0;
+    }
+    u64 skipped = 0;
+    int cnt[4] = {0, 0, 0, 0};                             // list lengths, identical in all lanes
+
+    auto flush = [&]() {
+        __syncwarp();
+        const int n = grp == 0 ? cnt[0] : grp == 1 ? cnt[1] : grp == 2 ? cnt[2] : cnt[3];
+        const unsigned short *lst = myList + grp * PR_LIST;
+        int k = 0;
+        for (; k + 2 <= n; k += 2) {                      // two surviving blocks in flight
+            const int c0 = 1 + PR_FB * (int)lst[k] + l8, c1 = 1 + PR_FB * (int)lst[k + 1] + l8;
+            const ColRec a0 = sCol[c0], a1 = sCol[c1];
+            const double t0 = __dadd_rn(self_score<AI>(a0.C, a0.L, rc2, gtab, ltab), a0.P);
+            const double t1 = __dadd_rn(self_score<AI>(a1.C, a1.L, rc2, gtab, ltab), a1.P);
+            if (t0 > best) { best = t0; arg = c0; }
+            if (t1 > best) { best = t1; arg = c1; }
         }
-        unsigned mask = __ballot_sync(0xffffffffu, surv);
-        while (mask) {
-            // the four lowest survivors are evaluated together, 8 lanes (columns) each
-            int sel = -1;
-            unsigned m = mask;
+        if (k < n) {
+            const int c0 = 1 + PR_FB * (int)lst[k] + l8;
+            const ColRec a0 = sCol[c0];
+            const double t0 = __dadd_rn(self_score<AI>(a0.C, a0.L, rc2, gtab, ltab), a0.P);
+            if (t0 > best) { best = t0; arg = c0; }
+        }
+        cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+        __syncwarp();
+    };
+
+    for (int cb0 = 0; cb0 < nfar; cb0 += 8 * UF) {
+        bool surv[UF];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int bit = m ? (__ffs(m) - 1) : -1;
-                if (k == sub) sel = bit;
-                m &= m - 1;                                         // 0 & anything stays 0
-            }
-            mask = m;
-            double t = -INFINITY;
-            int col = 0x7fffffff, row2 = 0;
-            if (sel >= 0) {
-                row2 = 4 * warp + (sel & 3);
-                const int b2 = cb0 + (sel >> 2);
-                col = 1 + PR_FB * b2 + l8;
-                const ColRec rowrec = sCol[jb + row2];
-                const RowConst<AI> r2 = make_row<AI>(rowrec.C, rowrec.L, alpha_int, alpha);
-                const ColRec a = sCol[col];
-                t = __dadd_rn(self_score<AI>(a.C, a.L, r2, gtab, ltab), a.P);
-            }
-#pragma unroll
-            for (int off = 4; off > 0; off >>= 1) {
-                const double ot = __shfl_xor_sync(0xffffffffu, t, off);
-                const int oc = __shfl_xor_sync(0xffffffffu, col, off);
-                lex_max<AI>(t, col, ot, oc);
-            }
-            // two survivors may belong to the same row: apply the four results one after another
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (sub == k && l8 == 0 && sel >= 0) {
-                    double bv = sFarV[row2];
-                    int ba = sFarA[row2];
-                    lex_max<AI>(bv, ba, t, col);
-                    sFarV[row2] = bv;
-                    sFarA[row2] = ba;
-                }
-                __syncwarp();
+        for (int u = 0; u < UF; ++u) {
+            const int b = cb0 + 8 * u + cc;
+            surv[u] = false;
+            if (row1_ok && b < nfar) {
+                const ColRec a = sCol[1 + PR_FB * b];              // first column: largest count, longest length
+                const ColRec z = sCol[PR_FB * b + PR_FB];          // last column: smallest count, shortest length
+                const int x_hi = rc1.cjx - a.C, x_lo = rc1.cjx - z.C;
+                const double lg = __ldg(ltab + (rc1.lj - z.L));
+                const double s_hi = AI ? u32_to_double(x_hi) : __dsub_rn(rc1.aj, u32_to_double(a.C));
+                const double s_lo = AI ? u32_to_double(x_lo) : __dsub_rn(rc1.aj, u32_to_double(z.C));
+                const double f_hi = __dsub_rn(__ldg(gtab + x_hi), __dmul_rn(s_hi, lg));
+                const double f_lo = __dsub_rn(__ldg(gtab + x_lo), __dmul_rn(s_lo, lg));
+                const double ub = fmax(f_hi, f_lo) + sBMax[b] + delta;
+                surv[u] = !(ub < lb1);                              // NaN keeps the block
+                if (!surv[u]) skipped += PR_FB;
             }
         }
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+            const unsigned mask = __ballot_sync(0xffffffffu, surv[u]);
+            const unsigned rowmask = 0x11111111u << rr;            // lanes of my row
+            if (surv[u]) {
+                const int at = (rr == 0 ? cnt[0] : rr == 1 ? cnt[1] : rr == 2 ? cnt[2] : cnt[3])
+                             + __popc(mask & rowmask & ((1u << lane) - 1u));
+                myList[rr * PR_LIST + at] = (unsigned short)(cb0 + 8 * u + cc);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cnt[q] += __popc(mask & (0x11111111u << q));
+        }
+        // each step adds at most 8*UF entries per row
+        if (max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3])) > PR_LIST - 8 * UF) flush();
+    }
+    flush();
+
+    // merge the 8 column lanes of each row (first maximum), publish
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (l8 == 0 && row2_ok) {
+        sFarV[r2] = best;
+        sFarA[r2] = arg;
     }
     return skipped;
 }
@@ -182,6 +237,7 @@ window_dp_kernel(WinDpParams p)
     double *sFarV = sLB + 32;
     double *sScal = sFarV + 32;                                     // [0] magnitude of the window's largest self score, [1] max |P|
     int *sFarA = reinterpret_cast<int *>(sScal + 4);
+    unsigned short *sList = reinterpret_cast<unsigned short *>(sFarA + 32);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -248,18 +304,16 @@ window_dp_kernel(WinDpParams p)
                 dp_block_step<AI, WD_WARPS, U, RPL>(jb, N, 0, sCol, sPrev, nullptr, sPartV, sPartA, sTri,
                                                     p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
             } else {
-                // (1) nearest columns + triangle, (2) provisional chain -> lower bounds
+                // (1) nearest columns + triangle self scores
                 block_rect_tri<AI, WD_WARPS, U, RPL>(jb, N, near_lo, sCol, sPartV, sPartA, sTri, p.gtab, p.ltab,
                                                      p.alpha_int, p.alpha);
-                if (warp == 0)
-                    block_chain<NQ>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen, -INFINITY, 0, 0, sLB);
+                // (2) far columns [1, near_lo): bound blocks of 8 against a lower bound of the row maximum,
+                //     evaluate the survivors exactly
+                const double delta = ldexp(sScal[0] + sScal[1] + fabs(p.pen) * DP_JB, -44);
+                skipped += far_pass<AI, NQ>(jb, N, (near_lo - 1) / PR_FB, sCol, sBMax, sPartV, sList, sFarV, sFarA,
+                                            delta, p.pen, p.gtab, p.ltab, p.alpha_int, p.alpha);
                 __syncthreads();
-                // (3) far columns [1, near_lo): bound blocks of 8, evaluate the survivors exactly
-                const double delta = ldexp(sScal[0] + sScal[1], -44);
-                skipped += far_pass<AI>(jb, N, (near_lo - 1) / PR_FB, sCol, sBMax, sLB, sFarV, sFarA, delta,
-                                          p.gtab, p.ltab, p.alpha_int, p.alpha);
-                __syncthreads();
-                // (4) final chain: far result first (smaller columns), then the near partials, then the triangle
+                // (3) chain: far result first (smaller columns), then the near partials, then the triangle
                 if (warp == 0)
                     block_chain<NQ>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen,
                                     jb + lane < N ? sFarV[lane] : -INFINITY, jb + lane < N ? sFarA[lane] : 0, 0, nullptr);
