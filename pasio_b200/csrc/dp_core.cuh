@@ -201,6 +201,7 @@ __device__ __forceinline__ void block_chain(int jb, int N, ColRec *sCol, unsigne
     }
     double mine = 0.0, lb = 0.0;
     const int rows = min(DP_JB, N - jb);
+#pragma unroll 8
     for (int k = 0; k < rows; ++k) {
         const double pf = __dadd_rn(best, pen);          // prefix_scores[j] = max + segment_creation_cost
         const double pk = __shfl_sync(0xffffffffu, pf, k);

@@ -49,13 +49,13 @@ __host__ __device__ inline size_t window_smem_bytes(int cap)
     const size_t capr = (size_t)((cap + 31) & ~31);
     return capr * 16                // sCol (L, C, P)
            + WD_WARPS * 32 * 8      // sPartV
-           + DP_JB * DP_JB * 8      // sTri
+           + DP_JB * DP_JB * 8      // sTri            (back-trace: sMark lives here, needs capr <= 8192)
            + WD_WARPS * 32 * 4      // sPartA
            + 16 * 4                 // sMisc
-           + capr * 2 * 2           // sPrev, sJump (back-trace ping-pong)
-           + capr                   // sMark
-           + (capr / PR_FB) * 8     // sBMax: max P of every 8-column block (pruned path)
-           + 32 * 8 * 2 + 32 * 4    // sLB (unused), sFarV, sFarA
+           + capr * 2               // sPrev
+           + (capr / PR_FB) * 16    // sBlkI: (C first, C last, L last) of every 8-column block   (back-trace: sJump lives here)
+           + (capr / PR_FB) * 8     // sBMax: max P of every 8-column block
+           + 32 * 8 + 32 * 4        // sFarV, sFarA
            + 32 * PR_LIST * 2       // survivor lists, one per row of the block
            + 4 * 8;                 // sScal
 }
@@ -92,7 +92,7 @@ __device__ __forceinline__ void lex_max(double &best, int &arg, double v, int a)
 //                  merged once at the end.  Lists are flushed whenever they might overflow.
 // Writes sFarV / sFarA for the warp's 4 rows; returns the number of cells skipped.
 template <bool AI, int NQ>
-__device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const double *sBMax,
+__device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const int4 *sBlkI, const double *sBMax,
                                         const double *sPartV, unsigned short *sList, double *sFarV, int *sFarA,
                                         double delta, double pen,
                                         const double *__restrict__ gtab, const double *__restrict__ ltab,
@@ -174,12 +174,13 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
             const int b = cb0 + 8 * u + cc;
             surv[u] = false;
             if (row1_ok && b < nfar) {
-                const ColRec a = sCol[1 + PR_FB * b];              // first column: largest count, longest length
-                const ColRec z = sCol[PR_FB * b + PR_FB];          // last column: smallest count, shortest length
-                const int x_hi = rc1.cjx - a.C, x_lo = rc1.cjx - z.C;
-                const double lg = __ldg(ltab + (rc1.lj - z.L));
-                const double s_hi = AI ? u32_to_double(x_hi) : __dsub_rn(rc1.aj, u32_to_double(a.C));
-                const double s_lo = AI ? u32_to_double(x_lo) : __dsub_rn(rc1.aj, u32_to_double(z.C));
+                // x = C of the block's first column (largest count), y = C and z = L of its last column
+                // (smallest count, shortest length); 8 consecutive 16-byte records: one wavefront
+                const int4 blk = sBlkI[b];
+                const int x_hi = rc1.cjx - blk.x, x_lo = rc1.cjx - blk.y;
+                const double lg = __ldg(ltab + (rc1.lj - blk.z));
+                const double s_hi = AI ? u32_to_double(x_hi) : __dsub_rn(rc1.aj, u32_to_double(blk.x));
+                const double s_lo = AI ? u32_to_double(x_lo) : __dsub_rn(rc1.aj, u32_to_double(blk.y));
                 const double f_hi = __dsub_rn(__ldg(gtab + x_hi), __dmul_rn(s_hi, lg));
                 const double f_lo = __dsub_rn(__ldg(gtab + x_lo), __dmul_rn(s_lo, lg));
                 const double ub = fmax(f_hi, f_lo) + sBMax[b] + delta;
@@ -230,14 +231,15 @@ window_dp_kernel(WinDpParams p)
     int *sPartA = reinterpret_cast<int *>(sTri + DP_JB * DP_JB);
     int *sMisc = sPartA + WD_WARPS * 32;
     unsigned short *sPrev = reinterpret_cast<unsigned short *>(sMisc + 16);
-    unsigned short *sJump = sPrev + capr;
-    unsigned char *sMark = reinterpret_cast<unsigned char *>(sJump + capr);
-    double *sBMax = reinterpret_cast<double *>(sMark + capr);      // capr is a multiple of 32: stays 8-byte aligned
-    double *sLB = sBMax + capr / PR_FB;
-    double *sFarV = sLB + 32;
-    double *sScal = sFarV + 32;                                     // [0] magnitude of the window's largest self score, [1] max |P|
+    int4 *sBlkI = reinterpret_cast<int4 *>(sPrev + capr);               // capr*2 bytes is a multiple of 16
+    double *sBMax = reinterpret_cast<double *>(sBlkI + capr / PR_FB);
+    double *sFarV = sBMax + capr / PR_FB;
+    double *sScal = sFarV + 32;                                         // [0] magnitude of the window's largest self score, [1] max |P|
     int *sFarA = reinterpret_cast<int *>(sScal + 4);
     unsigned short *sList = reinterpret_cast<unsigned short *>(sFarA + 32);
+    // the back-trace runs after the DP, when these are dead
+    unsigned short *sJump = reinterpret_cast<unsigned short *>(sBlkI);  // capr*2 bytes == (capr/8)*16
+    unsigned char *sMark = reinterpret_cast<unsigned char *>(sTri);     // capr <= 8192 bytes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -297,6 +299,12 @@ window_dp_kernel(WinDpParams p)
             sScal[0] = fabs(__ldg(p.gtab + x)) + ((double)z.C + p.alpha) * fabs(__ldg(p.ltab + z.L)) + 1.0;
             sScal[1] = 0.0;
         }
+        if (PRUNE) {
+            for (int b = tid; PR_FB * b + PR_FB < N; b += WD_THREADS) {
+                const ColRec a = sCol[1 + PR_FB * b], z = sCol[PR_FB * b + PR_FB];
+                sBlkI[b] = make_int4(a.C, z.C, z.L, 0);
+            }
+        }
         for (int jb = 1; jb < N; jb += DP_JB) {
             constexpr int NQ = WD_WARPS / (DP_JB / (DP_RPW * RPL));
             const int near_lo = jb - PR_NEAR;
@@ -310,7 +318,7 @@ window_dp_kernel(WinDpParams p)
                 // (2) far columns [1, near_lo): bound blocks of 8 against a lower bound of the row maximum,
                 //     evaluate the survivors exactly
                 const double delta = ldexp(sScal[0] + sScal[1] + fabs(p.pen) * DP_JB, -44);
-                skipped += far_pass<AI, NQ>(jb, N, (near_lo - 1) / PR_FB, sCol, sBMax, sPartV, sList, sFarV, sFarA,
+                skipped += far_pass<AI, NQ>(jb, N, (near_lo - 1) / PR_FB, sCol, sBlkI, sBMax, sPartV, sList, sFarV, sFarA,
                                             delta, p.pen, p.gtab, p.ltab, p.alpha_int, p.alpha);
                 __syncthreads();
                 // (3) chain: far result first (smaller columns), then the near partials, then the triangle
@@ -365,7 +373,7 @@ window_dp_kernel(WinDpParams p)
 int window_dp_max_candidates(pasio_ctx *ctx)
 {
     int cap = 32;
-    while (window_smem_bytes(cap + 32) <= (size_t)ctx->smem_optin) cap += 32;
+    while (cap + 32 <= 8192 && window_smem_bytes(cap + 32) <= (size_t)ctx->smem_optin) cap += 32;
     return cap;
 }
 
@@ -386,7 +394,7 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     p.pen = ctx->pen;
     i64 cap = (i64)wsize + 1;
     if (cap > ctx->m) cap = ctx->m;
-    if (cap > 65535 || window_smem_bytes((int)cap) > (size_t)ctx->smem_optin)
+    if (cap > 8192 || window_smem_bytes((int)cap) > (size_t)ctx->smem_optin)
         return pasio_fail(ctx, PASIO_E_TOO_LARGE, "window of %lld candidates does not fit one CTA's shared memory (max %d)",
                           (long long)cap, window_dp_max_candidates(ctx));
     p.cap = (int)cap;
