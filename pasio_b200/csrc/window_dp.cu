@@ -98,9 +98,8 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
                                         const double *__restrict__ gtab, const double *__restrict__ ltab,
                                         int alpha_int, double alpha)
 {
-    constexpr int UF = 4;
+    constexpr int UF = 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rr = lane & 3, cc = lane >> 2;              // F1: 4 rows x 8 column blocks
     const int grp = lane >> 3, l8 = lane & 7;             // F2: row grp, column l8 of a block
     unsigned short *myList = sList + (warp * 4) * PR_LIST;
 
@@ -123,11 +122,20 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
         for (int q = 1; q < NQ; ++q) nearbest = fmax(nearbest, sPartV[q * 32 + lane]);
         lb = fmax(path, nearbest);
     }
-    const int r1 = 4 * warp + rr;                          // F1 row
-    const bool row1_ok = jb + r1 < N;
-    const double lb1 = __shfl_sync(0xffffffffu, lb, r1);
-    const ColRec me1 = sCol[min(jb + r1, N - 1)];
-    const RowConst<AI> rc1 = make_row<AI>(me1.C, me1.L, alpha_int, alpha);
+    // F1 bounds one (4 rows of this warp) x (8 columns) rectangle per lane: the counts span
+    // [S_first_row - C_last_col, S_last_row - C_first_col], the shortest length is L_first_row - L_last_col,
+    // and the rectangle survives unless its bound is below the SMALLEST of the 4 lower bounds.
+    const int j0 = min(jb + 4 * warp, N - 1), j3 = min(jb + 4 * warp + 3, N - 1);
+    const bool grp_ok = jb + 4 * warp < N;
+    const ColRec mf = sCol[j0], ml = sCol[j3];
+    const RowConst<AI> rcF = make_row<AI>(mf.C, mf.L, alpha_int, alpha);    // first row: smallest S, shortest lengths
+    const RowConst<AI> rcL = make_row<AI>(ml.C, ml.L, alpha_int, alpha);    // last (valid) row: largest S
+    double lbmin = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double v = __shfl_sync(0xffffffffu, lb, min(4 * warp + k, 31));
+        if (jb + 4 * warp + k < N) lbmin = fmin(lbmin, v);
+    }
     const int r2 = 4 * warp + grp;                         // F2 row
     const bool row2_ok = jb + r2 < N;
     const ColRec me2 = sCol[min(jb + r2, N - 1)];
@@ -142,66 +150,58 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
         arg = 0;
     }
     u64 skipped = 0;
-    int cnt[4] = {0, 0, 0, 0};                             // list lengths, identical in all lanes
+    int cnt = 0;                                           // list length, identical in all lanes
+    const int nrow = min(4, N - (jb + 4 * warp));          // valid rows of this warp (may be <= 0)
 
     auto flush = [&]() {
         __syncwarp();
-        const int n = grp == 0 ? cnt[0] : grp == 1 ? cnt[1] : grp == 2 ? cnt[2] : cnt[3];
-        const unsigned short *lst = myList + grp * PR_LIST;
         int k = 0;
-        for (; k + 2 <= n; k += 2) {                      // two surviving blocks in flight
-            const int c0 = 1 + PR_FB * (int)lst[k] + l8, c1 = 1 + PR_FB * (int)lst[k + 1] + l8;
+        for (; k + 2 <= cnt; k += 2) {                    // two surviving blocks in flight
+            const int c0 = 1 + PR_FB * (int)myList[k] + l8, c1 = 1 + PR_FB * (int)myList[k + 1] + l8;
             const ColRec a0 = sCol[c0], a1 = sCol[c1];
             const double t0 = __dadd_rn(self_score<AI>(a0.C, a0.L, rc2, gtab, ltab), a0.P);
             const double t1 = __dadd_rn(self_score<AI>(a1.C, a1.L, rc2, gtab, ltab), a1.P);
             if (t0 > best) { best = t0; arg = c0; }
             if (t1 > best) { best = t1; arg = c1; }
         }
-        if (k < n) {
-            const int c0 = 1 + PR_FB * (int)lst[k] + l8;
+        if (k < cnt) {
+            const int c0 = 1 + PR_FB * (int)myList[k] + l8;
             const ColRec a0 = sCol[c0];
             const double t0 = __dadd_rn(self_score<AI>(a0.C, a0.L, rc2, gtab, ltab), a0.P);
             if (t0 > best) { best = t0; arg = c0; }
         }
-        cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+        cnt = 0;
         __syncwarp();
     };
 
-    for (int cb0 = 0; cb0 < nfar; cb0 += 8 * UF) {
+    for (int cb0 = 0; cb0 < nfar; cb0 += 32 * UF) {
         bool surv[UF];
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
-            const int b = cb0 + 8 * u + cc;
+            const int b = cb0 + 32 * u + lane;
             surv[u] = false;
-            if (row1_ok && b < nfar) {
+            if (grp_ok && b < nfar) {
                 // x = C of the block's first column (largest count), y = C and z = L of its last column
-                // (smallest count, shortest length); 8 consecutive 16-byte records: one wavefront
                 const int4 blk = sBlkI[b];
-                const int x_hi = rc1.cjx - blk.x, x_lo = rc1.cjx - blk.y;
-                const double lg = __ldg(ltab + (rc1.lj - blk.z));
-                const double s_hi = AI ? u32_to_double(x_hi) : __dsub_rn(rc1.aj, u32_to_double(blk.x));
-                const double s_lo = AI ? u32_to_double(x_lo) : __dsub_rn(rc1.aj, u32_to_double(blk.y));
+                const int x_hi = rcL.cjx - blk.x, x_lo = rcF.cjx - blk.y;
+                const double lg = __ldg(ltab + (rcF.lj - blk.z));
+                const double s_hi = AI ? u32_to_double(x_hi) : __dsub_rn(rcL.aj, u32_to_double(blk.x));
+                const double s_lo = AI ? u32_to_double(x_lo) : __dsub_rn(rcF.aj, u32_to_double(blk.y));
                 const double f_hi = __dsub_rn(__ldg(gtab + x_hi), __dmul_rn(s_hi, lg));
                 const double f_lo = __dsub_rn(__ldg(gtab + x_lo), __dmul_rn(s_lo, lg));
                 const double ub = fmax(f_hi, f_lo) + sBMax[b] + delta;
-                surv[u] = !(ub < lb1);                              // NaN keeps the block
-                if (!surv[u]) skipped += PR_FB;
+                surv[u] = !(ub < lbmin);                            // NaN keeps the block
+                if (!surv[u]) skipped += (u64)(PR_FB * nrow);
             }
         }
 #pragma unroll
         for (int u = 0; u < UF; ++u) {
             const unsigned mask = __ballot_sync(0xffffffffu, surv[u]);
-            const unsigned rowmask = 0x11111111u << rr;            // lanes of my row
-            if (surv[u]) {
-                const int at = (rr == 0 ? cnt[0] : rr == 1 ? cnt[1] : rr == 2 ? cnt[2] : cnt[3])
-                             + __popc(mask & rowmask & ((1u << lane) - 1u));
-                myList[rr * PR_LIST + at] = (unsigned short)(cb0 + 8 * u + cc);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) cnt[q] += __popc(mask & (0x11111111u << q));
+            if (surv[u]) myList[cnt + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)(cb0 + 32 * u + lane);
+            cnt += __popc(mask);
+            // the next ballot may add 32 more entries
+            if (cnt > 4 * PR_LIST - 32) flush();
         }
-        // each step adds at most 8*UF entries per row
-        if (max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3])) > PR_LIST - 8 * UF) flush();
     }
     flush();
 
