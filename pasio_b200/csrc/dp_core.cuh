@@ -172,11 +172,21 @@ __device__ __forceinline__ void block_rect_tri(int jb, int N, int col0, const Co
     {   // lane = row here
         const ColRec me = sCol[min(jb + lane, N - 1)];
         const RowConst<AI> r = make_row<AI>(me.C, me.L, alpha_int, alpha);
-        for (int k = warp; k < DP_JB; k += NW) {
+        static_assert(DP_JB % NW == 0, "warps must tile the triangle rows");
+        double w[DP_JB / NW];
+#pragma unroll
+        for (int kk = 0; kk < DP_JB / NW; ++kk) {                 // all gathers of the warp's columns in flight together
+            const int k = warp + kk * NW;
+            w[kk] = 0.0;
             if (k < lane && jb + lane < N) {
                 const ColRec a = sCol[jb + k];
-                sTri[k * DP_JB + lane] = self_score<AI>(a.C, a.L, r, gtab, ltab);
+                w[kk] = self_score<AI>(a.C, a.L, r, gtab, ltab);
             }
+        }
+#pragma unroll
+        for (int kk = 0; kk < DP_JB / NW; ++kk) {
+            const int k = warp + kk * NW;
+            if (k < lane && jb + lane < N) sTri[k * DP_JB + lane] = w[kk];
         }
     }
     __syncthreads();

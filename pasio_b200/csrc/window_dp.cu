@@ -155,16 +155,25 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
 
     auto flush = [&]() {
         __syncwarp();
+        constexpr int UX = 4;                              // surviving blocks in flight
         int k = 0;
-        for (; k + 2 <= cnt; k += 2) {                    // two surviving blocks in flight
-            const int c0 = 1 + PR_FB * (int)myList[k] + l8, c1 = 1 + PR_FB * (int)myList[k + 1] + l8;
-            const ColRec a0 = sCol[c0], a1 = sCol[c1];
-            const double t0 = __dadd_rn(self_score<AI>(a0.C, a0.L, rc2, gtab, ltab), a0.P);
-            const double t1 = __dadd_rn(self_score<AI>(a1.C, a1.L, rc2, gtab, ltab), a1.P);
-            if (t0 > best) { best = t0; arg = c0; }
-            if (t1 > best) { best = t1; arg = c1; }
+        for (; k + UX <= cnt; k += UX) {
+            ColRec a[UX];
+            int c[UX];
+            double t[UX];
+#pragma unroll
+            for (int u = 0; u < UX; ++u) {
+                c[u] = 1 + PR_FB * (int)myList[k + u] + l8;
+                a[u] = sCol[c[u]];
+                t[u] = self_score<AI>(a[u].C, a[u].L, rc2, gtab, ltab);
+            }
+#pragma unroll
+            for (int u = 0; u < UX; ++u) {
+                const double tv = __dadd_rn(t[u], a[u].P);
+                if (tv > best) { best = tv; arg = c[u]; }
+            }
         }
-        if (k < cnt) {
+        for (; k < cnt; ++k) {
             const int c0 = 1 + PR_FB * (int)myList[k] + l8;
             const ColRec a0 = sCol[c0];
             const double t0 = __dadd_rn(self_score<AI>(a0.C, a0.L, rc2, gtab, ltab), a0.P);
@@ -258,7 +267,50 @@ window_dp_kernel(WinDpParams p)
         const i64 cg_first = __ldg(p.cg + first);
         const bool all_zero = (p.constraint == PASIO_CONSTRAINT_ZEROS) && (__ldg(p.cg + last) == cg_first);
         int count = 0;
-        for (int base = 0; base < nq; base += WD_THREADS) {
+        const bool by_words = !p.cand && p.constraint == PASIO_CONSTRAINT_CONSTANTS;
+        if (by_words) {
+            // all positions are candidates (round 1): the survivors of the NotConstant filter are the set
+            // bits of the change-point bitmap inside [first, last], plus both ends -- one thread per word
+            const i64 w0 = first >> 5, w1 = last >> 5;
+            const int nwords = (int)(w1 - w0 + 1);
+            for (int base = 0; base < nwords; base += WD_THREADS) {
+                const int t = base + tid;
+                unsigned word = 0;
+                if (t < nwords) {
+                    word = __ldg(p.cpbits + w0 + t);
+                    if (t == 0) word = (word & (0xffffffffu << (first & 31))) | (1u << (first & 31));
+                    if (t == nwords - 1) word = (word & (0xffffffffu >> (31 - (last & 31)))) | (1u << (last & 31));
+                }
+                int incl = __popc(word);
+                const int mine = incl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                if (lane == 31) sMisc[4 + warp] = incl;
+                __syncthreads();
+                int woff = 0, tot = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < WD_WARPS; ++w2) {
+                    const int c = sMisc[4 + w2];
+                    if (w2 < warp) woff += c;
+                    tot += c;
+                }
+                int k = count + woff + incl - mine;
+                const i64 pos0 = (w0 + t) << 5;
+                while (word) {
+                    const i64 pos = pos0 + (__ffs(word) - 1);
+                    word &= word - 1;
+                    sCol[k].L = (int)(pos - first);
+                    sCol[k].C = (int)(__ldg(p.cg + pos) - cg_first);
+                    ++k;
+                }
+                count += tot;
+                __syncthreads();
+            }
+        }
+        for (int base = 0; !by_words && base < nq; base += WD_THREADS) {
             const int q = base + tid;
             i64 pos = 0;
             bool take = false;
