@@ -140,6 +140,12 @@ int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *segment_counts
                          double *mean_counts, double *logfac_cumsum, int64_t capacity,
                          int64_t *n_segments);
 
+/* ---- pinned host buffers --------------------------------------------------------------------------
+ * Page-locked host memory for callers that want full-rate PCIe copies (any host pointer works, pinned
+ * is faster).  Plain cudaHostAlloc / cudaFreeHost behind a C symbol so a binding needs no CUDA headers. */
+int pasio_host_alloc(int64_t bytes, void **out);
+int pasio_host_free(void *ptr);
+
 /* ---- measurement hooks (bench.py / profiles) ------------------------------------------
  * Device time (ms, CUDA events on the context's stream) and launch count accumulated per
  * kernel family since the last reset: 0 scan, 1 window DP, 2 compaction+prepass,

@@ -47,6 +47,8 @@ SIGNATURES = {
     'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
     'pasio_suffix_scores': (ctypes.c_int, [_vp, _i64, _f64p]),
     'pasio_segment_scores': (ctypes.c_int, [_vp, _f64p, _i64p, _f64p, _f64p, _i64, _i64p]),
+    'pasio_host_alloc': (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
+    'pasio_host_free': (ctypes.c_int, [_vp]),
     'pasio_timing_reset': (ctypes.c_int, [_vp, ctypes.c_int]),
     'pasio_timing_get': (ctypes.c_int, [_vp, ctypes.c_int, _f64p, _i64p]),
     'pasio_stream': (_vp, [_vp]),
@@ -82,6 +84,50 @@ class PasioDeviceError(RuntimeError):
     pass
 
 
+class _PinnedPool(object):
+    """Result arrays live in page-locked buffers so device->host copies run at PCIe rate and touch no
+    fresh pages.  Every call still hands out an array nobody else references (the reference returns new
+    arrays); a buffer goes back to the pool when its array is garbage collected."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.free = {}            # capacity -> [pointer, ...]
+        self.lock = threading.Lock()
+        self.total = 0
+
+    @staticmethod
+    def _capacity(nbytes):
+        cap = 1 << 16
+        while cap < nbytes:
+            cap <<= 1
+        return cap
+
+    def empty(self, n, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = max(1, int(n) * dtype.itemsize)
+        cap = self._capacity(nbytes)
+        with self.lock:
+            bucket = self.free.get(cap)
+            ptr = bucket.pop() if bucket else None
+        if ptr is None:
+            if self.total + cap > (8 << 30):          # do not pin without bound; fall back to pageable memory
+                return np.empty(int(n), dtype=dtype)
+            out = _vp()
+            if self.lib.pasio_host_alloc(cap, ctypes.byref(out)) != OK:
+                return np.empty(int(n), dtype=dtype)
+            ptr = out.value
+            self.total += cap
+        buf = (ctypes.c_char * cap).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        weakref.finalize(buf, self._give_back, cap, ptr)
+        return arr
+
+    def _give_back(self, cap, ptr):
+        with self.lock:
+            self.free.setdefault(cap, []).append(ptr)
+
+
 class Engine(object):
     """One CUDA context + stream of this process: tables, one loaded contig batch, candidates."""
 
@@ -100,6 +146,7 @@ class Engine(object):
         self._loaded = None          # strong ref to the loaded counts array (identity cache)
         self._loaded_offsets = None
         self._cands_obj = None       # array object the device candidates correspond to (identity cache)
+        self._pool = _PinnedPool(self.lib)
 
     def close(self):
         if self.ctx:
@@ -244,7 +291,7 @@ class Engine(object):
     def candidates(self):
         m = _i64(0)
         self._check(self.lib.pasio_candidates_count(self.ctx, ctypes.byref(m)))
-        out = np.empty(m.value, dtype=np.int64)
+        out = self._pool.empty(m.value, np.int64)
         self._check(self.lib.pasio_candidates_download(self.ctx, _ptr(out, ctypes.c_int64), len(out), None))
         self._cands_obj = out
         return out
@@ -325,10 +372,10 @@ class Engine(object):
     def segment_scores(self, scores=True, counts=False, means=False, logfac=False):
         m = self.candidate_count()
         nseg = m - 1
-        s = np.empty(nseg) if scores else None
-        c = np.empty(nseg, dtype=np.int64) if counts else None
-        mu = np.empty(nseg) if means else None
-        lf = np.empty(m) if logfac else None
+        s = self._pool.empty(nseg, np.float64) if scores else None
+        c = self._pool.empty(nseg, np.int64) if counts else None
+        mu = self._pool.empty(nseg, np.float64) if means else None
+        lf = self._pool.empty(m, np.float64) if logfac else None
         nout = _i64(0)
         self._retry(lambda: self.lib.pasio_segment_scores(
             self.ctx, _ptr(s, ctypes.c_double) if scores else None, _ptr(c, ctypes.c_int64) if counts else None,

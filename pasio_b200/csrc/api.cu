@@ -632,6 +632,22 @@ extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *seg
     return PASIO_OK;
 }
 
+// ---- pinned host buffers ------------------------------------------------------------------------
+extern "C" int pasio_host_alloc(int64_t bytes, void **out)
+{
+    if (!out || bytes < 0) return PASIO_E_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) return pasio_fail(nullptr, PASIO_E_NOMEM, "cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    return PASIO_OK;
+}
+
+extern "C" int pasio_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+    return PASIO_OK;
+}
+
 // ---- measurement hooks --------------------------------------------------------------------------
 extern "C" void *pasio_stream(pasio_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 

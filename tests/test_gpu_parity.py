@@ -258,6 +258,39 @@ def test_default_pipeline_5mb_vs_oracle(eng):
     assert r >= 2
 
 
+@pytest.mark.parametrize('case', ['dense_none', 'dense_real', 'ties_zero_one', 'big_counts'])
+def test_pruned_far_columns_are_exact(eng, case):
+    """full-size windows (2500/1250) where the branch-and-bound skips most far columns: every round must
+    still equal the oracle, and the kernel must really have skipped cells (so the path under test ran)"""
+    rs = np.random.RandomState(5)
+    if case == 'dense_none':
+        counts, ab, constraint = synth.piecewise_poisson(60000, 21), (1.0, 1.0), 'none'
+    elif case == 'dense_real':
+        counts, ab, constraint = synth.piecewise_poisson(150000, 22), (0.37, 2.5), 'constants'
+    elif case == 'ties_zero_one':
+        counts, ab, constraint = (rs.random_sample(400000) < 0.3).astype(np.int64), (1.0, 1.0), 'constants'
+    else:
+        counts, ab, constraint = (synth.piecewise_poisson(120000, 23) * 500 + rs.poisson(3, 120000)).astype(np.int64), (2.0, 0.5), 'constants'
+    fo = c_oracle.FlatOracle(counts, *ab)
+    eng.use_scorer(factory(*ab))
+    eng.load(counts)
+    eng.set_candidates(None)
+    cands = np.arange(len(counts) + 1, dtype=np.int64)
+    skipped_total = 0
+    for r in range(6):
+        eng.round(2500, 1250, constraint)
+        got = eng.candidates()
+        want, o_cells = fo.round(cands, 2500, 1250, constraint)
+        cells, skipped = eng.round_stats()
+        assert np.array_equal(got, want), (case, r)
+        assert cells == o_cells and 0 <= skipped < cells
+        skipped_total += skipped
+        if len(want) == len(cands):
+            break
+        cands = want
+    assert skipped_total > 0
+
+
 def test_timing_hooks(eng):
     counts = synth.dnase_like(100000, 9, hotspot_share=0.3)
     eng.use_scorer(factory(1.0, 1.0))
