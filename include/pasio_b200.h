@@ -140,6 +140,11 @@ int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *segment_counts
                          double *mean_counts, double *logfac_cumsum, int64_t capacity,
                          int64_t *n_segments);
 
+/* log_marginal_likelyhoods() (log_marginal_likelyhood.py:76-78) over the current candidates, formed on the
+ * device: lmm[k] = score[k] - (logfac_cumsum[k+1] - logfac_cumsum[k]), same two roundings as numpy.
+ * sum_logfac = total_sum_logfac() (:64-65).  lmm has m-1 entries. */
+int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, double *sum_logfac);
+
 /* ---- pinned host buffers --------------------------------------------------------------------------
  * Page-locked host memory for callers that want full-rate PCIe copies (any host pointer works, pinned
  * is faster).  Plain cudaHostAlloc / cudaFreeHost behind a C symbol so a binding needs no CUDA headers. */

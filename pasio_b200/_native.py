@@ -47,6 +47,7 @@ SIGNATURES = {
     'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
     'pasio_suffix_scores': (ctypes.c_int, [_vp, _i64, _f64p]),
     'pasio_segment_scores': (ctypes.c_int, [_vp, _f64p, _i64p, _f64p, _f64p, _i64, _i64p]),
+    'pasio_segment_lmm': (ctypes.c_int, [_vp, _f64p, _i64, _f64p]),
     'pasio_host_alloc': (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     'pasio_host_free': (ctypes.c_int, [_vp]),
     'pasio_timing_reset': (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -382,6 +383,14 @@ class Engine(object):
             _ptr(mu, ctypes.c_double) if means else None, _ptr(lf, ctypes.c_double) if logfac else None,
             max(nseg, m if logfac else 0), ctypes.byref(nout)))
         return s, c, mu, lf
+
+    def segment_lmm(self):
+        """(log_marginal_likelyhoods per segment, total_sum_logfac), formed on the device"""
+        nseg = self.candidate_count() - 1
+        out = self._pool.empty(nseg, np.float64)
+        total = ctypes.c_double(0.0)
+        self._retry(lambda: self.lib.pasio_segment_lmm(self.ctx, _ptr(out, ctypes.c_double), nseg, ctypes.byref(total)))
+        return out, total.value
 
     # -- timing ------------------------------------------------------------------------------
     def timing_reset(self, enable=True):

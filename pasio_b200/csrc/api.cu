@@ -632,6 +632,36 @@ extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *seg
     return PASIO_OK;
 }
 
+extern "C" int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, double *sum_logfac)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    const i64 nseg = ctx->m - 1;
+    if (lmm && capacity < nseg) return pasio_fail(ctx, PASIO_E_ARG, "capacity %lld < %lld segments", (long long)capacity, (long long)nseg);
+    if (!ctx->have_params) return pasio_fail(ctx, PASIO_E_STATE, "pasio_set_params has not been called");
+    i64 max_len = 0, max_cnt = 0;
+    {
+        const i64 saved = ctx->n_contigs;
+        ctx->n_contigs = 1;
+        int rc = launch_window_prepass(ctx, nseg, 1, 1, &max_len, &max_cnt);
+        ctx->n_contigs = saved;
+        PASIO_TRY(rc);
+    }
+    bool bad = false;
+    if (ctx->ntab[PASIO_TAB_LOG] < max_len + 1) { ctx->need[PASIO_TAB_LOG] = max_len + 1; bad = true; }
+    if (ctx->ntab[PASIO_TAB_LGAMMA_ALPHA] < max_cnt + 1) { ctx->need[PASIO_TAB_LGAMMA_ALPHA] = max_cnt + 1; bad = true; }
+    if (bad) return pasio_fail(ctx, PASIO_E_TABLE_TOO_SHORT, "tables too short for segment scores");
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)nseg * 8));
+    PASIO_TRY(launch_segment_scores(ctx, ctx->dpP.as<double>(), nullptr, nullptr));
+    PASIO_TRY(pasio_reserve(ctx, ctx->logfac_full, (size_t)(ctx->n + 1) * 8));
+    PASIO_TRY(launch_logfac_scan(ctx, ctx->logfac_full.as<double>()));
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)nseg * 8));
+    PASIO_TRY(launch_lmm(ctx, ctx->dpP.as<double>(), ctx->logfac_full.as<double>(), ctx->dpPart.as<double>()));
+    if (lmm) PASIO_TRY(d2h(ctx, lmm, ctx->dpPart.p, (size_t)nseg * 8));
+    if (sum_logfac) PASIO_TRY(d2h(ctx, sum_logfac, ctx->logfac_full.as<double>() + ctx->n, 8));
+    return PASIO_OK;
+}
+
 // ---- pinned host buffers ------------------------------------------------------------------------
 extern "C" int pasio_host_alloc(int64_t bytes, void **out)
 {

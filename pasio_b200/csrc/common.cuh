@@ -134,6 +134,7 @@ int launch_suffix_row(pasio_ctx *ctx, i64 stop, double *d_out);
 int launch_segment_scores(pasio_ctx *ctx, double *d_scores, i64 *d_segcounts, double *d_means);
 int launch_gather_i64(pasio_ctx *ctx, const i64 *d_src, const int32_t *d_idx32, const i64 *d_idx64, i64 m, i64 *d_out);
 int launch_gather_f64_at_cands(pasio_ctx *ctx, const double *d_src, double *d_out);
+int launch_lmm(pasio_ctx *ctx, const double *d_scores, const double *d_logfac_full, double *d_lmm);
 
 static inline const int32_t *cur_cand(const pasio_ctx *ctx) {
     return ctx->implicit_all ? nullptr : ctx->cand[ctx->cur].as<int32_t>();

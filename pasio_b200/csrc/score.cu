@@ -47,6 +47,16 @@ __global__ void gather_f64_kernel(const double *__restrict__ src, const int32_t 
     }
 }
 
+__global__ void lmm_kernel(const double *__restrict__ scores, const double *__restrict__ logfac_full,
+                           const int32_t *__restrict__ cand, i64 m, double *__restrict__ lmm)
+{
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < m - 1; k += (i64)gridDim.x * blockDim.x) {
+        const i64 a = cand ? (i64)__ldg(cand + k) : k;
+        const i64 b = cand ? (i64)__ldg(cand + k + 1) : k + 1;
+        lmm[k] = __dsub_rn(scores[k], __dsub_rn(logfac_full[b], logfac_full[a]));
+    }
+}
+
 inline unsigned grid_for(pasio_ctx *ctx, i64 n)
 {
     i64 g = (n + 255) / 256;
@@ -85,6 +95,14 @@ int launch_gather_i64(pasio_ctx *ctx, const i64 *d_src, const int32_t *d_idx32, 
 int launch_gather_f64_at_cands(pasio_ctx *ctx, const double *d_src, double *d_out)
 {
     gather_f64_kernel<<<grid_for(ctx, ctx->m), 256, 0, ctx->stream>>>(d_src, cur_cand(ctx), ctx->m, d_out);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}
+
+int launch_lmm(pasio_ctx *ctx, const double *d_scores, const double *d_logfac_full, double *d_lmm)
+{
+    TimingScope ts(ctx, TF_SCORE);
+    lmm_kernel<<<grid_for(ctx, ctx->m), 256, 0, ctx->stream>>>(d_scores, d_logfac_full, cur_cand(ctx), ctx->m, d_lmm);
     CUDA_TRY(ctx, cudaGetLastError());
     return PASIO_OK;
 }

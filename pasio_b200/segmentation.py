@@ -42,11 +42,11 @@ def segment_on_device(counts, plan, want_lmm=True):
     eng.set_candidates(None)                      # split_candidates = all positions (reference :8)
     score = _run_device_pipeline(eng, plan)
     splits = eng.candidates()
-    scores, _, means, logfac = eng.segment_scores(scores=True, means=True, logfac=want_lmm)
+    scores, _, means, _ = eng.segment_scores(scores=True, means=True)
     if plan['final'] == 'nop':
         score = np.sum(scores)                    # NopSplitter.split (nop_splitter.py:15-18)
-    lmm = scores - np.diff(logfac) if want_lmm else None
-    return score, splits, means, lmm, (logfac[-1] if want_lmm else None)
+    lmm, sum_logfac = eng.segment_lmm() if want_lmm else (None, None)
+    return score, splits, means, lmm, sum_logfac
 
 
 def segments_with_scores(profile, splitter):
