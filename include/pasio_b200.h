@@ -96,6 +96,12 @@ int pasio_candidates_set(pasio_ctx *ctx, const int64_t *cands, int64_t m);
 int pasio_candidates_count(const pasio_ctx *ctx, int64_t *m);
 int pasio_candidates_download(pasio_ctx *ctx, int64_t *out, int64_t capacity, int64_t *m);
 
+/* NotZeroReducer / NotConstantReducer applied to the whole contig as one slice (constants_reducer.py:5-21):
+ * zeros: if every count is 0 only the two ends survive, else nothing changes; constants: a candidate p
+ * survives when counts[p-1] != counts[p], both ends always survive.  Single-contig contexts only.
+ * The current candidates are replaced by the survivors. */
+int pasio_filter_candidates(pasio_ctx *ctx, int constraint, int64_t *n_in, int64_t *n_out);
+
 /* ---- one sliding-window round -------------------------------------------------------
  * Replaces SlidingWindowReducer.reduce_candidate_list (sliding_window_reducer.py:21-29)
  * with base reducer [NotConstantReducer|NotZeroReducer +] SquareSplitter

@@ -41,6 +41,7 @@ SIGNATURES = {
     'pasio_candidates_set': (ctypes.c_int, [_vp, _i64p, _i64]),
     'pasio_candidates_count': (ctypes.c_int, [_vp, _i64p]),
     'pasio_candidates_download': (ctypes.c_int, [_vp, _i64p, _i64, _i64p]),
+    'pasio_filter_candidates': (ctypes.c_int, [_vp, ctypes.c_int, _i64p, _i64p]),
     'pasio_round': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64p, _i64p, _i64p]),
     'pasio_round_stats': (ctypes.c_int, [_vp, _i64p, _i64p]),
     'pasio_rounds': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64, _i64p, _i64p, _i64p, _i64p, _i64]),
@@ -303,6 +304,13 @@ class Engine(object):
         return m.value
 
     # -- kernels -----------------------------------------------------------------------------
+    def filter_candidates(self, constraint):
+        """NotZero / NotConstant reducer over the whole loaded contig; returns (n_in, n_out)"""
+        a, b = _i64(0), _i64(0)
+        self._cands_obj = None
+        self._check(self.lib.pasio_filter_candidates(self.ctx, CONSTRAINTS[constraint], ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def round(self, window_size, window_shift, constraint):
         n_in, n_out, cells = _i64(0), _i64(0), _i64(0)
         self._cands_obj = None

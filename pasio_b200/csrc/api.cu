@@ -425,6 +425,25 @@ extern "C" int pasio_candidates_download(pasio_ctx *ctx, int64_t *out, int64_t c
     return d2h(ctx, out, ctx->dpJump.p, (size_t)ctx->m * 8);
 }
 
+extern "C" int pasio_filter_candidates(pasio_ctx *ctx, int constraint, int64_t *n_in, int64_t *n_out)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (ctx->n_contigs != 1) return pasio_fail(ctx, PASIO_E_STATE, "pasio_filter_candidates works on a single-contig context");
+    if (constraint < 0 || constraint > 2) return pasio_fail(ctx, PASIO_E_ARG, "unknown constraint %d", constraint);
+    if (n_in) *n_in = ctx->m;
+    PASIO_TRY(launch_filter_candidates(ctx, constraint));
+    const int nxt = 1 - ctx->cur;
+    PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)ctx->m * 4));
+    i64 m_new = 0;
+    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    ctx->cur = nxt;
+    ctx->implicit_all = false;
+    ctx->m = m_new;
+    if (n_out) *n_out = m_new;
+    return refresh_boundary_ranks(ctx);
+}
+
 // ---- rounds -------------------------------------------------------------------------------------
 // Window table of a batch: windows are generated per contig over that contig's slice of the
 // candidate list (dto/sliding_window.py:9-15 applied per contig).

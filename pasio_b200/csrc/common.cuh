@@ -119,6 +119,7 @@ int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count);  // k
 int launch_boundary_ranks(pasio_ctx *ctx);                    // brank from current candidates
 int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt);  // syncs
 int launch_validate_candidates(pasio_ctx *ctx, i64 *h_bad);   // syncs
+int launch_filter_candidates(pasio_ctx *ctx, int constraint);  // current candidates -> keepbits
 
 // window_dp.cu
 int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constraint);

@@ -159,7 +159,36 @@ __global__ void validate_candidates_kernel(const int32_t *__restrict__ cand, i64
     if (b) *bad = 1;
 }
 
+// constants_reducer.py:5-21 over the whole contig: mark the surviving candidates in the position bitmap
+__global__ void filter_candidates_kernel(const int32_t *__restrict__ cand, i64 m, int constraint, int all_zero,
+                                         const uint32_t *__restrict__ cpbits, uint32_t *keepbits)
+{
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (i64)gridDim.x * blockDim.x) {
+        const i64 pos = cand ? (i64)__ldg(cand + k) : k;
+        bool keep = (k == 0) || (k == m - 1);
+        if (!keep) {
+            if (constraint == PASIO_CONSTRAINT_CONSTANTS) keep = bit_test(cpbits, pos);
+            else if (constraint == PASIO_CONSTRAINT_ZEROS) keep = !all_zero;
+            else keep = true;
+        }
+        if (keep) atomicOr(keepbits + (pos >> 5), 1u << (pos & 31));
+    }
+}
+
 }  // namespace
+
+int launch_filter_candidates(pasio_ctx *ctx, int constraint)
+{
+    const size_t bit_bytes = (size_t)((ctx->n + 1 + 31) / 32 + 2) * 4;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->keepbits.p, 0, bit_bytes, ctx->stream));
+    i64 g = (ctx->m + 255) / 256;
+    if (g > (i64)ctx->sm_count * 16) g = (i64)ctx->sm_count * 16;
+    TimingScope ts(ctx, TF_COMPACT);
+    filter_candidates_kernel<<<(unsigned)g, 256, 0, ctx->stream>>>(cur_cand(ctx), ctx->m, constraint, ctx->total == 0,
+                                                                  ctx->cpbits.as<uint32_t>(), ctx->keepbits.as<uint32_t>());
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}
 
 WinGeom make_geom(const pasio_ctx *ctx, int wsize, int wshift)
 {

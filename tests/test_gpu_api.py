@@ -233,3 +233,69 @@ def test_regularized_split_uses_device_rows():
     score, splits = sp.split(counts, cands)
     o = po.square_split_regularized(counts, cands, po.Tables(1, 1.0), len_mult=1.5, len_fn=lambda x: 1 / np.log(1 + x))
     assert score == o[0] and np.array_equal(splits, o[1])
+
+
+# ---- the reference's NotZero / NotConstant tests (tests/test_pasio.py:304-325): int profiles run on the GPU ----
+class _SimpleScorer:
+    def __init__(self, sequence, split_candidates):
+        self.sequence = sequence
+        self.split_candidates = split_candidates
+        self.segment_creation_cost = 0
+
+    def self_score(self, start, stop):
+        start = self.split_candidates[start]
+        stop = self.split_candidates[stop]
+        if len(set(self.sequence[start:stop])) == 1:
+            return (stop - start) ** 2
+        return stop - start
+
+    def all_suffixes_self_score(self, stop):
+        return np.array([self.self_score(i, stop) for i in range(stop)], dtype='float64')
+
+
+class _GreedyScorer(_SimpleScorer):
+    def self_score(self, start, stop):
+        return (self.split_candidates[stop] - self.split_candidates[start]) ** 0.5
+
+
+_simple = lambda counts, cands: _SimpleScorer(counts, cands)
+_greedy = lambda counts, cands: _GreedyScorer(counts, cands)
+
+
+def test_not_constant_and_not_zero():
+    seq = np.array([1, 1, 1, 2, 2, 2, 2])
+    allp = np.arange(len(seq) + 1)
+    assert np.array_equal(ReducerCombiner(NotZeroReducer(), SquareSplitter(_simple)).split(seq, allp)[1], [0, 3, 7])
+    assert np.array_equal(ReducerCombiner(NotZeroReducer(), SquareSplitter(_greedy)).split(seq, allp)[1], list(range(8)))
+    assert np.array_equal(ReducerCombiner(NotConstantReducer(), SquareSplitter(_greedy)).split(seq, allp)[1], [0, 3, 7])
+    assert np.array_equal(ReducerCombiner(NotConstantReducer(), SquareSplitter(_greedy)).split(seq, np.array([0, 1, 2, 3, 4, 5, 7]))[1], [0, 3, 7])
+    nc = NotConstantReducer()
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.array([0, 3, 7])), [0, 3, 7])
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.arange(8)), [0, 3, 7])
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.array([0, 3, 5, 7])), [0, 3, 7])
+    assert np.array_equal(nc.reduce_candidate_list(seq, np.array([0, 5, 7])), [0, 7])
+    assert np.array_equal(NotZeroReducer().reduce_candidate_list(np.zeros(5, dtype=int), np.arange(6)), [0, 5])
+    assert np.array_equal(NotZeroReducer().reduce_candidate_list(seq, np.array([0, 5, 7])), [0, 5, 7])
+
+
+def test_reducers_vs_reference_fixture(golden):
+    g = golden('reducers.npz')
+    for k in range(6):
+        c, cands = g['r%d.counts' % k], g['r%d.cands' % k]
+        assert np.array_equal(NotZeroReducer().reduce_candidate_list(c, cands), g['r%d.notzero' % k])
+        assert np.array_equal(NotConstantReducer().reduce_candidate_list(c, cands), g['r%d.notconstant' % k])
+
+
+
+def test_constant_reducers_random_vs_oracle():
+    rs = np.random.RandomState(3)
+    for _ in range(10):
+        n = int(rs.randint(2, 5000))
+        counts = (rs.poisson(0.5, n) * (rs.random_sample(n) < 0.5)).astype(np.int64)
+        inner = np.sort(rs.choice(np.arange(1, n), size=int(rs.randint(0, n - 1)), replace=False)) if n > 2 else np.array([], dtype=int)
+        cands = np.concatenate([[0], inner, [n]]).astype(np.int64)
+        assert np.array_equal(NotConstantReducer().reduce_candidate_list(counts, cands), po.not_constant(counts, cands))
+        assert np.array_equal(NotZeroReducer().reduce_candidate_list(counts, cands), po.not_zero(counts, cands))
+    z = np.zeros(100, dtype=np.int64)
+    assert np.array_equal(NotZeroReducer().reduce_candidate_list(z, np.arange(101)), [0, 100])
+    assert np.array_equal(NotConstantReducer().reduce_candidate_list(z, np.arange(101)), [0, 100])
