@@ -157,6 +157,22 @@ int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, double *sum
 int pasio_host_alloc(int64_t bytes, void **out);
 int pasio_host_free(void *ptr);
 
+/* ---- bedgraph text in / segment text out (host C++, csrc/textio.cpp) --------------------------------
+ * pasio_bedgraph_parse replaces BedgraphInterval.from_string / each_in_stream (dto/intervals.py:16-39):
+ * whitespace-separated `chrom start stop count` lines, blank lines skipped, a count that is not an integer
+ * literal is read as float and truncated.  Per interval it returns start, stop, count and the byte range of
+ * the chromosome token inside buf; new_chrom[i] = 1 where the token differs from the previous interval's
+ * (the consecutive grouping of process_bedgraph.py:33).  On a malformed line returns PASIO_E_ARG with
+ * *n_out = 0-based line number.  pasio_format_segments replaces the %-formatting of
+ * process_bedgraph.py:71-89: mode 0 `chrom\tstart\tstop\tmean`, 1 `chrom\tstart\tstop`,
+ * 2 `chrom\tstart\tstop\tmean\tlength\tlmm`; returns bytes written or a negative value if cap is too small. */
+int64_t pasio_bedgraph_count_lines(const char *buf, int64_t len);
+int pasio_bedgraph_parse(const char *buf, int64_t len, int64_t cap, int64_t *starts, int64_t *stops,
+                         int64_t *counts, int64_t *name_off, int32_t *name_len, uint8_t *new_chrom,
+                         int64_t *n_out, int64_t *float_counts);
+int64_t pasio_format_segments(const char *chrom, int64_t offset, const int64_t *splits, int64_t n_splits,
+                              const double *means, const double *lmm, int mode, char *out, int64_t cap);
+
 /* ---- measurement hooks (bench.py / profiles) ------------------------------------------
  * Device time (ms, CUDA events on the context's stream) and launch count accumulated per
  * kernel family since the last reset: 0 scan, 1 window DP, 2 compaction+prepass,

@@ -284,3 +284,56 @@ def extended_tables(tables, n_log, n_gam):
     g = scipy.special.gammaln(np.arange(n_gam) + 0)
     ga = scipy.special.gammaln(np.arange(n_gam) + tables.alpha)
     return lg, g, ga
+
+
+# ---------------------------------------------------------------------------
+# Bedgraph text -> per-contig dense profiles, the reference's way (per-line Python loop).
+# dto/intervals.py:16-39 (from_string / each_in_stream), process_bedgraph.py:9-60
+# (fill_interval_gaps, interval_groups, parse_bedgraph_stream).
+# ---------------------------------------------------------------------------
+
+def parse_bedgraph_text(text, split_at_gaps=False):
+    """-> list of (chrom, dense int64 profile, chrom_start)"""
+    intervals = []
+    for line in text.splitlines():
+        line = line.strip()
+        if line == '':
+            continue
+        chrom, start, stop, count_str = line.split()[0:4]          # intervals.py:17
+        try:
+            count = int(count_str)
+        except ValueError:
+            count = int(float(count_str))                          # intervals.py:23
+        intervals.append((chrom, int(start), int(stop), count))
+    # consecutive grouping by chromosome (itertools.groupby, process_bedgraph.py:33)
+    groups, k = [], 0
+    while k < len(intervals):
+        j = k
+        while j < len(intervals) and intervals[j][0] == intervals[k][0]:
+            j += 1
+        groups.append(intervals[k:j])
+        k = j
+    contigs = []
+    for grp in groups:
+        if split_at_gaps:                                          # slice_when(intervals_not_adjacent), :34-36
+            parts, cur = [], [grp[0]]
+            for prev, nxt in zip(grp[:-1], grp[1:]):
+                if prev[2] != nxt[1]:
+                    parts.append(cur)
+                    cur = []
+                cur.append(nxt)
+            parts.append(cur)
+        else:                                                      # fill_interval_gaps, :9-16
+            filled, previous_stop = [], None
+            for iv in grp:
+                if previous_stop and previous_stop != iv[1]:
+                    filled.append((iv[0], previous_stop, iv[1], 0))
+                filled.append(iv)
+                previous_stop = iv[2]
+            parts = [filled]
+        for part in parts:                                         # :49-60
+            data = []
+            for (chrom, start, stop, cov) in part:
+                data.extend([cov] * (stop - start))
+            contigs.append((part[0][0], np.array(data, dtype=int), part[0][1]))
+    return contigs

@@ -51,6 +51,11 @@ SIGNATURES = {
     'pasio_segment_lmm': (ctypes.c_int, [_vp, _f64p, _i64, _f64p]),
     'pasio_host_alloc': (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     'pasio_host_free': (ctypes.c_int, [_vp]),
+    'pasio_bedgraph_count_lines': (_i64, [ctypes.c_char_p, _i64]),
+    'pasio_bedgraph_parse': (ctypes.c_int, [ctypes.c_char_p, _i64, _i64, _i64p, _i64p, _i64p, _i64p,
+                                            ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8), _i64p, _i64p]),
+    'pasio_format_segments': (_i64, [ctypes.c_char_p, _i64, _i64p, _i64, _f64p, _f64p, ctypes.c_int,
+                                     ctypes.c_char_p, _i64]),
     'pasio_timing_reset': (ctypes.c_int, [_vp, ctypes.c_int]),
     'pasio_timing_get': (ctypes.c_int, [_vp, ctypes.c_int, _f64p, _i64p]),
     'pasio_stream': (_vp, [_vp]),
@@ -411,6 +416,54 @@ class Engine(object):
             self._check(self.lib.pasio_timing_get(self.ctx, k, ctypes.byref(ms), ctypes.byref(n)))
             out[name] = (ms.value, n.value)
         return out
+
+
+def parse_bedgraph_text(data):
+    """data: bytes of a bedgraph file.  Returns dict of arrays: starts, stops, counts (int64), name_off, name_len,
+    new_chrom, plus n_float (counts that needed int(float(x)))."""
+    lib = load_library()
+    cap = lib.pasio_bedgraph_count_lines(data, len(data))
+    starts = np.empty(cap, dtype=np.int64)
+    stops = np.empty(cap, dtype=np.int64)
+    counts = np.empty(cap, dtype=np.int64)
+    name_off = np.empty(cap, dtype=np.int64)
+    name_len = np.empty(cap, dtype=np.int32)
+    new_chrom = np.empty(cap, dtype=np.uint8)
+    n, nfloat = _i64(0), _i64(0)
+    rc = lib.pasio_bedgraph_parse(data, len(data), cap, _ptr(starts, ctypes.c_int64), _ptr(stops, ctypes.c_int64),
+                                  _ptr(counts, ctypes.c_int64), _ptr(name_off, ctypes.c_int64),
+                                  _ptr(name_len, ctypes.c_int32), _ptr(new_chrom, ctypes.c_uint8),
+                                  ctypes.byref(n), ctypes.byref(nfloat))
+    if rc != OK:
+        raise ValueError('malformed bedgraph line %d (need: chrom start stop count)' % (n.value + 1))
+    k = n.value
+    return dict(starts=starts[:k], stops=stops[:k], counts=counts[:k], name_off=name_off[:k], name_len=name_len[:k],
+                new_chrom=new_chrom[:k], n_float=nfloat.value)
+
+
+def format_segments(chrom, offset, splits, means, lmm, mode):
+    """bytes of the output lines of one contig (mode 0 bedgraph, 1 bed, 2 bedgraph+length+LMM)"""
+    lib = load_library()
+    splits = np.ascontiguousarray(splits, dtype=np.int64)
+    name = chrom.encode()
+    pieces = []
+    step = 1 << 20
+    for lo in range(0, len(splits) - 1, step):
+        hi = min(lo + step, len(splits) - 1)
+        sub = splits[lo:hi + 1]
+        m = np.ascontiguousarray(means[lo:hi]) if means is not None else None
+        l = np.ascontiguousarray(lmm[lo:hi]) if lmm is not None else None
+        cap = (hi - lo) * (len(name) + 96) + 1024
+        while True:
+            buf = ctypes.create_string_buffer(cap)
+            w = lib.pasio_format_segments(name, int(offset), _ptr(sub, ctypes.c_int64), len(sub),
+                                          _ptr(m, ctypes.c_double) if m is not None else None,
+                                          _ptr(l, ctypes.c_double) if l is not None else None, mode, buf, cap)
+            if w >= 0:
+                pieces.append(buf.raw[:w])
+                break
+            cap = max(2 * cap, -w)
+    return b''.join(pieces)
 
 
 _engine = None

@@ -39,6 +39,7 @@ struct WinDpParams {
     double alpha;
     double pen;
     int cap;                    // max candidates in a window
+    int near;                   // pruned path: columns this close to the row block are always evaluated (multiple of 32)
     u64 *cells;                 // algorithmic cells N(N-1)/2
     u64 *cells_skipped;         // cells proven irrelevant by the far-column bound (0 without pruning)
     unsigned *work_counter;
@@ -359,7 +360,7 @@ window_dp_kernel(WinDpParams p)
         }
         for (int jb = 1; jb < N; jb += DP_JB) {
             constexpr int NQ = WD_WARPS / (DP_JB / (DP_RPW * RPL));
-            const int near_lo = jb - PR_NEAR;
+            const int near_lo = jb - p.near;
             if (!PRUNE || near_lo < 1 + PR_FB) {
                 dp_block_step<AI, WD_WARPS, U, RPL>(jb, N, 0, sCol, sPrev, nullptr, sPartV, sPartA, sTri,
                                                     p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
@@ -450,6 +451,8 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
         return pasio_fail(ctx, PASIO_E_TOO_LARGE, "window of %lld candidates does not fit one CTA's shared memory (max %d)",
                           (long long)cap, window_dp_max_candidates(ctx));
     p.cap = (int)cap;
+    static const int near_env = getenv("PASIO_WD_NEAR") ? atoi(getenv("PASIO_WD_NEAR")) : PR_NEAR;
+    p.near = (near_env >= 32 && near_env % 32 == 0) ? near_env : PR_NEAR;
     p.cells = ctx->scalars.as<u64>() + 10;
     p.cells_skipped = ctx->scalars.as<u64>() + 12;
     p.work_counter = ctx->scalars.as<unsigned>() + 2 * 11;   // scalars[11]

@@ -1,21 +1,26 @@
 """Bedgraph in, segments out (reference: /root/reference/src/pasio/process_bedgraph.py:9-92).
 
-Same functions and semantics: gaps between intervals are zero-filled unless `split_at_gaps`,
-a contig starts at its first interval's start, three output modes with the reference's %-formats.
-The dense profile is built with np.repeat instead of a Python list.
+Same functions and semantics as the reference: intervals are grouped per chromosome (consecutive lines),
+gaps between intervals are zero-filled unless `split_at_gaps`, a contig starts at its first interval's
+start, three output modes with the reference's %-formats.  What differs is where the time goes: the text
+is parsed by one C++ pass (csrc/textio.cpp) instead of a per-line Python loop, contigs are handed to the
+GPU as run-length intervals (pasio_contig_load_rle expands them on the device: the dense 8 B/nt profile
+never exists on the host), and the output lines are formatted in C++.
 """
-import itertools
-
 import numpy as np
 
+from . import _native
 from .logging import logger
-from .utils.slice_when import slice_when
-from .segmentation import segments_with_scores
+from .segmentation import segments_with_scores, run_loaded_pipeline
 from .dto.intervals import BedgraphInterval
 from .utils.gzip_utils import open_for_read, open_for_write
+from .splitters import _fusion
+
+OUTPUT_MODES = {'bedgraph': 0, 'bed': 1, 'bedgraph+length+LMM': 2}
 
 
 def fill_interval_gaps(intervals):
+    """Reference helper kept for API compatibility: yields the intervals with zero-coverage gap tuples."""
     previous_stop = None
     for interval in intervals:
         start = interval[1]
@@ -30,15 +35,63 @@ def intervals_not_adjacent(interval_1, interval_2):
 
 
 def interval_groups(intervals, split_at_gaps):
-    """Groups of intervals that form one contig each: per chromosome, and additionally cut at
-    uncovered positions when `split_at_gaps`; otherwise inner gaps are filled with zeros.
-    Chromosome flanks are never filled (the chromosome length is unknown)."""
+    """Reference helper kept for API compatibility (groups of BedgraphInterval objects forming one contig)."""
+    import itertools
+    from .utils.slice_when import slice_when
     for _, chromosome_intervals in itertools.groupby(intervals, key=lambda interval: interval.chrom):
         if split_at_gaps:
             for group in slice_when(chromosome_intervals, condition=intervals_not_adjacent):
                 yield group
         else:
             yield fill_interval_gaps(chromosome_intervals)
+
+
+def _read_all(stream):
+    data = stream.read()
+    return data.encode() if isinstance(data, str) else bytes(data)
+
+
+def contig_runs(data, split_at_gaps=False):
+    """Parse bedgraph bytes and yield (chrom, run_lengths, run_values, chrom_start) per contig.
+
+    Vectorised restatement of interval_groups + the accumulation loop of parse_bedgraph_stream
+    (reference process_bedgraph.py:26-60): consecutive lines of one chromosome form a group; with
+    split_at_gaps a group also ends where an interval does not start at the previous stop; otherwise a
+    zero run is inserted between non-adjacent intervals (when the previous stop is non-zero, as in the
+    reference's `if previous_stop and ...`).  Runs of non-positive length contribute nothing."""
+    rec = _native.parse_bedgraph_text(data)
+    n = len(rec['starts'])
+    if rec['n_float']:
+        logger.warning("Pasio cannot be used with floating point counts. %d count(s) were automatically converted "
+                       "to integers as an approximation. Make sure these values were designed to actually be "
+                       "integer counts." % rec['n_float'])
+    if n == 0:
+        return
+    starts, stops, counts = rec['starts'], rec['stops'], rec['counts']
+    cut = rec['new_chrom'].astype(bool)
+    adjacent = np.ones(n, dtype=bool)
+    adjacent[1:] = starts[1:] == stops[:-1]
+    if split_at_gaps:
+        cut = cut | ~adjacent
+    bounds = np.flatnonzero(cut).tolist() + [n]
+    for g0, g1 in zip(bounds[:-1], bounds[1:]):
+        off, ln = int(rec['name_off'][g0]), int(rec['name_len'][g0])
+        chrom = data[off:off + ln].decode()
+        lengths = np.maximum(stops[g0:g1] - starts[g0:g1], 0)
+        values = counts[g0:g1]
+        if not split_at_gaps and g1 - g0 > 1:
+            prev_stop = stops[g0:g1 - 1]
+            need = (prev_stop != 0) & ~adjacent[g0 + 1:g1]
+            gap = np.where(need, np.maximum(starts[g0 + 1:g1] - prev_stop, 0), 0)
+            run_len = np.empty(2 * (g1 - g0) - 1, dtype=np.int64)
+            run_val = np.zeros(2 * (g1 - g0) - 1, dtype=np.int64)
+            run_len[0::2] = lengths
+            run_len[1::2] = gap
+            run_val[0::2] = values
+        else:
+            run_len, run_val = lengths.astype(np.int64), values.astype(np.int64)
+        keep = run_len > 0
+        yield chrom, run_len[keep], run_val[keep], int(starts[g0])
 
 
 def parse_bedgraph(filename, split_at_gaps=False):
@@ -49,17 +102,8 @@ def parse_bedgraph(filename, split_at_gaps=False):
 
 
 def parse_bedgraph_stream(input_stream, split_at_gaps=False):
-    intervals_stream = BedgraphInterval.each_in_stream(input_stream)
-    for group in interval_groups(intervals_stream, split_at_gaps=split_at_gaps):
-        chromosome = chromosome_start = None
-        lengths, values = [], []
-        for (chrom, start, stop, coverage) in group:
-            if chromosome_start is None:
-                chromosome_start, chromosome = start, chrom
-            lengths.append(max(stop - start, 0))
-            values.append(coverage)
-        profile = np.repeat(np.array(values, dtype=int), np.array(lengths, dtype=int))
-        yield chromosome, profile, chromosome_start
+    for chrom, run_len, run_val, chrom_start in contig_runs(_read_all(input_stream), split_at_gaps):
+        yield chrom, np.repeat(run_val.astype(int), run_len), chrom_start
 
 
 def split_bedgraph(in_filename, out_filename, splitter, split_at_gaps=False, output_mode='bedgraph'):
@@ -69,21 +113,40 @@ def split_bedgraph(in_filename, out_filename, splitter, split_at_gaps=False, out
                                   split_at_gaps=split_at_gaps, output_mode=output_mode)
 
 
-_FORMATS = {
-    'bedgraph': lambda chrom, off, s: '%s\t%d\t%d\t%f\n' % (chrom, s.start + off, s.stop + off, s.mean_count),
-    'bed': lambda chrom, off, s: '%s\t%d\t%d\n' % (chrom, s.start + off, s.stop + off),
-    'bedgraph+length+LMM': lambda chrom, off, s: '%s\t%d\t%d\t%f\t%d\t%f\n' % (
-        chrom, s.start + off, s.stop + off, s.mean_count, s.length, s.log_marginal_likelyhood),
-}
+def _write(output_stream, payload):
+    raw = getattr(output_stream, 'buffer', None)
+    if raw is not None and not getattr(output_stream, 'closed', False):
+        output_stream.flush()
+        raw.write(payload)
+    else:
+        try:
+            output_stream.write(payload.decode('ascii'))
+        except TypeError:
+            output_stream.write(payload)
 
 
 def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=False, output_mode='bedgraph'):
     logger.info('Reading input file')
-    for chrom, counts, chrom_start in parse_bedgraph_stream(input_stream, split_at_gaps=split_at_gaps):
-        logger.info('Starting chrom %s of length %d' % (chrom, len(counts)))
-        if output_mode not in _FORMATS:
+    plan = _fusion.pipeline_plan(splitter)
+    for chrom, run_len, run_val, chrom_start in contig_runs(_read_all(input_stream), split_at_gaps):
+        n = int(run_len.sum())
+        logger.info('Starting chrom %s of length %d' % (chrom, n))
+        if output_mode not in OUTPUT_MODES:
             raise ValueError('Unknown output mode `%s`' % output_mode)
-        fmt = _FORMATS[output_mode]
-        for scored_interval in segments_with_scores(counts, splitter):
-            output_stream.write(fmt(chrom, chrom_start, scored_interval))
+        mode = OUTPUT_MODES[output_mode]
+        if plan is not None:
+            # canonical splitter graph: run-length intervals go straight to the device
+            assert n > 0
+            eng = _native.engine()
+            eng.use_scorer(plan['factory'])
+            eng.load_rle(np.concatenate([[0], np.cumsum(run_len)]), run_val)
+            _, splits, means, lmm, _ = run_loaded_pipeline(eng, plan, want_lmm=(mode == 2))
+        else:
+            counts = np.repeat(run_val.astype(int), run_len)
+            segs = list(segments_with_scores(counts, splitter))
+            splits = np.array([s.start for s in segs] + [segs[-1].stop], dtype=np.int64)
+            means = np.array([s.mean_count for s in segs], dtype=np.float64)
+            lmm = np.array([s.log_marginal_likelyhood for s in segs], dtype=np.float64)
+        _write(output_stream, _native.format_segments(chrom, chrom_start, splits, means if mode != 1 else None,
+                                                      lmm if mode == 2 else None, mode))
         logger.info('Output of chromosome %s finished' % chrom)

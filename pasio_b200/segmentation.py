@@ -34,11 +34,9 @@ def _run_device_pipeline(eng, plan):
     return score
 
 
-def segment_on_device(counts, plan, want_lmm=True):
-    """-> (score, splits, mean_counts, log_marginal_likelyhoods or None, sum_logfac or None)"""
-    eng = _native.engine()
-    eng.use_scorer(plan['factory'])
-    eng.load(counts)
+def run_loaded_pipeline(eng, plan, want_lmm=True):
+    """The device pipeline over whatever contig the engine has loaded (dense, RLE or device-resident).
+    -> (score, splits, mean_counts, log_marginal_likelyhoods or None, sum_logfac or None)"""
     eng.set_candidates(None)                      # split_candidates = all positions (reference :8)
     score = _run_device_pipeline(eng, plan)
     splits = eng.candidates()
@@ -47,6 +45,14 @@ def segment_on_device(counts, plan, want_lmm=True):
         score = np.sum(scores)                    # NopSplitter.split (nop_splitter.py:15-18)
     lmm, sum_logfac = eng.segment_lmm() if want_lmm else (None, None)
     return score, splits, means, lmm, sum_logfac
+
+
+def segment_on_device(counts, plan, want_lmm=True):
+    """-> (score, splits, mean_counts, log_marginal_likelyhoods or None, sum_logfac or None)"""
+    eng = _native.engine()
+    eng.use_scorer(plan['factory'])
+    eng.load(counts)
+    return run_loaded_pipeline(eng, plan, want_lmm)
 
 
 def segments_with_scores(profile, splitter):

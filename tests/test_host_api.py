@@ -246,3 +246,48 @@ def test_lpt_assignment():
     assert np.array_equal(sharding.lpt_assign(lens, 4), sharding.lpt_assign(list(lens), 4))
     res = sharding.segment_contigs([('a', np.zeros(3), 0), ('b', np.zeros(9), 0)], lambda n, c, s: n + str(len(c)))
     assert res == ['a3', 'b9']
+
+
+def test_cpp_bedgraph_parser_equals_reference_semantics():
+    """csrc/textio.cpp + process_bedgraph.contig_runs against the per-line restatement of the reference parser
+    (oracle.parse_bedgraph_text): blank lines, mixed whitespace, float counts, gaps, overlaps, a chromosome that
+    comes back later, a first interval ending at 0."""
+    import io
+    from oracle import pasio_oracle as po
+    rs = np.random.RandomState(9)
+    lines = ['', 'chr1\t5 8   2', 'chr1 8 12 7.0', '  ', 'chr1\t20\t25\t3e0', 'chr1 25 25 9', 'chr1 23 30 4', 'chr2 0 3 1',
+             'chr1 30 33 2', 'chrZ -2 0 5', 'chrZ 0 4 6', 'chrZ 9 11 1\r']
+    pos = 0
+    for k in range(400):
+        pos += int(rs.randint(0, 3)) * int(rs.randint(0, 50))
+        ln = int(rs.randint(1, 40))
+        lines.append('%s%s%d %d\t%d' % ('ctg%d' % (k // 97), ' \t'[k % 2], pos, pos + ln, int(rs.poisson(2))))
+        pos += ln
+    text = '\n'.join(lines) + '\n'
+    for gaps in [False, True]:
+        want = po.parse_bedgraph_text(text, split_at_gaps=gaps)
+        got = list(parse_bedgraph_stream(io.StringIO(text), split_at_gaps=gaps))
+        assert len(got) == len(want)
+        for (c1, p1, s1), (c2, p2, s2) in zip(got, want):
+            assert c1 == c2 and s1 == s2 and np.array_equal(p1, p2) and p1.dtype == int
+    with pytest.raises(ValueError):
+        list(parse_bedgraph_stream(io.StringIO('chr1 0 5\n')))
+    with pytest.raises(ValueError):
+        list(parse_bedgraph_stream(io.StringIO('chr1 a 5 1\n')))
+    assert list(parse_bedgraph_stream(io.StringIO('\n\n'))) == []
+
+
+def test_cpp_segment_formatter_equals_python_formatting():
+    from pasio_b200 import _native
+    rs = np.random.RandomState(1)
+    splits = np.concatenate([[0], np.cumsum(rs.randint(1, 10 ** 6, 5000))]).astype(np.int64)
+    means = np.concatenate([rs.gamma(1.0, 3.0, 4990), [0.0, 1e-7, 0.5000005, 123456789.1234565, 2.5e-7, 1e15, 0.1, 2.675, 1 / 3, 7.0]])
+    lmm = -rs.gamma(2.0, 50.0, 5000)
+    off = 12345
+    want0 = ''.join('%s\t%d\t%d\t%f\n' % ('chrQ', a + off, b + off, m) for a, b, m in zip(splits[:-1], splits[1:], means))
+    want1 = ''.join('%s\t%d\t%d\n' % ('chrQ', a + off, b + off) for a, b in zip(splits[:-1], splits[1:]))
+    want2 = ''.join('%s\t%d\t%d\t%f\t%d\t%f\n' % ('chrQ', a + off, b + off, m, b - a, l)
+                    for a, b, m, l in zip(splits[:-1], splits[1:], means, lmm))
+    assert _native.format_segments('chrQ', off, splits, means, None, 0).decode() == want0
+    assert _native.format_segments('chrQ', off, splits, None, None, 1).decode() == want1
+    assert _native.format_segments('chrQ', off, splits, means, lmm, 2).decode() == want2
