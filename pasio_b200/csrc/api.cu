@@ -237,8 +237,8 @@ static int finish_load(pasio_ctx *ctx, const int64_t *offsets, int64_t n_contigs
         ctx->h_bounds[1] = (int32_t)n;
     }
     ctx->n_contigs = n_contigs;
-    // bitmaps over positions 0..n, padded to whole scan tiles (2048 positions) so the scan writes 64-bit words freely
-    const size_t bit_bytes = (size_t)((n + 1 + 2047) / 2048) * 256 + 16;
+    // bitmaps over positions 0..n, padded to whole scan tiles (4096 positions) so the scan writes 64-bit words freely
+    const size_t bit_bytes = (size_t)((n + 1 + 4095) / 4096) * 512 + 16;
     PASIO_TRY(pasio_reserve(ctx, ctx->cg, (size_t)(n + 2) * 8));
     PASIO_TRY(pasio_reserve(ctx, ctx->cpbits, bit_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->keepbits, bit_bytes));

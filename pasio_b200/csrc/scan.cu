@@ -10,7 +10,9 @@
 namespace {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_TILE = SCAN_THREADS * 8;      // elements per CTA (8 warps x 256)
+constexpr int SCAN_SLABS = 8;                    // 64-element slabs per warp
+constexpr int SCAN_WARP_ELEMS = 64 * SCAN_SLABS;
+constexpr int SCAN_TILE = (SCAN_THREADS / 32) * SCAN_WARP_ELEMS;   // elements per CTA
 
 // tile status word: top 2 bits = flag (0 invalid, 1 aggregate, 2 inclusive prefix), low 62 = value
 __device__ __forceinline__ u64 pack_state(u64 flag, i64 v) { return (flag << 62) | (u64)v; }
@@ -28,7 +30,7 @@ __device__ __forceinline__ u64 spread_bits(unsigned x)   // bit k of x -> bit 2k
     return v;
 }
 
-// Each warp owns 256 consecutive elements: 4 slabs of 32 lanes x one 16-byte pair, so every load
+// Each warp owns SCAN_WARP_ELEMS consecutive elements: SCAN_SLABS slabs of 32 lanes x one 16-byte pair, so every load
 // and store instruction of a warp is one fully coalesced 512-byte access.  cg[p] is the EXCLUSIVE
 // prefix at p, which makes the (cg[2m], cg[2m+1]) pair an aligned 16-byte store.  The change-point
 // bits of a slab come from two ballots interleaved into one 64-bit word.
@@ -44,12 +46,12 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);   // tiles start in issue order: look-back never waits on an unscheduled tile
     __syncthreads();
     const i64 tile = s_tile;
-    const i64 wbase = tile * SCAN_TILE + (i64)warp * 256;     // first element of this warp's chunk
+    const i64 wbase = tile * SCAN_TILE + (i64)warp * SCAN_WARP_ELEMS;     // first element of this warp's chunk
 
-    i64 v0[4], v1[4];
+    i64 v0[SCAN_SLABS], v1[SCAN_SLABS];
     bool neg = false;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < SCAN_SLABS; ++k) {
         const i64 e = wbase + 64 * k + 2 * lane;
         if (e + 1 < n) {
             const longlong2 t = __ldg(reinterpret_cast<const longlong2 *>(counts + e));
@@ -66,9 +68,9 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
     // change-point words: position p flagged when counts[p-1] != counts[p], 1 <= p <= n-1
     {
         i64 carry = (wbase > 0 && wbase - 1 < n) ? __ldg(counts + wbase - 1) : 0;   // element before the chunk
-        u64 word[4];
+        u64 word[SCAN_SLABS];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < SCAN_SLABS; ++k) {
             const i64 e = wbase + 64 * k + 2 * lane;
             i64 before = __shfl_up_sync(0xffffffffu, v1[k], 1);
             if (lane == 0) before = carry;
@@ -79,17 +81,18 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
             word[k] = spread_bits(b0) | (spread_bits(b1) << 1);
             carry = __shfl_sync(0xffffffffu, v1[k], 31);
         }
-        if (lane < 4 && wbase + 64 * lane <= n) {
-            const u64 w = lane == 0 ? word[0] : lane == 1 ? word[1] : lane == 2 ? word[2] : word[3];
-            cpwords[(wbase >> 6) + lane] = w;
-        }
+        u64 mine = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_SLABS; ++k)
+            if (lane == k) mine = word[k];
+        if (lane < SCAN_SLABS && wbase + 64 * lane <= n) cpwords[(wbase >> 6) + lane] = mine;
     }
 
     // warp-level inclusive scans of the pair sums, slab by slab
-    i64 ex[4];
+    i64 ex[SCAN_SLABS];
     i64 run = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < SCAN_SLABS; ++k) {
         const i64 pair = v0[k] + v1[k];
         i64 incl = pair;
 #pragma unroll
@@ -140,7 +143,7 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
     __syncthreads();
     const i64 off = s_prefix + warp_off;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < SCAN_SLABS; ++k) {
         const i64 e = wbase + 64 * k + 2 * lane;
         const i64 c0 = off + ex[k];
         const i64 c1 = c0 + v0[k];
