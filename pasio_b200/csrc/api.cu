@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -490,6 +491,12 @@ extern "C" int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_s
     PASIO_TRY(build_window_table(ctx, window_size, window_shift, &nwin));
     i64 max_span = 0, max_cnt = 0;
     PASIO_TRY(launch_window_prepass(ctx, nwin, (int)window_size, (int)window_shift, &max_span, &max_cnt));
+    static const bool debug = getenv("PASIO_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "[pasio_round] n=%lld contigs=%lld m=%lld implicit=%d nwin=%lld size=%lld shift=%lld max_span=%lld max_cnt=%lld ntab=%lld,%lld,%lld\n",
+                (long long)ctx->n, (long long)ctx->n_contigs, (long long)ctx->m, (int)ctx->implicit_all, (long long)nwin,
+                (long long)window_size, (long long)window_shift, (long long)max_span, (long long)max_cnt,
+                (long long)ctx->ntab[0], (long long)ctx->ntab[1], (long long)ctx->ntab[2]);
     PASIO_TRY(check_dp_tables(ctx, max_span, max_cnt));
 
     const size_t bit_bytes = (size_t)((ctx->n + 1 + 31) / 32 + 2) * 4;

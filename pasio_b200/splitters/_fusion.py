@@ -11,6 +11,10 @@ window by window through the objects and still reach the GPU inside SquareSplitt
 """
 from ..log_marginal_likelyhood import ScorerFactory
 
+# one window is one CTA: its candidates must fit shared memory (csrc/window_dp.cu, window_dp_max_candidates).
+# Larger windows are not fused: they go window by window through the objects, i.e. through the exact-DP kernel.
+MAX_FUSED_WINDOW_CANDIDATES = 8192
+
 
 def base_plan(reducer):
     """-> (factory, constraint) or None"""
@@ -44,6 +48,8 @@ def window_plan(reducer):
         return None
     size, shift = reducer.sliding_window.window_size, reducer.sliding_window.window_shift
     if not (isinstance(size, int) and isinstance(shift, int) and size >= 1 and shift >= 1):
+        return None
+    if size + 1 > MAX_FUSED_WINDOW_CANDIDATES:
         return None
     return base[0], size, shift, base[1]
 

@@ -16,6 +16,7 @@ from pasio_b200.dto.sliding_window import SlidingWindow
 from pasio_b200.process_bedgraph import split_bedgraph_stream
 from pasio_b200 import synth
 from oracle import pasio_oracle as po
+from oracle import c_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -299,3 +300,27 @@ def test_constant_reducers_random_vs_oracle():
     z = np.zeros(100, dtype=np.int64)
     assert np.array_equal(NotZeroReducer().reduce_candidate_list(z, np.arange(101)), [0, 100])
     assert np.array_equal(NotConstantReducer().reduce_candidate_list(z, np.arange(101)), [0, 100])
+
+
+def test_window_larger_than_one_cta_goes_through_exact_kernel():
+    """window_size beyond the fused limit is not an error at the API level: windows run one by one on the exact-DP kernel"""
+    from pasio_b200.splitters import _fusion
+    counts = synth.piecewise_poisson(12000, 5) + 1           # every position is a change point
+    splitter = configure_splitter(window_size=9000, window_shift=4500, split_constraints='none', num_rounds=1)
+    assert _fusion.pipeline_plan(splitter) is None
+    score, splits = splitter.split(counts, np.arange(len(counts) + 1))
+    t = po.Tables(1, 1.0)
+    want = po.sliding_window_round(counts, np.arange(len(counts) + 1), t, 9000, 4500, 'none')
+    assert np.array_equal(splits, want)
+
+
+def test_deep_coverage_total_beyond_int32():
+    """prefix sums are int64: a contig whose total count exceeds 2^31 runs through the default pipeline
+    (the 32-bit limit applies to the count inside one window's DP, not to the contig)"""
+    rs = np.random.RandomState(6)
+    counts = np.repeat(rs.poisson(110, 400000), 50).astype(np.int64)          # 20 Mb, runs of 50 nt
+    assert counts.sum() > 2 ** 31
+    splitter = configure_splitter(window_size=500, window_shift=250)
+    score, splits = splitter.split(counts, np.arange(len(counts) + 1))
+    want, _, _ = c_oracle.FlatOracle(counts, 1.0, 1.0).rounds(500, 250, 'constants')
+    assert np.array_equal(splits, want)
