@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpasio_b200.so')
+LIB_PATH = os.environ.get('PASIO_B200_LIB') or os.path.join(_HERE, 'libpasio_b200.so')   # override: kernel experiments
 
 OK = 0
 E_CUDA, E_ARG, E_COUNTS, E_CANDIDATES, E_TABLE_TOO_SHORT, E_STATE, E_TOO_LARGE, E_NOMEM = range(-1, -9, -1)

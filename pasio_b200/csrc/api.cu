@@ -497,6 +497,11 @@ extern "C" int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_s
                 (long long)ctx->n, (long long)ctx->n_contigs, (long long)ctx->m, (int)ctx->implicit_all, (long long)nwin,
                 (long long)window_size, (long long)window_shift, (long long)max_span, (long long)max_cnt,
                 (long long)ctx->ntab[0], (long long)ctx->ntab[1], (long long)ctx->ntab[2]);
+    if (max_cnt > ctx->total || max_span > ctx->n)      // cannot happen with a consistent prefix-sum / candidate state
+        return pasio_fail(ctx, PASIO_E_CUDA, "internal inconsistency before the window DP: window count %lld / span %lld exceed "
+                          "contig total %lld / length %lld (m=%lld, implicit=%d, windows=%lld)", (long long)max_cnt,
+                          (long long)max_span, (long long)ctx->total, (long long)ctx->n, (long long)ctx->m,
+                          (int)ctx->implicit_all, (long long)nwin);
     PASIO_TRY(check_dp_tables(ctx, max_span, max_cnt));
 
     const size_t bit_bytes = (size_t)((ctx->n + 1 + 31) / 32 + 2) * 4;

@@ -15,15 +15,39 @@
 // doubling and an atomicOr scatter of the survivors into the position bitmap.
 // CTAs are persistent and pull windows from an atomic counter (window cost varies as N^2).
 #include "dp_core.cuh"
+#include <cstdio>
 #include <cstdlib>
 
 namespace {
 
 constexpr int WD_THREADS = 256;
+
+// Development-only phase timers (make PROF=1): cycles seen by thread 0 of every CTA, summed per phase.
+#ifdef PASIO_WD_PROF
+__device__ unsigned long long g_wd_prof[24];
+struct ProfAcc { long long t0; long long a0, a1, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12; };
+#define PROF_DECL ProfAcc prof = {clock64(), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_T(i) do { asm volatile("" ::: "memory"); const long long t1__ = clock64(); prof.a##i += t1__ - prof.t0; prof.t0 = t1__; asm volatile("" ::: "memory"); } while (0)
+#define PROF_FLUSH do { if (threadIdx.x == 0) { \
+    atomicAdd(g_wd_prof + 0, (unsigned long long)prof.a0); atomicAdd(g_wd_prof + 1, (unsigned long long)prof.a1); \
+    atomicAdd(g_wd_prof + 3, (unsigned long long)prof.a3); atomicAdd(g_wd_prof + 4, (unsigned long long)prof.a4); \
+    atomicAdd(g_wd_prof + 5, (unsigned long long)prof.a5); atomicAdd(g_wd_prof + 6, (unsigned long long)prof.a6); \
+    atomicAdd(g_wd_prof + 7, (unsigned long long)prof.a7); atomicAdd(g_wd_prof + 8, (unsigned long long)prof.a8); \
+    atomicAdd(g_wd_prof + 9, (unsigned long long)prof.a9); atomicAdd(g_wd_prof + 10, (unsigned long long)prof.a10); \
+    atomicAdd(g_wd_prof + 11, (unsigned long long)prof.a11); atomicAdd(g_wd_prof + 12, (unsigned long long)prof.a12); } \
+    prof.a0 = prof.a1 = prof.a3 = prof.a4 = prof.a5 = prof.a6 = prof.a7 = prof.a8 = prof.a9 = prof.a10 = prof.a11 = prof.a12 = 0; } while (0)
+#define PROF_ARGS , ProfAcc &prof
+#define PROF_PASS , prof
+#else
+#define PROF_DECL
+#define PROF_T(i) do { } while (0)
+#define PROF_FLUSH do { } while (0)
+#define PROF_ARGS
+#define PROF_PASS
+#endif
 constexpr int WD_WARPS = WD_THREADS / 32;
-constexpr int PR_NEAR = 64;     // pruned path: columns this close to the row block are always evaluated
-constexpr int PR_FB = 8;        // pruned path: far columns are bounded in blocks of 8
-constexpr int PR_LIST = 64;     // pruned path: per-row survivor list capacity (entries = far block numbers)
+constexpr int PR_CB = 32;       // pruned path: far columns are first bounded in blocks of 32 ...
+constexpr int PR_FB = 8;        // ... and the surviving blocks again in sub-blocks of 8
 
 struct WinDpParams {
     WinGeom geom;
@@ -39,10 +63,34 @@ struct WinDpParams {
     double alpha;
     double pen;
     int cap;                    // max candidates in a window
-    int near;                   // pruned path: columns this close to the row block are always evaluated (multiple of 32)
     u64 *cells;                 // algorithmic cells N(N-1)/2
     u64 *cells_skipped;         // cells proven irrelevant by the far-column bound (0 without pruning)
     unsigned *work_counter;
+#ifdef PASIO_WD_EXP
+    int exp_skip;               // timing experiments only (results are wrong): 1 far pass, 2 record fit, 4 chain, 8 near rectangle
+#endif
+};
+#ifdef PASIO_WD_EXP
+#define EXP_SKIP(bit) (p.exp_skip & (bit))
+#else
+#define EXP_SKIP(bit) false
+#endif
+
+// One finished block of 32 columns [1+32b, 32+32b], as the far pass sees it.
+struct __align__(16) CoarseRec {
+    int c_first, c_last, l_first, l_last;   // C and L of its first / last column
+    double a, b;                            // tilt: P_i + a*C_i + b*L_i is nearly constant over the block
+    double mpt;                             // max_i (P_i + a*C_i + b*L_i) over the block, raised by the tilt's rounding slack
+    double mpt8[4];                         // the same over each 8-column sub-block
+    double pad;
+};
+static_assert(sizeof(CoarseRec) == 80, "CoarseRec layout");
+
+// One row of the current 32-row block step: a lower bound of its maximum, its C and L.
+struct __align__(16) RowLB {
+    double lb;
+    int C;
+    int L;
 };
 
 __host__ __device__ inline size_t window_smem_bytes(int cap)
@@ -54,63 +102,71 @@ __host__ __device__ inline size_t window_smem_bytes(int cap)
            + WD_WARPS * 32 * 4      // sPartA
            + 16 * 4                 // sMisc
            + capr * 2               // sPrev
-           + (capr / PR_FB) * 16    // sBlkI: (C first, C last, L last) of every 8-column block   (back-trace: sJump lives here)
-           + (capr / PR_FB) * 8     // sBMax: max P of every 8-column block
-           + 32 * 8 + 32 * 4        // sFarV, sFarA
-           + 32 * PR_LIST * 2       // survivor lists, one per row of the block
+           + (capr / PR_CB) * sizeof(CoarseRec)   // sCoarse  (back-trace: sJump lives here, capr*2 bytes)
+           + WD_WARPS * 32 * sizeof(RowLB)        // sRow: every warp keeps its own copy of the 32 row records
+           + WD_WARPS * 32 * 8 + WD_WARPS * 32 * 4   // sFarV, sFarA: per-warp far results of the 32 rows
            + 4 * 8;                 // sScal
 }
 
 // ---- exact pruning of far columns (branch and bound) -----------------------------------------
-// For row j and a block I of consecutive columns [i0, i1):  every cell value
-//     t_ij = (G[s_ij] - s_ij * Lg[len_ij]) + P_i ,  s_ij = S_j - C_i ,  len_ij = L_j - L_i
-// obeys   t_ij <= max(F(s_lo, len_lo), F(s_hi, len_lo)) + max_{i in I} P_i + delta   where
-// F(s, len) = G[s] - s*Lg[len], s_lo/s_hi are the block's extreme counts and len_lo its shortest
-// length: F decreases in len (s >= 0, log non-decreasing) and lgamma(s) - s*c is convex in s, so over
-// the block it is largest at an end point; delta covers the table and rounding errors (2^-44 of the
-// window's largest magnitudes, >1000x the worst case, <1e-6 in absolute terms).
-// A block whose bound is strictly below a LOWER bound of the row's maximum cannot hold the
-// arg-max nor tie with it, so skipping it leaves P, prev and the back-trace bit-identical.
-// The lower bound is the row's maximum over the PR_NEAR nearest columns plus the triangle, obtained
-// by running the block chain once on those columns only (a feasible segmentation, hence <= optimum).
-// Surviving blocks are evaluated exactly, cell by cell, in the reference's operation order.
+// For rows j in [j0, j1] and columns i in [i0, i1] every cell value
+//     t_ij = F(u_ij, len_ij) + P_i ,  F(u, len) = G[u (+alpha)] - s*Lg[len],  u_ij = C_j - C_i,  len_ij = L_j - L_i
+// satisfies, for ANY real a, b (the "tilt"),
+//     t_ij - LB_j = [P_i + a*C_i + b*L_i] + [F(u_ij, len_ij) + a*u_ij + b*len_ij] - [LB_j + a*C_j + b*L_j]
+//                <= max_i [P_i + a*C_i + b*L_i]  +  max_box [F(u, len) + a*u + b*len]  -  min_j [LB_j + a*C_j + b*L_j]
+// where the box is [C_j0 - C_i1, C_j1 - C_i0] x [L_j0 - L_i1, L_j1 - L_i0].  F + a*u + b*len is convex in u for fixed
+// len (lgamma is convex, the rest is linear) and convex in len for fixed u (-s*log(len + beta) with s >= 0), so
+// its maximum over the box is at one of the 4 corners.  With a, b fitted to the block's own P (least squares: along
+// an optimal path P is close to linear in (C, L)) the first bracket hardly varies and the bound is tight to second
+// order; without the tilt it is loose by the block's whole range of P.  If the right-hand side (plus delta, which
+// covers table and rounding errors: 2^-44 of the window's largest magnitudes, > 50x the worst case, < 1e-6 in
+// absolute terms) is negative, no cell of the rectangle reaches the lower bound LB_j of its row's maximum: it can
+// hold neither the arg-max nor a tie, so skipping it leaves P, prev and the back-trace bit-identical.
+// LB_j = max( best over the nearest 32 columns, the "split at every candidate" path through the block's own rows ):
+// both are feasible segmentations; the path value is formed with a parallel prefix sum and lowered by delta to
+// stay below the sequentially rounded value the chain would produce.
+// Two levels: 32 rows x 32 columns first (one lane per rectangle), the survivors again as 4 rows x 8 columns
+// (one warp per surviving rectangle); what survives both is evaluated exactly, cell by cell, in the reference's
+// operation order.
 template <bool AI>
-__device__ __forceinline__ void lex_max(double &best, int &arg, double v, int a)
+__device__ __forceinline__ double tilted_box_max(int u_lo, int u_hi, int len_lo, int len_hi, double a, double b,
+                                                 const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                                 int alpha_int, double alpha)
 {
-    if (v > best || (v == best && a < arg)) { best = v; arg = a; }
+    const double g_lo = __ldg(gtab + (AI ? u_lo + alpha_int : u_lo)), g_hi = __ldg(gtab + (AI ? u_hi + alpha_int : u_hi));
+    const double l_lo = __ldg(ltab + len_lo), l_hi = __ldg(ltab + len_hi);
+    const double ud_lo = u32_to_double(u_lo), ud_hi = u32_to_double(u_hi);
+    const double s_lo = ud_lo + alpha, s_hi = ud_hi + alpha;
+    const double ta_lo = a * ud_lo, ta_hi = a * ud_hi;
+    const double tb_lo = b * u32_to_double(len_lo), tb_hi = b * u32_to_double(len_hi);
+    const double f00 = (g_lo - s_lo * l_lo) + (ta_lo + tb_lo);
+    const double f01 = (g_lo - s_lo * l_hi) + (ta_lo + tb_hi);
+    const double f10 = (g_hi - s_hi * l_lo) + (ta_hi + tb_lo);
+    const double f11 = (g_hi - s_hi * l_hi) + (ta_hi + tb_hi);
+    return fmax(fmax(f00, f01), fmax(f10, f11));
 }
 
-
-// Far columns of one 32-row block.  Warp w owns rows 4w..4w+3.
-//   lower bounds : LB_j = max( best over the near columns (sPartV),  the "split at every candidate"
-//                  path through the block's own rows ) -- both are feasible segmentations; the path
-//                  value is formed with a parallel prefix sum and lowered by delta to stay below the
-//                  sequentially rounded value the chain would produce.
-//   F1 (bounds)  : lane = (row rr, column block cc), 4 x 8 per step, UF steps in flight; surviving
-//                  block numbers are appended to per-row lists in shared memory.
-//   F2 (exact)   : 8-lane group g walks the list of row g: lane l8 evaluates column l8 of every
-//                  surviving block, keeping its own running (max, first arg-max); the 8 lanes are
-//                  merged once at the end.  Lists are flushed whenever they might overflow.
-// Writes sFarV / sFarA for the warp's 4 rows; returns the number of cells skipped.
+// Far columns [1, 1 + 32*nfar) of one 32-row block step.  Coarse block cb is bounded by warp cb % 8, lane cb / 8.
+// Every warp keeps a running (max, first arg-max) for all 32 rows (lane = row) over the cells it evaluated exactly
+// and publishes it in its slice of sFarV / sFarA; warp 0 also covers column 0, which is in no block.
+// Returns the number of cells skipped (per lane; the caller sums).
 template <bool AI, int NQ>
-__device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const int4 *sBlkI, const double *sBMax,
-                                        const double *sPartV, unsigned short *sList, double *sFarV, int *sFarA,
+__device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const CoarseRec *sCoarse,
+                                        const double *sPartV, RowLB *sRowW, double *sFarVW, int *sFarAW,
                                         double delta, double pen,
                                         const double *__restrict__ gtab, const double *__restrict__ ltab,
-                                        int alpha_int, double alpha)
+                                        int alpha_int, double alpha PROF_ARGS)
 {
-    constexpr int UF = 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = lane >> 3, l8 = lane & 7;             // F2: row grp, column l8 of a block
-    unsigned short *myList = sList + (warp * 4) * PR_LIST;
+    const int nrows = min(DP_JB, N - jb);
 
     // ---- lower bounds for all 32 rows (every warp computes them; no block-wide sync needed) ----
-    double lb;
+    const int jrow = min(jb + lane, N - 1);
+    const ColRec me = sCol[jrow];
+    const RowConst<AI> rme = make_row<AI>(me.C, me.L, alpha_int, alpha);
     {
-        const int j = min(jb + lane, N - 1);
-        const ColRec me = sCol[j], before = sCol[j - 1];
-        const RowConst<AI> rj = make_row<AI>(me.C, me.L, alpha_int, alpha);
-        double run = self_score<AI>(before.C, before.L, rj, gtab, ltab) + (lane ? pen : 0.0);   // w(j-1, j) [+ pen of the previous row]
+        const ColRec before = sCol[jrow - 1];
+        double run = self_score<AI>(before.C, before.L, rme, gtab, ltab) + (lane ? pen : 0.0);   // w(j-1, j) [+ pen of the previous row]
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const double o = __shfl_up_sync(0xffffffffu, run, d);
@@ -121,112 +177,157 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
         double nearbest = sPartV[lane];
 #pragma unroll
         for (int q = 1; q < NQ; ++q) nearbest = fmax(nearbest, sPartV[q * 32 + lane]);
-        lb = fmax(path, nearbest);
+        RowLB r;
+        r.lb = fmax(path, nearbest);
+        r.C = me.C;
+        r.L = me.L;
+        sRowW[lane] = r;
     }
-    // F1 bounds one (4 rows of this warp) x (8 columns) rectangle per lane: the counts span
-    // [S_first_row - C_last_col, S_last_row - C_first_col], the shortest length is L_first_row - L_last_col,
-    // and the rectangle survives unless its bound is below the SMALLEST of the 4 lower bounds.
-    const int j0 = min(jb + 4 * warp, N - 1), j3 = min(jb + 4 * warp + 3, N - 1);
-    const bool grp_ok = jb + 4 * warp < N;
-    const ColRec mf = sCol[j0], ml = sCol[j3];
-    const RowConst<AI> rcF = make_row<AI>(mf.C, mf.L, alpha_int, alpha);    // first row: smallest S, shortest lengths
-    const RowConst<AI> rcL = make_row<AI>(ml.C, ml.L, alpha_int, alpha);    // last (valid) row: largest S
-    double lbmin = INFINITY;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double v = __shfl_sync(0xffffffffu, lb, min(4 * warp + k, 31));
-        if (jb + 4 * warp + k < N) lbmin = fmin(lbmin, v);
-    }
-    const int r2 = 4 * warp + grp;                         // F2 row
-    const bool row2_ok = jb + r2 < N;
-    const ColRec me2 = sCol[min(jb + r2, N - 1)];
-    const RowConst<AI> rc2 = make_row<AI>(me2.C, me2.L, alpha_int, alpha);
+    __syncwarp();
 
-    // running far result of this lane (F2 role): column 0 is in no 8-block, lane l8 == 0 takes it
+    // running far result of row `lane`
     double best = -INFINITY;
     int arg = 0x7fffffff;
-    if (l8 == 0 && row2_ok) {
-        const ColRec a = sCol[0];
-        best = __dadd_rn(self_score<AI>(a.C, a.L, rc2, gtab, ltab), a.P);
+    if (warp == 0 && lane < nrows) {
+        const ColRec a0 = sCol[0];
+        best = __dadd_rn(self_score<AI>(a0.C, a0.L, rme, gtab, ltab), a0.P);
         arg = 0;
     }
     u64 skipped = 0;
-    int cnt = 0;                                           // list length, identical in all lanes
-    const int nrow = min(4, N - (jb + 4 * warp));          // valid rows of this warp (may be <= 0)
+    PROF_T(10);
 
-    auto flush = [&]() {
-        __syncwarp();
-        constexpr int UX = 4;                              // surviving blocks in flight
-        int k = 0;
-        for (; k + UX <= cnt; k += UX) {
-            ColRec a[UX];
-            int c[UX];
-            double t[UX];
-#pragma unroll
-            for (int u = 0; u < UX; ++u) {
-                c[u] = 1 + PR_FB * (int)myList[k + u] + l8;
-                a[u] = sCol[c[u]];
-                t[u] = self_score<AI>(a[u].C, a[u].L, rc2, gtab, ltab);
+    // ---- level 1: 32 rows x 32 columns, one lane per rectangle ----
+    const RowLB rowF = sRowW[0], rowL = sRowW[nrows - 1];
+    const int cb = lane * WD_WARPS + warp;
+    bool surv1 = false;
+    if (cb < nfar) {
+        const CoarseRec *rec = sCoarse + cb;
+        const int4 ends = *reinterpret_cast<const int4 *>(rec);
+        const double a = rec->a, b = rec->b;
+        const double m2 = tilted_box_max<AI>(rowF.C - ends.y, rowL.C - ends.x, rowF.L - ends.w, rowL.L - ends.z, a, b,
+                                             gtab, ltab, alpha_int, alpha);
+        double m3 = INFINITY;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) {
+            const RowLB rr = sRowW[r];
+            m3 = fmin(m3, rr.lb + (a * u32_to_double(rr.C) + b * u32_to_double(rr.L)));
+        }
+        surv1 = !(rec->mpt + m2 - m3 + delta < 0.0);                 // NaN keeps the block
+        if (!surv1) skipped += (u64)(PR_CB * nrows);
+    }
+    unsigned mask1 = __ballot_sync(0xffffffffu, surv1);
+    PROF_T(11);
+
+    // ---- level 2: a surviving block as 8 row groups x 4 sub-blocks of 8 columns, one lane per rectangle ----
+    const int rg = lane >> 2, q = lane & 3;
+    const int r0 = 4 * rg, r1 = min(r0 + 3, nrows - 1);
+    const bool act2 = r0 < nrows;
+    const RowLB gF = sRowW[min(r0, nrows - 1)], gL = sRowW[r1];
+    while (mask1) {
+        const int cb1 = (__ffs(mask1) - 1) * WD_WARPS + warp;
+        mask1 &= mask1 - 1;
+        const CoarseRec *rec = sCoarse + cb1;
+        const double a = rec->a, b = rec->b;
+        bool surv2 = false;
+        if (act2) {
+            const int i0 = 1 + PR_CB * cb1 + PR_FB * q;
+            const ColRec cF = sCol[i0], cL = sCol[i0 + PR_FB - 1];
+            const double m2 = tilted_box_max<AI>(gF.C - cL.C, gL.C - cF.C, gF.L - cL.L, gL.L - cF.L, a, b,
+                                                 gtab, ltab, alpha_int, alpha);
+            double m3 = INFINITY;
+            for (int r = r0; r <= r1; ++r) {
+                const RowLB rr = sRowW[r];
+                m3 = fmin(m3, rr.lb + (a * u32_to_double(rr.C) + b * u32_to_double(rr.L)));
+            }
+            surv2 = !(rec->mpt8[q] + m2 - m3 + delta < 0.0);
+            if (!surv2) skipped += (u64)(PR_FB * (r1 - r0 + 1));
+        }
+        unsigned mask2 = __ballot_sync(0xffffffffu, surv2);
+
+        // ---- level 3: the survivors exactly; lane = (row r of the group, column c of the sub-block) ----
+        const int er = lane >> 3, ec = lane & 7;
+        while (mask2) {
+            const int l2 = __ffs(mask2) - 1;
+            mask2 &= mask2 - 1;
+            const int row = 4 * (l2 >> 2) + er;                    // row of the block step
+            const int col = 1 + PR_CB * cb1 + PR_FB * (l2 & 3) + ec;
+            double t = -INFINITY;
+            int ta = col;
+            if (row < nrows) {
+                const RowLB rr = sRowW[row];
+                const RowConst<AI> rc = make_row<AI>(rr.C, rr.L, alpha_int, alpha);
+                const ColRec cc = sCol[col];
+                t = __dadd_rn(self_score<AI>(cc.C, cc.L, rc, gtab, ltab), cc.P);
             }
 #pragma unroll
-            for (int u = 0; u < UX; ++u) {
-                const double tv = __dadd_rn(t[u], a[u].P);
-                if (tv > best) { best = tv; arg = c[u]; }
+            for (int off = 1; off < 8; off <<= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, t, off);
+                const int oa = __shfl_xor_sync(0xffffffffu, ta, off);
+                if (ob > t || (ob == t && oa < ta)) { t = ob; ta = oa; }
             }
-        }
-        for (; k < cnt; ++k) {
-            const int c0 = 1 + PR_FB * (int)myList[k] + l8;
-            const ColRec a0 = sCol[c0];
-            const double t0 = __dadd_rn(self_score<AI>(a0.C, a0.L, rc2, gtab, ltab), a0.P);
-            if (t0 > best) { best = t0; arg = c0; }
-        }
-        cnt = 0;
-        __syncwarp();
-    };
-
-    for (int cb0 = 0; cb0 < nfar; cb0 += 32 * UF) {
-        bool surv[UF];
-#pragma unroll
-        for (int u = 0; u < UF; ++u) {
-            const int b = cb0 + 32 * u + lane;
-            surv[u] = false;
-            if (grp_ok && b < nfar) {
-                // x = C of the block's first column (largest count), y = C and z = L of its last column
-                const int4 blk = sBlkI[b];
-                const int x_hi = rcL.cjx - blk.x, x_lo = rcF.cjx - blk.y;
-                const double lg = __ldg(ltab + (rcF.lj - blk.z));
-                const double s_hi = AI ? u32_to_double(x_hi) : __dsub_rn(rcL.aj, u32_to_double(blk.x));
-                const double s_lo = AI ? u32_to_double(x_lo) : __dsub_rn(rcF.aj, u32_to_double(blk.y));
-                const double f_hi = __dsub_rn(__ldg(gtab + x_hi), __dmul_rn(s_hi, lg));
-                const double f_lo = __dsub_rn(__ldg(gtab + x_lo), __dmul_rn(s_lo, lg));
-                const double ub = fmax(f_hi, f_lo) + sBMax[b] + delta;
-                surv[u] = !(ub < lbmin);                            // NaN keeps the block
-                if (!surv[u]) skipped += (u64)(PR_FB * nrow);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UF; ++u) {
-            const unsigned mask = __ballot_sync(0xffffffffu, surv[u]);
-            if (surv[u]) myList[cnt + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)(cb0 + 32 * u + lane);
-            cnt += __popc(mask);
-            // the next ballot may add 32 more entries
-            if (cnt > 4 * PR_LIST - 32) flush();
+            // hand the 4 row results (lanes 0, 8, 16, 24) to the lanes that own those rows
+            const int rel = lane - 4 * (l2 >> 2);
+            const double v = __shfl_sync(0xffffffffu, t, (rel & 3) * 8);
+            const int va = __shfl_sync(0xffffffffu, ta, (rel & 3) * 8);
+            if (rel >= 0 && rel < 4 && (v > best || (v == best && va < arg))) { best = v; arg = va; }
         }
     }
-    flush();
-
-    // merge the 8 column lanes of each row (first maximum), publish
-#pragma unroll
-    for (int off = 4; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-        const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
-        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-    }
-    if (l8 == 0 && row2_ok) {
-        sFarV[r2] = best;
-        sFarA[r2] = arg;
-    }
+    sFarVW[lane] = best;
+    sFarAW[lane] = arg;
+    PROF_T(12);
     return skipped;
+}
+
+// After the chain finished rows [jb, jb+32) (a full block of 32 columns from now on): least-squares tilt, tilted
+// maxima, end points.  One warp, lane = column.
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__device__ __forceinline__ void build_coarse_record(int jb, const ColRec *sCol, CoarseRec *rec, double tilt_scale_c,
+                                                    double tilt_scale_l)
+{
+    const int lane = threadIdx.x & 31;
+    const ColRec me = sCol[jb + lane];
+    const int c_first = __shfl_sync(0xffffffffu, me.C, 0), c_last = __shfl_sync(0xffffffffu, me.C, 31);
+    const int l_first = __shfl_sync(0xffffffffu, me.L, 0), l_last = __shfl_sync(0xffffffffu, me.L, 31);
+    const double p_first = __shfl_sync(0xffffffffu, me.P, 0);
+    const double x = u32_to_double(me.C - c_first), y = u32_to_double(me.L - l_first), p = me.P - p_first;
+    double a = 0.0, b = 0.0;                       // fit  -P ~ a*C + b*L + const
+#ifndef PASIO_NO_LS
+    const double inv_n = 1.0 / 32.0;
+    const double sx = warp_sum(x), sy = warp_sum(y), sp = warp_sum(p);
+    const double xc = x - sx * inv_n, yc = y - sy * inv_n, pc = p - sp * inv_n;
+    const double cxx = warp_sum(xc * xc), cyy = warp_sum(yc * yc), cxy = warp_sum(xc * yc);
+    const double cxp = warp_sum(xc * pc), cyp = warp_sum(yc * pc);
+    const double det = cxx * cyy - cxy * cxy;
+    if (det > 1e-9 * cxx * cyy) {
+        a = -(cxp * cyy - cyp * cxy) / det;
+        b = -(cyp * cxx - cxp * cxy) / det;
+    } else if (cxx > 0.0) {
+        a = -cxp / cxx;
+    } else if (cyy > 0.0) {
+        b = -cyp / cyy;
+    }
+    if (!(fabs(a) < 1e300) || !(fabs(b) < 1e300)) { a = 0.0; b = 0.0; }     // any finite tilt is valid; NaN / inf is not
+#endif
+    double m = me.P + (a * u32_to_double(me.C) + b * u32_to_double(me.L));
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    double m32 = m;
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) m32 = fmax(m32, __shfl_xor_sync(0xffffffffu, m32, off));
+    const double slack = ldexp(fabs(a) * tilt_scale_c + fabs(b) * tilt_scale_l, -44);
+    if ((lane & 7) == 0) rec->mpt8[lane >> 3] = m + slack;
+    if (lane == 0) {
+        *reinterpret_cast<int4 *>(rec) = make_int4(c_first, c_last, l_first, l_last);
+        rec->a = a;
+        rec->b = b;
+        rec->mpt = m32 + slack;
+    }
 }
 
 template <bool AI, int U, int RPL, bool PRUNE>
@@ -241,19 +342,21 @@ window_dp_kernel(WinDpParams p)
     int *sPartA = reinterpret_cast<int *>(sTri + DP_JB * DP_JB);
     int *sMisc = sPartA + WD_WARPS * 32;
     unsigned short *sPrev = reinterpret_cast<unsigned short *>(sMisc + 16);
-    int4 *sBlkI = reinterpret_cast<int4 *>(sPrev + capr);               // capr*2 bytes is a multiple of 16
-    double *sBMax = reinterpret_cast<double *>(sBlkI + capr / PR_FB);
-    double *sFarV = sBMax + capr / PR_FB;
-    double *sScal = sFarV + 32;                                         // [0] magnitude of the window's largest self score, [1] max |P|
+    CoarseRec *sCoarse = reinterpret_cast<CoarseRec *>(sPrev + capr);   // capr*2 bytes is a multiple of 16
+    RowLB *sRow = reinterpret_cast<RowLB *>(sCoarse + capr / PR_CB);
+    double *sFarV = reinterpret_cast<double *>(sRow + WD_WARPS * 32);
+    double *sScal = sFarV + WD_WARPS * 32;                              // [0] magnitude of the window's largest self score, [1] max |P|, [2], [3] tilt scales
     int *sFarA = reinterpret_cast<int *>(sScal + 4);
-    unsigned short *sList = reinterpret_cast<unsigned short *>(sFarA + 32);
     // the back-trace runs after the DP, when these are dead
-    unsigned short *sJump = reinterpret_cast<unsigned short *>(sBlkI);  // capr*2 bytes == (capr/8)*16
+    unsigned short *sJump = reinterpret_cast<unsigned short *>(sCoarse); // capr*2 bytes <= (capr/32)*80
     unsigned char *sMark = reinterpret_cast<unsigned char *>(sTri);     // capr <= 8192 bytes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    PROF_DECL;
 
     while (true) {
+        PROF_T(9);
+        PROF_FLUSH;
         if (tid == 0) sMisc[0] = (int)atomicAdd(p.work_counter, 1u);
         __syncthreads();
         const i64 w = (unsigned)sMisc[0];
@@ -340,6 +443,7 @@ window_dp_kernel(WinDpParams p)
             __syncthreads();
         }
         const int N = count;
+        PROF_T(0);
 
         // ---- (B) DP ---------------------------------------------------------------------------
         if (tid == 0) { sCol[0].P = 0.0; sPrev[0] = 0; }
@@ -351,46 +455,57 @@ window_dp_kernel(WinDpParams p)
             const int x = z.C + (AI ? p.alpha_int : 0);
             sScal[0] = fabs(__ldg(p.gtab + x)) + ((double)z.C + p.alpha) * fabs(__ldg(p.ltab + z.L)) + 1.0;
             sScal[1] = 0.0;
-        }
-        if (PRUNE) {
-            for (int b = tid; PR_FB * b + PR_FB < N; b += WD_THREADS) {
-                const ColRec a = sCol[1 + PR_FB * b], z = sCol[PR_FB * b + PR_FB];
-                sBlkI[b] = make_int4(a.C, z.C, z.L, 0);
-            }
+            sScal[2] = (double)z.C + p.alpha;       // |a*C| and |b*L| of a tilt stay below |a|*this and |b|*that
+            sScal[3] = (double)z.L;
         }
         for (int jb = 1; jb < N; jb += DP_JB) {
             constexpr int NQ = WD_WARPS / (DP_JB / (DP_RPW * RPL));
-            const int near_lo = jb - p.near;
-            if (!PRUNE || near_lo < 1 + PR_FB) {
+            const int nfar = (jb - 1) / PR_CB - 1;                  // finished 32-column blocks before the nearest one
+            if (!PRUNE || nfar < 1) {
                 dp_block_step<AI, WD_WARPS, U, RPL>(jb, N, 0, sCol, sPrev, nullptr, sPartV, sPartA, sTri,
                                                     p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
+                PROF_T(8);
             } else {
-                // (1) nearest columns + triangle self scores
-                block_rect_tri<AI, WD_WARPS, U, RPL>(jb, N, near_lo, sCol, sPartV, sPartA, sTri, p.gtab, p.ltab,
+                // (1) nearest 32 columns + triangle self scores
+                if (!EXP_SKIP(8))
+                block_rect_tri<AI, WD_WARPS, 2, RPL>(jb, N, jb - PR_CB, sCol, sPartV, sPartA, sTri, p.gtab, p.ltab,
                                                      p.alpha_int, p.alpha);
-                // (2) far columns [1, near_lo): bound blocks of 8 against a lower bound of the row maximum,
-                //     evaluate the survivors exactly
+                PROF_T(1);
+                // (2) far columns [1, jb - 32): two levels of bounds against a lower bound of the row maxima,
+                //     the survivors exactly
                 const double delta = ldexp(sScal[0] + sScal[1] + fabs(p.pen) * DP_JB, -44);
-                skipped += far_pass<AI, NQ>(jb, N, (near_lo - 1) / PR_FB, sCol, sBlkI, sBMax, sPartV, sList, sFarV, sFarA,
-                                            delta, p.pen, p.gtab, p.ltab, p.alpha_int, p.alpha);
+                if (!EXP_SKIP(1))
+                skipped += far_pass<AI, NQ>(jb, N, nfar, sCol, sCoarse, sPartV, sRow + warp * 32, sFarV + warp * 32,
+                                            sFarA + warp * 32, delta, p.pen, p.gtab, p.ltab, p.alpha_int, p.alpha PROF_PASS);
                 __syncthreads();
-                // (3) chain: far result first (smaller columns), then the near partials, then the triangle
-                if (warp == 0)
+                PROF_T(3);
+                // (3) chain: far results first (smaller columns; the warps' column sets interleave, hence the
+                //     index-aware merge), then the near partials, then the triangle
+                if (warp == 0 && !EXP_SKIP(4)) {
+                    double fbest = -INFINITY;
+                    int farg = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < WD_WARPS; ++w2) {
+                        const double v = sFarV[w2 * 32 + lane];
+                        const int a = sFarA[w2 * 32 + lane];
+                        if (v > fbest || (v == fbest && a < farg)) { fbest = v; farg = a; }
+                    }
                     block_chain<NQ>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen,
-                                    jb + lane < N ? sFarV[lane] : -INFINITY, jb + lane < N ? sFarA[lane] : 0, 0, nullptr);
+                                    jb + lane < N ? fbest : -INFINITY, jb + lane < N ? farg : 0, 0, nullptr);
+                }
+                PROF_T(4);
                 __syncthreads();
+                PROF_T(5);
             }
             if (PRUNE && warp == 0) {
-                // per-8-column maxima of the finished rows and the running max |P| (scale of delta)
-                const double pv = jb + lane < N ? sCol[jb + lane].P : -INFINITY;
-                double mx = pv, ab = jb + lane < N ? fabs(pv) : 0.0;
-#pragma unroll
-                for (int off = 4; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                // the finished rows become a block of 32 columns; running max |P| (scale of delta)
+                if (jb + DP_JB <= N && !EXP_SKIP(2)) build_coarse_record(jb, sCol, sCoarse + (jb - 1) / PR_CB, sScal[2], sScal[3]);
+                double ab = jb + lane < N ? fabs(sCol[jb + lane].P) : 0.0;
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) ab = fmax(ab, __shfl_xor_sync(0xffffffffu, ab, off));
-                if ((lane & 7) == 0) sBMax[(jb - 1) / PR_FB + (lane >> 3)] = mx;
                 if (lane == 0) sScal[1] = fmax(sScal[1], ab);
             }
+            PROF_T(6);
         }
 
         // ---- (C) back-trace by pointer doubling, scatter survivors ----------------------------
@@ -411,6 +526,7 @@ window_dp_kernel(WinDpParams p)
                 atomicOr(p.keepbits + (pos >> 5), 1u << (pos & 31));
             }
         }
+        PROF_T(7);
         if (tid == 0) atomicAdd(p.cells, (u64)N * (u64)(N - 1) / 2);
         if (PRUNE) {
 #pragma unroll
@@ -451,8 +567,6 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
         return pasio_fail(ctx, PASIO_E_TOO_LARGE, "window of %lld candidates does not fit one CTA's shared memory (max %d)",
                           (long long)cap, window_dp_max_candidates(ctx));
     p.cap = (int)cap;
-    static const int near_env = getenv("PASIO_WD_NEAR") ? atoi(getenv("PASIO_WD_NEAR")) : PR_NEAR;
-    p.near = (near_env >= 32 && near_env % 32 == 0) ? near_env : PR_NEAR;
     p.cells = ctx->scalars.as<u64>() + 10;
     p.cells_skipped = ctx->scalars.as<u64>() + 12;
     p.work_counter = ctx->scalars.as<unsigned>() + 2 * 11;   // scalars[11]
@@ -469,6 +583,13 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
+#if defined(PASIO_WD_EXP) || defined(PASIO_WD_PROF)
+    if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
+#endif
+#ifdef PASIO_WD_EXP
+    p.exp_skip = getenv("PASIO_WD_SKIP") ? atoi(getenv("PASIO_WD_SKIP")) : 0;
+    if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
+#endif
     i64 grid = (i64)ctx->sm_count * per_sm;     // persistent CTAs: one resident wave
     if (grid > nwin) grid = nwin;
     if (grid < 1) grid = 1;
@@ -477,5 +598,20 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
         kern<<<(unsigned)grid, WD_THREADS, smem, ctx->stream>>>(p);
     }
     CUDA_TRY(ctx, cudaGetLastError());
+#ifdef PASIO_WD_PROF
+    {
+        cudaStreamSynchronize(ctx->stream);
+        unsigned long long h[24], z[24] = {0};
+        cudaMemcpyFromSymbol(h, g_wd_prof, sizeof h);
+        cudaMemcpyToSymbol(g_wd_prof, z, sizeof z);
+        static const char *names[24] = {"compact", "rect_tri", "", "far+sync", "chain", "sync", "record", "backtrace", "plain_step",
+                                        "window_loop", "far:LB", "far:L1", "far:L2L3"};
+        double tot = 0;
+        for (int i = 0; i < 13; ++i) tot += (double)h[i];
+        fprintf(stderr, "[wd_prof] nwin=%lld grid=%lld:", (long long)nwin, (long long)grid);
+        for (int i = 0; i < 13; ++i) if (h[i]) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)h[i] / tot);
+        fprintf(stderr, " | cycles/CTA=%.3g\n", tot / (double)grid);
+    }
+#endif
     return PASIO_OK;
 }
