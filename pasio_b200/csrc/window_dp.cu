@@ -21,21 +21,37 @@
 namespace {
 
 constexpr int WD_THREADS = 256;
+constexpr int WD_WARPS = WD_THREADS / 32;
+constexpr int WD_FARW = WD_WARPS - 1;   // pruned path: warps 1..7 bound / evaluate columns while warp 0 runs the dependent chain
+constexpr int NEAR_Q = 4;               // pruned path: the nearest 32 columns are swept as 4 chunks of 8
+constexpr int PR_CB = 32;               // far columns are first bounded in blocks of 32 ...
+constexpr int PR_FB = 8;                // ... and the surviving blocks again in sub-blocks of 8
+constexpr int PR_MIN_N = 256;           // windows up to this many candidates are not worth bounding
+constexpr int PR_DENSE = 28;            // a block with this many surviving 4 x 8 rectangles (of 32) is swept whole
 
-// Development-only phase timers (make PROF=1): cycles seen by thread 0 of every CTA, summed per phase.
+// Development-only phase timers (make PROF=1): cycles seen by thread 0 (warp 0: chain side) and thread 32
+// (warp 1: far side) of every CTA, summed per phase.
 #ifdef PASIO_WD_PROF
-__device__ unsigned long long g_wd_prof[24];
-struct ProfAcc { long long t0; long long a0, a1, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12; };
-#define PROF_DECL ProfAcc prof = {clock64(), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
-#define PROF_T(i) do { asm volatile("" ::: "memory"); const long long t1__ = clock64(); prof.a##i += t1__ - prof.t0; prof.t0 = t1__; asm volatile("" ::: "memory"); } while (0)
-#define PROF_FLUSH do { if (threadIdx.x == 0) { \
-    atomicAdd(g_wd_prof + 0, (unsigned long long)prof.a0); atomicAdd(g_wd_prof + 1, (unsigned long long)prof.a1); \
-    atomicAdd(g_wd_prof + 3, (unsigned long long)prof.a3); atomicAdd(g_wd_prof + 4, (unsigned long long)prof.a4); \
-    atomicAdd(g_wd_prof + 5, (unsigned long long)prof.a5); atomicAdd(g_wd_prof + 6, (unsigned long long)prof.a6); \
-    atomicAdd(g_wd_prof + 7, (unsigned long long)prof.a7); atomicAdd(g_wd_prof + 8, (unsigned long long)prof.a8); \
-    atomicAdd(g_wd_prof + 9, (unsigned long long)prof.a9); atomicAdd(g_wd_prof + 10, (unsigned long long)prof.a10); \
-    atomicAdd(g_wd_prof + 11, (unsigned long long)prof.a11); atomicAdd(g_wd_prof + 12, (unsigned long long)prof.a12); } \
-    prof.a0 = prof.a1 = prof.a3 = prof.a4 = prof.a5 = prof.a6 = prof.a7 = prof.a8 = prof.a9 = prof.a10 = prof.a11 = prof.a12 = 0; } while (0)
+__device__ unsigned long long g_wd_prof[16];
+struct ProfAcc { long long t0; long long a0, a1, a2, a3, a4, a5, a6, a7; };
+#define PROF_DECL ProfAcc prof = {clock64(), 0, 0, 0, 0, 0, 0, 0, 0}
+// the clock read is made dependent on a shared-memory load: BAR.SYNC does not block at issue, only at the next
+// consumer, so a bare clock64() after __syncthreads() would charge the wait to the following phase
+__device__ __forceinline__ long long prof_clock()
+{
+    unsigned dummy;
+    long long t;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(0u) : "memory");
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dummy) : "memory");
+    return t;
+}
+#define PROF_T(i) do { const long long t1__ = prof_clock(); prof.a##i += t1__ - prof.t0; prof.t0 = t1__; } while (0)
+#define PROF_FLUSH do { if (threadIdx.x == 0 || threadIdx.x == 32) { unsigned long long *g__ = g_wd_prof + (threadIdx.x ? 8 : 0); \
+    atomicAdd(g__ + 0, (unsigned long long)prof.a0); atomicAdd(g__ + 1, (unsigned long long)prof.a1); \
+    atomicAdd(g__ + 2, (unsigned long long)prof.a2); atomicAdd(g__ + 3, (unsigned long long)prof.a3); \
+    atomicAdd(g__ + 4, (unsigned long long)prof.a4); atomicAdd(g__ + 5, (unsigned long long)prof.a5); \
+    atomicAdd(g__ + 6, (unsigned long long)prof.a6); atomicAdd(g__ + 7, (unsigned long long)prof.a7); } \
+    prof.a0 = prof.a1 = prof.a2 = prof.a3 = prof.a4 = prof.a5 = prof.a6 = prof.a7 = 0; } while (0)
 #define PROF_ARGS , ProfAcc &prof
 #define PROF_PASS , prof
 #else
@@ -45,9 +61,6 @@ struct ProfAcc { long long t0; long long a0, a1, a3, a4, a5, a6, a7, a8, a9, a10
 #define PROF_ARGS
 #define PROF_PASS
 #endif
-constexpr int WD_WARPS = WD_THREADS / 32;
-constexpr int PR_CB = 32;       // pruned path: far columns are first bounded in blocks of 32 ...
-constexpr int PR_FB = 8;        // ... and the surviving blocks again in sub-blocks of 8
 
 struct WinDpParams {
     WinGeom geom;
@@ -66,15 +79,7 @@ struct WinDpParams {
     u64 *cells;                 // algorithmic cells N(N-1)/2
     u64 *cells_skipped;         // cells proven irrelevant by the far-column bound (0 without pruning)
     unsigned *work_counter;
-#ifdef PASIO_WD_EXP
-    int exp_skip;               // timing experiments only (results are wrong): 1 far pass, 2 record fit, 4 chain, 8 near rectangle
-#endif
 };
-#ifdef PASIO_WD_EXP
-#define EXP_SKIP(bit) (p.exp_skip & (bit))
-#else
-#define EXP_SKIP(bit) false
-#endif
 
 // One finished block of 32 columns [1+32b, 32+32b], as the far pass sees it.
 struct __align__(16) CoarseRec {
@@ -86,26 +91,26 @@ struct __align__(16) CoarseRec {
 };
 static_assert(sizeof(CoarseRec) == 80, "CoarseRec layout");
 
-// One row of the current 32-row block step: a lower bound of its maximum, its C and L.
-struct __align__(16) RowLB {
-    double lb;
-    int C;
-    int L;
-};
-
 __host__ __device__ inline size_t window_smem_bytes(int cap)
 {
     const size_t capr = (size_t)((cap + 31) & ~31);
     return capr * 16                // sCol (L, C, P)
-           + WD_WARPS * 32 * 8      // sPartV
+           + NEAR_Q * 32 * 8        // sPartV
            + DP_JB * DP_JB * 8      // sTri            (back-trace: sMark lives here, needs capr <= 8192)
-           + WD_WARPS * 32 * 4      // sPartA
+           + NEAR_Q * 32 * 4        // sPartA
            + 16 * 4                 // sMisc
            + capr * 2               // sPrev
            + (capr / PR_CB) * sizeof(CoarseRec)   // sCoarse  (back-trace: sJump lives here, capr*2 bytes)
-           + WD_WARPS * 32 * sizeof(RowLB)        // sRow: every warp keeps its own copy of the 32 row records
-           + WD_WARPS * 32 * 8 + WD_WARPS * 32 * 4   // sFarV, sFarA: per-warp far results of the 32 rows
-           + 4 * 8;                 // sScal
+           + 32 * sizeof(float4)                  // sRow: the 32 rows being bounded (lower bound, C, L as floats)
+           + capr * 2                             // sList: fine rectangles that survived both bounds (< PR_DENSE per block)
+           + (capr / PR_CB) * 2 + 16              // sDense: blocks to sweep whole
+           + 2 * WD_FARW * 32 * (8 + 4)           // sFarV, sFarA: per-warp far results of the 32 rows, double-buffered
+           + 8 * 8;                 // sScal
+}
+
+__device__ __forceinline__ int2 col_lc(const ColRec *sCol, int i)      // (L, C) only: P of that column may be in flight
+{
+    return *reinterpret_cast<const int2 *>(sCol + i);
 }
 
 // ---- exact pruning of far columns (branch and bound) -----------------------------------------
@@ -122,9 +127,12 @@ __host__ __device__ inline size_t window_smem_bytes(int cap)
 // covers table and rounding errors: 2^-44 of the window's largest magnitudes, > 50x the worst case, < 1e-6 in
 // absolute terms) is negative, no cell of the rectangle reaches the lower bound LB_j of its row's maximum: it can
 // hold neither the arg-max nor a tie, so skipping it leaves P, prev and the back-trace bit-identical.
-// LB_j = max( best over the nearest 32 columns, the "split at every candidate" path through the block's own rows ):
-// both are feasible segmentations; the path value is formed with a parallel prefix sum and lowered by delta to
-// stay below the sequentially rounded value the chain would produce.
+// LB_j is the value of the "split at every candidate" path from the last finished row to row j -- a feasible
+// segmentation, hence a lower bound of the maximum, and in the later rounds (where nearly every candidate
+// survives) the maximum itself.  It needs no result of the block that is being chained at the moment, so the far
+// pass of block k+1 runs on warps 1..7 WHILE warp 0 resolves the dependent chain of block k.  The path value is
+// formed with parallel sums and lowered by delta_path (2^-39 of the largest magnitudes: at most 76 roundings of
+// partial sums below 64x that magnitude separate it from the sequentially rounded value the chain produces).
 // Two levels: 32 rows x 32 columns first (one lane per rectangle), the survivors again as 4 rows x 8 columns
 // (one warp per surviving rectangle); what survives both is evaluated exactly, cell by cell, in the reference's
 // operation order.
@@ -146,147 +154,318 @@ __device__ __forceinline__ double tilted_box_max(int u_lo, int u_hi, int len_lo,
     return fmax(fmax(f00, f01), fmax(f10, f11));
 }
 
-// Far columns [1, 1 + 32*nfar) of one 32-row block step.  Coarse block cb is bounded by warp cb % 8, lane cb / 8.
-// Every warp keeps a running (max, first arg-max) for all 32 rows (lane = row) over the cells it evaluated exactly
-// and publishes it in its slice of sFarV / sFarA; warp 0 also covers column 0, which is in no block.
-// Returns the number of cells skipped (per lane; the caller sums).
-template <bool AI, int NQ>
-__device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const CoarseRec *sCoarse,
-                                        const double *sPartV, RowLB *sRowW, double *sFarVW, int *sFarAW,
-                                        double delta, double pen,
-                                        const double *__restrict__ gtab, const double *__restrict__ ltab,
-                                        int alpha_int, double alpha PROF_ARGS)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nrows = min(DP_JB, N - jb);
-
-    // ---- lower bounds for all 32 rows (every warp computes them; no block-wide sync needed) ----
-    const int jrow = min(jb + lane, N - 1);
-    const ColRec me = sCol[jrow];
-    const RowConst<AI> rme = make_row<AI>(me.C, me.L, alpha_int, alpha);
-    {
-        const ColRec before = sCol[jrow - 1];
-        double run = self_score<AI>(before.C, before.L, rme, gtab, ltab) + (lane ? pen : 0.0);   // w(j-1, j) [+ pen of the previous row]
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double o = __shfl_up_sync(0xffffffffu, run, d);
-            if (lane >= d) run += o;
-        }
-        double path = sCol[jb - 1].P + run - delta;      // P_{jb-1} + sum_{m<=l} w(m-1,m) + l*pen, kept below its rounded value
-        if (!(path == path)) path = -INFINITY;           // inf - inf etc.: no information
-        double nearbest = sPartV[lane];
-#pragma unroll
-        for (int q = 1; q < NQ; ++q) nearbest = fmax(nearbest, sPartV[q * 32 + lane]);
-        RowLB r;
-        r.lb = fmax(path, nearbest);
-        r.C = me.C;
-        r.L = me.L;
-        sRowW[lane] = r;
-    }
-    __syncwarp();
-
-    // running far result of row `lane`
-    double best = -INFINITY;
-    int arg = 0x7fffffff;
-    if (warp == 0 && lane < nrows) {
-        const ColRec a0 = sCol[0];
-        best = __dadd_rn(self_score<AI>(a0.C, a0.L, rme, gtab, ltab), a0.P);
-        arg = 0;
-    }
-    u64 skipped = 0;
-    PROF_T(10);
-
-    // ---- level 1: 32 rows x 32 columns, one lane per rectangle ----
-    const RowLB rowF = sRowW[0], rowL = sRowW[nrows - 1];
-    const int cb = lane * WD_WARPS + warp;
-    bool surv1 = false;
-    if (cb < nfar) {
-        const CoarseRec *rec = sCoarse + cb;
-        const int4 ends = *reinterpret_cast<const int4 *>(rec);
-        const double a = rec->a, b = rec->b;
-        const double m2 = tilted_box_max<AI>(rowF.C - ends.y, rowL.C - ends.x, rowF.L - ends.w, rowL.L - ends.z, a, b,
-                                             gtab, ltab, alpha_int, alpha);
-        double m3 = INFINITY;
-#pragma unroll 4
-        for (int r = 0; r < nrows; ++r) {
-            const RowLB rr = sRowW[r];
-            m3 = fmin(m3, rr.lb + (a * u32_to_double(rr.C) + b * u32_to_double(rr.L)));
-        }
-        surv1 = !(rec->mpt + m2 - m3 + delta < 0.0);                 // NaN keeps the block
-        if (!surv1) skipped += (u64)(PR_CB * nrows);
-    }
-    unsigned mask1 = __ballot_sync(0xffffffffu, surv1);
-    PROF_T(11);
-
-    // ---- level 2: a surviving block as 8 row groups x 4 sub-blocks of 8 columns, one lane per rectangle ----
-    const int rg = lane >> 2, q = lane & 3;
-    const int r0 = 4 * rg, r1 = min(r0 + 3, nrows - 1);
-    const bool act2 = r0 < nrows;
-    const RowLB gF = sRowW[min(r0, nrows - 1)], gL = sRowW[r1];
-    while (mask1) {
-        const int cb1 = (__ffs(mask1) - 1) * WD_WARPS + warp;
-        mask1 &= mask1 - 1;
-        const CoarseRec *rec = sCoarse + cb1;
-        const double a = rec->a, b = rec->b;
-        bool surv2 = false;
-        if (act2) {
-            const int i0 = 1 + PR_CB * cb1 + PR_FB * q;
-            const ColRec cF = sCol[i0], cL = sCol[i0 + PR_FB - 1];
-            const double m2 = tilted_box_max<AI>(gF.C - cL.C, gL.C - cF.C, gF.L - cL.L, gL.L - cF.L, a, b,
-                                                 gtab, ltab, alpha_int, alpha);
-            double m3 = INFINITY;
-            for (int r = r0; r <= r1; ++r) {
-                const RowLB rr = sRowW[r];
-                m3 = fmin(m3, rr.lb + (a * u32_to_double(rr.C) + b * u32_to_double(rr.L)));
-            }
-            surv2 = !(rec->mpt8[q] + m2 - m3 + delta < 0.0);
-            if (!surv2) skipped += (u64)(PR_FB * (r1 - r0 + 1));
-        }
-        unsigned mask2 = __ballot_sync(0xffffffffu, surv2);
-
-        // ---- level 3: the survivors exactly; lane = (row r of the group, column c of the sub-block) ----
-        const int er = lane >> 3, ec = lane & 7;
-        while (mask2) {
-            const int l2 = __ffs(mask2) - 1;
-            mask2 &= mask2 - 1;
-            const int row = 4 * (l2 >> 2) + er;                    // row of the block step
-            const int col = 1 + PR_CB * cb1 + PR_FB * (l2 & 3) + ec;
-            double t = -INFINITY;
-            int ta = col;
-            if (row < nrows) {
-                const RowLB rr = sRowW[row];
-                const RowConst<AI> rc = make_row<AI>(rr.C, rr.L, alpha_int, alpha);
-                const ColRec cc = sCol[col];
-                t = __dadd_rn(self_score<AI>(cc.C, cc.L, rc, gtab, ltab), cc.P);
-            }
-#pragma unroll
-            for (int off = 1; off < 8; off <<= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, t, off);
-                const int oa = __shfl_xor_sync(0xffffffffu, ta, off);
-                if (ob > t || (ob == t && oa < ta)) { t = ob; ta = oa; }
-            }
-            // hand the 4 row results (lanes 0, 8, 16, 24) to the lanes that own those rows
-            const int rel = lane - 4 * (l2 >> 2);
-            const double v = __shfl_sync(0xffffffffu, t, (rel & 3) * 8);
-            const int va = __shfl_sync(0xffffffffu, ta, (rel & 3) * 8);
-            if (rel >= 0 && rel < 4 && (v > best || (v == best && va < arg))) { best = v; arg = va; }
-        }
-    }
-    sFarVW[lane] = best;
-    sFarAW[lane] = arg;
-    PROF_T(12);
-    return skipped;
-}
-
-// After the chain finished rows [jb, jb+32) (a full block of 32 columns from now on): least-squares tilt, tilted
-// maxima, end points.  One warp, lane = column.
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
 }
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
 
+// Lower bounds for the 32 rows of the block starting at jb, by one warp (lane = row), while the block before it
+// (rows [jbp, jb), jbp = jb - 32) is still to be chained; everything before row jbp is final.
+//   sRow[r] = (lb, C, L, -) as floats: the far pass takes min_r (lb_r + a*C_r + b*L_r) in float and subtracts a
+//   rigorous bound of the float error, 2^-20 * (max|lb| + |a|*C_max + |b|*L_max)  (sRowStat = max |lb|).
+template <bool AI>
+__device__ __forceinline__ void compute_row_lb(int jbp, int jb, int N, const ColRec *sCol, float4 *sRow, double *sRowStat,
+                                               double delta_path, double pen,
+                                               const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                               int alpha_int, double alpha)
+{
+    const int lane = threadIdx.x & 31;
+    const int jrow = min(jb + lane, N - 1);
+    const int2 me = col_lc(sCol, jrow);                     // (L, C)
+    const RowConst<AI> rme = make_row<AI>(me.y, me.x, alpha_int, alpha);
+    const int jp = jbp + lane;                              // a row of the block in flight
+    const int2 pm = col_lc(sCol, jp), pb = col_lc(sCol, jp - 1), before = col_lc(sCol, jrow - 1);
+    const RowConst<AI> rp = make_row<AI>(pm.y, pm.x, alpha_int, alpha);
+    const double wp = self_score<AI>(pb.y, pb.x, rp, gtab, ltab) + pen;          // w(m-1, m) + pen, m in [jbp, jb)
+    double run = self_score<AI>(before.y, before.x, rme, gtab, ltab) + (lane ? pen : 0.0);   // w(j-1, j) [+ pen of the previous row]
+    const double tot_prev = warp_sum(wp);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, run, d);
+        if (lane >= d) run += o;
+    }
+    double path = (sCol[jbp - 1].P + tot_prev) + run - delta_path;
+    if (!(fabs(path) < 1e30)) path = -INFINITY;             // NaN / inf / beyond float range: no information
+    float lbf = (float)path;                                // overflow gives -inf: no information, still valid
+    sRow[lane] = make_float4(lbf, (float)me.y, (float)me.x, 0.f);
+    double ab = (jb + lane < N && path > -1e300) ? fabs(path) : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ab = fmax(ab, __shfl_xor_sync(0xffffffffu, ab, off));
+    if (lane == 0) *sRowStat = ab;
+}
+
+// min over rows [r0, r1] of lb_r + a*C_r + b*L_r, as a rigorous lower bound (float arithmetic minus its error bound)
+__device__ __forceinline__ double tilted_row_min(const float4 *sRow, int r0, int r1, double a, double b, double lbabs,
+                                                 int c_max, int l_max)
+{
+    const float af = (float)a, bf = (float)b;
+    float m = INFINITY;
+#pragma unroll 4
+    for (int r = r0; r <= r1; ++r) {
+        const float4 rr = sRow[r];
+        m = fminf(m, fmaf(af, rr.y, fmaf(bf, rr.z, rr.x)));
+    }
+    const double err = (lbabs + fabs(a) * (double)c_max + fabs(b) * (double)l_max) * 9.5367431640625e-07;   // 2^-20
+    return (double)m - err;
+}
+
+// Far columns [1, 1 + 32*nfar) of the 32-row block starting at row jb, run by warps 1..7 while warp 0 chains the
+// block before it.  Part 1: coarse block cb is bounded by far warp cb % 7, lane cb / 7; the survivors are split into
+// 4-row x 8-column rectangles (one lane each) and what survives again goes to a shared list.  Part 2 (after a
+// barrier among the far warps): the listed rectangles are dealt round-robin and evaluated exactly, 4 in flight per
+// warp, lane = (row of the group, column of the sub-block).  Every far warp keeps a running (max, first arg-max) for
+// all 32 rows (lane = row) and publishes it in its slice of sFarV / sFarA; far warp 0 also covers column 0, which
+// is in no block.  Returns the number of cells skipped (per lane; the caller sums).
+template <bool AI>
+__device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const CoarseRec *sCoarse,
+                                        const float4 *sRow, double lbabs, unsigned short *sList, unsigned short *sDense, int *sListCount,
+                                        double *sFarVW, int *sFarAW, double delta,
+                                        const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                        int alpha_int, double alpha PROF_ARGS)
+{
+    const int lane = threadIdx.x & 31, w7 = (threadIdx.x >> 5) - 1;
+    const int nrows = min(DP_JB, N - jb);
+    const int2 rowF = col_lc(sCol, jb), rowL = col_lc(sCol, jb + nrows - 1);           // (L, C)
+    const int2 me = col_lc(sCol, min(jb + lane, N - 1));
+    const RowConst<AI> rme = make_row<AI>(me.y, me.x, alpha_int, alpha);
+
+    // running far result of row `lane`
+    double best = -INFINITY;
+    int arg = 0x7fffffff;
+    if (w7 == 0 && lane < nrows) {
+        const ColRec a0 = sCol[0];
+        best = __dadd_rn(self_score<AI>(a0.C, a0.L, rme, gtab, ltab), a0.P);
+        arg = 0;
+    }
+    u64 skipped = 0;
+
+    const int rg = lane >> 2, q = lane & 3;                 // level 2: row group, sub-block
+    const int r0 = 4 * rg, r1 = min(r0 + 3, nrows - 1);
+    const bool act2 = r0 < nrows;
+    const int2 gF = col_lc(sCol, jb + min(r0, nrows - 1)), gL = col_lc(sCol, jb + r1);
+    const float4 myrow = sRow[lane];                        // level 1: lane = row
+
+    for (int base = 0; base < nfar; base += 32 * WD_FARW) {
+        // ---- level 1: 32 rows x 32 columns, one lane per rectangle ----
+        const int cb = base + lane * WD_FARW + w7;
+        const bool act1 = cb < nfar;
+        double a1 = 0.0, b1 = 0.0, ub1 = 0.0;
+        if (act1) {
+            const CoarseRec *rec = sCoarse + cb;
+            const int4 ends = *reinterpret_cast<const int4 *>(rec);
+            a1 = rec->a;
+            b1 = rec->b;
+            ub1 = rec->mpt + tilted_box_max<AI>(rowF.y - ends.y, rowL.y - ends.x, rowF.x - ends.w, rowL.x - ends.z, a1, b1,
+                                                gtab, ltab, alpha_int, alpha);
+        }
+        // min_r (lb_r + a*C_r + b*L_r) of every rectangle of this warp: lane = row, one warp-wide integer min per rectangle
+        // (floats compare like their sign-folded bit patterns)
+        const int nact = __popc(__ballot_sync(0xffffffffu, act1));       // active lanes are 0 .. nact-1
+        const float a1f = (float)a1, b1f = (float)b1;
+        int key1 = 0;
+        for (int i = 0; i < nact; ++i) {
+            const float af = __shfl_sync(0xffffffffu, a1f, i), bf = __shfl_sync(0xffffffffu, b1f, i);
+            const float v = lane < nrows ? fmaf(af, myrow.y, fmaf(bf, myrow.z, myrow.x)) : INFINITY;
+            const int bits = __float_as_int(v);
+            const int mn = __reduce_min_sync(0xffffffffu, bits >= 0 ? bits : bits ^ 0x7fffffff);
+            if (lane == i) key1 = mn;
+        }
+        bool surv1 = false;
+        if (act1) {
+            const float m3f = __int_as_float(key1 >= 0 ? key1 : key1 ^ 0x7fffffff);
+            const double err = (lbabs + fabs(a1) * (double)rowL.y + fabs(b1) * (double)rowL.x) * 9.5367431640625e-07;   // 2^-20
+            surv1 = !(ub1 - ((double)m3f - err) + delta < 0.0);          // NaN keeps the block
+            if (!surv1) skipped += (u64)(PR_CB * nrows);
+        }
+        unsigned mask1 = __ballot_sync(0xffffffffu, surv1);
+        PROF_T(4);
+
+        // ---- level 2: a surviving block as 8 row groups x 4 sub-blocks of 8 columns, one lane per rectangle ----
+        while (mask1) {
+            const int cb1 = base + (__ffs(mask1) - 1) * WD_FARW + w7;
+            mask1 &= mask1 - 1;
+            const CoarseRec *rec = sCoarse + cb1;
+            const double a = rec->a, b = rec->b;
+            bool surv2 = false;
+            if (act2) {
+                const int i0 = 1 + PR_CB * cb1 + PR_FB * q;
+                const int2 cF = col_lc(sCol, i0), cL = col_lc(sCol, i0 + PR_FB - 1);
+                const double m2 = tilted_box_max<AI>(gF.y - cL.y, gL.y - cF.y, gF.x - cL.x, gL.x - cF.x, a, b,
+                                                     gtab, ltab, alpha_int, alpha);
+                const double m3 = tilted_row_min(sRow, r0, r1, a, b, lbabs, gL.y, gL.x);
+                surv2 = !(rec->mpt8[q] + m2 - m3 + delta < 0.0);
+                if (!surv2) skipped += (u64)(PR_FB * (r1 - r0 + 1));
+            }
+            const unsigned mask2 = __ballot_sync(0xffffffffu, surv2);
+            const int n2 = __popc(mask2);
+            if (n2 >= PR_DENSE) {
+                // most of the block is needed: the whole 32 x 32 block goes to the sweep list (its rectangles are not skipped)
+                if (act2 && !surv2) skipped -= (u64)(PR_FB * (r1 - r0 + 1));
+                if (lane == 0) sDense[atomicAdd(sListCount + 1, 1)] = (unsigned short)cb1;
+            } else if (n2) {
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(sListCount, n2);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (surv2) sList[slot + __popc(mask2 & ((1u << lane) - 1u))] = (unsigned short)((cb1 << 5) | lane);
+            }
+        }
+        PROF_T(5);
+    }
+    // ---- all far warps: the list is complete ----
+    asm volatile("bar.sync 1, %0;" ::"n"(WD_FARW * 32) : "memory");
+    const int total = *reinterpret_cast<volatile int *>(sListCount);
+    const int ndense = *reinterpret_cast<volatile int *>(sListCount + 1);
+    PROF_T(3);
+
+    // ---- dense blocks: plain sweeps, one warp per 32 x 32 block (a lane: 2 rows, 4 apart, x 4 columns, 8 apart) ----
+    for (int e = w7; e < ndense; e += WD_FARW) {
+        const int i0 = 1 + PR_CB * (int)sDense[e];
+        const int rr = lane & 3, cph = lane >> 2;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+            RowConst<AI> r[2];
+            double bst[2];
+            int ag[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int2 rl = col_lc(sCol, min(jb + g * 8 + k * 4 + rr, N - 1));
+                r[k] = make_row<AI>(rl.y, rl.x, alpha_int, alpha);
+                bst[k] = -INFINITY;
+                ag[k] = i0 + cph;
+            }
+            sweep_columns<AI, 4, 2>(i0, i0 + PR_CB, cph, 8, sCol, r, gtab, ltab, bst, ag);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                merge_column_phases<4>(bst[k], ag[k]);
+                // lanes 0..3 (column phase 0) hold rows g*8 + k*4 + rr: hand them to the lanes that own those rows
+                const double v = __shfl_sync(0xffffffffu, bst[k], lane & 3);
+                const int va = __shfl_sync(0xffffffffu, ag[k], lane & 3);
+                if ((lane >> 2) == g * 2 + k && lane < nrows && (v > best || (v == best && va < arg))) { best = v; arg = va; }
+            }
+        }
+    }
+
+    // ---- level 3: the survivors exactly; lane = (row er of the group, column ec of the sub-block) ----
+    constexpr int UX = 4;
+    const int er = lane >> 3, ec = lane & 7;
+    for (int e0 = w7 * UX; e0 < total; e0 += WD_FARW * UX) {
+        double t[UX];
+        int ta[UX], g4[UX];
+#pragma unroll
+        for (int u = 0; u < UX; ++u) {
+            t[u] = -INFINITY;
+            ta[u] = 0x7fffffff;
+            g4[u] = 0;
+            if (e0 + u < total) {
+                const int ent = sList[e0 + u];
+                const int l2 = ent & 31;
+                g4[u] = 4 * (l2 >> 2);
+                const int row = g4[u] + er;                            // row of the block step
+                const int col = 1 + PR_CB * (ent >> 5) + PR_FB * (l2 & 3) + ec;
+                ta[u] = col;
+                if (row < nrows) {
+                    const int2 rl = col_lc(sCol, jb + row);
+                    const RowConst<AI> rc = make_row<AI>(rl.y, rl.x, alpha_int, alpha);
+                    const ColRec cc = sCol[col];
+                    t[u] = __dadd_rn(self_score<AI>(cc.C, cc.L, rc, gtab, ltab), cc.P);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UX; ++u) {
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, t[u], off);
+                const int oa = __shfl_xor_sync(0xffffffffu, ta[u], off);
+                if (ob > t[u] || (ob == t[u] && oa < ta[u])) { t[u] = ob; ta[u] = oa; }
+            }
+            // hand the 4 row results (lanes 0, 8, 16, 24) to the lanes that own those rows
+            const int rel = lane - g4[u];
+            const double v = __shfl_sync(0xffffffffu, t[u], (rel & 3) * 8);
+            const int va = __shfl_sync(0xffffffffu, ta[u], (rel & 3) * 8);
+            if (rel >= 0 && rel < 4 && (v > best || (v == best && va < arg))) { best = v; arg = va; }
+        }
+    }
+    sFarVW[lane] = best;
+    sFarAW[lane] = arg;
+    return skipped;
+}
+
+// The nearest 32 columns [jb-32, jb) (all final) and the triangle self scores of the block starting at row jb,
+// by warps 1..7.  The rectangle is 16 tasks of 8 rows x 8 columns (a lane: 2 rows, 4 apart, one column; so the 32
+// addresses of one gather span 4+8 candidates); task t covers row group t & 3, column chunk t >> 2.  Per-chunk
+// (max, first arg-max) go to sPartV / sPartA [chunk*32 + row].
+template <bool AI>
+__device__ __forceinline__ void near_tri_farwarps(int jb, int N, const ColRec *sCol, double *sPartV, int *sPartA, double *sTri,
+                                                  const double *__restrict__ gtab, const double *__restrict__ ltab,
+                                                  int alpha_int, double alpha)
+{
+    const int lane = threadIdx.x & 31, w7 = (threadIdx.x >> 5) - 1;
+    const int rr = lane & 3, cc = lane >> 2;
+    constexpr int NT = (16 + WD_FARW - 1) / WD_FARW;     // tasks per warp (3)
+    double tv[NT][2];
+    int tcol[NT];
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+        const int t = w7 + u * WD_FARW;
+        const int grp = t & 3, qc = (t >> 2) & 3;
+        tcol[u] = jb - PR_CB + qc * 8 + cc;
+        const ColRec a = sCol[tcol[u]];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int j = min(jb + grp * 8 + k * 4 + rr, N - 1);
+            const int2 me = col_lc(sCol, j);
+            const RowConst<AI> r = make_row<AI>(me.y, me.x, alpha_int, alpha);
+            tv[u][k] = (t < 16) ? __dadd_rn(self_score<AI>(a.C, a.L, r, gtab, ltab), a.P) : -INFINITY;
+        }
+    }
+    // triangle: lane = row, this warp's columns k = w7, w7+7, ...
+    const int2 mt = col_lc(sCol, min(jb + lane, N - 1));
+    const RowConst<AI> rt = make_row<AI>(mt.y, mt.x, alpha_int, alpha);
+    constexpr int NK = (DP_JB + WD_FARW - 1) / WD_FARW;  // 5
+    double w[NK];
+#pragma unroll
+    for (int kk = 0; kk < NK; ++kk) {
+        const int k = w7 + kk * WD_FARW;
+        w[kk] = 0.0;
+        if (k < lane && jb + lane < N) {
+            const int2 a = col_lc(sCol, jb + k);
+            w[kk] = self_score<AI>(a.y, a.x, rt, gtab, ltab);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+        const int t = w7 + u * WD_FARW;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            double best = tv[u][k];
+            int arg = tcol[u];
+            merge_column_phases<4>(best, arg);
+            if (cc == 0 && t < 16) {
+                const int row = (t & 3) * 8 + k * 4 + rr;
+                sPartV[(t >> 2) * 32 + row] = best;
+                sPartA[(t >> 2) * 32 + row] = arg;
+            }
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < NK; ++kk) {
+        const int k = w7 + kk * WD_FARW;
+        if (k < lane && jb + lane < N) sTri[k * DP_JB + lane] = w[kk];
+    }
+}
+
+// After the chain finished rows [jb, jb+32) (a full block of 32 columns from now on): least-squares tilt, tilted
+// maxima, end points.  One warp, lane = column.  The fit only steers how tight the bound is (any finite a, b is
+// valid), so its sums run in float.
 __device__ __forceinline__ void build_coarse_record(int jb, const ColRec *sCol, CoarseRec *rec, double tilt_scale_c,
                                                     double tilt_scale_l)
 {
@@ -295,24 +474,27 @@ __device__ __forceinline__ void build_coarse_record(int jb, const ColRec *sCol, 
     const int c_first = __shfl_sync(0xffffffffu, me.C, 0), c_last = __shfl_sync(0xffffffffu, me.C, 31);
     const int l_first = __shfl_sync(0xffffffffu, me.L, 0), l_last = __shfl_sync(0xffffffffu, me.L, 31);
     const double p_first = __shfl_sync(0xffffffffu, me.P, 0);
-    const double x = u32_to_double(me.C - c_first), y = u32_to_double(me.L - l_first), p = me.P - p_first;
     double a = 0.0, b = 0.0;                       // fit  -P ~ a*C + b*L + const
 #ifndef PASIO_NO_LS
-    const double inv_n = 1.0 / 32.0;
-    const double sx = warp_sum(x), sy = warp_sum(y), sp = warp_sum(p);
-    const double xc = x - sx * inv_n, yc = y - sy * inv_n, pc = p - sp * inv_n;
-    const double cxx = warp_sum(xc * xc), cyy = warp_sum(yc * yc), cxy = warp_sum(xc * yc);
-    const double cxp = warp_sum(xc * pc), cyp = warp_sum(yc * pc);
-    const double det = cxx * cyy - cxy * cxy;
-    if (det > 1e-9 * cxx * cyy) {
-        a = -(cxp * cyy - cyp * cxy) / det;
-        b = -(cyp * cxx - cxp * cxy) / det;
-    } else if (cxx > 0.0) {
-        a = -cxp / cxx;
-    } else if (cyy > 0.0) {
-        b = -cyp / cyy;
+    {
+        const float x = (float)(me.C - c_first), y = (float)(me.L - l_first), p = (float)(me.P - p_first);
+        const float inv_n = 1.0f / 32.0f;
+        const float sx = warp_sum(x), sy = warp_sum(y), sp = warp_sum(p);
+        const float xc = x - sx * inv_n, yc = y - sy * inv_n, pc = p - sp * inv_n;
+        const float cxx = warp_sum(xc * xc), cyy = warp_sum(yc * yc), cxy = warp_sum(xc * yc);
+        const float cxp = warp_sum(xc * pc), cyp = warp_sum(yc * pc);
+        const float det = cxx * cyy - cxy * cxy;
+        float fa = 0.f, fb = 0.f;
+        if (det > 1e-4f * cxx * cyy) {
+            fa = -(cxp * cyy - cyp * cxy) / det;
+            fb = -(cyp * cxx - cxp * cxy) / det;
+        } else if (cxx > 0.f) {
+            fa = -cxp / cxx;
+        } else if (cyy > 0.f) {
+            fb = -cyp / cyy;
+        }
+        if (fabsf(fa) < 1e30f && fabsf(fb) < 1e30f) { a = (double)fa; b = (double)fb; }   // NaN / inf: no tilt
     }
-    if (!(fabs(a) < 1e300) || !(fabs(b) < 1e300)) { a = 0.0; b = 0.0; }     // any finite tilt is valid; NaN / inf is not
 #endif
     double m = me.P + (a * u32_to_double(me.C) + b * u32_to_double(me.L));
 #pragma unroll
@@ -320,7 +502,7 @@ __device__ __forceinline__ void build_coarse_record(int jb, const ColRec *sCol, 
     double m32 = m;
 #pragma unroll
     for (int off = 8; off < 32; off <<= 1) m32 = fmax(m32, __shfl_xor_sync(0xffffffffu, m32, off));
-    const double slack = ldexp(fabs(a) * tilt_scale_c + fabs(b) * tilt_scale_l, -44);
+    const double slack = (fabs(a) * tilt_scale_c + fabs(b) * tilt_scale_l) * 5.684341886080802e-14;   // 2^-44
     if ((lane & 7) == 0) rec->mpt8[lane >> 3] = m + slack;
     if (lane == 0) {
         *reinterpret_cast<int4 *>(rec) = make_int4(c_first, c_last, l_first, l_last);
@@ -338,15 +520,17 @@ window_dp_kernel(WinDpParams p)
     const int capr = (p.cap + 31) & ~31;
     ColRec *sCol = reinterpret_cast<ColRec *>(smem);
     double *sPartV = reinterpret_cast<double *>(sCol + capr);
-    double *sTri = sPartV + WD_WARPS * 32;
+    double *sTri = sPartV + NEAR_Q * 32;
     int *sPartA = reinterpret_cast<int *>(sTri + DP_JB * DP_JB);
-    int *sMisc = sPartA + WD_WARPS * 32;
+    int *sMisc = sPartA + NEAR_Q * 32;
     unsigned short *sPrev = reinterpret_cast<unsigned short *>(sMisc + 16);
     CoarseRec *sCoarse = reinterpret_cast<CoarseRec *>(sPrev + capr);   // capr*2 bytes is a multiple of 16
-    RowLB *sRow = reinterpret_cast<RowLB *>(sCoarse + capr / PR_CB);
-    double *sFarV = reinterpret_cast<double *>(sRow + WD_WARPS * 32);
-    double *sScal = sFarV + WD_WARPS * 32;                              // [0] magnitude of the window's largest self score, [1] max |P|, [2], [3] tilt scales
-    int *sFarA = reinterpret_cast<int *>(sScal + 4);
+    float4 *sRow = reinterpret_cast<float4 *>(sCoarse + capr / PR_CB);
+    double *sFarV = reinterpret_cast<double *>(sRow + 32);              // [2][WD_FARW][32]
+    int *sFarA = reinterpret_cast<int *>(sFarV + 2 * WD_FARW * 32);     // [2][WD_FARW][32]
+    double *sScal = reinterpret_cast<double *>(sFarA + 2 * WD_FARW * 32);   // [0] magnitude of the window's largest self score, [1] max |P|, [2], [3] tilt scales, [4] max |lb| of sRow
+    unsigned short *sList = reinterpret_cast<unsigned short *>(sScal + 8);
+    int *sListCount = sMisc + 12;
     // the back-trace runs after the DP, when these are dead
     unsigned short *sJump = reinterpret_cast<unsigned short *>(sCoarse); // capr*2 bytes <= (capr/32)*80
     unsigned char *sMark = reinterpret_cast<unsigned char *>(sTri);     // capr <= 8192 bytes
@@ -355,7 +539,7 @@ window_dp_kernel(WinDpParams p)
     PROF_DECL;
 
     while (true) {
-        PROF_T(9);
+        PROF_T(7);
         PROF_FLUSH;
         if (tid == 0) sMisc[0] = (int)atomicAdd(p.work_counter, 1u);
         __syncthreads();
@@ -458,54 +642,80 @@ window_dp_kernel(WinDpParams p)
             sScal[2] = (double)z.C + p.alpha;       // |a*C| and |b*L| of a tilt stay below |a|*this and |b|*that
             sScal[3] = (double)z.L;
         }
-        for (int jb = 1; jb < N; jb += DP_JB) {
-            constexpr int NQ = WD_WARPS / (DP_JB / (DP_RPW * RPL));
-            const int nfar = (jb - 1) / PR_CB - 1;                  // finished 32-column blocks before the nearest one
-            if (!PRUNE || nfar < 1) {
-                dp_block_step<AI, WD_WARPS, U, RPL>(jb, N, 0, sCol, sPrev, nullptr, sPartV, sPartA, sTri,
-                                                    p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
-                PROF_T(8);
-            } else {
-                // (1) nearest 32 columns + triangle self scores
-                if (!EXP_SKIP(8))
-                block_rect_tri<AI, WD_WARPS, 2, RPL>(jb, N, jb - PR_CB, sCol, sPartV, sPartA, sTri, p.gtab, p.ltab,
-                                                     p.alpha_int, p.alpha);
+        // finished rows [jb, jb+32) become a block of 32 columns; running max |P| (scale of delta).  Warp 0 only.
+        auto finish_block = [&](int jb) {
+            if (jb + DP_JB <= N) build_coarse_record(jb, sCol, sCoarse + (jb - 1) / PR_CB, sScal[2], sScal[3]);
+            double ab = jb + lane < N ? fabs(sCol[jb + lane].P) : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ab = fmax(ab, __shfl_xor_sync(0xffffffffu, ab, off));
+            if (lane == 0) sScal[1] = fmax(sScal[1], ab);
+        };
+        auto far_delta = [&]() { return (sScal[0] + sScal[1] + fabs(p.pen) * DP_JB) * 5.684341886080802e-14; };   // 2^-44
+        // warp 0: lower bounds of the rows of block [jbn, jbn+32) for the far pass that runs next
+        auto prepare_rows = [&](int jbn) {
+            const double delta_path = (sScal[0] + sScal[1] + fabs(p.pen) * DP_JB) * 1.8189894035458565e-12;   // 2^-39
+            compute_row_lb<AI>(jbn - DP_JB, jbn, N, sCol, sRow, sScal + 4, delta_path, p.pen, p.gtab, p.ltab,
+                               p.alpha_int, p.alpha);
+            if (lane == 0) { sListCount[0] = 0; sListCount[1] = 0; }
+        };
+        int jb = 1;
+        // the first two blocks (and everything without pruning, and small windows, where bounding costs more than
+        // it saves): plain block steps over all columns
+        const bool pipelined = PRUNE && N > PR_MIN_N;
+        for (; jb < N && (!pipelined || jb < 1 + 2 * DP_JB); jb += DP_JB) {
+            dp_block_step<AI, WD_WARPS, U, RPL>(jb, N, 0, sCol, sPrev, nullptr, sPartV, sPartA, sTri,
+                                                p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
+            if (pipelined && warp == 0) finish_block(jb);
+        }
+        PROF_T(6);
+        if (pipelined && jb < N) {
+            // Software pipeline over the remaining blocks k = 2, 3, ...:
+            //   phase X(k): warp 0 turns block k-1 into a column block and prepares the row bounds of block k+1;
+            //               warps 1..7 sweep the nearest 32 columns and the triangle of block k
+            //   phase Y(k): warp 0 merges and resolves the chain of block k; warps 1..7 run the far pass of block k+1
+            if (warp == 0) prepare_rows(jb);
+            __syncthreads();
+            if (warp > 0) {
+                const int buf = ((jb - 1) / DP_JB) & 1;
+                skipped += far_pass<AI>(jb, N, (jb - 1) / PR_CB - 1, sCol, sCoarse, sRow, sScal[4], sList, sList + capr, sListCount,
+                                        sFarV + (buf * WD_FARW + warp - 1) * 32, sFarA + (buf * WD_FARW + warp - 1) * 32,
+                                        far_delta(), p.gtab, p.ltab, p.alpha_int, p.alpha PROF_PASS);
+            }
+            __syncthreads();
+            for (; jb < N; jb += DP_JB) {
+                const int k = (jb - 1) / DP_JB, buf = k & 1;
+                if (warp == 0) {
+                    if (k > 2) finish_block(jb - DP_JB);
+                    if (jb + DP_JB < N) prepare_rows(jb + DP_JB);
+                } else {
+                    near_tri_farwarps<AI>(jb, N, sCol, sPartV, sPartA, sTri, p.gtab, p.ltab, p.alpha_int, p.alpha);
+                }
                 PROF_T(1);
-                // (2) far columns [1, jb - 32): two levels of bounds against a lower bound of the row maxima,
-                //     the survivors exactly
-                const double delta = ldexp(sScal[0] + sScal[1] + fabs(p.pen) * DP_JB, -44);
-                if (!EXP_SKIP(1))
-                skipped += far_pass<AI, NQ>(jb, N, nfar, sCol, sCoarse, sPartV, sRow + warp * 32, sFarV + warp * 32,
-                                            sFarA + warp * 32, delta, p.pen, p.gtab, p.ltab, p.alpha_int, p.alpha PROF_PASS);
                 __syncthreads();
-                PROF_T(3);
-                // (3) chain: far results first (smaller columns; the warps' column sets interleave, hence the
-                //     index-aware merge), then the near partials, then the triangle
-                if (warp == 0 && !EXP_SKIP(4)) {
+                PROF_T(6);
+                if (warp == 0) {
+                    // far results first (smaller columns; the warps' column sets interleave, hence the index-aware
+                    // merge), then the near chunks in ascending order, then the triangle
                     double fbest = -INFINITY;
                     int farg = 0;
 #pragma unroll
-                    for (int w2 = 0; w2 < WD_WARPS; ++w2) {
-                        const double v = sFarV[w2 * 32 + lane];
-                        const int a = sFarA[w2 * 32 + lane];
+                    for (int w2 = 0; w2 < WD_FARW; ++w2) {
+                        const double v = sFarV[(buf * WD_FARW + w2) * 32 + lane];
+                        const int a = sFarA[(buf * WD_FARW + w2) * 32 + lane];
                         if (v > fbest || (v == fbest && a < farg)) { fbest = v; farg = a; }
                     }
-                    block_chain<NQ>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen,
-                                    jb + lane < N ? fbest : -INFINITY, jb + lane < N ? farg : 0, 0, nullptr);
+                    block_chain<NEAR_Q>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen,
+                                        jb + lane < N ? fbest : -INFINITY, jb + lane < N ? farg : 0, 0, nullptr);
+                } else if (jb + DP_JB < N) {
+                    skipped += far_pass<AI>(jb + DP_JB, N, k, sCol, sCoarse, sRow, sScal[4], sList, sList + capr, sListCount,
+                                            sFarV + ((buf ^ 1) * WD_FARW + warp - 1) * 32,
+                                            sFarA + ((buf ^ 1) * WD_FARW + warp - 1) * 32,
+                                            far_delta(), p.gtab, p.ltab, p.alpha_int, p.alpha PROF_PASS);
                 }
-                PROF_T(4);
+                PROF_T(2);
                 __syncthreads();
-                PROF_T(5);
+                PROF_T(7);
             }
-            if (PRUNE && warp == 0) {
-                // the finished rows become a block of 32 columns; running max |P| (scale of delta)
-                if (jb + DP_JB <= N && !EXP_SKIP(2)) build_coarse_record(jb, sCol, sCoarse + (jb - 1) / PR_CB, sScal[2], sScal[3]);
-                double ab = jb + lane < N ? fabs(sCol[jb + lane].P) : 0.0;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) ab = fmax(ab, __shfl_xor_sync(0xffffffffu, ab, off));
-                if (lane == 0) sScal[1] = fmax(sScal[1], ab);
-            }
-            PROF_T(6);
         }
 
         // ---- (C) back-trace by pointer doubling, scatter survivors ----------------------------
@@ -526,7 +736,6 @@ window_dp_kernel(WinDpParams p)
                 atomicOr(p.keepbits + (pos >> 5), 1u << (pos & 31));
             }
         }
-        PROF_T(7);
         if (tid == 0) atomicAdd(p.cells, (u64)N * (u64)(N - 1) / 2);
         if (PRUNE) {
 #pragma unroll
@@ -586,10 +795,6 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
 #if defined(PASIO_WD_EXP) || defined(PASIO_WD_PROF)
     if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
 #endif
-#ifdef PASIO_WD_EXP
-    p.exp_skip = getenv("PASIO_WD_SKIP") ? atoi(getenv("PASIO_WD_SKIP")) : 0;
-    if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
-#endif
     i64 grid = (i64)ctx->sm_count * per_sm;     // persistent CTAs: one resident wave
     if (grid > nwin) grid = nwin;
     if (grid < 1) grid = 1;
@@ -601,16 +806,17 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
 #ifdef PASIO_WD_PROF
     {
         cudaStreamSynchronize(ctx->stream);
-        unsigned long long h[24], z[24] = {0};
+        unsigned long long h[16], z[16] = {0};
         cudaMemcpyFromSymbol(h, g_wd_prof, sizeof h);
         cudaMemcpyToSymbol(g_wd_prof, z, sizeof z);
-        static const char *names[24] = {"compact", "rect_tri", "", "far+sync", "chain", "sync", "record", "backtrace", "plain_step",
-                                        "window_loop", "far:LB", "far:L1", "far:L2L3"};
-        double tot = 0;
-        for (int i = 0; i < 13; ++i) tot += (double)h[i];
-        fprintf(stderr, "[wd_prof] nwin=%lld grid=%lld:", (long long)nwin, (long long)grid);
-        for (int i = 0; i < 13; ++i) if (h[i]) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)h[i] / tot);
-        fprintf(stderr, " | cycles/CTA=%.3g\n", tot / (double)grid);
+        static const char *names[8] = {"compact", "X:work", "Y:work(chain|far L3)", "far:listwait", "far:L1", "far:L2", "wait@X+plain", "wait@Y+rest"};
+        for (int side = 0; side < 2; ++side) {
+            double tot = 0;
+            for (int i = 0; i < 8; ++i) tot += (double)h[8 * side + i];
+            fprintf(stderr, "[wd_prof %s] nwin=%lld grid=%lld:", side ? "warp1" : "warp0", (long long)nwin, (long long)grid);
+            for (int i = 0; i < 8; ++i) if (h[8 * side + i]) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)h[8 * side + i] / tot);
+            fprintf(stderr, " | cycles/CTA=%.3g\n", tot / (double)grid);
+        }
     }
 #endif
     return PASIO_OK;
