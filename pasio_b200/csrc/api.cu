@@ -153,7 +153,7 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     drop_borrowed_counts(ctx);
     DevBuf *bufs[] = {&ctx->tab[0], &ctx->tab[1], &ctx->tab[2], &ctx->counts, &ctx->cg, &ctx->cpbits, &ctx->keepbits,
-                      &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en,
+                      &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
                       &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
@@ -490,7 +490,7 @@ extern "C" int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_s
     i64 nwin = 0;
     PASIO_TRY(build_window_table(ctx, window_size, window_shift, &nwin));
     i64 max_span = 0, max_cnt = 0;
-    PASIO_TRY(launch_window_prepass(ctx, nwin, (int)window_size, (int)window_shift, &max_span, &max_cnt));
+    PASIO_TRY(launch_window_prepass(ctx, nwin, (int)window_size, (int)window_shift, &max_span, &max_cnt, constraint));
     static const bool debug = getenv("PASIO_DEBUG") != nullptr;
     if (debug)
         fprintf(stderr, "[pasio_round] n=%lld contigs=%lld m=%lld implicit=%d nwin=%lld size=%lld shift=%lld max_span=%lld max_cnt=%lld ntab=%lld,%lld,%lld\n",

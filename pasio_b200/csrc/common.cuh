@@ -66,6 +66,8 @@ struct pasio_ctx {
 
     // per-round window table for batches (n_contigs > 1)
     DevBuf win_st, win_en;
+    DevBuf win_small, win_medium, win_large;  // per-round work lists of window numbers (small / medium: warp per window, large: CTA per window)
+    i64 n_small = 0, n_medium = 0, n_large = 0;
     std::vector<int32_t> h_win_st, h_win_en, h_brank;
 
     // scratch
@@ -117,7 +119,11 @@ int launch_logfac_scan(pasio_ctx *ctx, double *d_out);        // float64 prefix 
 // compact.cu
 int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count);  // keepbits -> sorted positions; syncs
 int launch_boundary_ranks(pasio_ctx *ctx);                    // brank from current candidates
-int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt);  // syncs
+// classify_constraint >= 0: also sort the windows into ctx->win_small / win_large (n_small, n_large) for launch_window_dp
+int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt,
+                          int classify_constraint = -1);  // syncs
+int small_window_max_candidates();                           // window_dp.cu: most candidates the warp-per-window kernels take
+int medium_window_max_candidates();
 int launch_validate_candidates(pasio_ctx *ctx, i64 *h_bad);   // syncs
 int launch_filter_candidates(pasio_ctx *ctx, int constraint);  // current candidates -> keepbits
 

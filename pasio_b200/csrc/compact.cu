@@ -114,9 +114,14 @@ __global__ void boundary_ranks_kernel(const int32_t *__restrict__ cand, i64 m,
     brank[c] = (int32_t)lo;
 }
 
-// largest window span (nt) and window count: the table lengths a round needs
+// largest window span (nt) and window count: the table lengths a round needs.  Optionally sorts the windows into
+// two work lists by an upper bound of their candidate count after the constraint filter: small windows go to the
+// warp-per-window kernel, the others to the CTA-per-window kernel (window_dp.cu).
 __global__ void window_prepass_kernel(WinGeom g, i64 nwin, const int32_t *__restrict__ cand,
-                                      const i64 *__restrict__ cg, u64 *out /* [0]=span, [1]=count */)
+                                      const i64 *__restrict__ cg, u64 *out /* [0]=span, [1]=count */,
+                                      const uint32_t *__restrict__ cpbits, int constraint, int small_max, int medium_max,
+                                      int32_t *__restrict__ small_list, int32_t *__restrict__ medium_list,
+                                      int32_t *__restrict__ large_list, unsigned *list_counts /* [0]=small, [1]=medium, [2]=large */)
 {
     i64 span = 0, cnt = 0;
     for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < nwin; w += (i64)gridDim.x * blockDim.x) {
@@ -126,6 +131,22 @@ __global__ void window_prepass_kernel(WinGeom g, i64 nwin, const int32_t *__rest
         i64 b = cand ? __ldg(cand + en - 1) : en - 1;
         span = max(span, b - a);
         cnt = max(cnt, __ldg(cg + b) - __ldg(cg + a));
+        if (small_list) {
+            i64 est = en - st;
+            if (est > small_max && !cand && constraint == PASIO_CONSTRAINT_CONSTANTS) {   // (est = all positions of the window here)
+                // all positions are candidates: change points strictly inside (a, b), plus both ends
+                est = 2;
+                for (i64 word = (a + 1) >> 5; word <= (b - 1) >> 5 && est <= medium_max; ++word) {
+                    uint32_t x = __ldg(cpbits + word);
+                    if (word == (a + 1) >> 5) x &= 0xffffffffu << ((a + 1) & 31);
+                    if (word == (b - 1) >> 5) x &= 0xffffffffu >> (31 - ((b - 1) & 31));
+                    est += __popc(x);
+                }
+            }
+            if (est <= small_max) small_list[atomicAdd(list_counts, 1u)] = (int32_t)w;
+            else if (est <= medium_max) medium_list[atomicAdd(list_counts + 1, 1u)] = (int32_t)w;
+            else large_list[atomicAdd(list_counts + 2, 1u)] = (int32_t)w;
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -236,23 +257,43 @@ int launch_boundary_ranks(pasio_ctx *ctx)
     return PASIO_OK;
 }
 
-int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt)
+int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt,
+                          int classify_constraint)
 {
     u64 *d_out = ctx->scalars.as<u64>() + 6;
     CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, 16, ctx->stream));
+    unsigned *d_counts = ctx->scalars.as<unsigned>() + 2 * 13;      // scalars[13], [14]: small / medium / large list lengths
+    const bool classify = classify_constraint >= 0;
+    if (classify) {
+        if (nwin > 2147483647LL) return pasio_fail(ctx, PASIO_E_TOO_LARGE, "too many windows");
+        PASIO_TRY(pasio_reserve(ctx, ctx->win_small, (size_t)nwin * 4));
+        PASIO_TRY(pasio_reserve(ctx, ctx->win_medium, (size_t)nwin * 4));
+        PASIO_TRY(pasio_reserve(ctx, ctx->win_large, (size_t)nwin * 4));
+        CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, 16, ctx->stream));
+    }
     unsigned blocks = (unsigned)((nwin + 255) / 256);
     if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     if (blocks == 0) blocks = 1;
     {
         TimingScope ts(ctx, TF_COMPACT);
-        window_prepass_kernel<<<blocks, 256, 0, ctx->stream>>>(make_geom(ctx, wsize, wshift), nwin, cur_cand(ctx),
-                                                              ctx->cg.as<i64>(), d_out);
+        window_prepass_kernel<<<blocks, 256, 0, ctx->stream>>>(
+            make_geom(ctx, wsize, wshift), nwin, cur_cand(ctx), ctx->cg.as<i64>(), d_out, ctx->cpbits.as<uint32_t>(),
+            classify_constraint, small_window_max_candidates(), medium_window_max_candidates(),
+            classify ? ctx->win_small.as<int32_t>() : nullptr, classify ? ctx->win_medium.as<int32_t>() : nullptr,
+            classify ? ctx->win_large.as<int32_t>() : nullptr, d_counts);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 6, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (classify) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 13, d_counts, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *h_max_span = ctx->h_scalars[6];
     *h_max_cnt = ctx->h_scalars[7];
+    if (classify) {
+        const unsigned *c = reinterpret_cast<const unsigned *>(ctx->h_scalars + 13);
+        ctx->n_small = c[0];
+        ctx->n_medium = c[1];
+        ctx->n_large = c[2];
+    }
     return PASIO_OK;
 }
 

@@ -79,6 +79,7 @@ struct WinDpParams {
     u64 *cells;                 // algorithmic cells N(N-1)/2
     u64 *cells_skipped;         // cells proven irrelevant by the far-column bound (0 without pruning)
     unsigned *work_counter;
+    const int32_t *list;        // window numbers to process (nwin of them); nullptr: 0 .. nwin-1
 };
 
 // One finished block of 32 columns [1+32b, 32+32b], as the far pass sees it.
@@ -543,8 +544,9 @@ window_dp_kernel(WinDpParams p)
         PROF_FLUSH;
         if (tid == 0) sMisc[0] = (int)atomicAdd(p.work_counter, 1u);
         __syncthreads();
-        const i64 w = (unsigned)sMisc[0];
-        if (w >= p.nwin) break;
+        const i64 widx = (unsigned)sMisc[0];
+        if (widx >= p.nwin) break;
+        const i64 w = p.list ? (i64)__ldg(p.list + widx) : widx;
 
         // ---- (A) candidates of the window, filtered, re-based ---------------------------------
         i64 st, en;
@@ -746,7 +748,170 @@ window_dp_kernel(WinDpParams p)
     }
 }
 
+// ---- small windows: one WARP per window ----------------------------------------------------------
+// Round 1 of the default pipeline is ~200 000 windows of ~100 candidates: a few thousand cells each, but every
+// window is a chain of ~100 dependent row steps.  With a CTA per window only three such chains run per SM; here
+// every warp owns a window (40 per SM), so the SM is busy with other windows while one waits on its chain.
+// Same arithmetic, same order and the same first-maximum rule as the CTA kernel: 16-row block steps, a lane
+// sweeps every second finished column for its row, the 16 x 16 triangle is resolved in order by shuffles.
+// Two size classes: up to 160 candidates (8 windows per CTA, 5 CTAs per SM) and up to 512 (4 per CTA, 4 CTAs per SM).
+constexpr int SW_JB = 16;
+constexpr int SW_SMALL_N = 160, SW_SMALL_WARPS = 8, SW_SMALL_CTAS = 5;
+constexpr int SW_MEDIUM_N = 512, SW_MEDIUM_WARPS = 4, SW_MEDIUM_CTAS = 4;
+
+template <int MAXN>
+struct __align__(16) SmallWin {
+    ColRec col[MAXN];
+    double tri[SW_JB * SW_JB];
+    unsigned short prev[MAXN];
+    unsigned char mark[MAXN];
+};
+
+template <bool AI, int MAXN, int NWARPS, int CTAS>
+__global__ void __launch_bounds__(NWARPS * 32, CTAS)
+small_window_dp_kernel(WinDpParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    SmallWin<MAXN> &W = reinterpret_cast<SmallWin<MAXN> *>(smem)[threadIdx.x >> 5];
+    u64 my_cells = 0;
+
+    while (true) {
+        unsigned widx = 0;
+        if (lane == 0) widx = atomicAdd(p.work_counter, 1u);
+        widx = __shfl_sync(0xffffffffu, widx, 0);
+        if ((i64)widx >= p.nwin) break;
+        const i64 w = __ldg(p.list + widx);
+
+        // ---- (A) candidates of the window, filtered, re-based ----
+        i64 st, en;
+        window_range(p.geom, w, st, en);
+        const int nq = (int)(en - st);
+        const i64 first = p.cand ? (i64)__ldg(p.cand + st) : st;
+        const i64 last = p.cand ? (i64)__ldg(p.cand + en - 1) : en - 1;
+        const i64 cg_first = __ldg(p.cg + first);
+        const bool all_zero = (p.constraint == PASIO_CONSTRAINT_ZEROS) && (__ldg(p.cg + last) == cg_first);
+        int count = 0;
+        if (!p.cand && p.constraint == PASIO_CONSTRAINT_CONSTANTS) {
+            const i64 w0 = first >> 5, w1 = last >> 5;
+            const int nwords = (int)(w1 - w0 + 1);
+            for (int base = 0; base < nwords; base += 32) {
+                const int t = base + lane;
+                unsigned word = 0;
+                if (t < nwords) {
+                    word = __ldg(p.cpbits + w0 + t);
+                    if (t == 0) word = (word & (0xffffffffu << (first & 31))) | (1u << (first & 31));
+                    if (t == nwords - 1) word = (word & (0xffffffffu >> (31 - (last & 31)))) | (1u << (last & 31));
+                }
+                int incl = __popc(word);
+                const int mine = incl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                int k = count + incl - mine;
+                const i64 pos0 = (w0 + t) << 5;
+                while (word) {
+                    const i64 pos = pos0 + (__ffs(word) - 1);
+                    word &= word - 1;
+                    W.col[k].L = (int)(pos - first);
+                    W.col[k].C = (int)(__ldg(p.cg + pos) - cg_first);
+                    ++k;
+                }
+                count += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        } else {
+            for (int base = 0; base < nq; base += 32) {
+                const int q = base + lane;
+                i64 pos = 0;
+                bool take = false;
+                if (q < nq) {
+                    pos = p.cand ? (i64)__ldg(p.cand + st + q) : st + q;
+                    if (q == 0 || q == nq - 1 || p.constraint == PASIO_CONSTRAINT_NONE) take = true;
+                    else if (p.constraint == PASIO_CONSTRAINT_CONSTANTS) take = bit_test(p.cpbits, pos);
+                    else take = !all_zero;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, take);
+                if (take) {
+                    const int k = count + __popc(bal & ((1u << lane) - 1u));
+                    W.col[k].L = (int)(pos - first);
+                    W.col[k].C = (int)(__ldg(p.cg + pos) - cg_first);
+                }
+                count += __popc(bal);
+            }
+        }
+        const int N = count;
+        if (lane == 0) { W.col[0].P = 0.0; W.prev[0] = 0; }
+        __syncwarp();
+
+        // ---- (B) DP, 16 rows per step: lane = (row r, column phase ph) ----
+        const int r = lane & 15, ph = lane >> 4;
+        for (int jb = 1; jb < N; jb += SW_JB) {
+            const ColRec me = W.col[min(jb + r, N - 1)];
+            RowConst<AI> rc[1] = {make_row<AI>(me.C, me.L, p.alpha_int, p.alpha)};
+            double best[1] = {-INFINITY};
+            int arg[1] = {ph};
+            sweep_columns<AI, 4, 1>(0, jb, ph, 2, W.col, rc, p.gtab, p.ltab, best, arg);
+            {   // the two column phases of a row: larger value, equal values keep the smaller column
+                const double ob = __shfl_xor_sync(0xffffffffu, best[0], 16);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg[0], 16);
+                if (ob > best[0] || (ob == best[0] && oa < arg[0])) { best[0] = ob; arg[0] = oa; }
+            }
+            // triangle self scores (independent of P)
+            for (int k = ph; k < r; k += 2)
+                if (jb + r < N) {
+                    const ColRec a = W.col[jb + k];
+                    W.tri[k * SW_JB + r] = self_score<AI>(a.C, a.L, rc[0], p.gtab, p.ltab);
+                }
+            __syncwarp();
+            double bst = best[0], mine = 0.0;
+            int ag = arg[0];
+            const int rows = min(SW_JB, N - jb);
+#pragma unroll 4
+            for (int k = 0; k < rows; ++k) {
+                const double pf = __dadd_rn(bst, p.pen);          // prefix_scores[j] = max + segment_creation_cost
+                const double pk = __shfl_sync(0xffffffffu, pf, k);
+                if (r == k) mine = pf;
+                if (r > k) {
+                    const double t = __dadd_rn(W.tri[k * SW_JB + r], pk);
+                    if (t > bst) { bst = t; ag = jb + k; }
+                }
+            }
+            if (lane < SW_JB && jb + r < N) {
+                W.col[jb + r].P = mine;
+                W.prev[jb + r] = (unsigned short)ag;
+            }
+            __syncwarp();
+        }
+
+        // ---- (C) back-trace, scatter survivors ----
+        for (int k = lane; k < N; k += 32) W.mark[k] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            int k = N - 1;
+            while (true) {
+                W.mark[k] = 1;
+                if (k == 0) break;
+                k = W.prev[k];
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < N; k += 32)
+            if (W.mark[k]) {
+                const i64 pos = first + W.col[k].L;
+                atomicOr(p.keepbits + (pos >> 5), 1u << (pos & 31));
+            }
+        my_cells += (u64)N * (u64)(N - 1) / 2;
+        __syncwarp();
+    }
+    if (lane == 0 && my_cells) atomicAdd(p.cells, my_cells);
+}
+
 }  // namespace
+
+int small_window_max_candidates() { return SW_SMALL_N; }
+int medium_window_max_candidates() { return SW_MEDIUM_N; }
 
 int window_dp_max_candidates(pasio_ctx *ctx)
 {
@@ -780,6 +945,47 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     p.cells_skipped = ctx->scalars.as<u64>() + 12;
     p.work_counter = ctx->scalars.as<unsigned>() + 2 * 11;   // scalars[11]
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 10, 0, 24, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 15, 0, 8, ctx->stream));    // work counters of the warp-per-window kernels
+
+    // the work lists of the prepass (launch_window_prepass with classification): small windows first, one warp each
+    static const int small_env = getenv("PASIO_WD_SMALL") ? atoi(getenv("PASIO_WD_SMALL")) : 1;
+    const bool use_lists = ctx->n_small + ctx->n_medium + ctx->n_large == nwin;
+    i64 n_large = nwin;
+    p.list = nullptr;
+    if (use_lists && small_env) {
+        auto launch_small = [&](auto kern, const int32_t *list, i64 n, int nwarps, int ctas, size_t smem_bytes, unsigned *counter) -> int {
+            if (n <= 0) return PASIO_OK;
+            WinDpParams ps = p;
+            ps.list = list;
+            ps.nwin = n;
+            ps.work_counter = counter;
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            i64 g = (n + nwarps - 1) / nwarps;
+            if (g > (i64)ctx->sm_count * ctas) g = (i64)ctx->sm_count * ctas;
+            TimingScope ts(ctx, TF_WINDOW_DP);
+            kern<<<(unsigned)g, nwarps * 32, smem_bytes, ctx->stream>>>(ps);
+            CUDA_TRY(ctx, cudaGetLastError());
+            return PASIO_OK;
+        };
+        unsigned *c_small = ctx->scalars.as<unsigned>() + 2 * 15, *c_medium = c_small + 1;     // scalars[15]
+        const size_t sm_small = sizeof(SmallWin<SW_SMALL_N>) * SW_SMALL_WARPS, sm_medium = sizeof(SmallWin<SW_MEDIUM_N>) * SW_MEDIUM_WARPS;
+        if (ctx->alpha_is_int) {
+            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS>, ctx->win_small.as<int32_t>(),
+                                   ctx->n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small));
+            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS>, ctx->win_medium.as<int32_t>(),
+                                   ctx->n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium));
+        } else {
+            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS>, ctx->win_small.as<int32_t>(),
+                                   ctx->n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small));
+            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS>, ctx->win_medium.as<int32_t>(),
+                                   ctx->n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium));
+        }
+        p.list = ctx->win_large.as<int32_t>();
+        n_large = ctx->n_large;
+    }                                           // PASIO_WD_SMALL=0 (experiments): every window through the CTA kernel
+    ctx->n_small = ctx->n_medium = ctx->n_large = -1;           // the lists are consumed
+    p.nwin = n_large;
+    if (n_large == 0) return PASIO_OK;
 
     const size_t smem = window_smem_bytes(p.cap);
     // PASIO_WD_PRUNE=0 disables the exact far-column pruning (experiments / cross-checks)
@@ -796,7 +1002,7 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
 #endif
     i64 grid = (i64)ctx->sm_count * per_sm;     // persistent CTAs: one resident wave
-    if (grid > nwin) grid = nwin;
+    if (grid > n_large) grid = n_large;
     if (grid < 1) grid = 1;
     {
         TimingScope ts(ctx, TF_WINDOW_DP);
