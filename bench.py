@@ -232,20 +232,24 @@ def run_b200(args):
     scan_ms, scan_launches = timing['scan']
     fp64_peak_nominal = 148 * 64 * peaks.get('sm_max_mhz', 1965.0) * 1e6
     cells_per_launch = cells / max(1, len(sizes))
-    wd_avg_s = (wd_ms / max(1, wd_launches)) * 1e-3
+    # one timed span per round: the CTA-per-window kernel and the two warp-per-window kernels of a round overlap
+    # (side stream), so the per-round span is the unit; wd_launches counts the kernels themselves
+    wd_rounds = max(1, len(sizes) * args.steps)
+    wd_avg_s = (wd_ms / wd_rounds) * 1e-3
     achieved = cells_per_launch * FP64_OPS_PER_CELL / wd_avg_s
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(prof):
         traffic = json.load(open(prof)).get('window_dp_dram_bytes_per_launch')
     roofline = {
-        'kernel': 'window_dp_kernel (one CTA per window, all windows of a round per launch)',
+        'kernel': 'window DP of one round: window_dp_kernel (CTA per window) + small_window_dp_kernel x2 (warp per window, '
+                  'side stream), timed as one span per round',
         'bound': 'fp64', 'achieved': achieved / 1e12, 'peak': fp64_peak_nominal / 1e12, 'unit': 'TFLOP/s',
         'frac': achieved / fp64_peak_nominal, 'traffic': traffic,
         'peak_source': '148 SM x 64 FP64 lanes x sm_max_mhz (%s MEASURED_PEAKS.json has no FP64 entry); '
                        'DFMA micro-benchmark on this box: %.3g instr/s' % (peak_kind, fp64_peak_measured),
         'algorithmic_ops_per_cell': FP64_OPS_PER_CELL, 'cells_per_launch': cells_per_launch,
-        'avg_launch_ms': wd_avg_s * 1e3, 'launches': wd_launches,
+        'avg_launch_ms': wd_avg_s * 1e3, 'launches': wd_rounds, 'kernels_launched': wd_launches,
         'share_of_step': wd_ms / (dev_ms if dev_ms > 0 else 1.0),
         'scan_kernel': {'bound': 'hbm', 'achieved': 16.0 * n / ((scan_ms / max(1, scan_launches)) * 1e-3) / 1e9,
                         'peak': peaks['hbm_gbs'], 'unit': 'GB/s',

@@ -135,6 +135,9 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void **)&ctx->h_scalars, 16 * sizeof(i64)) != cudaSuccess ||
         pasio_reserve(ctx, ctx->scalars, 16 * sizeof(i64)) != PASIO_OK) {
         g_create_error = "context allocation failed: " + ctx->err;
@@ -160,6 +163,9 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PASIO_OK;

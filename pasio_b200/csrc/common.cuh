@@ -31,6 +31,8 @@ struct pasio_ctx {
     int sm_count = 0;
     int smem_optin = 0;          // max dynamic shared memory per block (opt-in)
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // side stream: the warp-per-window kernels run beside the CTA-per-window kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
 
     // scorer parameters (log_marginal_likelyhood.py:6-16,62)

@@ -663,7 +663,9 @@ window_dp_kernel(WinDpParams p)
         int jb = 1;
         // the first two blocks (and everything without pruning, and small windows, where bounding costs more than
         // it saves): plain block steps over all columns
-        const bool pipelined = PRUNE && N > PR_MIN_N;
+        // (with all positions as candidates -- round 1 -- most candidates are noise, the arg-max is far away and the
+        // bounds cut little: plain sweeps are faster there)
+        const bool pipelined = PRUNE && N > PR_MIN_N && p.cand != nullptr;
         for (; jb < N && (!pipelined || jb < 1 + 2 * DP_JB); jb += DP_JB) {
             dp_block_step<AI, WD_WARPS, U, RPL>(jb, N, 0, sCol, sPrev, nullptr, sPartV, sPartA, sTri,
                                                 p.gtab, p.ltab, p.alpha_int, p.alpha, p.pen, -INFINITY, 0, 0);
