@@ -291,6 +291,33 @@ def test_pruned_far_columns_are_exact(eng, case):
     assert skipped_total > 0
 
 
+@pytest.mark.parametrize('wsize', [159, 160, 511, 512, 513])
+@pytest.mark.parametrize('explicit', [False, True])
+def test_window_size_class_edges(eng, wsize, explicit):
+    """windows of exactly 160 / 161 / 512 / 513 / 514 candidates sit on the edges between the warp-per-window
+    kernels (<= 160, <= 512 candidates) and the CTA-per-window kernel; all three must give the oracle's rounds"""
+    rs = np.random.RandomState(wsize)
+    counts = rs.poisson(3.0, 9000).astype(np.int64)
+    fo = c_oracle.FlatOracle(counts, 1.0, 1.0)
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.load(counts)
+    if explicit:
+        cands = np.concatenate([[0], np.flatnonzero(rs.random_sample(len(counts) - 1) < 0.7) + 1, [len(counts)]]).astype(np.int64)
+        eng.set_candidates(cands)
+    else:
+        cands = np.arange(len(counts) + 1, dtype=np.int64)
+        eng.set_candidates(None)
+    for r in range(3):
+        eng.round(wsize, wsize // 2, 'none')
+        got = eng.candidates()
+        want, o_cells = fo.round(cands, wsize, wsize // 2, 'none')
+        assert np.array_equal(got, want), (wsize, explicit, r)
+        assert eng.round_stats()[0] == o_cells
+        if len(want) == len(cands):
+            break
+        cands = want
+
+
 def test_timing_hooks(eng):
     counts = synth.dnase_like(100000, 9, hotspot_share=0.3)
     eng.use_scorer(factory(1.0, 1.0))

@@ -31,7 +31,7 @@ while time.time() < t_end:
         counts = rs.randint(0, 3, n).astype(np.int64)
     alpha = float(rs.choice([1.0, 1.0, 2.0, 0.5, 0.01, 3.7, 25.0]))
     beta = float(rs.choice([1.0, 1.0, 0.1, 2.5, 10.0]))
-    wsize = int(rs.choice([150, 700, 2500, 2500, 5000]))
+    wsize = int(rs.choice([150, 159, 160, 300, 511, 512, 700, 2500, 2500, 5000]))   # 159/160, 511/512: size-class edges of the window kernels
     wshift = int(rs.choice([wsize // 2, wsize // 2, wsize // 3 + 1, wsize]))
     constraint = str(rs.choice(['constants', 'constants', 'none', 'zeros']))
     if constraint != 'constants' and n > 60000:
@@ -43,8 +43,14 @@ while time.time() < t_end:
     fo = c_oracle.FlatOracle(counts, alpha, beta)
     eng.use_scorer(factories[key])
     eng.load(counts)
-    eng.set_candidates(None)
-    cands = np.arange(n + 1, dtype=np.int64)
+    if rs.random_sample() < 0.5:
+        # explicit first list: a random subset of the positions -- noisy candidates through the pruned (pipelined) path
+        inner = np.flatnonzero(rs.random_sample(n - 1) < rs.uniform(0.03, 0.6)) + 1
+        cands = np.concatenate([[0], inner, [n]]).astype(np.int64)
+        eng.set_candidates(cands)
+    else:
+        eng.set_candidates(None)
+        cands = np.arange(n + 1, dtype=np.int64)
     for r in range(4):
         eng.round(wsize, wshift, constraint)
         got = eng.candidates()
