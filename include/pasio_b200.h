@@ -81,6 +81,15 @@ int pasio_contig_load(pasio_ctx *ctx, const int64_t *counts, int64_t n,
  * run r covers [starts[r], starts[r+1]) with value values[r]; starts has n_runs+1 entries. */
 int pasio_contig_load_rle(pasio_ctx *ctx, const int64_t *starts, const int64_t *values,
                           int64_t n_runs, const int64_t *offsets, int64_t n_contigs);
+/* pasio_contig_load of ONE contig fused with the first pasio_round (all positions are candidates): the counts go
+ * up in 256 MB chunks on a copy stream while the chunks that have arrived are scanned and their windows run, so the
+ * host-to-device copy hides the scan and the first round (segments_with_scores, segmentation.py:5-20, always starts
+ * from np.arange(len(counts) + 1): segmentation.py:8).  Results and state are those of pasio_contig_load followed by
+ * pasio_round.  PASIO_E_TABLE_TOO_SHORT: the contig IS loaded, no round was completed -- upload longer tables
+ * (pasio_table_need) and call pasio_round. */
+int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, int64_t n, int64_t window_size,
+                            int64_t window_shift, int constraint, int64_t *n_in, int64_t *n_out, int64_t *cells);
+
 /* Same as pasio_contig_load with the counts already resident in device memory (no copy is made;
  * the caller keeps d_counts alive and unmodified until the next load). */
 int pasio_contig_load_device(pasio_ctx *ctx, const int64_t *d_counts_device, int64_t n,

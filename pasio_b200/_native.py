@@ -34,6 +34,7 @@ SIGNATURES = {
     'pasio_table_upload': (ctypes.c_int, [_vp, ctypes.c_int, _f64p, _i64]),
     'pasio_table_need': (ctypes.c_int, [_vp, _i64p, _i64p, _i64p]),
     'pasio_contig_load': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _i64]),
+    'pasio_contig_load_round': (ctypes.c_int, [_vp, _i64p, _i64, _i64, _i64, ctypes.c_int, _i64p, _i64p, _i64p]),
     'pasio_contig_load_rle': (ctypes.c_int, [_vp, _i64p, _i64p, _i64, _i64p, _i64]),
     'pasio_contig_load_device': (ctypes.c_int, [_vp, _vp, _i64, _i64p, _i64]),
     'pasio_contig_info': (ctypes.c_int, [_vp, _i64p, _i64p, _i64p]),
@@ -234,6 +235,28 @@ class Engine(object):
         self._loaded = counts
         self._loaded_offsets = None if offsets is None else np.array(offsets, dtype=np.int64)
 
+    def load_and_round(self, counts, window_size, window_shift, constraint):
+        """load(counts) fused with the first round(): the upload overlaps the scan and the round (pasio_contig_load_round).
+        Returns (n_in, n_out, cells) of that round."""
+        assert isinstance(counts, np.ndarray)
+        assert counts.dtype == int
+        assert len(counts) > 0
+        c = np.ascontiguousarray(counts)
+        self._loaded = None
+        self._cands_obj = None
+        n_in, n_out, cells = _i64(0), _i64(0), _i64(0)
+        rc = self.lib.pasio_contig_load_round(self.ctx, _ptr(c, ctypes.c_int64), len(c), window_size, window_shift,
+                                              CONSTRAINTS[constraint], ctypes.byref(n_in), ctypes.byref(n_out),
+                                              ctypes.byref(cells))
+        if rc != E_TABLE_TOO_SHORT:
+            self._check(rc)
+        self._loaded = counts
+        self._loaded_offsets = None
+        if rc == E_TABLE_TOO_SHORT:          # the contig is loaded; longer tables, then the round on its own
+            self._grow_tables()
+            return self.round(window_size, window_shift, constraint)
+        return n_in.value, n_out.value, cells.value
+
     def load_device(self, device_ptr, n, owner=None, offsets=None):
         """counts already in HBM (int64[n] at device_ptr, e.g. a torch tensor's data_ptr()); no copy."""
         self._loaded = None
@@ -329,12 +352,19 @@ class Engine(object):
         self._check(self.lib.pasio_round_stats(self.ctx, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
-    def rounds(self, window_size, window_shift, constraint, num_rounds=None):
-        """RoundReducer loop on the device.  Returns (sizes before each round run, final count, cells)."""
+    def rounds(self, window_size, window_shift, constraint, num_rounds=None, first=None):
+        """RoundReducer loop on the device.  Returns (sizes before each round run, final count, cells).
+        first: (n_in, n_out, cells) of a first round that load_and_round already ran."""
         n, _, _ = self.info()
         limit = max(1, n if num_rounds is None else num_rounds)   # round_reducer.py:11-15
         self._cands_obj = None
         sizes, cells_total = [], 0
+        if first is not None:
+            sizes.append(first[0])
+            cells_total += first[2]
+            limit -= 1
+            if first[0] == first[1] or limit == 0:
+                return sizes, self.candidate_count(), cells_total
         while limit > 0:
             done, n_out, cells = _i64(0), _i64(0), _i64(0)
             buf = np.zeros(64, dtype=np.int64)

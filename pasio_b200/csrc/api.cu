@@ -3,6 +3,7 @@
 // All arithmetic of the hot path happens in the kernels; nothing here computes on the CPU.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -48,7 +49,7 @@ static cudaEvent_t take_event(pasio_ctx *ctx)
     return e;
 }
 
-TimingScope::TimingScope(pasio_ctx *c, int family, i64 launches) : ctx(c), idx(-1)
+TimingScope::TimingScope(pasio_ctx *c, int family, i64 launches, cudaStream_t stream) : ctx(c), idx(-1), on(stream ? stream : c->stream)
 {
     ctx->fam_launches[family] += launches;
     if (!ctx->timing) return;
@@ -56,19 +57,20 @@ TimingScope::TimingScope(pasio_ctx *c, int family, i64 launches) : ctx(c), idx(-
     s.family = family;
     s.a = take_event(ctx);
     s.b = take_event(ctx);
-    cudaEventRecord(s.a, ctx->stream);
+    cudaEventRecord(s.a, on);
     ctx->spans.push_back(s);
     idx = (int)ctx->spans.size() - 1;
 }
 TimingScope::~TimingScope()
 {
-    if (idx >= 0) cudaEventRecord(ctx->spans[idx].b, ctx->stream);
+    if (idx >= 0) cudaEventRecord(ctx->spans[idx].b, on);
 }
 
 static int resolve_spans(pasio_ctx *ctx)
 {
     if (ctx->spans.empty()) return PASIO_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream_copy) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_copy));
     for (auto &s : ctx->spans) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, s.a, s.b);
@@ -136,6 +138,7 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void **)&ctx->h_scalars, 16 * sizeof(i64)) != cudaSuccess ||
@@ -166,6 +169,8 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
+    for (auto e : ctx->chunk_events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PASIO_OK;
@@ -320,6 +325,125 @@ extern "C" int pasio_contig_load_rle(pasio_ctx *ctx, const int64_t *starts, cons
     PASIO_TRY(h2d(ctx, ctx->dpJump.p, values, (size_t)n_runs * 8));
     PASIO_TRY(launch_expand_rle(ctx, ctx->dpP.as<i64>(), ctx->dpJump.as<i64>(), n_runs));
     return finish_load(ctx, offsets, n_contigs);
+}
+
+
+static int refresh_boundary_ranks(pasio_ctx *ctx);
+
+// Load one contig from host memory AND run the first sliding-window round (all positions are candidates) while the
+// upload is still in flight: the counts go up in chunks on a copy stream; as soon as a chunk has arrived its tiles
+// are scanned and the windows that lie completely inside the scanned prefix are processed.
+extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, int64_t n, int64_t window_size,
+                                       int64_t window_shift, int constraint, int64_t *n_in, int64_t *n_out, int64_t *cells)
+{
+    NEED_CTX(ctx);
+    if (!counts) return pasio_fail(ctx, PASIO_E_ARG, "counts is NULL");
+    if (window_size < 1 || window_shift < 1 || window_size > 2147483000LL || window_shift > 2147483000LL)
+        return pasio_fail(ctx, PASIO_E_ARG, "window_size and window_shift must be positive");
+    if (constraint < 0 || constraint > 2) return pasio_fail(ctx, PASIO_E_ARG, "unknown constraint %d", constraint);
+    PASIO_TRY(check_load_args(ctx, n, nullptr, 1));
+    ctx->n = n;
+    drop_borrowed_counts(ctx);
+    PASIO_TRY(pasio_reserve(ctx, ctx->counts, (size_t)n * 8 + 16));
+    ctx->h_bounds.assign({0, (int32_t)n});
+    ctx->n_contigs = 1;
+    const size_t bit_alloc = (size_t)((n + 1 + 4095) / 4096) * 512 + 16;
+    PASIO_TRY(pasio_reserve(ctx, ctx->cg, (size_t)(n + 2) * 8));
+    PASIO_TRY(pasio_reserve(ctx, ctx->cpbits, bit_alloc));
+    PASIO_TRY(pasio_reserve(ctx, ctx->keepbits, bit_alloc));
+    PASIO_TRY(pasio_reserve(ctx, ctx->bounds, 2 * 4));
+    PASIO_TRY(pasio_reserve(ctx, ctx->brank, 2 * 4));
+    PASIO_TRY(h2d(ctx, ctx->bounds.p, ctx->h_bounds.data(), 2 * 4));
+    const size_t bit_bytes = (size_t)((n + 1 + 31) / 32 + 2) * 4;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->keepbits.p, 0, bit_bytes, ctx->stream));
+    i64 n_tiles = 0, tile_elems = 0;
+    PASIO_TRY(launch_scan_prepare(ctx, &n_tiles, &tile_elems));
+    ctx->implicit_all = true;
+    ctx->m = n + 1;
+    ctx->cur = 0;
+    ctx->n_small = ctx->n_medium = ctx->n_large = -1;
+
+    // chunk copies are queued two ahead of the chunk being processed: a pinned source keeps the link busy back to
+    // back, a pageable source (whose staging blocks the host) is staged while the GPU works on the chunks before it
+    const i64 chunk_tiles = (i64)(32 << 20) / tile_elems;              // 32 Mi positions = 256 MB per chunk
+    const i64 n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+    while ((i64)ctx->chunk_events.size() < n_chunks) {
+        cudaEvent_t e;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(e);
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));          // buffers may still be in use by earlier work
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_fork, 0));
+    i64 queued = 0;
+    auto queue_copies = [&](i64 upto) -> int {
+        for (; queued < upto && queued < n_chunks; ++queued) {
+            const i64 e0 = queued * chunk_tiles * tile_elems, e1 = std::min<i64>(n, (queued + 1) * chunk_tiles * tile_elems);
+            if (e1 > e0) {
+                TimingScope ts(ctx, TF_H2D, 1, ctx->stream_copy);
+                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->counts.as<i64>() + e0, counts + e0, (size_t)(e1 - e0) * 8,
+                                              cudaMemcpyHostToDevice, ctx->stream_copy));
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_events[(size_t)queued], ctx->stream_copy));
+        }
+        return PASIO_OK;
+    };
+
+    const i64 nwin_total = (ctx->m - 1 + window_shift - 1) / window_shift;
+    i64 w_done = 0;
+    int table_rc = ctx->have_params ? PASIO_OK : pasio_fail(ctx, PASIO_E_STATE, "pasio_set_params has not been called");
+    bool first_dp = true;
+    for (i64 c = 0; c < n_chunks; ++c) {
+        PASIO_TRY(queue_copies(c + 3));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[(size_t)c], 0));
+        const i64 t1 = std::min<i64>(n_tiles, (c + 1) * chunk_tiles);
+        PASIO_TRY(launch_scan_tiles(ctx, t1 - c * chunk_tiles));
+        // positions < scanned are final (prefix sums and change-point bits); the last chunk covers position n as well
+        const i64 scanned = t1 * tile_elems;
+        i64 w_ready = nwin_total;
+        if (c + 1 < n_chunks) {
+            w_ready = scanned > window_size ? (scanned - window_size - 1) / window_shift + 1 : 0;
+            if (w_ready > nwin_total) w_ready = nwin_total;
+        }
+        if (table_rc == PASIO_OK && w_ready > w_done) {
+            i64 max_span = 0, max_cnt = 0;
+            PASIO_TRY(launch_window_prepass(ctx, w_ready - w_done, (int)window_size, (int)window_shift, &max_span, &max_cnt,
+                                            constraint, w_done));
+            table_rc = check_dp_tables(ctx, max_span, max_cnt);
+            if (table_rc == PASIO_OK) {
+                PASIO_TRY(launch_window_dp(ctx, w_ready - w_done, (int)window_size, (int)window_shift, constraint, w_done,
+                                           !first_dp));
+                first_dp = false;
+            } else if (table_rc != PASIO_E_TABLE_TOO_SHORT) {
+                return table_rc;
+            }
+            w_done = w_ready;
+        }
+    }
+    PASIO_TRY(d2h(ctx, ctx->h_scalars, ctx->scalars.p, 2 * sizeof(i64)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_copy));
+    if (ctx->h_scalars[1]) return pasio_fail(ctx, PASIO_E_COUNTS, "counts must be >= 0");
+    ctx->total = ctx->h_scalars[0];
+    ctx->have_contig = true;
+    PASIO_TRY(launch_boundary_ranks(ctx));
+    ctx->h_brank = ctx->h_bounds;
+    if (n_in) *n_in = ctx->m;
+    if (n_out) *n_out = ctx->m;
+    if (cells) *cells = 0;
+    if (table_rc != PASIO_OK) return table_rc;        // the contig is loaded: grow the tables, then pasio_round
+
+    const int nxt = 1 - ctx->cur;
+    PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)ctx->m * 4));
+    i64 m_new = 0;
+    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    PASIO_TRY(d2h(ctx, ctx->h_scalars + 10, ctx->scalars.as<i64>() + 10, 24));
+    if (cells) *cells = ctx->h_scalars[10];
+    ctx->last_cells = ctx->h_scalars[10];
+    ctx->last_cells_skipped = ctx->h_scalars[12];
+    ctx->cur = nxt;
+    ctx->implicit_all = false;
+    ctx->m = m_new;
+    if (n_out) *n_out = m_new;
+    return refresh_boundary_ranks(ctx);
 }
 
 extern "C" int pasio_contig_info(const pasio_ctx *ctx, int64_t *n, int64_t *total_count, int64_t *n_contigs)

@@ -33,6 +33,8 @@ struct pasio_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;      // side stream: the warp-per-window kernels run beside the CTA-per-window kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream_copy = nullptr;  // host->device chunks of pasio_contig_load_round
+    std::vector<cudaEvent_t> chunk_events;
     std::string err;
 
     // scorer parameters (log_marginal_likelyhood.py:6-16,62)
@@ -107,7 +109,8 @@ int pasio_reserve(pasio_ctx *ctx, DevBuf &b, size_t bytes);   // grow-only; retu
 struct TimingScope {
     pasio_ctx *ctx;
     int idx;
-    TimingScope(pasio_ctx *c, int family, i64 launches = 1);
+    cudaStream_t on;
+    TimingScope(pasio_ctx *c, int family, i64 launches = 1, cudaStream_t stream = nullptr);
     ~TimingScope();
 };
 
@@ -115,6 +118,8 @@ struct TimingScope {
 
 // scan.cu
 int launch_scan_counts(pasio_ctx *ctx);                       // counts -> cg, cpbits, validation, total
+int launch_scan_prepare(pasio_ctx *ctx, i64 *n_tiles, i64 *tile_elems);   // the same in pieces: reset the tile states ...
+int launch_scan_tiles(pasio_ctx *ctx, i64 tiles);             // ... then the next `tiles` tiles, in order
 int launch_expand_rle(pasio_ctx *ctx, const i64 *d_starts, const i64 *d_values, i64 n_runs);
 int launch_logfac_scan(pasio_ctx *ctx, double *d_out);        // float64 prefix sums of G[counts+1], n+1 entries
 
@@ -123,14 +128,15 @@ int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count);  // k
 int launch_boundary_ranks(pasio_ctx *ctx);                    // brank from current candidates
 // classify_constraint >= 0: also sort the windows into ctx->win_small / win_large (n_small, n_large) for launch_window_dp
 int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt,
-                          int classify_constraint = -1);  // syncs
+                          int classify_constraint = -1, i64 w_begin = 0);  // windows [w_begin, w_begin + nwin); syncs
 int small_window_max_candidates();                           // window_dp.cu: most candidates the warp-per-window kernels take
 int medium_window_max_candidates();
 int launch_validate_candidates(pasio_ctx *ctx, i64 *h_bad);   // syncs
 int launch_filter_candidates(pasio_ctx *ctx, int constraint);  // current candidates -> keepbits
 
 // window_dp.cu
-int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constraint);
+int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constraint, i64 w_begin = 0,
+                     bool keep_cell_counters = false);   // windows [w_begin, w_begin + nwin)
 int window_dp_max_candidates(pasio_ctx *ctx);
 
 // exact_dp.cu

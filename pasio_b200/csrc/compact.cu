@@ -117,14 +117,15 @@ __global__ void boundary_ranks_kernel(const int32_t *__restrict__ cand, i64 m,
 // largest window span (nt) and window count: the table lengths a round needs.  Optionally sorts the windows into
 // two work lists by an upper bound of their candidate count after the constraint filter: small windows go to the
 // warp-per-window kernel, the others to the CTA-per-window kernel (window_dp.cu).
-__global__ void window_prepass_kernel(WinGeom g, i64 nwin, const int32_t *__restrict__ cand,
+__global__ void window_prepass_kernel(WinGeom g, i64 w_begin, i64 nwin, const int32_t *__restrict__ cand,
                                       const i64 *__restrict__ cg, u64 *out /* [0]=span, [1]=count */,
                                       const uint32_t *__restrict__ cpbits, int constraint, int small_max, int medium_max,
                                       int32_t *__restrict__ small_list, int32_t *__restrict__ medium_list,
                                       int32_t *__restrict__ large_list, unsigned *list_counts /* [0]=small, [1]=medium, [2]=large */)
 {
     i64 span = 0, cnt = 0;
-    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < nwin; w += (i64)gridDim.x * blockDim.x) {
+    for (i64 wi = (i64)blockIdx.x * blockDim.x + threadIdx.x; wi < nwin; wi += (i64)gridDim.x * blockDim.x) {
+        const i64 w = w_begin + wi;
         i64 st, en;
         window_range(g, w, st, en);
         i64 a = cand ? __ldg(cand + st) : st;
@@ -258,14 +259,14 @@ int launch_boundary_ranks(pasio_ctx *ctx)
 }
 
 int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt,
-                          int classify_constraint)
+                          int classify_constraint, i64 w_begin)
 {
     u64 *d_out = ctx->scalars.as<u64>() + 6;
     CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, 16, ctx->stream));
     unsigned *d_counts = ctx->scalars.as<unsigned>() + 2 * 13;      // scalars[13], [14]: small / medium / large list lengths
     const bool classify = classify_constraint >= 0;
     if (classify) {
-        if (nwin > 2147483647LL) return pasio_fail(ctx, PASIO_E_TOO_LARGE, "too many windows");
+        if (w_begin + nwin > 2147483647LL) return pasio_fail(ctx, PASIO_E_TOO_LARGE, "too many windows");
         PASIO_TRY(pasio_reserve(ctx, ctx->win_small, (size_t)nwin * 4));
         PASIO_TRY(pasio_reserve(ctx, ctx->win_medium, (size_t)nwin * 4));
         PASIO_TRY(pasio_reserve(ctx, ctx->win_large, (size_t)nwin * 4));
@@ -277,7 +278,7 @@ int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *
     {
         TimingScope ts(ctx, TF_COMPACT);
         window_prepass_kernel<<<blocks, 256, 0, ctx->stream>>>(
-            make_geom(ctx, wsize, wshift), nwin, cur_cand(ctx), ctx->cg.as<i64>(), d_out, ctx->cpbits.as<uint32_t>(),
+            make_geom(ctx, wsize, wshift), w_begin, nwin, cur_cand(ctx), ctx->cg.as<i64>(), d_out, ctx->cpbits.as<uint32_t>(),
             classify_constraint, small_window_max_candidates(), medium_window_max_candidates(),
             classify ? ctx->win_small.as<int32_t>() : nullptr, classify ? ctx->win_medium.as<int32_t>() : nullptr,
             classify ? ctx->win_large.as<int32_t>() : nullptr, d_counts);

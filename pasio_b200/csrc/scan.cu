@@ -278,23 +278,40 @@ __global__ void max_count_kernel(const i64 *__restrict__ counts, i64 n, u64 *out
 
 }  // namespace
 
-int launch_scan_counts(pasio_ctx *ctx)
+int launch_scan_prepare(pasio_ctx *ctx, i64 *n_tiles, i64 *tile_elems)
 {
     const i64 n = ctx->n;
     const i64 tiles = (n + 1 + SCAN_TILE - 1) / SCAN_TILE;    // positions 0..n
     PASIO_TRY(pasio_reserve(ctx, ctx->tilestate, (size_t)(tiles + 1) * 8 + 16));
-    u64 *state = ctx->tilestate.as<u64>() + 2;
-    unsigned *counter = ctx->tilestate.as<unsigned>();
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->tilestate.p, 0, (size_t)(tiles + 1) * 8 + 16, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(i64), ctx->stream));
+    if (n_tiles) *n_tiles = tiles;
+    if (tile_elems) *tile_elems = SCAN_TILE;
+    return PASIO_OK;
+}
+
+// The next `tiles` tiles: CTAs take consecutive tile numbers from the counter in the tile-state buffer, so
+// successive launches continue where the previous one stopped and look back into its finished tiles.
+int launch_scan_tiles(pasio_ctx *ctx, i64 tiles)
+{
+    if (tiles <= 0) return PASIO_OK;
+    u64 *state = ctx->tilestate.as<u64>() + 2;
+    unsigned *counter = ctx->tilestate.as<unsigned>();
     {
         TimingScope ts(ctx, TF_SCAN);
         scan_counts_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(
-            ctx->counts.as<i64>(), n, ctx->cg.as<i64>(), ctx->cpbits.as<u64>(), state, counter,
+            ctx->counts.as<i64>(), ctx->n, ctx->cg.as<i64>(), ctx->cpbits.as<u64>(), state, counter,
             ctx->scalars.as<i64>());
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return PASIO_OK;
+}
+
+int launch_scan_counts(pasio_ctx *ctx)
+{
+    i64 tiles = 0;
+    PASIO_TRY(launch_scan_prepare(ctx, &tiles, nullptr));
+    return launch_scan_tiles(ctx, tiles);
 }
 
 int launch_expand_rle(pasio_ctx *ctx, const i64 *d_starts, const i64 *d_values, i64 n_runs)

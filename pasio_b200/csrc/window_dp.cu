@@ -79,7 +79,8 @@ struct WinDpParams {
     u64 *cells;                 // algorithmic cells N(N-1)/2
     u64 *cells_skipped;         // cells proven irrelevant by the far-column bound (0 without pruning)
     unsigned *work_counter;
-    const int32_t *list;        // window numbers to process (nwin of them); nullptr: 0 .. nwin-1
+    const int32_t *list;        // window numbers to process (nwin of them); nullptr: w_begin .. w_begin+nwin-1
+    i64 w_begin;
 };
 
 // One finished block of 32 columns [1+32b, 32+32b], as the far pass sees it.
@@ -546,7 +547,7 @@ window_dp_kernel(WinDpParams p)
         __syncthreads();
         const i64 widx = (unsigned)sMisc[0];
         if (widx >= p.nwin) break;
-        const i64 w = p.list ? (i64)__ldg(p.list + widx) : widx;
+        const i64 w = p.list ? (i64)__ldg(p.list + widx) : p.w_begin + widx;
 
         // ---- (A) candidates of the window, filtered, re-based ---------------------------------
         i64 st, en;
@@ -922,7 +923,7 @@ int window_dp_max_candidates(pasio_ctx *ctx)
     return cap;
 }
 
-int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constraint)
+int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constraint, i64 w_begin, bool keep_cell_counters)
 {
     WinDpParams p;
     p.geom = make_geom(ctx, wsize, wshift);
@@ -946,7 +947,9 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     p.cells = ctx->scalars.as<u64>() + 10;
     p.cells_skipped = ctx->scalars.as<u64>() + 12;
     p.work_counter = ctx->scalars.as<unsigned>() + 2 * 11;   // scalars[11]
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 10, 0, 24, ctx->stream));
+    p.w_begin = w_begin;
+    if (keep_cell_counters) CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 11, 0, 8, ctx->stream));   // work counter only
+    else CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 10, 0, 24, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 15, 0, 8, ctx->stream));    // work counters of the warp-per-window kernels
 
     // the work lists of the prepass (launch_window_prepass with classification): small windows first, one warp each

@@ -6,6 +6,8 @@ np.arange(n+1), 2 GB for chr1), rounds / exact DP run back to back, and only the
 and per-segment outputs are copied back.  Any other splitter object is driven through the
 reference's own protocol.
 """
+import os
+
 import numpy as np
 
 from . import _native
@@ -14,14 +16,17 @@ from .dto.intervals import ScoredInterval
 from .splitters import _fusion
 
 
-def _run_device_pipeline(eng, plan):
-    """Run the device steps of a pipeline plan on the loaded batch.  Returns (score or None, splits)."""
+def _run_device_pipeline(eng, plan, first=None):
+    """Run the device steps of a pipeline plan on the loaded batch.  Returns (score or None, splits).
+    first: result of the first step's first round when the load already ran it (Engine.load_and_round)."""
     score = None
-    for step in plan['steps']:
+    for k, step in enumerate(plan['steps']):
+        if k == 0 and first is not None and step[0] == 'window':
+            continue
         if step[0] == 'rounds':
             _, factory, size, shift, constraint, num_rounds = step
             eng.use_scorer(factory)
-            sizes, final, _ = eng.rounds(size, shift, constraint, num_rounds)
+            sizes, final, _ = eng.rounds(size, shift, constraint, num_rounds, first=first if k == 0 else None)
             from .splitters.round_reducer import _log_rounds
             _log_rounds(sizes, final)
         else:
@@ -34,11 +39,12 @@ def _run_device_pipeline(eng, plan):
     return score
 
 
-def run_loaded_pipeline(eng, plan, want_lmm=True):
+def run_loaded_pipeline(eng, plan, want_lmm=True, first=None):
     """The device pipeline over whatever contig the engine has loaded (dense, RLE or device-resident).
     -> (score, splits, mean_counts, log_marginal_likelyhoods or None, sum_logfac or None)"""
-    eng.set_candidates(None)                      # split_candidates = all positions (reference :8)
-    score = _run_device_pipeline(eng, plan)
+    if first is None:
+        eng.set_candidates(None)                  # split_candidates = all positions (reference :8)
+    score = _run_device_pipeline(eng, plan, first)
     splits = eng.candidates()
     scores, _, means, _ = eng.segment_scores(scores=True, means=True)
     if plan['final'] == 'nop':
@@ -50,6 +56,14 @@ def run_loaded_pipeline(eng, plan, want_lmm=True):
 def segment_on_device(counts, plan, want_lmm=True):
     """-> (score, splits, mean_counts, log_marginal_likelyhoods or None, sum_logfac or None)"""
     eng = _native.engine()
+    steps = plan['steps']
+    if (steps and steps[0][0] in ('rounds', 'window') and isinstance(counts, np.ndarray)
+            and not os.environ.get('PASIO_B200_NO_FUSED_LOAD')):      # (switch for A/B measurements)
+        # the first round always starts from all positions: run it while the counts are still going up
+        _, factory, size, shift, constraint = steps[0][:5]
+        eng.use_scorer(factory)
+        first = eng.load_and_round(counts, size, shift, constraint)
+        return run_loaded_pipeline(eng, plan, want_lmm, first=first)
     eng.use_scorer(plan['factory'])
     eng.load(counts)
     return run_loaded_pipeline(eng, plan, want_lmm)

@@ -318,6 +318,45 @@ def test_window_size_class_edges(eng, wsize, explicit):
         cands = want
 
 
+@pytest.mark.parametrize('n,constraint', [(70000, 'constants'), (5000000, 'constants'), (40000000, 'constants'),
+                                          (300000, 'none'), (300000, 'zeros')])
+def test_load_and_round_equals_load_then_round(eng, n, constraint):
+    """pasio_contig_load_round (chunked upload overlapped with the scan and the first round; 40 Mb = two chunks)
+    gives the state and the candidates of pasio_contig_load + pasio_round, and the rounds after it agree too"""
+    counts = synth.dnase_like(n, 77, hotspot_share=0.2)
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.invalidate()
+    eng.load(counts)
+    eng.set_candidates(None)
+    a_in, a_out, a_cells = eng.round(2500, 1250, constraint)
+    want1 = eng.candidates().copy()
+    sizes_a, final_a, _ = eng.rounds(2500, 1250, constraint)
+    want = eng.candidates().copy()
+    total_a = eng.info()[1]
+    eng.invalidate()
+    first = eng.load_and_round(counts, 2500, 1250, constraint)
+    assert first == (a_in, a_out, a_cells)
+    assert eng.info() == (n, total_a, 1)
+    assert np.array_equal(eng.candidates(), want1)
+    sizes_b, final_b, _ = eng.rounds(2500, 1250, constraint, first=first)
+    assert sizes_b == [a_in] + sizes_a and final_b == final_a
+    assert np.array_equal(eng.candidates(), want)
+
+
+def test_load_and_round_asserts_and_table_growth(eng):
+    """negative counts still raise; a first round that needs longer tables falls back to load + grow + round"""
+    eng.use_scorer(ScorerFactory(1.0, 1.0))            # fresh factory: tables at their initial 2^20 entries
+    bad = np.ones(5000, dtype=np.int64)
+    bad[1234] = -1
+    with pytest.raises(AssertionError):
+        eng.load_and_round(bad, 2500, 1250, 'constants')
+    deep = np.repeat(np.random.RandomState(3).poisson(900, 4000), 25).astype(np.int64)      # window counts > 2^20
+    fo = c_oracle.FlatOracle(deep, 1.0, 1.0)
+    first = eng.load_and_round(deep, 2500, 1250, 'constants')
+    want, cells = fo.round(np.arange(len(deep) + 1, dtype=np.int64), 2500, 1250, 'constants')
+    assert np.array_equal(eng.candidates(), want) and first == (len(deep) + 1, len(want), cells)
+
+
 def test_timing_hooks(eng):
     counts = synth.dnase_like(100000, 9, hotspot_share=0.3)
     eng.use_scorer(factory(1.0, 1.0))
