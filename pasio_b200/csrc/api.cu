@@ -136,8 +136,10 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // main stream: highest priority, side stream: lowest
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, 0) != cudaSuccess ||      // (lowest priority)
         cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -159,7 +161,7 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     drop_borrowed_counts(ctx);
     DevBuf *bufs[] = {&ctx->tab[0], &ctx->tab[1], &ctx->tab[2], &ctx->counts, &ctx->cg, &ctx->cpbits, &ctx->keepbits,
-                      &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large,
+                      &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large, &ctx->win_flags,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
                       &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);

@@ -70,8 +70,10 @@ struct pasio_ctx {
 
     // per-round window table for batches (n_contigs > 1)
     DevBuf win_st, win_en;
+    DevBuf win_flags;            // per window of the round (index relative to w_begin): 1 once a phase-1 window of the CTA kernel is done (others start at 1)
     DevBuf win_small, win_medium, win_large;  // per-round work lists of window numbers (small / medium: warp per window, large: CTA per window)
     i64 n_small = 0, n_medium = 0, n_large = 0;
+    i64 n_large_p1 = 0;          // win_large[0 .. n_large_p1) are phase-1 windows, the rest (filled from the back of the nwin-long buffer) phase 2
     std::vector<int32_t> h_win_st, h_win_en, h_brank;
 
     // scratch

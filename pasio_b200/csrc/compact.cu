@@ -121,7 +121,8 @@ __global__ void window_prepass_kernel(WinGeom g, i64 w_begin, i64 nwin, const in
                                       const i64 *__restrict__ cg, u64 *out /* [0]=span, [1]=count */,
                                       const uint32_t *__restrict__ cpbits, int constraint, int small_max, int medium_max,
                                       int32_t *__restrict__ small_list, int32_t *__restrict__ medium_list,
-                                      int32_t *__restrict__ large_list, unsigned *list_counts /* [0]=small, [1]=medium, [2]=large */)
+                                      int32_t *__restrict__ large_list, int p1_stride, unsigned char *__restrict__ done_flags,
+                                      unsigned *list_counts /* [0]=small, [1]=medium, [2]=large phase 1, [3]=large phase 2 */)
 {
     i64 span = 0, cnt = 0;
     for (i64 wi = (i64)blockIdx.x * blockDim.x + threadIdx.x; wi < nwin; wi += (i64)gridDim.x * blockDim.x) {
@@ -144,9 +145,12 @@ __global__ void window_prepass_kernel(WinGeom g, i64 w_begin, i64 nwin, const in
                     est += __popc(x);
                 }
             }
+            const bool large_p1 = est > medium_max && (p1_stride <= 1 || w % p1_stride == 0);
+            done_flags[wi] = large_p1 ? 0 : 1;          // a phase-2 window waits for the phase-1 windows next to it; others never block it
             if (est <= small_max) small_list[atomicAdd(list_counts, 1u)] = (int32_t)w;
             else if (est <= medium_max) medium_list[atomicAdd(list_counts + 1, 1u)] = (int32_t)w;
-            else large_list[atomicAdd(list_counts + 2, 1u)] = (int32_t)w;
+            else if (p1_stride <= 1 || w % p1_stride == 0) large_list[atomicAdd(list_counts + 2, 1u)] = (int32_t)w;   // from the front
+            else large_list[nwin - 1 - atomicAdd(list_counts + 3, 1u)] = (int32_t)w;                               // from the back
         }
     }
 #pragma unroll
@@ -270,6 +274,7 @@ int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *
         PASIO_TRY(pasio_reserve(ctx, ctx->win_small, (size_t)nwin * 4));
         PASIO_TRY(pasio_reserve(ctx, ctx->win_medium, (size_t)nwin * 4));
         PASIO_TRY(pasio_reserve(ctx, ctx->win_large, (size_t)nwin * 4));
+        PASIO_TRY(pasio_reserve(ctx, ctx->win_flags, (size_t)nwin + 16));
         CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, 16, ctx->stream));
     }
     unsigned blocks = (unsigned)((nwin + 255) / 256);
@@ -281,7 +286,10 @@ int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *
             make_geom(ctx, wsize, wshift), w_begin, nwin, cur_cand(ctx), ctx->cg.as<i64>(), d_out, ctx->cpbits.as<uint32_t>(),
             classify_constraint, small_window_max_candidates(), medium_window_max_candidates(),
             classify ? ctx->win_small.as<int32_t>() : nullptr, classify ? ctx->win_medium.as<int32_t>() : nullptr,
-            classify ? ctx->win_large.as<int32_t>() : nullptr, d_counts);
+            classify ? ctx->win_large.as<int32_t>() : nullptr,
+            // phase 1 = every (size / shift)-th window: together they cover every candidate; a phase-2 window whose
+            // candidates all survived phase 1 cannot add a survivor (window_dp.cu).  Explicit candidate lists only.
+            (cur_cand(ctx) && wshift > 0) ? wsize / wshift : 0, classify ? ctx->win_flags.as<unsigned char>() : nullptr, d_counts);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 6, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -293,7 +301,8 @@ int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *
         const unsigned *c = reinterpret_cast<const unsigned *>(ctx->h_scalars + 13);
         ctx->n_small = c[0];
         ctx->n_medium = c[1];
-        ctx->n_large = c[2];
+        ctx->n_large = (i64)c[2] + (i64)c[3];
+        ctx->n_large_p1 = c[2];
     }
     return PASIO_OK;
 }

@@ -81,6 +81,13 @@ struct WinDpParams {
     unsigned *work_counter;
     const int32_t *list;        // window numbers to process (nwin of them); nullptr: w_begin .. w_begin+nwin-1
     i64 w_begin;
+    // two phases (CTA kernel): list[0 .. n_p1) first; the other nwin - n_p1 windows (stored from the END of the
+    // list_len-long list backwards) start once all of phase 1 is done and are skipped if every one of their candidates
+    // already survived
+    i64 n_p1, list_len;
+    unsigned char *done_flags;  // [list_len], index = window number - w_begin
+    int p1_stride;
+    int skip_covered;           // 0: phase-2 windows neither wait nor get skipped (experiments)
 };
 
 // One finished block of 32 columns [1+32b, 32+32b], as the far pass sees it.
@@ -547,7 +554,22 @@ window_dp_kernel(WinDpParams p)
         __syncthreads();
         const i64 widx = (unsigned)sMisc[0];
         if (widx >= p.nwin) break;
-        const i64 w = p.list ? (i64)__ldg(p.list + widx) : p.w_begin + widx;
+        const bool second = widx >= p.n_p1;          // stored from the back of the list
+        const bool phase2 = second && p.skip_covered;
+        const i64 w = !p.list ? p.w_begin + widx
+                              : (second ? (i64)__ldg(p.list + (p.list_len - 1 - (widx - p.n_p1))) : (i64)__ldg(p.list + widx));
+        if (phase2) {
+            // wait for the phase-1 windows on both sides (they overlap this one).  Every phase-1 window was handed out
+            // before this one, so each is finished or being worked on: no deadlock.
+            if (tid == 0) {
+                const i64 rel = w - p.w_begin, lo = rel - rel % p.p1_stride, hi = lo + p.p1_stride;
+                const volatile unsigned char *f = p.done_flags;
+                while (!f[lo] || (hi < p.list_len && !f[hi])) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        int kept_all = 1;                           // phase 2: are all candidates of this window survivors already?
 
         // ---- (A) candidates of the window, filtered, re-based ---------------------------------
         i64 st, en;
@@ -610,6 +632,7 @@ window_dp_kernel(WinDpParams p)
                 if (q == 0 || q == nq - 1 || p.constraint == PASIO_CONSTRAINT_NONE) take = true;
                 else if (p.constraint == PASIO_CONSTRAINT_CONSTANTS) take = bit_test(p.cpbits, pos);
                 else take = !all_zero;
+                if (phase2 && !((__ldcg(p.keepbits + (pos >> 5)) >> (pos & 31)) & 1u)) kept_all = 0;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, take);
             if (lane == 0) sMisc[4 + warp] = __popc(bal);
@@ -631,6 +654,16 @@ window_dp_kernel(WinDpParams p)
         }
         const int N = count;
         PROF_T(0);
+        if (phase2 && __syncthreads_and(kept_all)) {
+            // the window's survivors are a subset of its candidates, and those are all marked: nothing to add
+            // (sliding_window_reducer.py:22-29 takes the UNION over the windows).  Its cells count as skipped.
+            if (tid == 0) {
+                const u64 c = (u64)N * (u64)(N - 1) / 2;
+                atomicAdd(p.cells, c);
+                atomicAdd(p.cells_skipped, c);
+            }
+            continue;
+        }
 
         // ---- (B) DP ---------------------------------------------------------------------------
         if (tid == 0) { sCol[0].P = 0.0; sPrev[0] = 0; }
@@ -739,6 +772,14 @@ window_dp_kernel(WinDpParams p)
             if (sMark[k]) {
                 const i64 pos = first + sCol[k].L;
                 atomicOr(p.keepbits + (pos >> 5), 1u << (pos & 31));
+            }
+        }
+        if (!second && p.skip_covered && p.n_p1 < p.nwin) {             // phase-2 windows wait for this
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                *reinterpret_cast<volatile unsigned char *>(p.done_flags + (w - p.w_begin)) = 1;
             }
         }
         if (tid == 0) atomicAdd(p.cells, (u64)N * (u64)(N - 1) / 2);
@@ -952,68 +993,94 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     else CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 10, 0, 24, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.as<u64>() + 15, 0, 8, ctx->stream));    // work counters of the warp-per-window kernels
 
-    // the work lists of the prepass (launch_window_prepass with classification): small windows first, one warp each
+    // The work lists of the prepass (launch_window_prepass with classification).  The CTA-per-window kernel is
+    // submitted first, on the main (high-priority) stream; the warp-per-window kernels follow on the low-priority side
+    // stream and fill the SMs as the persistent CTAs of the big kernel run out of windows.  All of them only OR bits
+    // into the survivor bitmap.
     static const int small_env = getenv("PASIO_WD_SMALL") ? atoi(getenv("PASIO_WD_SMALL")) : 1;
-    const bool use_lists = ctx->n_small + ctx->n_medium + ctx->n_large == nwin;
-    i64 n_large = nwin;
-    p.list = nullptr;
-    if (use_lists && small_env) {
-        auto launch_small = [&](auto kern, const int32_t *list, i64 n, int nwarps, int ctas, size_t smem_bytes, unsigned *counter) -> int {
-            if (n <= 0) return PASIO_OK;
-            WinDpParams ps = p;
-            ps.list = list;
-            ps.nwin = n;
-            ps.work_counter = counter;
-            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-            i64 g = (n + nwarps - 1) / nwarps;
-            if (g > (i64)ctx->sm_count * ctas) g = (i64)ctx->sm_count * ctas;
-            TimingScope ts(ctx, TF_WINDOW_DP);
-            kern<<<(unsigned)g, nwarps * 32, smem_bytes, ctx->stream>>>(ps);
-            CUDA_TRY(ctx, cudaGetLastError());
-            return PASIO_OK;
-        };
+    static const int phase_env = getenv("PASIO_WD_PHASES") ? atoi(getenv("PASIO_WD_PHASES")) : 1;
+    const bool use_lists = small_env && ctx->n_small + ctx->n_medium + ctx->n_large == nwin;
+    const i64 n_small = use_lists ? ctx->n_small : 0, n_medium = use_lists ? ctx->n_medium : 0;
+    const i64 n_large = use_lists ? ctx->n_large : nwin;
+    p.list = use_lists ? ctx->win_large.as<int32_t>() : nullptr;     // PASIO_WD_SMALL=0 (experiments): every window through the CTA kernel
+    p.nwin = n_large;
+    p.list_len = nwin;
+    p.n_p1 = use_lists ? ctx->n_large_p1 : n_large;
+    p.skip_covered = phase_env;                                       // PASIO_WD_PHASES=0 (experiments): no window is skipped
+    p.done_flags = ctx->win_flags.as<unsigned char>();
+    p.p1_stride = wshift > 0 && wsize / wshift > 1 ? wsize / wshift : 1;
+    if (!use_lists) p.skip_covered = 0;
+    ctx->n_small = ctx->n_medium = ctx->n_large = ctx->n_large_p1 = -1;           // the lists are consumed
+    TimingScope ts_all(ctx, TF_WINDOW_DP, 0);      // one span over all window kernels of the round (they overlap)
+    // a handful of small windows (the tail windows of the later rounds) run beside the big kernel on the side stream;
+    // when there are many (round 1) the kernels are faster one after the other, the longest chains first
+    const bool fork = n_small + n_medium > 0 && n_small + n_medium <= 64;
+    const bool serial_small = n_small + n_medium > 64;
+    if (fork) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));        // the side stream waits for the resets only
+
+    auto launch_small = [&](auto kern, const int32_t *list, i64 n, int nwarps, int ctas, size_t smem_bytes, unsigned *counter,
+                            cudaStream_t stream) -> int {
+        if (n <= 0) return PASIO_OK;
+        WinDpParams ps = p;
+        ps.list = list;
+        ps.nwin = n;
+        ps.n_p1 = n;
+        ps.work_counter = counter;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        i64 g = (n + nwarps - 1) / nwarps;
+        if (g > (i64)ctx->sm_count * ctas) g = (i64)ctx->sm_count * ctas;
+        ctx->fam_launches[TF_WINDOW_DP] += 1;
+        kern<<<(unsigned)g, nwarps * 32, smem_bytes, stream>>>(ps);
+        CUDA_TRY(ctx, cudaGetLastError());
+        return PASIO_OK;
+    };
+    auto launch_small_kernels = [&](cudaStream_t stream) -> int {
         unsigned *c_small = ctx->scalars.as<unsigned>() + 2 * 15, *c_medium = c_small + 1;     // scalars[15]
         const size_t sm_small = sizeof(SmallWin<SW_SMALL_N>) * SW_SMALL_WARPS, sm_medium = sizeof(SmallWin<SW_MEDIUM_N>) * SW_MEDIUM_WARPS;
         if (ctx->alpha_is_int) {
             PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS>, ctx->win_small.as<int32_t>(),
-                                   ctx->n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small));
+                                   n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small, stream));
             PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS>, ctx->win_medium.as<int32_t>(),
-                                   ctx->n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium));
+                                   n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium, stream));
         } else {
             PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS>, ctx->win_small.as<int32_t>(),
-                                   ctx->n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small));
+                                   n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small, stream));
             PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS>, ctx->win_medium.as<int32_t>(),
-                                   ctx->n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium));
+                                   n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium, stream));
         }
-        p.list = ctx->win_large.as<int32_t>();
-        n_large = ctx->n_large;
-    }                                           // PASIO_WD_SMALL=0 (experiments): every window through the CTA kernel
-    ctx->n_small = ctx->n_medium = ctx->n_large = -1;           // the lists are consumed
-    p.nwin = n_large;
-    if (n_large == 0) return PASIO_OK;
+        return PASIO_OK;
+    };
+    if (serial_small) PASIO_TRY(launch_small_kernels(ctx->stream));
 
-    const size_t smem = window_smem_bytes(p.cap);
-    // PASIO_WD_PRUNE=0 disables the exact far-column pruning (experiments / cross-checks)
-    static const int prune_env = getenv("PASIO_WD_PRUNE") ? atoi(getenv("PASIO_WD_PRUNE")) : 1;
-    const bool prune = prune_env != 0 && ctx->alpha >= 0.0009765625;   // tiny alpha: lgamma(alpha) dwarfs the delta scale; alpha = 0: G[0] = inf
-    void (*kern)(WinDpParams);
-    if (ctx->alpha_is_int) kern = prune ? window_dp_kernel<true, 4, 2, true> : window_dp_kernel<true, 4, 2, false>;
-    else kern = prune ? window_dp_kernel<false, 4, 2, true> : window_dp_kernel<false, 4, 2, false>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
+    i64 grid = 0;
+    if (n_large > 0) {
+        const size_t smem = window_smem_bytes(p.cap);
+        // PASIO_WD_PRUNE=0 disables the exact far-column pruning (experiments / cross-checks)
+        static const int prune_env = getenv("PASIO_WD_PRUNE") ? atoi(getenv("PASIO_WD_PRUNE")) : 1;
+        const bool prune = prune_env != 0 && ctx->alpha >= 0.0009765625;   // tiny alpha: lgamma(alpha) dwarfs the delta scale; alpha = 0: G[0] = inf
+        void (*kern)(WinDpParams);
+        if (ctx->alpha_is_int) kern = prune ? window_dp_kernel<true, 4, 2, true> : window_dp_kernel<true, 4, 2, false>;
+        else kern = prune ? window_dp_kernel<false, 4, 2, true> : window_dp_kernel<false, 4, 2, false>;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
 #if defined(PASIO_WD_EXP) || defined(PASIO_WD_PROF)
-    if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
+        if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
 #endif
-    i64 grid = (i64)ctx->sm_count * per_sm;     // persistent CTAs: one resident wave
-    if (grid > n_large) grid = n_large;
-    if (grid < 1) grid = 1;
-    {
-        TimingScope ts(ctx, TF_WINDOW_DP);
+        grid = (i64)ctx->sm_count * per_sm;     // persistent CTAs: one resident wave
+        if (grid > n_large) grid = n_large;
+        if (grid < 1) grid = 1;
+        ctx->fam_launches[TF_WINDOW_DP] += 1;
         kern<<<(unsigned)grid, WD_THREADS, smem, ctx->stream>>>(p);
+        CUDA_TRY(ctx, cudaGetLastError());
     }
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (fork) {
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        PASIO_TRY(launch_small_kernels(ctx->stream2));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
 #ifdef PASIO_WD_PROF
     {
         cudaStreamSynchronize(ctx->stream);
