@@ -318,6 +318,28 @@ def test_window_size_class_edges(eng, wsize, explicit):
         cands = want
 
 
+@pytest.mark.parametrize('wsize,wshift', [(600, 7), (600, 199), (600, 300), (600, 301), (600, 600), (600, 1000), (2500, 100)])
+def test_window_geometry_strides(eng, wsize, wshift):
+    """window skipping (a phase-2 window all of whose candidates already survived is not computed) for shifts that
+    are not half a window: many windows per candidate, no overlap at all, gaps between windows"""
+    rs = np.random.RandomState(wsize + wshift)
+    counts = synth.dnase_like(24000 if wshift < 100 else 60000, wsize + wshift, hotspot_share=0.4)
+    fo = c_oracle.FlatOracle(counts, 1.0, 1.0)
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.load(counts)
+    cands = np.concatenate([[0], np.flatnonzero(rs.random_sample(len(counts) - 1) < 0.5) + 1, [len(counts)]]).astype(np.int64)
+    eng.set_candidates(cands)
+    for r in range(4):
+        eng.round(wsize, wshift, 'none')
+        got = eng.candidates()
+        want, o_cells = fo.round(cands, wsize, wshift, 'none')
+        assert np.array_equal(got, want), (wsize, wshift, r)
+        assert eng.round_stats()[0] == o_cells
+        if len(want) == len(cands):
+            break
+        cands = want
+
+
 @pytest.mark.parametrize('n,constraint', [(70000, 'constants'), (5000000, 'constants'), (40000000, 'constants'),
                                           (300000, 'none'), (300000, 'zeros')])
 def test_load_and_round_equals_load_then_round(eng, n, constraint):

@@ -1,10 +1,6 @@
 set -x
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err || exit 1
 python tools/prune_stats.py 248956422 > gpurun_out/ps_chr1.log 2>&1
-python tools/workloads.py genome > gpurun_out/genome1.json 2> gpurun_out/genome1.err
-python tools/workloads.py transcripts > gpurun_out/transcripts.json 2> gpurun_out/transcripts.err
-python tools/cli_e2e.py > gpurun_out/cli_e2e.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_final2.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_l2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:window_dp -s 42 -c 8 -o gpurun_out/prof_wdp_final2 -f python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_f2.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_final2.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_l2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:window_dp -s 42 -c 10 -o gpurun_out/prof_wdp_final2 -f python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_f2.log 2>&1
 tail -2 gpurun_out/ncu_f2.log
