@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <thread>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -98,6 +99,70 @@ static int d2h(pasio_ctx *ctx, void *dst, const void *src, size_t bytes)
     return PASIO_OK;
 }
 
+
+// Host -> device copy of a large buffer that may be PAGEABLE (numpy arrays are): a plain cudaMemcpyAsync from
+// pageable memory is staged by the driver on one thread (~10 GB/s).  Here a few host threads copy slices into
+// page-locked staging buffers (3 x 32 MB, ring) and each slice is DMA'd as soon as it is staged.  A page-locked
+// source (cudaHostAlloc / cudaHostRegister / pasio_host_alloc) goes straight to cudaMemcpyAsync.
+static bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static void parallel_memcpy(char *dst, const char *src, size_t bytes, int threads)
+{
+    if (threads <= 1 || bytes < ((size_t)4 << 20)) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> pool;
+    const size_t per = ((bytes / threads) + 4095) & ~(size_t)4095;
+    for (int t = 1; t < threads; ++t) {
+        const size_t lo = (size_t)t * per;
+        if (lo >= bytes) break;
+        const size_t len = std::min(per, bytes - lo);
+        pool.emplace_back([=] { memcpy(dst + lo, src + lo, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &th : pool) th.join();
+}
+
+static int upload(pasio_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t stream)
+{
+    static const int staged_env = getenv("PASIO_B200_STAGED_UPLOAD") ? atoi(getenv("PASIO_B200_STAGED_UPLOAD")) : 1;
+    if (bytes < ((size_t)16 << 20) || !staged_env || host_is_pinned(src)) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return PASIO_OK;
+    }
+    constexpr size_t SLICE = (size_t)32 << 20;
+    constexpr int NBUF = 3;
+    if (!ctx->stage[0]) {
+        for (int k = 0; k < NBUF; ++k) {
+            if (cudaHostAlloc(&ctx->stage[k], SLICE, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->stage_free[k], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                for (int j = 0; j <= k; ++j) if (ctx->stage[j]) { cudaFreeHost(ctx->stage[j]); ctx->stage[j] = nullptr; }
+                CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));    // no staging memory: plain copy
+                return PASIO_OK;
+            }
+        }
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    const int threads = (int)std::max(1u, std::min(8u, hc ? hc / 2 : 4u));
+    size_t done = 0;
+    while (done < bytes) {
+        const int k = ctx->stage_next;
+        ctx->stage_next = (k + 1) % NBUF;
+        if (ctx->stage_used[k]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_free[k]));     // its last DMA has finished
+        const size_t len = std::min(SLICE, bytes - done);
+        parallel_memcpy((char *)ctx->stage[k], (const char *)src + done, len, threads);
+        CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + done, ctx->stage[k], len, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->stage_free[k], stream));
+        ctx->stage_used[k] = true;
+        done += len;
+    }
+    return PASIO_OK;
+}
+
 static void drop_borrowed_counts(pasio_ctx *ctx)
 {
     if (ctx->counts_borrowed) { ctx->counts.p = nullptr; ctx->counts.bytes = 0; ctx->counts_borrowed = false; }
@@ -168,6 +233,10 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    for (int k = 0; k < 3; ++k) {
+        if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+        if (ctx->stage_free[k]) cudaEventDestroy(ctx->stage_free[k]);
+    }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -290,7 +359,10 @@ extern "C" int pasio_contig_load(pasio_ctx *ctx, const int64_t *counts, int64_t 
     ctx->n = n;
     drop_borrowed_counts(ctx);
     PASIO_TRY(pasio_reserve(ctx, ctx->counts, (size_t)n * 8 + 16));
-    PASIO_TRY(h2d(ctx, ctx->counts.p, counts, (size_t)n * 8));
+    {
+        TimingScope ts(ctx, TF_H2D);
+        PASIO_TRY(upload(ctx, ctx->counts.p, counts, (size_t)n * 8, ctx->stream));
+    }
     return finish_load(ctx, offsets, n_contigs);
 }
 
@@ -382,8 +454,7 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
             const i64 e0 = queued * chunk_tiles * tile_elems, e1 = std::min<i64>(n, (queued + 1) * chunk_tiles * tile_elems);
             if (e1 > e0) {
                 TimingScope ts(ctx, TF_H2D, 1, ctx->stream_copy);
-                CUDA_TRY(ctx, cudaMemcpyAsync(ctx->counts.as<i64>() + e0, counts + e0, (size_t)(e1 - e0) * 8,
-                                              cudaMemcpyHostToDevice, ctx->stream_copy));
+                PASIO_TRY(upload(ctx, ctx->counts.as<i64>() + e0, counts + e0, (size_t)(e1 - e0) * 8, ctx->stream_copy));
             }
             CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_events[(size_t)queued], ctx->stream_copy));
         }

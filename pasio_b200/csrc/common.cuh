@@ -35,6 +35,10 @@ struct pasio_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream_copy = nullptr;  // host->device chunks of pasio_contig_load_round
     std::vector<cudaEvent_t> chunk_events;
+    void *stage[3] = {nullptr, nullptr, nullptr};   // page-locked staging ring for uploads from pageable memory
+    cudaEvent_t stage_free[3] = {nullptr, nullptr, nullptr};
+    bool stage_used[3] = {false, false, false};
+    int stage_next = 0;
     std::string err;
 
     // scorer parameters (log_marginal_likelyhood.py:6-16,62)

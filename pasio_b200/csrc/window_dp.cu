@@ -811,7 +811,7 @@ struct __align__(16) SmallWin {
     unsigned char mark[MAXN];
 };
 
-template <bool AI, int MAXN, int NWARPS, int CTAS>
+template <bool AI, int MAXN, int NWARPS, int CTAS, int U>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
 small_window_dp_kernel(WinDpParams p)
 {
@@ -896,7 +896,7 @@ small_window_dp_kernel(WinDpParams p)
             RowConst<AI> rc[1] = {make_row<AI>(me.C, me.L, p.alpha_int, p.alpha)};
             double best[1] = {-INFINITY};
             int arg[1] = {ph};
-            sweep_columns<AI, 4, 1>(0, jb, ph, 2, W.col, rc, p.gtab, p.ltab, best, arg);
+            sweep_columns<AI, U, 1>(0, jb, ph, 2, W.col, rc, p.gtab, p.ltab, best, arg);
             {   // the two column phases of a row: larger value, equal values keep the smaller column
                 const double ob = __shfl_xor_sync(0xffffffffu, best[0], 16);
                 const int oa = __shfl_xor_sync(0xffffffffu, arg[0], 16);
@@ -1038,14 +1038,14 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
         unsigned *c_small = ctx->scalars.as<unsigned>() + 2 * 15, *c_medium = c_small + 1;     // scalars[15]
         const size_t sm_small = sizeof(SmallWin<SW_SMALL_N>) * SW_SMALL_WARPS, sm_medium = sizeof(SmallWin<SW_MEDIUM_N>) * SW_MEDIUM_WARPS;
         if (ctx->alpha_is_int) {
-            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS>, ctx->win_small.as<int32_t>(),
+            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS, 4>, ctx->win_small.as<int32_t>(),
                                    n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small, stream));
-            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS>, ctx->win_medium.as<int32_t>(),
+            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, 8>, ctx->win_medium.as<int32_t>(),
                                    n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium, stream));
         } else {
-            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS>, ctx->win_small.as<int32_t>(),
+            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS, 4>, ctx->win_small.as<int32_t>(),
                                    n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small, stream));
-            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS>, ctx->win_medium.as<int32_t>(),
+            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, 8>, ctx->win_medium.as<int32_t>(),
                                    n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium, stream));
         }
         return PASIO_OK;
