@@ -1,3 +1,4 @@
+# Measurement batch of a round (run under gpurun): bench, per-round times, ncu launch list and full capture.
 set -x
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err || exit 1
 python tools/prune_stats.py 248956422 > gpurun_out/ps_chr1.log 2>&1
