@@ -1,4 +1,5 @@
-// K4: all windows of one sliding-window round in ONE launch, one CTA per window.
+// K4: all windows of one sliding-window round: one launch per size class (a CTA per large window, a warp per
+// small / medium window; the prepass in compact.cu sorts the windows).
 //
 // Replaces, per window, the chain
 //   SlidingWindowReducer.reduce_candidates_in_window   splitters/sliding_window_reducer.py:10-18
@@ -11,9 +12,11 @@
 // the window's first candidate exactly like counts[start:stop] / candidates - start.
 //
 // Per CTA: (A) warp-ballot stream compaction of the window's candidates (constraint filter)
-// into shared memory, (B) the DP in 32-row block steps (dp_core.cuh), (C) back-trace by pointer
+// into shared memory, (B) the DP in 32-row block steps (dp_core.cuh) -- plain sweeps, or, for explicit
+// candidate lists, pruned and software-pipelined steps (far_pass below), (C) back-trace by pointer
 // doubling and an atomicOr scatter of the survivors into the position bitmap.
-// CTAs are persistent and pull windows from an atomic counter (window cost varies as N^2).
+// CTAs are persistent and pull windows from an atomic counter (window cost varies as N^2); phase-2
+// windows whose candidates all survived already are skipped (see window_dp_kernel).
 #include "dp_core.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -1065,7 +1068,7 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
         int per_sm = 0;
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
-#if defined(PASIO_WD_EXP) || defined(PASIO_WD_PROF)
+#ifdef PASIO_WD_PROF
         if (getenv("PASIO_WD_CTAS") && atoi(getenv("PASIO_WD_CTAS")) < per_sm) per_sm = atoi(getenv("PASIO_WD_CTAS"));
 #endif
         grid = (i64)ctx->sm_count * per_sm;     // persistent CTAs: one resident wave
