@@ -164,7 +164,7 @@ def run_b200(args):
         eng.set_candidates(None)
         _run_device_pipeline(eng, plan)
         scores, _, means, _ = eng.segment_scores(scores=True, means=True)
-        return eng.candidate_count(), float(np.sum(scores))
+        return eng.candidate_count(), float(eng.segment_scores_sum())
 
     def step_e2e():
         eng.invalidate()                                     # force the H2D copy every step

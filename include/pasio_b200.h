@@ -155,6 +155,12 @@ int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *segment_counts
                          double *mean_counts, double *logfac_cumsum, int64_t capacity,
                          int64_t *n_segments);
 
+/* NopSplitter.split's total (nop_splitter.py:15-18: np.sum(scorer.scores())) over the current candidates, on the
+ * device and in numpy's own summation order -- pairwise: blocks of <= 128 elements with 8 running sums, halves split
+ * at multiples of 8 (numpy/core/src/umath/loops_utils.h.src, *_pairwise_sum) -- so the float64 result is the one
+ * np.sum gives on the downloaded scores (checked against numpy 2.3.5), without a host pass over 8 bytes/segment. */
+int pasio_segment_scores_sum(pasio_ctx *ctx, double *total);
+
 /* log_marginal_likelyhoods() (log_marginal_likelyhood.py:76-78) over the current candidates, formed on the
  * device: lmm[k] = score[k] - (logfac_cumsum[k+1] - logfac_cumsum[k]), same two roundings as numpy.
  * sum_logfac = total_sum_logfac() (:64-65).  lmm has m-1 entries. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
     'pasio_suffix_scores': (ctypes.c_int, [_vp, _i64, _f64p]),
     'pasio_segment_scores': (ctypes.c_int, [_vp, _f64p, _i64p, _f64p, _f64p, _i64, _i64p]),
+    'pasio_segment_scores_sum': (ctypes.c_int, [_vp, _f64p]),
     'pasio_segment_lmm': (ctypes.c_int, [_vp, _f64p, _i64, _f64p]),
     'pasio_host_alloc': (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     'pasio_host_free': (ctypes.c_int, [_vp]),
@@ -426,6 +427,12 @@ class Engine(object):
             _ptr(mu, ctypes.c_double) if means else None, _ptr(lf, ctypes.c_double) if logfac else None,
             max(nseg, m if logfac else 0), ctypes.byref(nout)))
         return s, c, mu, lf
+
+    def segment_scores_sum(self):
+        """np.sum(scores) of the current segments, on the device in numpy's pairwise order (same float64 result)"""
+        total = ctypes.c_double(0.0)
+        self._retry(lambda: self.lib.pasio_segment_scores_sum(self.ctx, ctypes.byref(total)))
+        return np.float64(total.value)
 
     def segment_lmm(self):
         """(log_marginal_likelyhoods per segment, total_sum_logfac), formed on the device"""

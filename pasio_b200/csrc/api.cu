@@ -866,6 +866,65 @@ extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *seg
     return PASIO_OK;
 }
 
+
+// ---- np.sum of the segment scores, in numpy's pairwise order ------------------------------------
+static void pw_leaves(i64 lo, i64 n, std::vector<i64> &starts)
+{
+    if (n <= 128) { starts.push_back(lo); return; }
+    i64 n2 = n / 2;
+    n2 -= n2 % 8;
+    pw_leaves(lo, n2, starts);
+    pw_leaves(lo + n2, n - n2, starts);
+}
+static double pw_combine(const double *leaf, i64 &next, i64 n)
+{
+    if (n <= 128) return leaf[next++];
+    i64 n2 = n / 2;
+    n2 -= n2 % 8;
+    const double a = pw_combine(leaf, next, n2);
+    const double b = pw_combine(leaf, next, n - n2);
+    return a + b;
+}
+
+extern "C" int pasio_segment_scores_sum(pasio_ctx *ctx, double *total)
+{
+    NEED_CTX(ctx);
+    if (!total) return pasio_fail(ctx, PASIO_E_ARG, "NULL output");
+    int64_t nseg = 0;
+    // scores of the current candidates into dpP (same checks and kernel as pasio_segment_scores)
+    PASIO_TRY(pasio_segment_scores(ctx, nullptr, nullptr, nullptr, nullptr, 0, &nseg));
+    {
+        const i64 saved_contigs = ctx->n_contigs;
+        ctx->n_contigs = 1;
+        i64 max_len = 0, max_cnt = 0;
+        int rc = launch_window_prepass(ctx, nseg, 1, 1, &max_len, &max_cnt);
+        ctx->n_contigs = saved_contigs;
+        PASIO_TRY(rc);
+        bool bad = false;
+        if (ctx->ntab[PASIO_TAB_LOG] < max_len + 1) { ctx->need[PASIO_TAB_LOG] = max_len + 1; bad = true; }
+        if (ctx->ntab[PASIO_TAB_LGAMMA_ALPHA] < max_cnt + 1) { ctx->need[PASIO_TAB_LGAMMA_ALPHA] = max_cnt + 1; bad = true; }
+        if (bad) return pasio_fail(ctx, PASIO_E_TABLE_TOO_SHORT, "tables too short for segment scores");
+    }
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)nseg * 8));
+    PASIO_TRY(launch_segment_scores(ctx, ctx->dpP.as<double>(), nullptr, nullptr));
+    if (ctx->pw_n != nseg) {
+        ctx->pw_leaf_start.clear();
+        pw_leaves(0, nseg, ctx->pw_leaf_start);
+        ctx->pw_leaf_start.push_back(nseg);
+        ctx->pw_n = nseg;
+    }
+    const i64 n_leaves = (i64)ctx->pw_leaf_start.size() - 1;
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpJump, (size_t)(n_leaves + 1) * 8));
+    PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)n_leaves * 8));
+    PASIO_TRY(h2d(ctx, ctx->dpJump.p, ctx->pw_leaf_start.data(), (size_t)(n_leaves + 1) * 8));
+    PASIO_TRY(launch_pairwise_leaves(ctx, ctx->dpP.as<double>(), ctx->dpJump.as<i64>(), n_leaves, ctx->dpPart.as<double>()));
+    ctx->pw_leaf_sum.resize((size_t)n_leaves);
+    PASIO_TRY(d2h(ctx, ctx->pw_leaf_sum.data(), ctx->dpPart.p, (size_t)n_leaves * 8));
+    i64 next = 0;
+    *total = pw_combine(ctx->pw_leaf_sum.data(), next, nseg);
+    return PASIO_OK;
+}
+
 extern "C" int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, double *sum_logfac)
 {
     NEED_CTX(ctx);

@@ -85,6 +85,9 @@ struct pasio_ctx {
     i64 *h_scalars = nullptr;    // pinned, 16 entries
 
     i64 last_cells = 0, last_cells_skipped = 0;   // of the most recent round
+    std::vector<i64> pw_leaf_start;      // leaf boundaries of numpy's pairwise sum for pw_n elements (pasio_segment_scores_sum)
+    i64 pw_n = -1;
+    std::vector<double> pw_leaf_sum;
 
     // timing
     bool timing = false;
@@ -153,6 +156,7 @@ int launch_suffix_row(pasio_ctx *ctx, i64 stop, double *d_out);
 
 // score.cu
 int launch_segment_scores(pasio_ctx *ctx, double *d_scores, i64 *d_segcounts, double *d_means);
+int launch_pairwise_leaves(pasio_ctx *ctx, const double *d_values, const i64 *d_leaf_start, i64 n_leaves, double *d_leaf_sum);
 int launch_gather_i64(pasio_ctx *ctx, const i64 *d_src, const int32_t *d_idx32, const i64 *d_idx64, i64 m, i64 *d_out);
 int launch_gather_f64_at_cands(pasio_ctx *ctx, const double *d_src, double *d_out);
 int launch_lmm(pasio_ctx *ctx, const double *d_scores, const double *d_logfac_full, double *d_lmm);

@@ -68,6 +68,44 @@ inline unsigned grid_for(pasio_ctx *ctx, i64 n)
 
 }  // namespace
 
+// numpy's pairwise summation, leaf level: one thread per leaf of <= 128 elements (the host walks the recursion that
+// splits n at multiples of 8 and combines the leaf sums in the same order): 8 running sums, then the fixed tree,
+// then the remainder -- operation for operation numpy's DOUBLE_pairwise_sum.
+__global__ void pairwise_leaf_kernel(const double *__restrict__ a, const i64 *__restrict__ leaf_start, i64 n_leaves,
+                                     double *__restrict__ leaf_sum)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_leaves) return;
+    const double *x = a + leaf_start[t];
+    const i64 n = leaf_start[t + 1] - leaf_start[t];
+    double res;
+    if (n < 8) {
+        res = 0.;
+        for (i64 i = 0; i < n; ++i) res = __dadd_rn(res, x[i]);
+    } else {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = x[k];
+        i64 i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], x[i + k]);
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, x[i]);
+    }
+    leaf_sum[t] = res;
+}
+
+int launch_pairwise_leaves(pasio_ctx *ctx, const double *d_values, const i64 *d_leaf_start, i64 n_leaves, double *d_leaf_sum)
+{
+    TimingScope ts(ctx, TF_SCORE);
+    pairwise_leaf_kernel<<<(unsigned)((n_leaves + 127) / 128), 128, 0, ctx->stream>>>(d_values, d_leaf_start, n_leaves, d_leaf_sum);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}
+
 int launch_segment_scores(pasio_ctx *ctx, double *d_scores, i64 *d_segcounts, double *d_means)
 {
     const double *ga = ctx->tab[PASIO_TAB_LGAMMA_ALPHA].as<double>();

@@ -48,7 +48,7 @@ def run_loaded_pipeline(eng, plan, want_lmm=True, first=None):
     splits = eng.candidates()
     scores, _, means, _ = eng.segment_scores(scores=True, means=True)
     if plan['final'] == 'nop':
-        score = np.sum(scores)                    # NopSplitter.split (nop_splitter.py:15-18)
+        score = eng.segment_scores_sum()          # NopSplitter.split (nop_splitter.py:15-18): np.sum(scores), numpy's order
     lmm, sum_logfac = eng.segment_lmm() if want_lmm else (None, None)
     return score, splits, means, lmm, sum_logfac
 

@@ -379,6 +379,21 @@ def test_load_and_round_asserts_and_table_growth(eng):
     assert np.array_equal(eng.candidates(), want) and first == (len(deep) + 1, len(want), cells)
 
 
+@pytest.mark.parametrize('n,wsize', [(3000, 50), (40000, 300), (700000, 2500), (6000000, 2500)])
+def test_segment_scores_sum_is_numpy_sum(eng, n, wsize):
+    """pasio_segment_scores_sum restates np.sum's pairwise order on the device: same float64 as np.sum(scores)"""
+    counts = synth.dnase_like(n, n % 97, hotspot_share=0.3)
+    eng.use_scorer(factory(1.0, 1.0))
+    eng.load(counts)
+    eng.set_candidates(None)
+    eng.rounds(wsize, wsize // 2, 'constants', 2)
+    scores, _, _, _ = eng.segment_scores(scores=True)
+    assert eng.segment_scores_sum() == np.sum(scores)
+    eng.set_candidates(np.array([0, n], dtype=np.int64))                 # one segment
+    scores, _, _, _ = eng.segment_scores(scores=True)
+    assert eng.segment_scores_sum() == np.sum(scores)
+
+
 def test_timing_hooks(eng):
     counts = synth.dnase_like(100000, 9, hotspot_share=0.3)
     eng.use_scorer(factory(1.0, 1.0))
