@@ -72,6 +72,7 @@ static int resolve_spans(pasio_ctx *ctx)
     if (ctx->spans.empty()) return PASIO_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->stream_copy) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_copy));
+    if (ctx->stream2) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream2));
     for (auto &s : ctx->spans) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, s.a, s.b);
@@ -329,9 +330,10 @@ static int finish_load(pasio_ctx *ctx, const int64_t *offsets, int64_t n_contigs
     PASIO_TRY(pasio_reserve(ctx, ctx->brank, (size_t)(n_contigs + 1) * 4));
     PASIO_TRY(h2d(ctx, ctx->bounds.p, ctx->h_bounds.data(), (size_t)(n_contigs + 1) * 4));
     PASIO_TRY(launch_scan_counts(ctx));
-    PASIO_TRY(d2h(ctx, ctx->h_scalars, ctx->scalars.p, 2 * sizeof(i64)));
+    PASIO_TRY(d2h(ctx, ctx->h_scalars, ctx->scalars.p, 3 * sizeof(i64)));
     if (ctx->h_scalars[1]) return pasio_fail(ctx, PASIO_E_COUNTS, "counts must be >= 0");
     ctx->total = ctx->h_scalars[0];
+    ctx->max_count = ctx->h_scalars[2];
     ctx->have_contig = true;
     ctx->implicit_all = true;
     ctx->m = n + 1;
@@ -343,6 +345,7 @@ static int finish_load(pasio_ctx *ctx, const int64_t *offsets, int64_t n_contigs
 
 static int check_load_args(pasio_ctx *ctx, int64_t n, const int64_t *offsets, int64_t n_contigs)
 {
+    ctx->logfac_ready = false;
     ctx->have_contig = false;
     if (n < 1) return pasio_fail(ctx, PASIO_E_COUNTS, "contig is empty");            // len(counts) > 0
     if (n > 2147483645LL) return pasio_fail(ctx, PASIO_E_TOO_LARGE, "contig of %lld nt exceeds 2^31-3", (long long)n);
@@ -492,10 +495,11 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
             w_done = w_ready;
         }
     }
-    PASIO_TRY(d2h(ctx, ctx->h_scalars, ctx->scalars.p, 2 * sizeof(i64)));
+    PASIO_TRY(d2h(ctx, ctx->h_scalars, ctx->scalars.p, 3 * sizeof(i64)));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_copy));
     if (ctx->h_scalars[1]) return pasio_fail(ctx, PASIO_E_COUNTS, "counts must be >= 0");
     ctx->total = ctx->h_scalars[0];
+    ctx->max_count = ctx->h_scalars[2];
     ctx->have_contig = true;
     PASIO_TRY(launch_boundary_ranks(ctx));
     ctx->h_brank = ctx->h_bounds;
@@ -823,6 +827,18 @@ extern "C" int pasio_suffix_scores(pasio_ctx *ctx, int64_t stop, double *out)
 }
 
 // ---- per-segment outputs ------------------------------------------------------------------------
+// float64 prefix sums of lgamma(counts + 1) over the loaded contig (logfac_cumsum, log_marginal_likelyhood.py:59-60)
+// in ctx->logfac_full, computed once per loaded contig.  (Running it on a side stream beside the rounds was tried:
+// the bandwidth-bound scan and the latency-bound window kernels slow each other down by as much as is hidden.)
+static int ensure_logfac(pasio_ctx *ctx)
+{
+    if (ctx->logfac_ready) return PASIO_OK;
+    PASIO_TRY(pasio_reserve(ctx, ctx->logfac_full, (size_t)(ctx->n + 1) * 8));
+    PASIO_TRY(launch_logfac_scan(ctx, ctx->logfac_full.as<double>()));
+    ctx->logfac_ready = true;
+    return PASIO_OK;
+}
+
 extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *segment_counts, double *mean_counts,
                                     double *logfac_cumsum, int64_t capacity, int64_t *n_segments)
 {
@@ -857,8 +873,7 @@ extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *seg
     if (logfac_cumsum) {
         if (capacity < nseg) return pasio_fail(ctx, PASIO_E_ARG, "capacity too small");
         // n+1 doubles of scratch, kept for the next call (a 2 GB cudaMalloc/cudaFree per contig is not free)
-        PASIO_TRY(pasio_reserve(ctx, ctx->logfac_full, (size_t)(ctx->n + 1) * 8));
-        PASIO_TRY(launch_logfac_scan(ctx, ctx->logfac_full.as<double>()));
+        PASIO_TRY(ensure_logfac(ctx));
         PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)ctx->m * 8));
         PASIO_TRY(launch_gather_f64_at_cands(ctx, ctx->logfac_full.as<double>(), ctx->dpP.as<double>()));
         PASIO_TRY(d2h(ctx, logfac_cumsum, ctx->dpP.p, (size_t)ctx->m * 8));
@@ -946,8 +961,7 @@ extern "C" int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, 
     if (bad) return pasio_fail(ctx, PASIO_E_TABLE_TOO_SHORT, "tables too short for segment scores");
     PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)nseg * 8));
     PASIO_TRY(launch_segment_scores(ctx, ctx->dpP.as<double>(), nullptr, nullptr));
-    PASIO_TRY(pasio_reserve(ctx, ctx->logfac_full, (size_t)(ctx->n + 1) * 8));
-    PASIO_TRY(launch_logfac_scan(ctx, ctx->logfac_full.as<double>()));
+    PASIO_TRY(ensure_logfac(ctx));
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)nseg * 8));
     PASIO_TRY(launch_lmm(ctx, ctx->dpP.as<double>(), ctx->logfac_full.as<double>(), ctx->dpPart.as<double>()));
     if (lmm) PASIO_TRY(d2h(ctx, lmm, ctx->dpPart.p, (size_t)nseg * 8));

@@ -56,6 +56,8 @@ struct pasio_ctx {
     bool have_contig = false;
     i64 n = 0;                   // total nt
     i64 total = 0;               // total count
+    i64 max_count = 0;           // largest count
+    bool logfac_ready = false;   // logfac_full holds the prefix sums of the loaded contig
     i64 n_contigs = 0;
     std::vector<int32_t> h_bounds;   // n_contigs+1 boundary positions (host copy)
     DevBuf counts;               // int64[n]
@@ -130,7 +132,7 @@ int launch_scan_counts(pasio_ctx *ctx);                       // counts -> cg, c
 int launch_scan_prepare(pasio_ctx *ctx, i64 *n_tiles, i64 *tile_elems);   // the same in pieces: reset the tile states ...
 int launch_scan_tiles(pasio_ctx *ctx, i64 tiles);             // ... then the next `tiles` tiles, in order
 int launch_expand_rle(pasio_ctx *ctx, const i64 *d_starts, const i64 *d_values, i64 n_runs);
-int launch_logfac_scan(pasio_ctx *ctx, double *d_out);        // float64 prefix sums of G[counts+1], n+1 entries
+int launch_logfac_scan(pasio_ctx *ctx, double *d_out, cudaStream_t stream = nullptr);   // float64 prefix sums of G[counts+1], n+1 entries
 
 // compact.cu
 int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count);  // keepbits -> sorted positions; syncs

@@ -37,7 +37,7 @@ __device__ __forceinline__ u64 spread_bits(unsigned x)   // bit k of x -> bit 2k
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
                    u64 *__restrict__ cpwords, u64 *tile_state, unsigned *tile_counter,
-                   i64 *scalars /* [0]=total, [1]=negative seen */)
+                   i64 *scalars /* [0]=total, [1]=negative seen, [2]=largest count */)
 {
     __shared__ unsigned s_tile;
     __shared__ i64 s_warp[SCAN_THREADS / 32];
@@ -50,6 +50,7 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
 
     i64 v0[SCAN_SLABS], v1[SCAN_SLABS];
     bool neg = false;
+    i64 vmax = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_SLABS; ++k) {
         const i64 e = wbase + 64 * k + 2 * lane;
@@ -62,8 +63,13 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
             v1[k] = 0;
         }
         neg |= (v0[k] < 0) | (v1[k] < 0);
+        vmax = max(vmax, max(v0[k], v1[k]));
     }
     if (neg) scalars[1] = 1;
+    // largest count (the log-factorial table must reach it): one atomic per warp, and only when it raises the maximum
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    if (lane == 0 && vmax > *reinterpret_cast<volatile i64 *>(scalars + 2)) atomicMax(reinterpret_cast<long long *>(scalars + 2), vmax);
 
     // change-point words: position p flagged when counts[p-1] != counts[p], 1 <= p <= n-1
     {
@@ -266,16 +272,6 @@ logfac_scan_apply(const i64 *__restrict__ counts, i64 n, const double *__restric
         if (base + k < n) out[base + k + 1] = off + v[k];
 }
 
-__global__ void max_count_kernel(const i64 *__restrict__ counts, i64 n, u64 *out)
-{
-    i64 mx = 0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-        mx = max(mx, __ldg(counts + i));
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if ((threadIdx.x & 31) == 0) atomicMax(out, (u64)mx);
-}
-
 }  // namespace
 
 int launch_scan_prepare(pasio_ctx *ctx, i64 *n_tiles, i64 *tile_elems)
@@ -325,16 +321,12 @@ int launch_expand_rle(pasio_ctx *ctx, const i64 *d_starts, const i64 *d_values, 
     return PASIO_OK;
 }
 
-int launch_logfac_scan(pasio_ctx *ctx, double *d_out)
+int launch_logfac_scan(pasio_ctx *ctx, double *d_out, cudaStream_t stream)
 {
     const i64 n = ctx->n;
-    // the lgamma table must cover max(counts)+1
-    u64 *d_max = ctx->scalars.as<u64>() + 8;
-    CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, 8, ctx->stream));
-    max_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, d_max);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 8, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    const i64 max_count = ctx->h_scalars[8];
+    if (!stream) stream = ctx->stream;
+    // the lgamma table must cover max(counts)+1 (the scan kernel recorded the maximum)
+    const i64 max_count = ctx->max_count;
     if (max_count + 2 > ctx->ntab[PASIO_TAB_LGAMMA]) {
         ctx->need[PASIO_TAB_LGAMMA] = max_count + 2;
         return pasio_fail(ctx, PASIO_E_TABLE_TOO_SHORT, "lgamma table has %lld entries, logfac needs %lld",
@@ -343,12 +335,12 @@ int launch_logfac_scan(pasio_ctx *ctx, double *d_out)
     const i64 tiles = (n + FS_TILE - 1) / FS_TILE;
     PASIO_TRY(pasio_reserve(ctx, ctx->fscan, (size_t)tiles * 8));
     const double *gtab = ctx->tab[PASIO_TAB_LGAMMA].as<double>();
-    TimingScope ts(ctx, TF_SCORE, 3);
-    logfac_tile_sums<<<(unsigned)tiles, FS_THREADS, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, gtab,
-                                                                     ctx->fscan.as<double>());
-    logfac_scan_tile_sums<<<1, FS_THREADS, 0, ctx->stream>>>(ctx->fscan.as<double>(), tiles);
-    logfac_scan_apply<<<(unsigned)tiles, FS_THREADS, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, gtab,
-                                                                      ctx->fscan.as<double>(), d_out);
+    TimingScope ts(ctx, TF_SCORE, 3, stream);
+    logfac_tile_sums<<<(unsigned)tiles, FS_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab,
+                                                                ctx->fscan.as<double>());
+    logfac_scan_tile_sums<<<1, FS_THREADS, 0, stream>>>(ctx->fscan.as<double>(), tiles);
+    logfac_scan_apply<<<(unsigned)tiles, FS_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab,
+                                                                 ctx->fscan.as<double>(), d_out);
     CUDA_TRY(ctx, cudaGetLastError());
     return PASIO_OK;
 }
