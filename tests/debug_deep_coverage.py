@@ -1,4 +1,4 @@
-"""Debug helper: step the rounds of a deep-coverage contig one by one against the C oracle."""
+"""Test-side debug helper (imports the oracle): step the rounds of a deep-coverage contig one by one against the C oracle."""
 import os
 import sys
 import numpy as np

@@ -1,5 +1,5 @@
 """Randomised differential test of the rounds path (incl. the branch-and-bound pruning) against the C oracle.
-python tools/fuzz_parity.py [seconds] [seed]"""
+python tests/fuzz_parity.py [seconds] [seed]"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

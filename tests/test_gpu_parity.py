@@ -408,12 +408,12 @@ def test_timing_hooks(eng):
 
 
 def test_randomised_rounds_fuzz():
-    """tools/fuzz_parity.py for a few seconds: random data kinds, alpha/beta, window geometry and constraints,
+    """tests/fuzz_parity.py for a few seconds: random data kinds, alpha/beta, window geometry and constraints,
     every round compared with the oracle (the longer runs are recorded in profiles/)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_parity.py'), '20', '7'],
+    out = subprocess.run([sys.executable, os.path.join(root, 'tests', 'fuzz_parity.py'), '20', '7'],
                          capture_output=True, text=True, cwd=root)
     assert out.returncode == 0 and 'fuzz ok' in out.stdout, out.stdout + out.stderr
