@@ -99,7 +99,7 @@ __device__ __forceinline__ void xd_tile(int row0, int N, int ncol, const ColRec 
         best[k] = -INFINITY;
         arg[k] = cc;
     }
-    sweep_columns<AI, 2, XT_RPL>(0, ncol, cc, 8, sCol, r, gtab, ltab, best, arg);
+    sweep_columns<AI, 4, XT_RPL>(0, ncol, cc, 8, sCol, r, gtab, ltab, best, arg);
 #pragma unroll
     for (int k = 0; k < XT_RPL; ++k) merge_column_phases<4>(best[k], arg[k]);
 }
