@@ -484,22 +484,23 @@ def format_segments(chrom, offset, splits, means, lmm, mode):
     splits = np.ascontiguousarray(splits, dtype=np.int64)
     name = chrom.encode()
     pieces = []
-    step = 1 << 20
+    step = 1 << 22
     for lo in range(0, len(splits) - 1, step):
         hi = min(lo + step, len(splits) - 1)
         sub = splits[lo:hi + 1]
         m = np.ascontiguousarray(means[lo:hi]) if means is not None else None
         l = np.ascontiguousarray(lmm[lo:hi]) if lmm is not None else None
-        cap = (hi - lo) * (len(name) + 96) + 1024
+        cap = (hi - lo) * (len(name) + 56) + 1024
         while True:
-            buf = ctypes.create_string_buffer(cap)
+            buf = np.empty(cap, dtype=np.uint8)                # not zero-filled
             w = lib.pasio_format_segments(name, int(offset), _ptr(sub, ctypes.c_int64), len(sub),
                                           _ptr(m, ctypes.c_double) if m is not None else None,
-                                          _ptr(l, ctypes.c_double) if l is not None else None, mode, buf, cap)
+                                          _ptr(l, ctypes.c_double) if l is not None else None, mode,
+                                          buf.ctypes.data_as(ctypes.c_char_p), cap)
             if w >= 0:
-                pieces.append(buf.raw[:w])
+                pieces.append(buf[:w].tobytes())
                 break
-            cap = max(2 * cap, -w)
+            cap = -w
     return b''.join(pieces)
 
 

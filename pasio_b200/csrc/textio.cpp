@@ -8,12 +8,18 @@
 //   pasio_format_segments  replaces the '%s\t%d\t%d\t%f\n' style writes of split_bedgraph_stream
 //                          (/root/reference/src/pasio/process_bedgraph.py:71-89); snprintf("%f") rounds
 //                          exactly like Python's '%f'.
+// Both split their input into pieces (at line / segment boundaries) over a few host threads; the result is the
+// same bytes / arrays the single-threaded walk gives.
 // Grouping into contigs, gap filling and --split-at-gaps stay in Python (process_bedgraph.py), vectorised.
+#include <algorithm>
 #include <cerrno>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/pasio_b200.h"
 
@@ -53,16 +59,19 @@ extern "C" int64_t pasio_bedgraph_count_lines(const char *buf, int64_t len)
     return n;
 }
 
-// Parses up to `cap` intervals.  Per interval: start, stop, count, and the byte range of the chromosome
-// token inside buf (name_off, name_len).  new_chrom[i] = 1 when the token differs from the previous
-// interval's (itertools.groupby over consecutive lines, process_bedgraph.py:33).
-// float_counts receives how many counts needed the int(float(x)) conversion (the reference warns).
-// Returns PASIO_OK, or PASIO_E_ARG with *n_out = index of the offending line.
-extern "C" int pasio_bedgraph_parse(const char *buf, int64_t len, int64_t cap, int64_t *starts, int64_t *stops,
-                                    int64_t *counts, int64_t *name_off, int32_t *name_len, uint8_t *new_chrom,
-                                    int64_t *n_out, int64_t *float_counts)
+namespace {
+
+struct ParseOut {
+    int64_t *starts, *stops, *counts, *name_off;
+    int32_t *name_len;
+    uint8_t *new_chrom;
+};
+
+// Parses the lines that start in [p, end) (p is a line start) into out[0 ..], at most cap of them.
+// Returns true, or false with *err_line = number of the offending line counted from p.
+bool parse_range(const char *buf, const char *p, const char *end, int64_t cap, const ParseOut &o, int64_t *n_out,
+                 int64_t *nfloat_out, int64_t *err_line)
 {
-    const char *p = buf, *end = buf + len;
     int64_t n = 0, line_no = 0, nfloat = 0;
     const char *prev_name = nullptr;
     int32_t prev_len = 0;
@@ -81,30 +90,30 @@ extern "C" int pasio_bedgraph_parse(const char *buf, int64_t len, int64_t cap, i
             ++nt;
         }
         if (nt != 0) {                                   // blank lines are skipped
-            if (nt < 4 || n >= cap) { *n_out = line_no; return PASIO_E_ARG; }
+            if (nt < 4 || n >= cap) { *err_line = line_no; return false; }
             int64_t a, b, c;
-            if (!parse_int(tok[1], tok_end[1], &a) || !parse_int(tok[2], tok_end[2], &b)) { *n_out = line_no; return PASIO_E_ARG; }
+            if (!parse_int(tok[1], tok_end[1], &a) || !parse_int(tok[2], tok_end[2], &b)) { *err_line = line_no; return false; }
             if (!parse_int(tok[3], tok_end[3], &c)) {
                 char tmp[64];
                 const size_t l = (size_t)(tok_end[3] - tok[3]);
-                if (l >= sizeof tmp) { *n_out = line_no; return PASIO_E_ARG; }
+                if (l >= sizeof tmp) { *err_line = line_no; return false; }
                 memcpy(tmp, tok[3], l);
                 tmp[l] = 0;
                 char *endp = nullptr;
                 errno = 0;
                 const double d = strtod(tmp, &endp);
-                if (endp == tmp || *endp != 0 || d != d || d > 9.2e18 || d < -9.2e18) { *n_out = line_no; return PASIO_E_ARG; }
+                if (endp == tmp || *endp != 0 || d != d || d > 9.2e18 || d < -9.2e18) { *err_line = line_no; return false; }
                 c = (int64_t)d;                              // int(float(x)) truncates toward zero
                 ++nfloat;
             }
-            starts[n] = a;
-            stops[n] = b;
-            counts[n] = c;
-            name_off[n] = tok[0] - buf;
-            name_len[n] = (int32_t)(tok_end[0] - tok[0]);
-            new_chrom[n] = (prev_name == nullptr || prev_len != name_len[n] || memcmp(prev_name, tok[0], (size_t)prev_len) != 0);
+            o.starts[n] = a;
+            o.stops[n] = b;
+            o.counts[n] = c;
+            o.name_off[n] = tok[0] - buf;
+            o.name_len[n] = (int32_t)(tok_end[0] - tok[0]);
+            o.new_chrom[n] = (prev_name == nullptr || prev_len != o.name_len[n] || memcmp(prev_name, tok[0], (size_t)prev_len) != 0);
             prev_name = tok[0];
-            prev_len = name_len[n];
+            prev_len = o.name_len[n];
             ++n;
         }
         ++line_no;
@@ -112,28 +121,154 @@ extern "C" int pasio_bedgraph_parse(const char *buf, int64_t len, int64_t cap, i
         p = nl + 1;
     }
     *n_out = n;
+    *nfloat_out = nfloat;
+    return true;
+}
+
+int host_threads()
+{
+    static const int env = getenv("PASIO_B200_HOST_THREADS") ? atoi(getenv("PASIO_B200_HOST_THREADS")) : 0;
+    if (env > 0) return env;
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(8u, hc ? hc / 2 : 4u));
+}
+
+}  // namespace
+
+// Parses up to `cap` intervals.  Per interval: start, stop, count, and the byte range of the chromosome
+// token inside buf (name_off, name_len).  new_chrom[i] = 1 when the token differs from the previous
+// interval's (itertools.groupby over consecutive lines, process_bedgraph.py:33).
+// float_counts receives how many counts needed the int(float(x)) conversion (the reference warns).
+// Returns PASIO_OK, or PASIO_E_ARG with *n_out = index of the offending line.
+// Large buffers are cut at line starts into one piece per host thread; every piece is parsed into the slot its
+// line count reserves, then the pieces are closed up (blank lines leave holes) and new_chrom is fixed at the seams.
+extern "C" int pasio_bedgraph_parse(const char *buf, int64_t len, int64_t cap, int64_t *starts, int64_t *stops,
+                                    int64_t *counts, int64_t *name_off, int32_t *name_len, uint8_t *new_chrom,
+                                    int64_t *n_out, int64_t *float_counts)
+{
+    const ParseOut all = {starts, stops, counts, name_off, name_len, new_chrom};
+    const int T = len >= ((int64_t)4 << 20) ? host_threads() : 1;
+    if (T > 1) {
+        // piece boundaries at line starts
+        std::vector<const char *> cut((size_t)T + 1);
+        const char *end = buf + len;
+        cut[0] = buf;
+        cut[(size_t)T] = end;
+        for (int t = 1; t < T; ++t) {
+            const char *g = buf + len / T * t;
+            if (g < cut[(size_t)t - 1]) g = cut[(size_t)t - 1];
+            const char *nl = (const char *)memchr(g, '\n', (size_t)(end - g));
+            cut[(size_t)t] = nl ? nl + 1 : end;
+        }
+        std::vector<int64_t> lines((size_t)T, 0), got((size_t)T, 0), nfl((size_t)T, 0), err((size_t)T, -1);
+        {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < T; ++t)
+                pool.emplace_back([&, t] { lines[(size_t)t] = pasio_bedgraph_count_lines(cut[(size_t)t], cut[(size_t)t + 1] - cut[(size_t)t]); });
+            for (auto &th : pool) th.join();
+        }
+        int64_t total_lines = 0;
+        for (int t = 0; t < T; ++t) total_lines += lines[(size_t)t];
+        if (total_lines <= cap) {
+            std::vector<int64_t> slot((size_t)T, 0);
+            for (int t = 1; t < T; ++t) slot[(size_t)t] = slot[(size_t)t - 1] + lines[(size_t)t - 1];
+            {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < T; ++t)
+                    pool.emplace_back([&, t] {
+                        const int64_t s0 = slot[(size_t)t];
+                        const ParseOut o = {starts + s0, stops + s0, counts + s0, name_off + s0, name_len + s0, new_chrom + s0};
+                        int64_t e = 0;
+                        if (!parse_range(buf, cut[(size_t)t], cut[(size_t)t + 1], lines[(size_t)t], o, &got[(size_t)t], &nfl[(size_t)t], &e))
+                            err[(size_t)t] = e;
+                    });
+                for (auto &th : pool) th.join();
+            }
+            int64_t before = 0;
+            for (int t = 0; t < T; ++t) {
+                if (err[(size_t)t] >= 0) { *n_out = before + err[(size_t)t]; return PASIO_E_ARG; }
+                before += lines[(size_t)t];
+            }
+            int64_t n = 0, nfloat = 0;
+            for (int t = 0; t < T; ++t) {
+                const int64_t s0 = slot[(size_t)t], g = got[(size_t)t];
+                if (g > 0) {
+                    if (s0 != n) {
+                        memmove(starts + n, starts + s0, (size_t)g * 8);
+                        memmove(stops + n, stops + s0, (size_t)g * 8);
+                        memmove(counts + n, counts + s0, (size_t)g * 8);
+                        memmove(name_off + n, name_off + s0, (size_t)g * 8);
+                        memmove(name_len + n, name_len + s0, (size_t)g * 4);
+                        memmove(new_chrom + n, new_chrom + s0, (size_t)g);
+                    }
+                    if (n > 0)          // the piece's first interval against the one before the seam
+                        new_chrom[n] = (name_len[n] != name_len[n - 1] ||
+                                        memcmp(buf + name_off[n], buf + name_off[n - 1], (size_t)name_len[n]) != 0);
+                }
+                n += g;
+                nfloat += nfl[(size_t)t];
+            }
+            *n_out = n;
+            if (float_counts) *float_counts = nfloat;
+            return PASIO_OK;
+        }
+    }
+    int64_t n = 0, nfloat = 0, e = 0;
+    if (!parse_range(buf, buf, buf + len, cap, all, &n, &nfloat, &e)) { *n_out = e; return PASIO_E_ARG; }
+    *n_out = n;
     if (float_counts) *float_counts = nfloat;
     return PASIO_OK;
 }
 
+namespace {
+
+// lines of segments [k0, k1) appended to dst
+void format_range(const char *chrom, size_t clen, int64_t offset, const int64_t *splits, int64_t k0, int64_t k1,
+                  const double *means, const double *lmm, int mode, std::string &dst)
+{
+    char line[400];
+    dst.reserve((size_t)(k1 - k0) * (clen + 40));
+    for (int64_t k = k0; k < k1; ++k) {
+        const long long a = (long long)(splits[k] + offset), b = (long long)(splits[k + 1] + offset);
+        int m;
+        if (mode == 1) m = snprintf(line, sizeof line, "\t%lld\t%lld\n", a, b);
+        else if (mode == 0) m = snprintf(line, sizeof line, "\t%lld\t%lld\t%f\n", a, b, means[k]);
+        else m = snprintf(line, sizeof line, "\t%lld\t%lld\t%f\t%lld\t%f\n", a, b, means[k], b - a, lmm[k]);
+        if (m < 0) m = 0;
+        if (m >= (int)sizeof line) m = (int)sizeof line - 1;       // cannot happen: two int64 and two %f of finite doubles fit
+        dst.append(chrom, clen);
+        dst.append(line, (size_t)m);
+    }
+}
+
+}  // namespace
+
 // mode 0: chrom start stop mean ; 1: chrom start stop ; 2: chrom start stop mean length lmm
-// Writes at most cap bytes; returns the number of bytes written, or -(bytes needed estimate) if cap is too small.
+// Writes at most cap bytes; returns the number of bytes written, or -(bytes needed) if cap is too small.
 extern "C" int64_t pasio_format_segments(const char *chrom, int64_t offset, const int64_t *splits, int64_t n_splits,
                                          const double *means, const double *lmm, int mode, char *out, int64_t cap)
 {
     const size_t clen = strlen(chrom);
+    const int64_t nseg = n_splits > 0 ? n_splits - 1 : 0;
+    const int T = nseg >= 100000 ? host_threads() : 1;
+    std::vector<std::string> part((size_t)T);
+    if (T == 1) {
+        format_range(chrom, clen, offset, splits, 0, nseg, means, lmm, mode, part[0]);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t)
+            pool.emplace_back([&, t] {
+                format_range(chrom, clen, offset, splits, nseg * t / T, nseg * (t + 1) / T, means, lmm, mode, part[(size_t)t]);
+            });
+        for (auto &th : pool) th.join();
+    }
+    int64_t need = 0;
+    for (auto &p : part) need += (int64_t)p.size();
+    if (need > cap) return -need;
     int64_t w = 0;
-    for (int64_t k = 0; k + 1 < n_splits; ++k) {
-        if (cap - w < (int64_t)clen + 400) return -((int64_t)(clen + 400) * (n_splits - 1));
-        memcpy(out + w, chrom, clen);
-        w += (int64_t)clen;
-        const long long a = (long long)(splits[k] + offset), b = (long long)(splits[k + 1] + offset);
-        int m;
-        if (mode == 1) m = snprintf(out + w, 400, "\t%lld\t%lld\n", a, b);
-        else if (mode == 0) m = snprintf(out + w, 400, "\t%lld\t%lld\t%f\n", a, b, means[k]);
-        else m = snprintf(out + w, 400, "\t%lld\t%lld\t%f\t%lld\t%f\n", a, b, means[k], b - a, lmm[k]);
-        if (m < 0 || m >= 400) return -((int64_t)(clen + 400) * (n_splits - 1));
-        w += m;
+    for (auto &p : part) {
+        memcpy(out + w, p.data(), p.size());
+        w += (int64_t)p.size();
     }
     return w;
 }

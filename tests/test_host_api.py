@@ -291,3 +291,49 @@ def test_cpp_segment_formatter_equals_python_formatting():
     assert _native.format_segments('chrQ', off, splits, means, None, 0).decode() == want0
     assert _native.format_segments('chrQ', off, splits, None, None, 1).decode() == want1
     assert _native.format_segments('chrQ', off, splits, means, lmm, 2).decode() == want2
+
+
+def test_threaded_text_io_equals_single_pass():
+    """large inputs take the multi-threaded paths of csrc/textio.cpp (pieces cut at line / segment boundaries):
+    same arrays as a per-line Python walk, same bytes as Python's % formatting; errors report the global line"""
+    from pasio_b200 import _native
+    rs = np.random.RandomState(4)
+    # ~6 MB of text: blank lines, float counts, name changes right at and away from the piece seams
+    n = 260000
+    names = np.array(['chr%d' % (k // 17000) for k in range(n)])
+    starts = np.cumsum(rs.randint(1, 30, n))
+    stops = starts + rs.randint(1, 9, n)
+    counts = rs.poisson(3, n)
+    lines = []
+    for k in range(n):
+        c = '%d' % counts[k] if k % 1000 else '%d.0' % counts[k]
+        lines.append('%s\t%d %d\t%s' % (names[k], starts[k], stops[k], c))
+        if k % 7919 == 0:
+            lines.append('   ')
+    text = ('\n'.join(lines) + '\n').encode()
+    assert len(text) > (4 << 20)
+    r = _native.parse_bedgraph_text(text)
+    assert np.array_equal(r['starts'], starts) and np.array_equal(r['stops'], stops) and np.array_equal(r['counts'], counts)
+    got_names = np.array([text[o:o + l].decode() for o, l in zip(r['name_off'][::997], r['name_len'][::997])])
+    assert np.array_equal(got_names, names[::997])
+    want_new = np.concatenate([[1], (names[1:] != names[:-1]).astype(np.uint8)])
+    assert np.array_equal(r['new_chrom'], want_new)
+    assert r['n_float'] == len(range(0, n, 1000))
+    # a malformed line late in the text: the error names its global line number (0-based, blank lines counted)
+    bad_at = len(lines) - 5
+    bad = list(lines)
+    bad[bad_at] = 'chrX 1 2'
+    with pytest.raises(ValueError) as ei:
+        _native.parse_bedgraph_text(('\n'.join(bad) + '\n').encode())
+    assert 'line %d ' % (bad_at + 1) in str(ei.value)
+
+    m = 250000
+    splits = np.concatenate([[0], np.cumsum(rs.randint(1, 5000, m))]).astype(np.int64)
+    means = rs.gamma(1.0, 3.0, m)
+    means[::501] = [0.5000005, 2.675, 1e-7][0]
+    lmm = -rs.gamma(2.0, 50.0, m)
+    want2 = ''.join('%s\t%d\t%d\t%f\t%d\t%f\n' % ('chr7', a + 9, b + 9, mu, b - a, l)
+                    for a, b, mu, l in zip(splits[:-1].tolist(), splits[1:].tolist(), means.tolist(), lmm.tolist()))
+    assert _native.format_segments('chr7', 9, splits, means, lmm, 2).decode() == want2
+    want1 = ''.join('%s\t%d\t%d\n' % ('chr7', a + 9, b + 9) for a, b in zip(splits[:-1].tolist(), splits[1:].tolist()))
+    assert _native.format_segments('chr7', 9, splits, None, None, 1).decode() == want1
