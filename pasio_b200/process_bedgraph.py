@@ -125,28 +125,81 @@ def _write(output_stream, payload):
             output_stream.write(payload)
 
 
+# Short contigs (scaffolds, transcripts) are segmented many per launch: consecutive contigs are collected until the
+# batch holds BATCH_NT positions or BATCH_CONTIGS contigs and go to the device as one "super-contig" with forced
+# boundaries (pasio_contig_load_rle with offsets); contigs never interact (reference process_bedgraph.py:69 handles
+# them one by one), so the output is the same, in input order.  A contig of BATCH_ALONE positions or more runs alone.
+BATCH_NT = 1 << 27
+BATCH_CONTIGS = 20000
+BATCH_ALONE = 1 << 24
+
+
+def _segment_runs_on_device(plan, contigs, want_lmm):
+    """contigs: list of (run_len, run_val).  -> list of (splits, means, lmm or None), positions relative to each contig"""
+    eng = _native.engine()
+    eng.use_scorer(plan['factory'])
+    if len(contigs) == 1:
+        run_len, run_val = contigs[0]
+        eng.load_rle(np.concatenate([[0], np.cumsum(run_len)]), run_val)
+        _, splits, means, lmm, _ = run_loaded_pipeline(eng, plan, want_lmm=want_lmm)
+        return [(splits, means, lmm)]
+    lengths = np.array([int(rl.sum()) for rl, _ in contigs], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum(np.concatenate([rl for rl, _ in contigs]))]).astype(np.int64)
+    eng.load_rle(starts, np.concatenate([rv for _, rv in contigs]), offsets=offsets)
+    _, splits, means, lmm, _ = run_loaded_pipeline(eng, plan, want_lmm=want_lmm)
+    # every contig boundary is a split point: cut the global lists there
+    at = np.searchsorted(splits, offsets)
+    assert np.array_equal(splits[at], offsets)
+    out = []
+    for c in range(len(contigs)):
+        i0, i1 = int(at[c]), int(at[c + 1])
+        out.append((splits[i0:i1 + 1] - offsets[c], means[i0:i1], lmm[i0:i1] if lmm is not None else None))
+    return out
+
+
 def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=False, output_mode='bedgraph'):
     logger.info('Reading input file')
     plan = _fusion.pipeline_plan(splitter)
+    if output_mode not in OUTPUT_MODES:
+        raise ValueError('Unknown output mode `%s`' % output_mode)
+    mode = OUTPUT_MODES[output_mode]
+    pending, pending_nt = [], 0          # (chrom, chrom_start, run_len, run_val) waiting for a batched launch
+
+    def flush():
+        if not pending:
+            return
+        results = _segment_runs_on_device(plan, [(rl, rv) for _, _, rl, rv in pending], want_lmm=(mode == 2))
+        for (chrom, chrom_start, _, _), (splits, means, lmm) in zip(pending, results):
+            _write(output_stream, _native.format_segments(chrom, chrom_start, splits, means if mode != 1 else None,
+                                                          lmm if mode == 2 else None, mode))
+            logger.info('Output of chromosome %s finished' % chrom)
+        del pending[:]
+
     for chrom, run_len, run_val, chrom_start in contig_runs(_read_all(input_stream), split_at_gaps):
         n = int(run_len.sum())
         logger.info('Starting chrom %s of length %d' % (chrom, n))
-        if output_mode not in OUTPUT_MODES:
-            raise ValueError('Unknown output mode `%s`' % output_mode)
-        mode = OUTPUT_MODES[output_mode]
         if plan is not None:
             # canonical splitter graph: run-length intervals go straight to the device
             assert n > 0
-            eng = _native.engine()
-            eng.use_scorer(plan['factory'])
-            eng.load_rle(np.concatenate([[0], np.cumsum(run_len)]), run_val)
-            _, splits, means, lmm, _ = run_loaded_pipeline(eng, plan, want_lmm=(mode == 2))
-        else:
-            counts = np.repeat(run_val.astype(int), run_len)
-            segs = list(segments_with_scores(counts, splitter))
-            splits = np.array([s.start for s in segs] + [segs[-1].stop], dtype=np.int64)
-            means = np.array([s.mean_count for s in segs], dtype=np.float64)
-            lmm = np.array([s.log_marginal_likelyhood for s in segs], dtype=np.float64)
+            if n >= BATCH_ALONE or BATCH_NT <= 0 or plan['final'] != 'nop':      # (the exact DP is a single-contig kernel)
+                flush()
+                pending_nt = 0
+                pending.append((chrom, chrom_start, run_len, run_val))
+                flush()
+                continue
+            if pending and (pending_nt + n > BATCH_NT or len(pending) >= BATCH_CONTIGS):
+                flush()
+                pending_nt = 0
+            pending.append((chrom, chrom_start, run_len, run_val))
+            pending_nt += n
+            continue
+        counts = np.repeat(run_val.astype(int), run_len)
+        segs = list(segments_with_scores(counts, splitter))
+        splits = np.array([s.start for s in segs] + [segs[-1].stop], dtype=np.int64)
+        means = np.array([s.mean_count for s in segs], dtype=np.float64)
+        lmm = np.array([s.log_marginal_likelyhood for s in segs], dtype=np.float64)
         _write(output_stream, _native.format_segments(chrom, chrom_start, splits, means if mode != 1 else None,
                                                       lmm if mode == 2 else None, mode))
         logger.info('Output of chromosome %s finished' % chrom)
+    flush()

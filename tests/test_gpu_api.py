@@ -324,3 +324,39 @@ def test_deep_coverage_total_beyond_int32():
     score, splits = splitter.split(counts, np.arange(len(counts) + 1))
     want, _, _ = c_oracle.FlatOracle(counts, 1.0, 1.0).rounds(500, 250, 'constants')
     assert np.array_equal(splits, want)
+
+
+def test_split_bedgraph_batches_short_contigs():
+    """many short contigs go to the device as one batch per launch: byte-identical to contig-by-contig processing,
+    in input order, for the three output modes; a long contig in between runs alone; exact mode is never batched"""
+    import io
+    from pasio_b200 import process_bedgraph as pb
+    rs = np.random.RandomState(12)
+    lines = []
+    for c in range(240):
+        n = int(rs.randint(1000, 30000)) if c != 100 else 400000
+        counts = synth.dnase_like(n, 700 + c, hotspot_share=0.3)
+        lines.extend(synth.to_bedgraph_lines('tx%d' % c, counts, chrom_start=int(rs.randint(0, 50))))
+    text = ''.join(lines)
+
+    def run(splitter, mode, batch_nt, alone=pb.BATCH_ALONE):
+        old = pb.BATCH_NT, pb.BATCH_ALONE
+        pb.BATCH_NT, pb.BATCH_ALONE = batch_nt, alone
+        try:
+            out = io.StringIO()
+            split_bedgraph_stream(io.StringIO(text), out, splitter, output_mode=mode)
+            return out.getvalue()
+        finally:
+            pb.BATCH_NT, pb.BATCH_ALONE = old
+
+    splitter = configure_splitter(window_size=800, window_shift=400)
+    for mode in ['bedgraph', 'bed', 'bedgraph+length+LMM']:
+        one_by_one = run(splitter, mode, 0)
+        assert run(splitter, mode, 1 << 27, alone=300000) == one_by_one          # contig 100 alone, the others batched
+        assert run(splitter, mode, 200000) == one_by_one                        # several small batches
+    assert one_by_one.count('\n') > 240
+    exact = configure_splitter(algorithm='exact')
+    short_text = ''.join(l for l in lines if l.split('\t')[0] in ('tx3', 'tx4'))
+    out = io.StringIO()
+    split_bedgraph_stream(io.StringIO(short_text), out, exact)
+    assert out.getvalue().startswith('tx3\t')
