@@ -188,6 +188,14 @@ int pasio_bedgraph_parse(const char *buf, int64_t len, int64_t cap, int64_t *sta
 int64_t pasio_format_segments(const char *chrom, int64_t offset, const int64_t *splits, int64_t n_splits,
                               const double *means, const double *lmm, int mode, char *out, int64_t cap);
 
+/* pasio_format_segments for a batch of contigs segmented as one super-contig (splits hold every contig boundary):
+ * first_split[c] = index of contig c's first split point (n_contigs + 1 entries), shift[c] = what to add to its
+ * positions, names[name_off[c] .. name_off[c+1]) = its name.  Same lines as per-contig calls, in contig order. */
+int64_t pasio_format_segments_batch(const char *names, const int64_t *name_off, const int64_t *shift,
+                                    const int64_t *first_split, int64_t n_contigs, const int64_t *splits,
+                                    const double *means, const double *lmm, int mode, char *out, int64_t cap);
+
+
 /* ---- measurement hooks (bench.py / profiles) ------------------------------------------
  * Device time (ms, CUDA events on the context's stream) and launch count accumulated per
  * kernel family since the last reset: 0 scan, 1 window DP, 2 compaction+prepass,

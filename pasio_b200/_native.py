@@ -58,6 +58,8 @@ SIGNATURES = {
                                             ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8), _i64p, _i64p]),
     'pasio_format_segments': (_i64, [ctypes.c_char_p, _i64, _i64p, _i64, _f64p, _f64p, ctypes.c_int,
                                      ctypes.c_char_p, _i64]),
+    'pasio_format_segments_batch': (_i64, [ctypes.c_char_p, _i64p, _i64p, _i64p, _i64, _i64p, _f64p, _f64p, ctypes.c_int,
+                                           ctypes.c_char_p, _i64]),
     'pasio_timing_reset': (ctypes.c_int, [_vp, ctypes.c_int]),
     'pasio_timing_get': (ctypes.c_int, [_vp, ctypes.c_int, _f64p, _i64p]),
     'pasio_stream': (_vp, [_vp]),
@@ -502,6 +504,32 @@ def format_segments(chrom, offset, splits, means, lmm, mode):
                 break
             cap = -w
     return b''.join(pieces)
+
+
+def format_segments_batch(chroms, shifts, first_split, splits, means, lmm, mode):
+    """format_segments for a batch segmented as one super-contig: chroms[c], shifts[c] (added to the positions) and
+    first_split[c] (index of the contig's first split point; len(chroms) + 1 entries) per contig"""
+    lib = load_library()
+    names = [c.encode() for c in chroms]
+    blob = b''.join(names)
+    name_off = np.concatenate([[0], np.cumsum([len(x) for x in names])]).astype(np.int64)
+    shifts = np.ascontiguousarray(shifts, dtype=np.int64)
+    first_split = np.ascontiguousarray(first_split, dtype=np.int64)
+    splits = np.ascontiguousarray(splits, dtype=np.int64)
+    m = np.ascontiguousarray(means) if means is not None else None
+    l = np.ascontiguousarray(lmm) if lmm is not None else None
+    nseg = int(first_split[-1] - first_split[0])
+    cap = nseg * (max(len(x) for x in names) + 56) + 1024
+    while True:
+        buf = np.empty(cap, dtype=np.uint8)
+        w = lib.pasio_format_segments_batch(blob, _ptr(name_off, ctypes.c_int64), _ptr(shifts, ctypes.c_int64),
+                                            _ptr(first_split, ctypes.c_int64), len(names), _ptr(splits, ctypes.c_int64),
+                                            _ptr(m, ctypes.c_double) if m is not None else None,
+                                            _ptr(l, ctypes.c_double) if l is not None else None, mode,
+                                            buf.ctypes.data_as(ctypes.c_char_p), cap)
+        if w >= 0:
+            return buf[:w].tobytes()
+        cap = -w
 
 
 _engine = None

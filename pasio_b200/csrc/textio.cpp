@@ -272,3 +272,49 @@ extern "C" int64_t pasio_format_segments(const char *chrom, int64_t offset, cons
     }
     return w;
 }
+
+// The same for a batch of contigs that were segmented as one super-contig (pasio_contig_load* with offsets): splits
+// are positions in the super-contig and contain every contig boundary; first_split[c] is the index of contig c's
+// first split point (first_split[n_contigs] = index of the last split point of the batch), shift[c] is added to its
+// positions (chromosome start minus the contig's offset in the super-contig), names[name_off[c] .. name_off[c+1])
+// is its name.  Lines come out in contig order, exactly those of per-contig pasio_format_segments calls.
+extern "C" int64_t pasio_format_segments_batch(const char *names, const int64_t *name_off, const int64_t *shift,
+                                               const int64_t *first_split, int64_t n_contigs, const int64_t *splits,
+                                               const double *means, const double *lmm, int mode, char *out, int64_t cap)
+{
+    const int64_t nseg = n_contigs > 0 ? first_split[n_contigs] - first_split[0] : 0;
+    const int64_t seg0 = n_contigs > 0 ? first_split[0] : 0;
+    const int T = nseg >= 100000 ? host_threads() : 1;
+    std::vector<std::string> part((size_t)T);
+    auto work = [&](int t) {
+        const int64_t k0 = seg0 + nseg * t / T, k1 = seg0 + nseg * (t + 1) / T;
+        if (k0 >= k1) return;
+        // contig of segment k0: last c with first_split[c] <= k0
+        int64_t c = std::upper_bound(first_split, first_split + n_contigs + 1, k0) - first_split - 1;
+        std::string &dst = part[(size_t)t];
+        int64_t k = k0;
+        while (k < k1) {
+            const int64_t kend = std::min(k1, first_split[c + 1]);
+            const std::string name(names + name_off[c], (size_t)(name_off[c + 1] - name_off[c]));
+            format_range(name.c_str(), name.size(), shift[c], splits, k, kend, means, lmm, mode, dst);
+            k = kend;
+            ++c;
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    int64_t need = 0;
+    for (auto &p : part) need += (int64_t)p.size();
+    if (need > cap) return -need;
+    int64_t w = 0;
+    for (auto &p : part) {
+        memcpy(out + w, p.data(), p.size());
+        w += (int64_t)p.size();
+    }
+    return w;
+}

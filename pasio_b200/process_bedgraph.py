@@ -135,27 +135,23 @@ BATCH_ALONE = 1 << 24
 
 
 def _segment_runs_on_device(plan, contigs, want_lmm):
-    """contigs: list of (run_len, run_val).  -> list of (splits, means, lmm or None), positions relative to each contig"""
+    """contigs: list of (run_len, run_val), segmented in one launch sequence.
+    -> (splits, means, lmm or None, first_split, offsets): split positions of the concatenation (they contain every
+    contig boundary), per-segment outputs, the index of each contig's first split point, the contig offsets"""
     eng = _native.engine()
     eng.use_scorer(plan['factory'])
+    lengths = np.array([int(rl.sum()) for rl, _ in contigs], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
     if len(contigs) == 1:
         run_len, run_val = contigs[0]
         eng.load_rle(np.concatenate([[0], np.cumsum(run_len)]), run_val)
-        _, splits, means, lmm, _ = run_loaded_pipeline(eng, plan, want_lmm=want_lmm)
-        return [(splits, means, lmm)]
-    lengths = np.array([int(rl.sum()) for rl, _ in contigs], dtype=np.int64)
-    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
-    starts = np.concatenate([[0], np.cumsum(np.concatenate([rl for rl, _ in contigs]))]).astype(np.int64)
-    eng.load_rle(starts, np.concatenate([rv for _, rv in contigs]), offsets=offsets)
+    else:
+        starts = np.concatenate([[0], np.cumsum(np.concatenate([rl for rl, _ in contigs]))]).astype(np.int64)
+        eng.load_rle(starts, np.concatenate([rv for _, rv in contigs]), offsets=offsets)
     _, splits, means, lmm, _ = run_loaded_pipeline(eng, plan, want_lmm=want_lmm)
-    # every contig boundary is a split point: cut the global lists there
-    at = np.searchsorted(splits, offsets)
-    assert np.array_equal(splits[at], offsets)
-    out = []
-    for c in range(len(contigs)):
-        i0, i1 = int(at[c]), int(at[c + 1])
-        out.append((splits[i0:i1 + 1] - offsets[c], means[i0:i1], lmm[i0:i1] if lmm is not None else None))
-    return out
+    first_split = np.searchsorted(splits, offsets)           # every contig boundary is a split point
+    assert np.array_equal(splits[first_split], offsets)
+    return splits, means, lmm, first_split, offsets
 
 
 def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=False, output_mode='bedgraph'):
@@ -169,10 +165,12 @@ def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=F
     def flush():
         if not pending:
             return
-        results = _segment_runs_on_device(plan, [(rl, rv) for _, _, rl, rv in pending], want_lmm=(mode == 2))
-        for (chrom, chrom_start, _, _), (splits, means, lmm) in zip(pending, results):
-            _write(output_stream, _native.format_segments(chrom, chrom_start, splits, means if mode != 1 else None,
-                                                          lmm if mode == 2 else None, mode))
+        splits, means, lmm, first_split, offsets = _segment_runs_on_device(
+            plan, [(rl, rv) for _, _, rl, rv in pending], want_lmm=(mode == 2))
+        shifts = np.array([cs for _, cs, _, _ in pending], dtype=np.int64) - offsets[:-1]
+        _write(output_stream, _native.format_segments_batch([c for c, _, _, _ in pending], shifts, first_split, splits,
+                                                            means if mode != 1 else None, lmm if mode == 2 else None, mode))
+        for chrom, _, _, _ in pending:
             logger.info('Output of chromosome %s finished' % chrom)
         del pending[:]
 

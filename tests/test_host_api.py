@@ -337,3 +337,36 @@ def test_threaded_text_io_equals_single_pass():
     assert _native.format_segments('chr7', 9, splits, means, lmm, 2).decode() == want2
     want1 = ''.join('%s\t%d\t%d\n' % ('chr7', a + 9, b + 9) for a, b in zip(splits[:-1].tolist(), splits[1:].tolist()))
     assert _native.format_segments('chr7', 9, splits, None, None, 1).decode() == want1
+
+
+def test_batch_segment_formatter_equals_per_contig_calls():
+    """pasio_format_segments_batch (a batch of contigs segmented as one super-contig) writes the lines of per-contig
+    pasio_format_segments calls, single- and multi-threaded (>= 100 000 segments)"""
+    from pasio_b200 import _native
+    rs = np.random.RandomState(8)
+    for n_contigs, seg_hi in [(7, 40), (900, 400)]:
+        nseg = rs.randint(1, seg_hi, n_contigs)
+        offsets = [0]
+        splits = [np.array([0], dtype=np.int64)]
+        for c in range(n_contigs):
+            inner = np.cumsum(rs.randint(1, 3000, nseg[c])).astype(np.int64)
+            splits.append(offsets[-1] + inner)
+            offsets.append(int(offsets[-1] + inner[-1]))
+        splits = np.concatenate(splits)
+        offsets = np.array(offsets, dtype=np.int64)
+        first_split = np.searchsorted(splits, offsets)
+        means = rs.gamma(1.0, 3.0, len(splits) - 1)
+        lmm = -rs.gamma(2.0, 50.0, len(splits) - 1)
+        chroms = ['ctg%d_%s' % (c, 'x' * (c % 5)) for c in range(n_contigs)]
+        chrom_starts = rs.randint(0, 1000, n_contigs).astype(np.int64)
+        for mode in (0, 1, 2):
+            want = b''.join(
+                _native.format_segments(chroms[c], int(chrom_starts[c]),
+                                        splits[first_split[c]:first_split[c + 1] + 1] - offsets[c],
+                                        means[first_split[c]:first_split[c + 1]] if mode != 1 else None,
+                                        lmm[first_split[c]:first_split[c + 1]] if mode == 2 else None, mode)
+                for c in range(n_contigs))
+            got = _native.format_segments_batch(chroms, chrom_starts - offsets[:-1], first_split, splits,
+                                                means if mode != 1 else None, lmm if mode == 2 else None, mode)
+            assert got == want, (n_contigs, mode)
+    assert len(splits) > 100000
