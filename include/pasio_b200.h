@@ -172,6 +172,14 @@ int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, double *sum
 int pasio_host_alloc(int64_t bytes, void **out);
 int pasio_host_free(void *ptr);
 
+/* Groups parsed intervals into contigs and builds each contig's run lengths / values (interval_groups and the
+ * accumulation loop of parse_bedgraph_stream, process_bedgraph.py:26-60; gap filling and --split-at-gaps as there).
+ * run_len / run_val: capacity 2n; group_line[g] = first line of group g, group_run[g] = its first run
+ * (n_groups + 1 entries).  Returns the number of groups. */
+int64_t pasio_bedgraph_runs(const int64_t *starts, const int64_t *stops, const int64_t *counts,
+                            const uint8_t *new_chrom, int64_t n, int split_at_gaps, int64_t *run_len,
+                            int64_t *run_val, int64_t *group_line, int64_t *group_run, int64_t *n_runs);
+
 /* ---- bedgraph text in / segment text out (host C++, csrc/textio.cpp) --------------------------------
  * pasio_bedgraph_parse replaces BedgraphInterval.from_string / each_in_stream (dto/intervals.py:16-39):
  * whitespace-separated `chrom start stop count` lines, blank lines skipped, a count that is not an integer

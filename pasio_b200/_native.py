@@ -56,6 +56,8 @@ SIGNATURES = {
     'pasio_bedgraph_count_lines': (_i64, [ctypes.c_char_p, _i64]),
     'pasio_bedgraph_parse': (ctypes.c_int, [ctypes.c_char_p, _i64, _i64, _i64p, _i64p, _i64p, _i64p,
                                             ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8), _i64p, _i64p]),
+    'pasio_bedgraph_runs': (_i64, [_i64p, _i64p, _i64p, ctypes.POINTER(ctypes.c_uint8), _i64, ctypes.c_int, _i64p, _i64p, _i64p,
+                                   _i64p, _i64p]),
     'pasio_format_segments': (_i64, [ctypes.c_char_p, _i64, _i64p, _i64, _f64p, _f64p, ctypes.c_int,
                                      ctypes.c_char_p, _i64]),
     'pasio_format_segments_batch': (_i64, [ctypes.c_char_p, _i64p, _i64p, _i64p, _i64, _i64p, _f64p, _f64p, ctypes.c_int,
@@ -478,6 +480,22 @@ def parse_bedgraph_text(data):
     k = n.value
     return dict(starts=starts[:k], stops=stops[:k], counts=counts[:k], name_off=name_off[:k], name_len=name_len[:k],
                 new_chrom=new_chrom[:k], n_float=nfloat.value)
+
+
+def bedgraph_runs(rec, split_at_gaps):
+    """parsed intervals (parse_bedgraph_text) -> (run_len, run_val, group_line, group_run): contigs as run lengths"""
+    lib = load_library()
+    n = len(rec['starts'])
+    run_len = np.empty(2 * n, dtype=np.int64)
+    run_val = np.empty(2 * n, dtype=np.int64)
+    group_line = np.empty(n + 1, dtype=np.int64)
+    group_run = np.empty(n + 1, dtype=np.int64)
+    n_runs = _i64(0)
+    g = lib.pasio_bedgraph_runs(_ptr(rec['starts'], ctypes.c_int64), _ptr(rec['stops'], ctypes.c_int64),
+                                _ptr(rec['counts'], ctypes.c_int64), _ptr(rec['new_chrom'], ctypes.c_uint8), n,
+                                int(bool(split_at_gaps)), _ptr(run_len, ctypes.c_int64), _ptr(run_val, ctypes.c_int64),
+                                _ptr(group_line, ctypes.c_int64), _ptr(group_run, ctypes.c_int64), ctypes.byref(n_runs))
+    return run_len[:n_runs.value], run_val[:n_runs.value], group_line[:g], group_run[:g + 1]
 
 
 def format_segments(chrom, offset, splits, means, lmm, mode):

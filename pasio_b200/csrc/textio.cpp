@@ -318,3 +318,34 @@ extern "C" int64_t pasio_format_segments_batch(const char *names, const int64_t 
     }
     return w;
 }
+
+// Groups the parsed intervals into contigs and turns every contig into run lengths / run values: the accumulation
+// loop of parse_bedgraph_stream and interval_groups (/root/reference/src/pasio/process_bedgraph.py:26-60).
+// Consecutive lines of one chromosome form a group; with split_at_gaps a group also ends where an interval does not
+// start at the previous stop; otherwise a zero run is inserted between non-adjacent intervals (when the previous
+// stop is non-zero, as in the reference's `if previous_stop and ...`).  Runs of non-positive length are dropped.
+// Outputs: run_len / run_val (capacity 2n), and per group its first line and its first run (group_run has
+// n_groups + 1 entries).  Returns the number of groups.
+extern "C" int64_t pasio_bedgraph_runs(const int64_t *starts, const int64_t *stops, const int64_t *counts,
+                                       const uint8_t *new_chrom, int64_t n, int split_at_gaps, int64_t *run_len,
+                                       int64_t *run_val, int64_t *group_line, int64_t *group_run, int64_t *n_runs)
+{
+    int64_t g = 0, r = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const bool adjacent = i == 0 || starts[i] == stops[i - 1];
+        const bool cut = new_chrom[i] || (split_at_gaps && !adjacent);
+        if (cut) {
+            group_line[g] = i;
+            group_run[g] = r;
+            ++g;
+        } else if (!split_at_gaps && !adjacent && stops[i - 1] != 0) {
+            const int64_t gap = starts[i] - stops[i - 1];
+            if (gap > 0) { run_len[r] = gap; run_val[r] = 0; ++r; }
+        }
+        const int64_t len = stops[i] - starts[i];
+        if (len > 0) { run_len[r] = len; run_val[r] = counts[i]; ++r; }
+    }
+    group_run[g] = r;
+    *n_runs = r;
+    return g;
+}

@@ -54,7 +54,7 @@ def _read_all(stream):
 def contig_runs(data, split_at_gaps=False):
     """Parse bedgraph bytes and yield (chrom, run_lengths, run_values, chrom_start) per contig.
 
-    Vectorised restatement of interval_groups + the accumulation loop of parse_bedgraph_stream
+    Restatement (csrc/textio.cpp: pasio_bedgraph_runs) of interval_groups + the accumulation loop of parse_bedgraph_stream
     (reference process_bedgraph.py:26-60): consecutive lines of one chromosome form a group; with
     split_at_gaps a group also ends where an interval does not start at the previous stop; otherwise a
     zero run is inserted between non-adjacent intervals (when the previous stop is non-zero, as in the
@@ -67,31 +67,13 @@ def contig_runs(data, split_at_gaps=False):
                        "integer counts." % rec['n_float'])
     if n == 0:
         return
-    starts, stops, counts = rec['starts'], rec['stops'], rec['counts']
-    cut = rec['new_chrom'].astype(bool)
-    adjacent = np.ones(n, dtype=bool)
-    adjacent[1:] = starts[1:] == stops[:-1]
-    if split_at_gaps:
-        cut = cut | ~adjacent
-    bounds = np.flatnonzero(cut).tolist() + [n]
-    for g0, g1 in zip(bounds[:-1], bounds[1:]):
-        off, ln = int(rec['name_off'][g0]), int(rec['name_len'][g0])
-        chrom = data[off:off + ln].decode()
-        lengths = np.maximum(stops[g0:g1] - starts[g0:g1], 0)
-        values = counts[g0:g1]
-        if not split_at_gaps and g1 - g0 > 1:
-            prev_stop = stops[g0:g1 - 1]
-            need = (prev_stop != 0) & ~adjacent[g0 + 1:g1]
-            gap = np.where(need, np.maximum(starts[g0 + 1:g1] - prev_stop, 0), 0)
-            run_len = np.empty(2 * (g1 - g0) - 1, dtype=np.int64)
-            run_val = np.zeros(2 * (g1 - g0) - 1, dtype=np.int64)
-            run_len[0::2] = lengths
-            run_len[1::2] = gap
-            run_val[0::2] = values
-        else:
-            run_len, run_val = lengths.astype(np.int64), values.astype(np.int64)
-        keep = run_len > 0
-        yield chrom, run_len[keep], run_val[keep], int(starts[g0])
+    run_len, run_val, group_line, group_run = _native.bedgraph_runs(rec, split_at_gaps)
+    name_off, name_len = rec['name_off'][group_line].tolist(), rec['name_len'][group_line].tolist()
+    first_start = rec['starts'][group_line].tolist()
+    bounds = group_run.tolist()
+    for k in range(len(group_line)):
+        chrom = data[name_off[k]:name_off[k] + name_len[k]].decode()
+        yield chrom, run_len[bounds[k]:bounds[k + 1]], run_val[bounds[k]:bounds[k + 1]], first_start[k]
 
 
 def parse_bedgraph(filename, split_at_gaps=False):
