@@ -47,6 +47,16 @@ def interval_groups(intervals, split_at_gaps):
 
 
 def _read_all(stream):
+    # a text stream over a binary one (open(..., 'rt'), gzip.open(..., 'rt'), sys.stdin): take the bytes underneath
+    # instead of decoding gigabytes of ASCII to str and encoding them back
+    raw = getattr(stream, 'buffer', None)
+    if raw is not None and hasattr(raw, 'read'):
+        try:
+            data = raw.read()
+            if isinstance(data, (bytes, bytearray)):
+                return bytes(data)
+        except (OSError, ValueError):
+            pass
     data = stream.read()
     return data.encode() if isinstance(data, str) else bytes(data)
 

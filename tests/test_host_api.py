@@ -370,3 +370,20 @@ def test_batch_segment_formatter_equals_per_contig_calls():
                                                 means if mode != 1 else None, lmm if mode == 2 else None, mode)
             assert got == want, (n_contigs, mode)
     assert len(splits) > 100000
+
+
+def test_parse_bedgraph_from_files_plain_and_gzip(tmp_path):
+    """files are opened in text mode like in the reference; the parser reads the bytes underneath"""
+    import gzip
+    import io
+    from pasio_b200 import parse_bedgraph
+    text = 'chr1\t0\t5\t2\nchr1\t5\t9\t0\nchr2 3 4 7\n\nchr2 10 12 1\n'
+    want = [(c, p.tolist(), s) for c, p, s in parse_bedgraph_stream(io.StringIO(text))]
+    assert want[0] == ('chr1', [2] * 5 + [0] * 4, 0) and want[1][0] == 'chr2'
+    plain = tmp_path / 'a.bedgraph'
+    plain.write_text(text)
+    gz = tmp_path / 'a.bedgraph.gz'
+    with gzip.open(str(gz), 'wt') as f:
+        f.write(text)
+    for fn in (plain, gz):
+        assert [(c, p.tolist(), s) for c, p, s in parse_bedgraph(str(fn))] == want
