@@ -13,6 +13,8 @@
 // Grouping into contigs, gap filling and --split-at-gaps stay in Python (process_bedgraph.py), vectorised.
 #include <algorithm>
 #include <cerrno>
+#include <charconv>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -222,22 +224,43 @@ extern "C" int pasio_bedgraph_parse(const char *buf, int64_t len, int64_t cap, i
 
 namespace {
 
+// '%f' of a double and '%d' of an integer with std::to_chars: by the standard the fixed/6 conversion writes the
+// characters printf("%f") writes in the C locale (checked on 2e7 random doubles), several times faster.
+inline char *put_f(char *p, char *end, double v)
+{
+    if (std::isnan(v)) { memcpy(p, "nan", 3); return p + 3; }          // Python writes 'nan' whatever the sign bit
+    if (!std::isfinite(v)) return p + snprintf(p, (size_t)(end - p), "%f", v);
+    return std::to_chars(p, end, v, std::chars_format::fixed, 6).ptr;
+}
+inline char *put_d(char *p, char *end, long long v) { return std::to_chars(p, end, v).ptr; }
+
 // lines of segments [k0, k1) appended to dst
 void format_range(const char *chrom, size_t clen, int64_t offset, const int64_t *splits, int64_t k0, int64_t k1,
                   const double *means, const double *lmm, int mode, std::string &dst)
 {
-    char line[400];
+    char line[800];
+    char *const end = line + sizeof line - 8;       // two int64, one more, two %f of doubles up to 1e308: < 700 chars; room for the separators
     dst.reserve((size_t)(k1 - k0) * (clen + 40));
     for (int64_t k = k0; k < k1; ++k) {
         const long long a = (long long)(splits[k] + offset), b = (long long)(splits[k + 1] + offset);
-        int m;
-        if (mode == 1) m = snprintf(line, sizeof line, "\t%lld\t%lld\n", a, b);
-        else if (mode == 0) m = snprintf(line, sizeof line, "\t%lld\t%lld\t%f\n", a, b, means[k]);
-        else m = snprintf(line, sizeof line, "\t%lld\t%lld\t%f\t%lld\t%f\n", a, b, means[k], b - a, lmm[k]);
-        if (m < 0) m = 0;
-        if (m >= (int)sizeof line) m = (int)sizeof line - 1;       // cannot happen: two int64 and two %f of finite doubles fit
+        char *p = line;
+        *p++ = '\t';
+        p = put_d(p, end, a);
+        *p++ = '\t';
+        p = put_d(p, end, b);
+        if (mode != 1) {
+            *p++ = '\t';
+            p = put_f(p, end, means[k]);
+        }
+        if (mode == 2) {
+            *p++ = '\t';
+            p = put_d(p, end, b - a);
+            *p++ = '\t';
+            p = put_f(p, end, lmm[k]);
+        }
+        *p++ = '\n';
         dst.append(chrom, clen);
-        dst.append(line, (size_t)m);
+        dst.append(line, (size_t)(p - line));
     }
 }
 

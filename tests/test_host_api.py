@@ -387,3 +387,19 @@ def test_parse_bedgraph_from_files_plain_and_gzip(tmp_path):
         f.write(text)
     for fn in (plain, gz):
         assert [(c, p.tolist(), s) for c, p, s in parse_bedgraph(str(fn))] == want
+
+
+def test_formatter_float_text_equals_python_percent_f():
+    """'%f' through std::to_chars(fixed, 6): the characters Python's '%f' writes, for ties, tiny, huge, negative zero,
+    random bit patterns"""
+    from pasio_b200 import _native
+    rs = np.random.RandomState(3)
+    bits = rs.randint(0, 2 ** 63, 60000, dtype=np.int64).view(np.float64)
+    vals = np.concatenate([bits[np.isfinite(bits)],
+                           [0.0, -0.0, 0.5000005, 2.675, 1e-7, 2.5e-7, 5e-7, 1.5e-6, 2.5e-6, 0.9999995, 1e15, 1e22, 1e300,
+                            -1e300, 5e-324, -4e-7, -5e-7, 123456789.1234565, float('inf'), float('-inf'), float('nan')],
+                           rs.standard_normal(20000) * 10.0 ** rs.uniform(-8, 12, 20000)])
+    splits = np.arange(len(vals) + 1, dtype=np.int64)
+    got = _native.format_segments('c', 0, splits, vals, -vals, 2).decode().split('\n')[:-1]
+    for k in range(len(vals)):
+        assert got[k] == 'c\t%d\t%d\t%f\t%d\t%f' % (k, k + 1, vals[k], 1, -vals[k]), (k, vals[k])
