@@ -14,9 +14,11 @@ for j, n in enumerate(lens):
 text = ''.join(lines)
 print('generated %d contigs, %.3g nt, %.1f MB of bedgraph text in %.1f s' % (n_contigs, lens.sum(), len(text) / 1e6, time.time() - t0), flush=True)
 splitter = configure_splitter()
+data = text.encode()
+del text, lines
 for rep in range(2):
     out = io.StringIO()
     t0 = time.perf_counter()
-    pb.split_bedgraph_stream(io.StringIO(text), out, splitter)
+    pb.split_bedgraph_stream(io.TextIOWrapper(io.BytesIO(data)), out, splitter)       # like a file opened in text mode
     dt = time.perf_counter() - t0
     print('run %d: %.2f s -> %.3g nt/s, %.0f contigs/s, %d output lines' % (rep, dt, lens.sum() / dt, n_contigs / dt, out.getvalue().count('\n')), flush=True)
