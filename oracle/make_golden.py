@@ -101,6 +101,29 @@ def gen_exact(full):
         np.savez_compressed(os.path.join(OUT, 'config1.npz'), **store)
 
 
+def gen_config3():
+    """BASELINE config 3 in full through the UNMODIFIED reference: N = 200 000 candidates over 2 Mb
+    (SURVEY 8d); several minutes of one core.  Stores the reference's score and splits; the candidates and
+    counts are regenerated from their seeds (pasio_b200.synth)."""
+    import time
+    store = {}
+    c = synth.piecewise_poisson(2000000, 1)
+    cands = synth.random_candidates(len(c), 200000, 1)
+    t0 = time.time()
+    score, splits = SquareSplitter(ScorerFactory(1.0, 1.0)).split(c, cands)
+    store['config3.gen'] = np.array('piecewise_poisson(2000000, 1)')
+    store['config3.cands_gen'] = np.array('random_candidates(2000000, 200000, 1)')
+    store['config3.counts_sha1'] = np.array(hashlib.sha1(c.tobytes()).hexdigest())
+    store['config3.cands_sha1'] = np.array(hashlib.sha1(cands.tobytes()).hexdigest())
+    store['config3.ab'] = np.array([1.0, 1.0])
+    store['config3.score'] = np.float64(score)
+    store['config3.splits'] = np.asarray(splits, dtype=np.int64)
+    store['config3.reference_seconds'] = np.float64(time.time() - t0)
+    store['tables_sha1'] = np.array(tables_sha1())
+    np.savez_compressed(os.path.join(OUT, 'config3.npz'), **store)
+    print('config3 N=%d score=%r splits=%d (%.0f s of the reference)' % (len(cands), float(score), len(splits), time.time() - t0))
+
+
 def gen_reducers():
     store = {}
     rs = np.random.RandomState(21)
@@ -207,6 +230,9 @@ def gen_pipeline():
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     np.seterr(all='ignore')
+    if "--config3" in sys.argv:          # only this one (minutes of CPU)
+        gen_config3()
+        sys.exit(0)
     if "--only-fast" not in sys.argv:
         gen_exact("--full" in sys.argv)
     gen_reducers()

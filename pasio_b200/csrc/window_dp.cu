@@ -18,6 +18,7 @@
 // CTAs are persistent and pull windows from an atomic counter (window cost varies as N^2); phase-2
 // windows whose candidates all survived already are skipped (see window_dp_kernel).
 #include "dp_core.cuh"
+#include "bound.cuh"
 #include <cstdio>
 #include <cstdlib>
 
@@ -93,16 +94,6 @@ struct WinDpParams {
     int skip_covered;           // 0: phase-2 windows neither wait nor get skipped (experiments)
 };
 
-// One finished block of 32 columns [1+32b, 32+32b], as the far pass sees it.
-struct __align__(16) CoarseRec {
-    int c_first, c_last, l_first, l_last;   // C and L of its first / last column
-    double a, b;                            // tilt: P_i + a*C_i + b*L_i is nearly constant over the block
-    double mpt;                             // max_i (P_i + a*C_i + b*L_i) over the block, raised by the tilt's rounding slack
-    double mpt8[4];                         // the same over each 8-column sub-block
-    double pad;
-};
-static_assert(sizeof(CoarseRec) == 80, "CoarseRec layout");
-
 __host__ __device__ inline size_t window_smem_bytes(int cap)
 {
     const size_t capr = (size_t)((cap + 31) & ~31);
@@ -148,37 +139,6 @@ __device__ __forceinline__ int2 col_lc(const ColRec *sCol, int i)      // (L, C)
 // Two levels: 32 rows x 32 columns first (one lane per rectangle), the survivors again as 4 rows x 8 columns
 // (one warp per surviving rectangle); what survives both is evaluated exactly, cell by cell, in the reference's
 // operation order.
-template <bool AI>
-__device__ __forceinline__ double tilted_box_max(int u_lo, int u_hi, int len_lo, int len_hi, double a, double b,
-                                                 const double *__restrict__ gtab, const double *__restrict__ ltab,
-                                                 int alpha_int, double alpha)
-{
-    const double g_lo = __ldg(gtab + (AI ? u_lo + alpha_int : u_lo)), g_hi = __ldg(gtab + (AI ? u_hi + alpha_int : u_hi));
-    const double l_lo = __ldg(ltab + len_lo), l_hi = __ldg(ltab + len_hi);
-    const double ud_lo = u32_to_double(u_lo), ud_hi = u32_to_double(u_hi);
-    const double s_lo = ud_lo + alpha, s_hi = ud_hi + alpha;
-    const double ta_lo = a * ud_lo, ta_hi = a * ud_hi;
-    const double tb_lo = b * u32_to_double(len_lo), tb_hi = b * u32_to_double(len_hi);
-    const double f00 = (g_lo - s_lo * l_lo) + (ta_lo + tb_lo);
-    const double f01 = (g_lo - s_lo * l_hi) + (ta_lo + tb_hi);
-    const double f10 = (g_hi - s_hi * l_lo) + (ta_hi + tb_lo);
-    const double f11 = (g_hi - s_hi * l_hi) + (ta_hi + tb_hi);
-    return fmax(fmax(f00, f01), fmax(f10, f11));
-}
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
-__device__ __forceinline__ float warp_sum(float v)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
-
 // Lower bounds for the 32 rows of the block starting at jb, by one warp (lane = row), while the block before it
 // (rows [jbp, jb), jbp = jb - 32) is still to be chained; everything before row jbp is final.
 //   sRow[r] = (lb, C, L, -) as floats: the far pass takes min_r (lb_r + a*C_r + b*L_r) in float and subtracts a
@@ -476,52 +436,12 @@ __device__ __forceinline__ void near_tri_farwarps(int jb, int N, const ColRec *s
 }
 
 // After the chain finished rows [jb, jb+32) (a full block of 32 columns from now on): least-squares tilt, tilted
-// maxima, end points.  One warp, lane = column.  The fit only steers how tight the bound is (any finite a, b is
-// valid), so its sums run in float.
+// maxima, end points (fit_column_record in bound.cuh).  One warp, lane = column.
 __device__ __forceinline__ void build_coarse_record(int jb, const ColRec *sCol, CoarseRec *rec, double tilt_scale_c,
                                                     double tilt_scale_l)
 {
-    const int lane = threadIdx.x & 31;
-    const ColRec me = sCol[jb + lane];
-    const int c_first = __shfl_sync(0xffffffffu, me.C, 0), c_last = __shfl_sync(0xffffffffu, me.C, 31);
-    const int l_first = __shfl_sync(0xffffffffu, me.L, 0), l_last = __shfl_sync(0xffffffffu, me.L, 31);
-    const double p_first = __shfl_sync(0xffffffffu, me.P, 0);
-    double a = 0.0, b = 0.0;                       // fit  -P ~ a*C + b*L + const
-#ifndef PASIO_NO_LS
-    {
-        const float x = (float)(me.C - c_first), y = (float)(me.L - l_first), p = (float)(me.P - p_first);
-        const float inv_n = 1.0f / 32.0f;
-        const float sx = warp_sum(x), sy = warp_sum(y), sp = warp_sum(p);
-        const float xc = x - sx * inv_n, yc = y - sy * inv_n, pc = p - sp * inv_n;
-        const float cxx = warp_sum(xc * xc), cyy = warp_sum(yc * yc), cxy = warp_sum(xc * yc);
-        const float cxp = warp_sum(xc * pc), cyp = warp_sum(yc * pc);
-        const float det = cxx * cyy - cxy * cxy;
-        float fa = 0.f, fb = 0.f;
-        if (det > 1e-4f * cxx * cyy) {
-            fa = -(cxp * cyy - cyp * cxy) / det;
-            fb = -(cyp * cxx - cxp * cxy) / det;
-        } else if (cxx > 0.f) {
-            fa = -cxp / cxx;
-        } else if (cyy > 0.f) {
-            fb = -cyp / cyy;
-        }
-        if (fabsf(fa) < 1e30f && fabsf(fb) < 1e30f) { a = (double)fa; b = (double)fb; }   // NaN / inf: no tilt
-    }
-#endif
-    double m = me.P + (a * u32_to_double(me.C) + b * u32_to_double(me.L));
-#pragma unroll
-    for (int off = 1; off < 8; off <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-    double m32 = m;
-#pragma unroll
-    for (int off = 8; off < 32; off <<= 1) m32 = fmax(m32, __shfl_xor_sync(0xffffffffu, m32, off));
-    const double slack = (fabs(a) * tilt_scale_c + fabs(b) * tilt_scale_l) * 5.684341886080802e-14;   // 2^-44
-    if ((lane & 7) == 0) rec->mpt8[lane >> 3] = m + slack;
-    if (lane == 0) {
-        *reinterpret_cast<int4 *>(rec) = make_int4(c_first, c_last, l_first, l_last);
-        rec->a = a;
-        rec->b = b;
-        rec->mpt = m32 + slack;
-    }
+    const ColRec me = sCol[jb + (threadIdx.x & 31)];
+    fit_column_record(me.C, me.L, me.P, rec, tilt_scale_c, tilt_scale_l);
 }
 
 template <bool AI, int U, int RPL, bool PRUNE>
