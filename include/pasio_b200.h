@@ -48,6 +48,14 @@ enum { PASIO_TAB_LOG = 0,          /* Lg[k] = log(k + beta)      cached_log.py:9
 /* split_constraints of default_splitters.py:52-59 */
 enum { PASIO_CONSTRAINT_NONE = 0, PASIO_CONSTRAINT_ZEROS = 1, PASIO_CONSTRAINT_CONSTANTS = 2 };
 
+/* tuning switches of pasio_set_tuning (results never depend on them; they exist for A/B parity
+ * tests and measurements) */
+enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (default), 0: every cell evaluated */
+       PASIO_TUNE_WINDOW_PHASES = 1,  /* 1: windows whose candidates all survived already are skipped      */
+       PASIO_TUNE_EXACT_PRUNE = 2,    /* 1: whole-contig exact DP bounds far columns (csrc/exact_pruned.cu) */
+       PASIO_TUNE_EXACT_LAG = 3,      /* far columns start this many 128-row blocks behind the diagonal (3 or 4) */
+       PASIO_TUNE_COUNT = 4 };
+
 /* ---- context ------------------------------------------------------------------------ */
 int pasio_ctx_create(int device, pasio_ctx **out);
 int pasio_ctx_destroy(pasio_ctx *ctx);
@@ -123,8 +131,13 @@ int pasio_filter_candidates(pasio_ctx *ctx, int constraint, int64_t *n_in, int64
 int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int constraint,
                 int64_t *n_in, int64_t *n_out, int64_t *cells);
 /* Of the most recent pasio_round: algorithmic cells, and how many of them the kernel proved irrelevant
- * with the exact far-column bound (csrc/window_dp.cu) instead of evaluating them. */
+ * with the exact far-column bound (csrc/window_dp.cu) instead of evaluating them.  After
+ * pasio_square_split: the same two numbers for the whole-contig DP. */
 int pasio_round_stats(const pasio_ctx *ctx, int64_t *cells, int64_t *cells_skipped);
+/* Switch a kernel variant on or off (PASIO_TUNE_*).  Every variant returns identical results
+ * (the bounds are exact); defaults come from PASIO_WD_PRUNE / PASIO_WD_PHASES / PASIO_XD_PRUNE /
+ * PASIO_XD_LAG in the environment. */
+int pasio_set_tuning(pasio_ctx *ctx, int key, int value);
 /* RoundReducer.reduce_candidate_list (round_reducer.py:10-31): rounds until fixed point or
  * max_rounds (<=0: len(counts)).  Stops with PASIO_E_TABLE_TOO_SHORT when tables must grow
  * (state is kept; call again after uploading longer tables).

@@ -44,6 +44,10 @@ def lib():
                                       f64p, ctypes.c_int64, f64p, ctypes.c_int64,
                                       ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                       u8p, i64p]
+        _lib.dp_oracle_mt.restype = ctypes.c_int
+        _lib.dp_oracle_mt.argtypes = _lib.dp_oracle.argtypes + [ctypes.c_int]
+        _lib.round_oracle_mt.restype = ctypes.c_int
+        _lib.round_oracle_mt.argtypes = _lib.round_oracle.argtypes + [ctypes.c_int]
     return _lib
 
 
@@ -55,7 +59,10 @@ class FlatOracle(object):
     """Whole-contig state for the flat formulation: global cumsum,
     change-point flags and host tables extended on demand."""
 
-    def __init__(self, counts, alpha, beta):
+    def __init__(self, counts, alpha, beta, threads=1):
+        """threads > 1: columns of a DP row / windows of a round spread over OpenMP threads (same cells, same
+        first-maximum rule; test_oracle_golden.py checks mt == single-threaded)."""
+        self.threads = int(threads)
         counts = np.ascontiguousarray(counts, dtype=np.int64)
         assert len(counts) > 0 and np.all(counts >= 0)
         self.counts = counts
@@ -88,11 +95,12 @@ class FlatOracle(object):
         self._ensure_tables(int(cands[-1] - cands[0]) + 1, int(C[-1] - C[0]) + a_int + 1)
         P = np.empty(N)
         prev = np.empty(N, dtype=np.int64)
-        rc = lib().dp_oracle(_p(C, ctypes.c_int64), _p(cands, ctypes.c_int64), N,
-                             _p(self.g, ctypes.c_double), len(self.g),
-                             _p(self.lg, ctypes.c_double), len(self.lg),
-                             int(self.int_alpha), float(self.alpha), self.pen,
-                             _p(P, ctypes.c_double), _p(prev, ctypes.c_int64))
+        args = (_p(C, ctypes.c_int64), _p(cands, ctypes.c_int64), N,
+                _p(self.g, ctypes.c_double), len(self.g),
+                _p(self.lg, ctypes.c_double), len(self.lg),
+                int(self.int_alpha), float(self.alpha), self.pen,
+                _p(P, ctypes.c_double), _p(prev, ctypes.c_int64))
+        rc = lib().dp_oracle_mt(*(args + (self.threads,))) if self.threads > 1 else lib().dp_oracle(*args)
         assert rc == 0, rc
         idx = po.backtrace(prev)
         return P[-1], cands[idx], P, prev
@@ -110,13 +118,14 @@ class FlatOracle(object):
         self._ensure_tables(span + 1, cnt + a_int + 1)
         keep = np.zeros(self.n + 1, dtype=np.uint8)
         cells = ctypes.c_int64(0)
-        rc = lib().round_oracle(_p(self.Cg, ctypes.c_int64), _p(self.cp, ctypes.c_uint8), self.n,
-                                _p(cands, ctypes.c_int64), m, window_size, window_shift,
-                                CONSTRAINTS[constraint],
-                                _p(self.g, ctypes.c_double), len(self.g),
-                                _p(self.lg, ctypes.c_double), len(self.lg),
-                                int(self.int_alpha), float(self.alpha), self.pen,
-                                _p(keep, ctypes.c_uint8), ctypes.byref(cells))
+        args = (_p(self.Cg, ctypes.c_int64), _p(self.cp, ctypes.c_uint8), self.n,
+                _p(cands, ctypes.c_int64), m, window_size, window_shift,
+                CONSTRAINTS[constraint],
+                _p(self.g, ctypes.c_double), len(self.g),
+                _p(self.lg, ctypes.c_double), len(self.lg),
+                int(self.int_alpha), float(self.alpha), self.pen,
+                _p(keep, ctypes.c_uint8), ctypes.byref(cells))
+        rc = lib().round_oracle_mt(*(args + (self.threads,))) if self.threads > 1 else lib().round_oracle(*args)
         assert rc == 0, rc
         return np.flatnonzero(keep).astype(np.int64), cells.value
 

@@ -17,6 +17,7 @@ OK = 0
 E_CUDA, E_ARG, E_COUNTS, E_CANDIDATES, E_TABLE_TOO_SHORT, E_STATE, E_TOO_LARGE, E_NOMEM = range(-1, -9, -1)
 TAB_LOG, TAB_LGAMMA, TAB_LGAMMA_ALPHA = 0, 1, 2
 CONSTRAINTS = {'none': 0, 'zeros': 1, 'constants': 2}
+TUNE = {'window_prune': 0, 'window_phases': 1, 'exact_prune': 2, 'exact_lag': 3}
 TIMING_FAMILIES = ['scan', 'window_dp', 'compact', 'exact_dp', 'score', 'h2d', 'd2h']
 
 _i64 = ctypes.c_int64
@@ -45,6 +46,7 @@ SIGNATURES = {
     'pasio_filter_candidates': (ctypes.c_int, [_vp, ctypes.c_int, _i64p, _i64p]),
     'pasio_round': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64p, _i64p, _i64p]),
     'pasio_round_stats': (ctypes.c_int, [_vp, _i64p, _i64p]),
+    'pasio_set_tuning': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     'pasio_rounds': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64, _i64p, _i64p, _i64p, _i64p, _i64]),
     'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
     'pasio_suffix_scores': (ctypes.c_int, [_vp, _i64, _f64p]),
@@ -350,6 +352,10 @@ class Engine(object):
         self._retry(lambda: self.lib.pasio_round(self.ctx, window_size, window_shift, CONSTRAINTS[constraint],
                                                  ctypes.byref(n_in), ctypes.byref(n_out), ctypes.byref(cells)))
         return n_in.value, n_out.value, cells.value
+
+    def set_tuning(self, key, value):
+        """kernel variant switches (TUNE); results never depend on them"""
+        self._check(self.lib.pasio_set_tuning(self.ctx, TUNE[key], int(value)))
 
     def round_stats(self):
         """(algorithmic cells, cells skipped by the exact bound) of the most recent round"""

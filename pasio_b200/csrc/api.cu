@@ -216,6 +216,12 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
         return PASIO_E_CUDA;
     }
     memset(ctx->h_scalars, 0, 16 * sizeof(i64));
+    auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; };
+    ctx->tune[PASIO_TUNE_WINDOW_PRUNE] = env_int("PASIO_WD_PRUNE", 1);
+    ctx->tune[PASIO_TUNE_WINDOW_PHASES] = env_int("PASIO_WD_PHASES", 1);
+    ctx->tune[PASIO_TUNE_EXACT_PRUNE] = env_int("PASIO_XD_PRUNE", 1);
+    ctx->tune[PASIO_TUNE_EXACT_LAG] = env_int("PASIO_XD_LAG", 3);
+    if (ctx->tune[PASIO_TUNE_EXACT_LAG] < 3 || ctx->tune[PASIO_TUNE_EXACT_LAG] > 4) ctx->tune[PASIO_TUNE_EXACT_LAG] = 3;
     *out = ctx;
     return PASIO_OK;
 }
@@ -229,7 +235,8 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     DevBuf *bufs[] = {&ctx->tab[0], &ctx->tab[1], &ctx->tab[2], &ctx->counts, &ctx->cg, &ctx->cpbits, &ctx->keepbits,
                       &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large, &ctx->win_flags,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
-                      &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full};
+                      &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full,
+                      &ctx->xpRing, &ctx->xpRec, &ctx->xpTasks};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -762,6 +769,15 @@ extern "C" int pasio_round_stats(const pasio_ctx *ctx, int64_t *cells, int64_t *
     if (!ctx) return PASIO_E_ARG;
     if (cells) *cells = ctx->last_cells;
     if (cells_skipped) *cells_skipped = ctx->last_cells_skipped;
+    return PASIO_OK;
+}
+
+extern "C" int pasio_set_tuning(pasio_ctx *ctx, int key, int value)
+{
+    if (!ctx) return PASIO_E_ARG;
+    if (key < 0 || key >= PASIO_TUNE_COUNT) return pasio_fail(ctx, PASIO_E_ARG, "unknown tuning key %d", key);
+    if (key == PASIO_TUNE_EXACT_LAG && (value < 3 || value > 4)) return pasio_fail(ctx, PASIO_E_ARG, "exact lag must be 3 or 4");
+    ctx->tune[key] = value;
     return PASIO_OK;
 }
 

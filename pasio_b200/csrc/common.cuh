@@ -84,6 +84,10 @@ struct pasio_ctx {
 
     // scratch
     DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan, logfac_full;
+    DevBuf xpRing, xpRec, xpTasks;   // exact_pruned.cu: self-score ring, column-block records, task list
+
+    // tuning switches (pasio_set_tuning; defaults from the PASIO_WD_* / PASIO_XD_* environment variables)
+    int tune[PASIO_TUNE_COUNT];
     i64 *h_scalars = nullptr;    // pinned, 16 entries
 
     i64 last_cells = 0, last_cells_skipped = 0;   // of the most recent round
@@ -152,6 +156,7 @@ int window_dp_max_candidates(pasio_ctx *ctx);
 
 // exact_dp.cu
 int launch_exact_dp(pasio_ctx *ctx, i64 N);                   // over ctx->dpL/dpC -> dpP/dpPrev
+int launch_exact_dp_pruned(pasio_ctx *ctx, i64 N, int lag);   // exact_pruned.cu: the same result, far columns bounded
 int launch_gather_candidates(pasio_ctx *ctx);                 // current candidates -> dpL/dpC (rebased)
 int launch_backtrace_mark(pasio_ctx *ctx, i64 N);             // dpPrev -> keepbits (positions on the optimal path)
 int launch_suffix_row(pasio_ctx *ctx, i64 stop, double *d_out);

@@ -322,6 +322,13 @@ static int run_exact_dp(pasio_ctx *ctx, i64 N)
 
 int launch_exact_dp(pasio_ctx *ctx, i64 N)
 {
+    // tiny alpha: lgamma(alpha) dwarfs the delta scale of the bound; alpha = 0: G[0] = inf (as in window_dp.cu)
+    if (ctx->tune[PASIO_TUNE_EXACT_PRUNE] && ctx->alpha >= 0.0009765625) {
+        ctx->fam_launches[TF_EXACT_DP] += 0;
+        return launch_exact_dp_pruned(ctx, N, ctx->tune[PASIO_TUNE_EXACT_LAG]);
+    }
+    ctx->last_cells = N * (N - 1) / 2;
+    ctx->last_cells_skipped = 0;
     const i64 nB = (N - 1 + XD_ROWS - 1) / XD_ROWS;
     PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)N * 8));
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPrev, (size_t)N * 4));

@@ -921,7 +921,7 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     // stream and fill the SMs as the persistent CTAs of the big kernel run out of windows.  All of them only OR bits
     // into the survivor bitmap.
     static const int small_env = getenv("PASIO_WD_SMALL") ? atoi(getenv("PASIO_WD_SMALL")) : 1;
-    static const int phase_env = getenv("PASIO_WD_PHASES") ? atoi(getenv("PASIO_WD_PHASES")) : 1;
+    const int phase_env = ctx->tune[PASIO_TUNE_WINDOW_PHASES];
     const bool use_lists = small_env && ctx->n_small + ctx->n_medium + ctx->n_large == nwin;
     const i64 n_small = use_lists ? ctx->n_small : 0, n_medium = use_lists ? ctx->n_medium : 0;
     const i64 n_large = use_lists ? ctx->n_large : nwin;
@@ -979,7 +979,7 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     if (n_large > 0) {
         const size_t smem = window_smem_bytes(p.cap);
         // PASIO_WD_PRUNE=0 disables the exact far-column pruning (experiments / cross-checks)
-        static const int prune_env = getenv("PASIO_WD_PRUNE") ? atoi(getenv("PASIO_WD_PRUNE")) : 1;
+        const int prune_env = ctx->tune[PASIO_TUNE_WINDOW_PRUNE];
         const bool prune = prune_env != 0 && ctx->alpha >= 0.0009765625;   // tiny alpha: lgamma(alpha) dwarfs the delta scale; alpha = 0: G[0] = inf
         void (*kern)(WinDpParams);
         if (ctx->alpha_is_int) kern = prune ? window_dp_kernel<true, 4, 2, true> : window_dp_kernel<true, 4, 2, false>;

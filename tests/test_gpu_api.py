@@ -179,7 +179,7 @@ def test_segments_with_scores_vs_reference_fixture(golden, name, kwargs):
     g.check_splits(np.concatenate([starts, stops[-1:]]), np.concatenate([g[name + '.starts'], g[name + '.stops'][-1:]]),
                    score, g[name + '.score'], name)
     assert np.array_equal(splits[:-1], starts)
-    if g.same_tables:
+    if g.bit_exact(name):
         assert np.array_equal(means, g[name + '.mean'])
         # logfac_cumsum is a parallel scan here and a sequential sum in the reference: tolerance only
         assert np.allclose(lmm, g[name + '.lmm'], rtol=1e-9, atol=1e-7)
@@ -194,8 +194,9 @@ def test_split_bedgraph_text_vs_reference_fixture(golden):
             split_bedgraph_stream(io.StringIO(text), out, configure_splitter(window_size=500, window_shift=250),
                                   split_at_gaps=gaps, output_mode=mode)
             want = str(g['bg.%s.%d' % (mode, int(gaps))])
-            if not g.same_tables:
-                continue
+            if not g.bit_exact('bedgraph text %s gaps=%d' % (mode, gaps)):
+                pytest.skip('host np.log/gammaln tables differ from the fixtures\' (see the pytest header): the text '
+                            'comparison with the reference fixture cannot be made on this host')
             if mode != 'bedgraph+length+LMM':
                 assert out.getvalue() == want, (mode, gaps)
             else:

@@ -114,7 +114,7 @@ def test_rounds_vs_reference_fixture(eng, golden, name):
         want, o_cells = fo.round(cands, wsize, wshift, constraint)
         assert np.array_equal(got, want), (name, r)
         assert (n_in, n_out, cells) == (len(cands), len(want), o_cells)
-        if g.same_tables:
+        if g.bit_exact(name):
             assert np.array_equal(got, g[name + '.round%d' % r]), (name, r)
         cands = got
     # the whole loop in one call
@@ -219,6 +219,80 @@ def test_config1_full_vs_reference_fixture(eng, golden):
     assert abs(np.sum(scores) - score) <= 1e-9 * abs(score)
     score2, splits2 = eng.square_split()
     assert np.array_equal(splits2, splits)
+
+
+def _oracle_threads():
+    import os
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+def test_config1_full_dp_arrays_vs_oracle(eng):
+    """config 1 at its stated shape: every prefix score and arg-max of the 100 001 rows equals the C oracle
+    (the pruned kernel skips > 95 % of the cells: a wrong bound would show here)."""
+    counts = synth.piecewise_poisson(100000, 0)
+    cands = np.arange(len(counts) + 1, dtype=np.int64)
+    score, splits, P, prev = gpu_exact(eng, counts, cands, 1.0, 1.0)
+    cells, skipped = eng.round_stats()
+    assert cells == len(cands) * (len(cands) - 1) // 2 and 0 < skipped < cells
+    o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, 1.0, 1.0, threads=_oracle_threads()).square_split(cands)
+    assert np.array_equal(P, o_P) and np.array_equal(prev, o_prev)
+    assert score == o_score and np.array_equal(splits, o_splits)
+
+
+def test_config3_full_vs_reference_fixture_and_oracle(eng, golden):
+    """BASELINE config 3 at its stated shape (N = 200 000 candidates over 2 Mb, 2.0e10 cells): splits and score
+    equal the UNMODIFIED reference's (tests/golden/config3.npz, 827 s of the reference), and the complete P / prev
+    arrays equal the C oracle's."""
+    import hashlib
+    g = golden('config3.npz')
+    counts = g.counts('config3')
+    cands = synth.random_candidates(len(counts), 200000, 1)
+    assert hashlib.sha1(cands.tobytes()).hexdigest() == str(g['config3.cands_sha1'])
+    score, splits, P, prev = gpu_exact(eng, counts, cands, 1.0, 1.0)
+    g.check_splits(splits, g['config3.splits'], score, g['config3.score'], 'config3')
+    o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, 1.0, 1.0, threads=_oracle_threads()).square_split(cands)
+    assert np.array_equal(P, o_P) and np.array_equal(prev, o_prev)
+    assert score == o_score and np.array_equal(splits, o_splits)
+    # the un-pruned kernel (every cell evaluated) gives the same arrays
+    eng.set_tuning('exact_prune', 0)
+    try:
+        score0, splits0, P0, prev0 = gpu_exact(eng, counts, cands, 1.0, 1.0)
+    finally:
+        eng.set_tuning('exact_prune', 1)
+    assert np.array_equal(P0, P) and np.array_equal(prev0, prev)
+
+
+PRUNED_EXACT_CASES = {
+    'zeros': lambda: (np.zeros(20000, dtype=np.int64), None),                      # arg-max is always column 0 (far)
+    'const': lambda: (np.full(20000, 3, dtype=np.int64), None),
+    'sparse_ties': lambda: (synth.dnase_like(30000, 5, hotspot_share=0.3), None),  # exact ties in the arg-max
+    'dense': lambda: (synth.two_level_poisson(12000, seed=3), None),
+    'pp_cands': lambda: (synth.piecewise_poisson(300000, 9), synth.random_candidates(300000, 25000, 9)),
+    'long_segments': lambda: (np.repeat(np.random.RandomState(4).poisson(20, 12), 2500).astype(np.int64)
+                              + np.random.RandomState(5).poisson(3, 30000), None),
+}
+
+
+@pytest.mark.parametrize('case', sorted(PRUNED_EXACT_CASES))
+@pytest.mark.parametrize('ab', [(1.0, 1.0), (2.5, 3.0)])
+def test_exact_pruned_vs_oracle_and_unpruned(eng, case, ab):
+    """the pruned whole-contig DP (bounded far columns, both lags) against the oracle and against the kernel
+    that evaluates every cell: P and prev bit for bit, on data where the far columns win, tie, or never matter"""
+    counts, cands = PRUNED_EXACT_CASES[case]()
+    if cands is None:
+        cands = np.arange(len(counts) + 1, dtype=np.int64)
+    o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, *ab, threads=_oracle_threads()).square_split(cands)
+    try:
+        for prune, lag in [(1, 3), (1, 4), (0, 3)]:
+            eng.set_tuning('exact_prune', prune)
+            eng.set_tuning('exact_lag', lag)
+            score, splits, P, prev = gpu_exact(eng, counts, cands, *ab)
+            assert np.array_equal(P, o_P), (case, prune, lag)
+            assert np.array_equal(prev, o_prev), (case, prune, lag)
+            assert score == o_score and np.array_equal(splits, o_splits)
+    finally:
+        eng.set_tuning('exact_prune', 1)
+        eng.set_tuning('exact_lag', 3)
 
 
 def test_config3_prefix_property(eng):

@@ -62,7 +62,7 @@ def test_rounds_numpy_and_c_oracle(golden, name):
         if r < 2:       # the object-faithful numpy loop is slow; two rounds pin it
             obj = po.sliding_window_round(counts, cands, t, wsize, wshift, constraint)
             assert np.array_equal(obj, flat)
-        if g.same_tables:
+        if g.bit_exact(name):
             assert np.array_equal(flat, want), (name, r)
         cands = flat
     score, splits = po.nop_split(counts, cands, t)
@@ -75,7 +75,7 @@ def test_default_pipeline_oracle(golden):
     counts = g[name + '.counts'].astype(np.int64)
     t = po.Tables(1, 1.0)
     out = po.default_pipeline(counts, t, window_size=1000, window_shift=500, num_rounds=2)
-    if g.same_tables:
+    if g.bit_exact(name):
         assert np.array_equal(out['splits'][:-1], g[name + '.starts'])
         assert np.array_equal(out['splits'][1:], g[name + '.stops'])
         assert np.array_equal(out['mean_counts'], g[name + '.mean'])
@@ -91,7 +91,7 @@ def test_flat_rounds_match_pipeline_fixture(golden):
         counts = g[name + '.counts'].astype(np.int64)
         fo = c_oracle.FlatOracle(counts, kw['a'], kw['b'])
         cands, sizes, cells = fo.rounds(kw['w'], kw['s'], kw['c'])
-        if g.same_tables:
+        if g.bit_exact(name):
             assert np.array_equal(cands[:-1], g[name + '.starts']), name
             assert np.array_equal(cands[1:], g[name + '.stops']), name
 
@@ -121,3 +121,31 @@ def test_config1_fixture_is_consistent(golden):
     assert len(splits) == 5123 and counts.sum() == 954615
     sc = po.Scorer(counts, splits, po.Tables(1, 1.0))
     assert abs(np.sum(sc.scores()) - float(g['config1.score'])) <= 1e-9 * abs(float(g['config1.score']))
+
+
+def test_mt_oracle_equals_single_thread():
+    """dp_oracle_mt / round_oracle_mt (OpenMP, used for the full-size comparisons) == the single-threaded loops"""
+    from pasio_b200 import synth
+    for counts, cands, ab in [(synth.piecewise_poisson(6000, 3), np.arange(6001), (1.0, 1.0)),
+                              (synth.dnase_like(8000, 5, hotspot_share=0.4), np.arange(8001), (2.5, 3.0)),
+                              (np.zeros(3000, dtype=np.int64), np.arange(3001), (1.0, 1.0))]:
+        a = c_oracle.FlatOracle(counts, *ab).square_split(cands)
+        b = c_oracle.FlatOracle(counts, *ab, threads=5).square_split(cands)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    counts = synth.dnase_like(400000, 6)
+    a = c_oracle.FlatOracle(counts, 1.0, 1.0).rounds(2500, 1250, 'constants')
+    b = c_oracle.FlatOracle(counts, 1.0, 1.0, threads=5).rounds(2500, 1250, 'constants')
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2]
+
+
+def test_config3_oracle_vs_reference_fixture(golden):
+    """BASELINE config 3 (N = 200 000 candidates, 2.0e10 cells): the C oracle reproduces the score and the
+    6 923 splits of the unmodified reference (tests/golden/config3.npz)."""
+    import os
+    from pasio_b200 import synth
+    g = golden('config3.npz')
+    counts = g.counts('config3')
+    cands = synth.random_candidates(len(counts), 200000, 1)
+    fo = c_oracle.FlatOracle(counts, 1.0, 1.0, threads=max(1, min(32, os.cpu_count() or 1)))
+    score, splits, _, _ = fo.square_split(cands)
+    g.check_splits(splits, g['config3.splits'], score, g['config3.score'], 'config3')

@@ -33,6 +33,8 @@ def exact(args, which):
         cands = synth.random_candidates(len(counts), 200000, 1)
         N = len(cands)
     eng.load(counts)
+    eng.set_tuning('exact_prune', args.prune)
+    eng.set_tuning('exact_lag', args.lag)
     times = []
     for rep in range(args.reps + 1):
         eng.set_candidates(cands)
@@ -44,7 +46,14 @@ def exact(args, which):
         times.append((wall, eng.timing()['exact_dp'][0]))
     wall, kern = min(times[1:])
     cells = N * (N - 1) // 2
+    _, skipped = eng.round_stats()
+    peak = 148 * 64 * 1.965e9
     print(json.dumps({'workload': 'config%d exact SquareSplitter' % which, 'N': N, 'cells': cells,
+                      'prune': args.prune, 'lag': args.lag, 'cells_skipped': skipped,
+                      'cells_evaluated': cells - skipped, 'evaluated_frac': (cells - skipped) / cells,
+                      'fp64_roofline_frac_algorithmic': cells / (kern * 1e-3) * 4 / peak,
+                      'fp64_roofline_frac_evaluated': (cells - skipped) / (kern * 1e-3) * 4 / peak,
+                      'ns_per_row': kern * 1e6 / N,
                       'wall_ms': wall * 1e3, 'kernel_ms': kern, 'cells_per_s_wall': cells / wall,
                       'cells_per_s_kernel': cells / (kern * 1e-3), 'splits': len(splits), 'score': float(score)}))
 
@@ -143,6 +152,8 @@ if __name__ == '__main__':
     ap.add_argument('--reps', type=int, default=2)
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--contigs', type=int, default=100000)
+    ap.add_argument('--prune', type=int, default=1, help='exact DP: 1 = bounded far columns (default), 0 = every cell')
+    ap.add_argument('--lag', type=int, default=3, help='exact DP: far columns start this many blocks behind (3 or 4)')
     a = ap.parse_args()
     if a.what == 'exact1':
         exact(a, 1)
