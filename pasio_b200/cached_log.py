@@ -38,6 +38,11 @@ class _TableComputer(object):
         self.precomputed = type(self)._fn(np.arange(self.cache_size) + shift)
         self._extended = self.precomputed
 
+    def __reduce__(self):
+        # pickled as its constructor arguments (device_pool.py sends splitters to worker processes): the tables are
+        # rebuilt by the same numpy / scipy calls on the other side, not shipped
+        return (type(self), (self.shift, self.cache_size))
+
     def table(self, n):
         """float64 table of at least n entries; entry k is fn(k + shift)."""
         if n > len(self._extended):

@@ -49,6 +49,9 @@ def get_argparser():
                    help='By default gaps between intervals are filled with zeros.\n'
                         'Split at gaps overrides this behavior so that\n'
                         'non-adjacent intervals are segmented independently.')
+    p.add_argument('--devices', type=int, default=None, metavar='N',
+                   help='(pasio_b200) shard the contigs over N GPUs, one worker process per GPU,\n'
+                        'longest contig first; the output is the same text in the same order')
     p.add_argument('--verbosity', metavar='LEVEL', default='WARNING',
                    help='Set logging level (default: %(default)s)\nUse `INFO` to show work progress')
     p.add_argument('--version', action='version', version='%(prog)s ' + __version__)
@@ -61,7 +64,7 @@ def process(argv=None):
     logger.info("Pasio:" + str(args))
     splitter = configure_splitter(**vars(args))
     split_bedgraph(in_filename=args.bedgraph, out_filename=args.output_file, splitter=splitter,
-                   split_at_gaps=args.split_at_gaps, output_mode=args.output_mode)
+                   split_at_gaps=args.split_at_gaps, output_mode=args.output_mode, devices=args.devices)
 
 
 def main():

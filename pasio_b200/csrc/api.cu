@@ -489,8 +489,16 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
         }
         if (table_rc == PASIO_OK && w_ready > w_done) {
             i64 max_span = 0, max_cnt = 0;
+            // the scan's "negative count seen" flag comes back with the prepass results: a negative count makes the
+            // prefix sums non-monotone and the DP's table indices meaningless, so no window is processed after it
+            // (the reference asserts counts >= 0 before anything else, log_marginal_likelyhood.py:33)
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 1, ctx->scalars.as<i64>() + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
             PASIO_TRY(launch_window_prepass(ctx, w_ready - w_done, (int)window_size, (int)window_shift, &max_span, &max_cnt,
                                             constraint, w_done));
+            if (ctx->h_scalars[1]) {
+                cudaStreamSynchronize(ctx->stream_copy);      // the caller's buffer must not be read after we return
+                return pasio_fail(ctx, PASIO_E_COUNTS, "counts must be >= 0");
+            }
             table_rc = check_dp_tables(ctx, max_span, max_cnt);
             if (table_rc == PASIO_OK) {
                 PASIO_TRY(launch_window_dp(ctx, w_ready - w_done, (int)window_size, (int)window_shift, constraint, w_done,

@@ -36,12 +36,14 @@ inline bool parse_int(const char *s, const char *e, int64_t *out)
     bool neg = false;
     if (*s == '+' || *s == '-') { neg = *s == '-'; ++s; }
     if (s == e) return false;
-    int64_t v = 0;
+    uint64_t v = 0;
     for (; s < e; ++s) {
         if (*s < '0' || *s > '9') return false;
-        v = v * 10 + (*s - '0');
+        const uint64_t d = (uint64_t)(*s - '0');
+        if (v > (UINT64_C(9223372036854775807) - d) / 10) return false;   // beyond int64: not representable here (Python ints
+        v = v * 10 + d;                                                    // are unbounded; numpy's int64 profile is not)
     }
-    *out = neg ? -v : v;
+    *out = neg ? -(int64_t)v : (int64_t)v;
     return true;
 }
 
@@ -101,6 +103,8 @@ bool parse_range(const char *buf, const char *p, const char *end, int64_t cap, c
                 if (l >= sizeof tmp) { *err_line = line_no; return false; }
                 memcpy(tmp, tok[3], l);
                 tmp[l] = 0;
+                // Python's float() takes no hexadecimal literals (strtod does)
+                if (memchr(tmp, 'x', l) || memchr(tmp, 'X', l) || memchr(tmp, 'p', l) || memchr(tmp, 'P', l)) { *err_line = line_no; return false; }
                 char *endp = nullptr;
                 errno = 0;
                 const double d = strtod(tmp, &endp);

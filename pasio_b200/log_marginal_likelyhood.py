@@ -38,6 +38,9 @@ class ScorerFactory(object):
         self.log_computer = LogComputer(shift=beta)
         self.segment_creation_cost = _creation_cost(self.alpha, self.log_computer, self.log_gamma_alpha_computer)
 
+    def __reduce__(self):
+        return (ScorerFactory, (self.alpha, self.beta))      # tables are rebuilt, not pickled
+
     def __call__(self, counts, split_candidates):
         cls = (LogMarginalLikelyhoodIntAlphaComputer if isinstance(self.alpha, int)
                else LogMarginalLikelyhoodRealAlphaComputer)

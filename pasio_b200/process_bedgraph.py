@@ -46,44 +46,125 @@ def interval_groups(intervals, split_at_gaps):
             yield fill_interval_gaps(chromosome_intervals)
 
 
-def _read_all(stream):
-    # a text stream over a binary one (open(..., 'rt'), gzip.open(..., 'rt'), sys.stdin): take the bytes underneath
-    # instead of decoding gigabytes of ASCII to str and encoding them back
+CHUNK_BYTES = 64 << 20        # the input is read in pieces of this size, cut at line starts
+
+
+def _binary_reader(stream):
+    """read(n) -> bytes over the input.  A text stream over a binary one (open(..., 'rt'), gzip.open(..., 'rt'),
+    sys.stdin) is read through the binary object underneath instead of decoding gigabytes of ASCII to str and
+    encoding them back.  If the caller already consumed part of a seekable text stream, the binary object is first
+    moved to the text layer's position (its read-ahead would otherwise be lost); a NON-seekable text stream (a pipe)
+    must not have been read from before: its read-ahead cannot be recovered."""
     raw = getattr(stream, 'buffer', None)
     if raw is not None and hasattr(raw, 'read'):
         try:
-            data = raw.read()
-            if isinstance(data, (bytes, bytearray)):
-                return bytes(data)
-        except (OSError, ValueError):
+            if stream.seekable():
+                pos = stream.tell()              # byte offset of the next character (plain cookie for ASCII / UTF-8)
+                if 0 <= pos < (1 << 62):
+                    raw.seek(pos)
+                    return raw.read
+            else:
+                return raw.read
+        except (OSError, ValueError, AttributeError):
             pass
-    data = stream.read()
-    return data.encode() if isinstance(data, str) else bytes(data)
+
+    def read_text(n):
+        data = stream.read(n)
+        return data.encode() if isinstance(data, str) else bytes(data)
+    return read_text
+
+
+def _read_all(stream):
+    read = _binary_reader(stream)
+    pieces = []
+    while True:
+        piece = read(CHUNK_BYTES)
+        if not piece:
+            break
+        pieces.append(piece)
+    return b''.join(pieces)
+
+
+def _contig_runs_chunked(read, split_at_gaps=False):
+    """Generator over the contigs of a bedgraph stream read in bounded pieces: yields
+    (chrom, run_lengths, run_values, chrom_start) as soon as a contig is complete (the reference also yields contig by
+    contig, process_bedgraph.py:46-60).  Memory: one piece of text plus the parsed lines of the contig in progress.
+
+    Restatement (csrc/textio.cpp: pasio_bedgraph_parse / pasio_bedgraph_runs) of BedgraphInterval.each_in_stream,
+    interval_groups and the accumulation loop of parse_bedgraph_stream (reference process_bedgraph.py:26-60): consecutive
+    lines of one chromosome form a group; with split_at_gaps a group also ends where an interval does not start at the
+    previous stop; otherwise a zero run is inserted between non-adjacent intervals (when the previous stop is non-zero,
+    as in the reference's `if previous_stop and ...`).  Runs of non-positive length contribute nothing."""
+    tail = b''
+    pend = None          # lines of the last (possibly unfinished) group: (chrom, starts, stops, counts)
+    while True:
+        chunk = read(CHUNK_BYTES)
+        eof = len(chunk) == 0
+        data = tail + chunk if tail else chunk
+        if eof:
+            tail = b''
+        else:
+            cut = data.rfind(b'\n') + 1
+            tail = data[cut:]
+            data = data[:cut]
+        rec = _native.parse_bedgraph_text(data) if data else None
+        n_new = len(rec['starts']) if rec is not None else 0
+        if rec is not None and rec['n_float']:
+            logger.warning("Pasio cannot be used with floating point counts. %d count(s) were automatically converted "
+                           "to integers as an approximation. Make sure these values were designed to actually be "
+                           "integer counts." % rec['n_float'])
+        if n_new == 0 and not eof:
+            continue
+        if pend is not None:
+            n_old = len(pend[1])
+            if n_new:
+                first = data[rec['name_off'][0]:rec['name_off'][0] + rec['name_len'][0]]
+                new_chrom = np.concatenate([np.zeros(n_old, dtype=np.uint8), rec['new_chrom']])
+                new_chrom[0] = 1
+                new_chrom[n_old] = first != pend[0]
+                lines = dict(starts=np.concatenate([pend[1], rec['starts']]), stops=np.concatenate([pend[2], rec['stops']]),
+                             counts=np.concatenate([pend[3], rec['counts']]), new_chrom=new_chrom)
+            else:
+                new_chrom = np.zeros(n_old, dtype=np.uint8)
+                new_chrom[0] = 1
+                lines = dict(starts=pend[1], stops=pend[2], counts=pend[3], new_chrom=new_chrom)
+        elif n_new:
+            n_old = 0
+            lines = rec
+        else:
+            return                                   # end of an empty input
+        run_len, run_val, group_line, group_run = _native.bedgraph_runs(lines, split_at_gaps)
+        first_line = group_line.tolist()
+        bounds = group_run.tolist()
+        n_groups = len(first_line)
+        first_start = lines['starts'][group_line].tolist()
+
+        def name_of(k):
+            gl = first_line[k]
+            if gl < n_old:
+                return pend[0]
+            off, ln = int(rec['name_off'][gl - n_old]), int(rec['name_len'][gl - n_old])
+            return data[off:off + ln]
+        done = n_groups if eof else n_groups - 1     # the last group may continue in the next piece
+        for k in range(done):
+            yield name_of(k).decode(), run_len[bounds[k]:bounds[k + 1]], run_val[bounds[k]:bounds[k + 1]], first_start[k]
+        if eof:
+            return
+        gl = first_line[-1]
+        pend = (bytes(name_of(n_groups - 1)), lines['starts'][gl:].copy(), lines['stops'][gl:].copy(),
+                lines['counts'][gl:].copy())
 
 
 def contig_runs(data, split_at_gaps=False):
-    """Parse bedgraph bytes and yield (chrom, run_lengths, run_values, chrom_start) per contig.
+    """The contigs of a bedgraph text held in memory (bytes): (chrom, run_lengths, run_values, chrom_start) each."""
+    view = memoryview(data)
+    pos = [0]
 
-    Restatement (csrc/textio.cpp: pasio_bedgraph_runs) of interval_groups + the accumulation loop of parse_bedgraph_stream
-    (reference process_bedgraph.py:26-60): consecutive lines of one chromosome form a group; with
-    split_at_gaps a group also ends where an interval does not start at the previous stop; otherwise a
-    zero run is inserted between non-adjacent intervals (when the previous stop is non-zero, as in the
-    reference's `if previous_stop and ...`).  Runs of non-positive length contribute nothing."""
-    rec = _native.parse_bedgraph_text(data)
-    n = len(rec['starts'])
-    if rec['n_float']:
-        logger.warning("Pasio cannot be used with floating point counts. %d count(s) were automatically converted "
-                       "to integers as an approximation. Make sure these values were designed to actually be "
-                       "integer counts." % rec['n_float'])
-    if n == 0:
-        return
-    run_len, run_val, group_line, group_run = _native.bedgraph_runs(rec, split_at_gaps)
-    name_off, name_len = rec['name_off'][group_line].tolist(), rec['name_len'][group_line].tolist()
-    first_start = rec['starts'][group_line].tolist()
-    bounds = group_run.tolist()
-    for k in range(len(group_line)):
-        chrom = data[name_off[k]:name_off[k] + name_len[k]].decode()
-        yield chrom, run_len[bounds[k]:bounds[k + 1]], run_val[bounds[k]:bounds[k + 1]], first_start[k]
+    def read(n):
+        piece = bytes(view[pos[0]:pos[0] + n])
+        pos[0] += len(piece)
+        return piece
+    return _contig_runs_chunked(read, split_at_gaps)
 
 
 def parse_bedgraph(filename, split_at_gaps=False):
@@ -94,15 +175,17 @@ def parse_bedgraph(filename, split_at_gaps=False):
 
 
 def parse_bedgraph_stream(input_stream, split_at_gaps=False):
-    for chrom, run_len, run_val, chrom_start in contig_runs(_read_all(input_stream), split_at_gaps):
+    for chrom, run_len, run_val, chrom_start in _contig_runs_chunked(_binary_reader(input_stream), split_at_gaps):
         yield chrom, np.repeat(run_val.astype(int), run_len), chrom_start
 
 
-def split_bedgraph(in_filename, out_filename, splitter, split_at_gaps=False, output_mode='bedgraph'):
+def split_bedgraph(in_filename, out_filename, splitter, split_at_gaps=False, output_mode='bedgraph', devices=None):
+    """devices (new, not in the reference): number of GPUs to shard the contigs over, one worker process per GPU
+    (pasio_b200/device_pool.py); None / 1 = this process's GPU."""
     with open_for_write(out_filename) as output_stream:
         with open_for_read(in_filename) as input_stream:
             split_bedgraph_stream(input_stream, output_stream, splitter,
-                                  split_at_gaps=split_at_gaps, output_mode=output_mode)
+                                  split_at_gaps=split_at_gaps, output_mode=output_mode, devices=devices)
 
 
 def _write(output_stream, payload):
@@ -146,50 +229,153 @@ def _segment_runs_on_device(plan, contigs, want_lmm):
     return splits, means, lmm, first_split, offsets
 
 
-def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=False, output_mode='bedgraph'):
+def _batches(contigs, plan):
+    """Group the contig stream into launches: lists of (chrom, chrom_start, run_len, run_val), in input order."""
+    pending, pending_nt = [], 0
+    for chrom, run_len, run_val, chrom_start in contigs:
+        n = int(run_len.sum())
+        logger.info('Starting chrom %s of length %d' % (chrom, n))
+        item = (chrom, chrom_start, run_len, run_val)
+        # the exact DP is a single-contig kernel; other splitter objects go contig by contig through their protocol
+        if plan is None or n >= BATCH_ALONE or BATCH_NT <= 0 or plan['final'] != 'nop':
+            if pending:
+                yield pending
+                pending, pending_nt = [], 0
+            yield [item]
+            continue
+        if pending and (pending_nt + n > BATCH_NT or len(pending) >= BATCH_CONTIGS):
+            yield pending
+            pending, pending_nt = [], 0
+        pending.append(item)
+        pending_nt += n
+    if pending:
+        yield pending
+
+
+def _segment_batch(splitter, plan, batch, mode):
+    """One launch sequence -> the arrays the formatter needs."""
+    if plan is not None:
+        # canonical splitter graph: run-length intervals go straight to the device
+        assert all(int(rl.sum()) > 0 for _, _, rl, _ in batch)
+        splits, means, lmm, first_split, offsets = _segment_runs_on_device(
+            plan, [(rl, rv) for _, _, rl, rv in batch], want_lmm=(mode == 2))
+        shifts = np.array([cs for _, cs, _, _ in batch], dtype=np.int64) - offsets[:-1]
+        return [c for c, _, _, _ in batch], shifts, first_split, splits, means, lmm
+    (chrom, chrom_start, run_len, run_val), = batch
+    counts = np.repeat(run_val.astype(int), run_len)
+    segs = list(segments_with_scores(counts, splitter))
+    splits = np.array([s.start for s in segs] + [segs[-1].stop], dtype=np.int64)
+    means = np.array([s.mean_count for s in segs], dtype=np.float64)
+    lmm = np.array([s.log_marginal_likelyhood for s in segs], dtype=np.float64)
+    return [chrom], np.array([chrom_start], dtype=np.int64), np.array([0, len(splits) - 1], dtype=np.int64), splits, means, lmm
+
+
+def _format_batch(result, mode):
+    chroms, shifts, first_split, splits, means, lmm = result
+    return _native.format_segments_batch(chroms, shifts, first_split, splits, means if mode != 1 else None,
+                                         lmm if mode == 2 else None, mode)
+
+
+def segment_and_format(splitter, plan, batch, mode):
+    """bytes of the output lines of one batch (device_pool workers call this)"""
+    return _format_batch(_segment_batch(splitter, plan, batch, mode), mode)
+
+
+class _Stage(object):
+    """A pipeline stage on its own thread: items from `source` (an iterator) go through fn into a bounded queue.  The
+    C calls behind fn (parser, kernels, formatter) release the GIL, so the stages overlap."""
+    _END = object()
+
+    def __init__(self, source, fn, depth=2):
+        import queue
+        import threading
+        self.q = queue.Queue(maxsize=depth)
+        self.error = None
+        self.stop = False
+
+        def run():
+            try:
+                for item in source:
+                    if self.stop:
+                        break
+                    self.q.put(fn(item))
+            except BaseException as e:       # noqa: BLE001 -- re-raised in the consumer
+                self.error = e
+            finally:
+                self.q.put(self._END)
+        self.thread = threading.Thread(target=run, daemon=True)
+        self.thread.start()
+
+    def __iter__(self):
+        while True:
+            item = self.q.get()
+            if item is self._END:
+                if self.error is not None:
+                    raise self.error
+                return
+            yield item
+
+    def cancel(self):
+        self.stop = True
+        try:
+            while True:
+                self.q.get_nowait()
+        except Exception:                    # noqa: BLE001 -- queue.Empty
+            pass
+
+
+def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=False, output_mode='bedgraph',
+                          devices=None):
+    """Reference: process_bedgraph.py:67-92.  The input is read in bounded pieces and a contig (or a batch of short
+    contigs) is segmented and written as soon as it is complete; reading + parsing of the next piece, the device work
+    and the formatting + writing of the previous batch run on three threads.  devices > 1: the batches are sharded over
+    that many GPUs by longest-processing-time-first, one worker process per GPU, the text gathered on the host in
+    input order (device_pool.py)."""
     logger.info('Reading input file')
     plan = _fusion.pipeline_plan(splitter)
     if output_mode not in OUTPUT_MODES:
         raise ValueError('Unknown output mode `%s`' % output_mode)
     mode = OUTPUT_MODES[output_mode]
-    pending, pending_nt = [], 0          # (chrom, chrom_start, run_len, run_val) waiting for a batched launch
+    contigs = _contig_runs_chunked(_binary_reader(input_stream), split_at_gaps)
+    if devices is not None and int(devices) > 1:
+        from . import device_pool
+        for payload, chroms in device_pool.run(list(_batches(contigs, plan)), splitter, mode, int(devices)):
+            _write(output_stream, payload)
+            for chrom in chroms:
+                logger.info('Output of chromosome %s finished' % chrom)
+        return
+    import queue
+    import threading
+    parsed = _Stage(_batches(contigs, plan), lambda b: b)          # thread 1: read + parse + group
+    out_q = queue.Queue(maxsize=2)
+    writer_error = []
 
-    def flush():
-        if not pending:
-            return
-        splits, means, lmm, first_split, offsets = _segment_runs_on_device(
-            plan, [(rl, rv) for _, _, rl, rv in pending], want_lmm=(mode == 2))
-        shifts = np.array([cs for _, cs, _, _ in pending], dtype=np.int64) - offsets[:-1]
-        _write(output_stream, _native.format_segments_batch([c for c, _, _, _ in pending], shifts, first_split, splits,
-                                                            means if mode != 1 else None, lmm if mode == 2 else None, mode))
-        for chrom, _, _, _ in pending:
-            logger.info('Output of chromosome %s finished' % chrom)
-        del pending[:]
-
-    for chrom, run_len, run_val, chrom_start in contig_runs(_read_all(input_stream), split_at_gaps):
-        n = int(run_len.sum())
-        logger.info('Starting chrom %s of length %d' % (chrom, n))
-        if plan is not None:
-            # canonical splitter graph: run-length intervals go straight to the device
-            assert n > 0
-            if n >= BATCH_ALONE or BATCH_NT <= 0 or plan['final'] != 'nop':      # (the exact DP is a single-contig kernel)
-                flush()
-                pending_nt = 0
-                pending.append((chrom, chrom_start, run_len, run_val))
-                flush()
-                continue
-            if pending and (pending_nt + n > BATCH_NT or len(pending) >= BATCH_CONTIGS):
-                flush()
-                pending_nt = 0
-            pending.append((chrom, chrom_start, run_len, run_val))
-            pending_nt += n
-            continue
-        counts = np.repeat(run_val.astype(int), run_len)
-        segs = list(segments_with_scores(counts, splitter))
-        splits = np.array([s.start for s in segs] + [segs[-1].stop], dtype=np.int64)
-        means = np.array([s.mean_count for s in segs], dtype=np.float64)
-        lmm = np.array([s.log_marginal_likelyhood for s in segs], dtype=np.float64)
-        _write(output_stream, _native.format_segments(chrom, chrom_start, splits, means if mode != 1 else None,
-                                                      lmm if mode == 2 else None, mode))
-        logger.info('Output of chromosome %s finished' % chrom)
-    flush()
+    def writer():                                                  # thread 3: format + write, in input order
+        try:
+            while True:
+                item = out_q.get()
+                if item is None:
+                    return
+                batch, result = item
+                _write(output_stream, _format_batch(result, mode))
+                for chrom, _, _, _ in batch:
+                    logger.info('Output of chromosome %s finished' % chrom)
+        except BaseException as e:           # noqa: BLE001 -- re-raised below
+            writer_error.append(e)
+            while out_q.get() is not None:   # keep draining so the producer never blocks
+                pass
+    thread = threading.Thread(target=writer, daemon=True)
+    thread.start()
+    try:
+        for batch in parsed:                                       # this thread: the device
+            if writer_error:
+                break
+            out_q.put((batch, _segment_batch(splitter, plan, batch, mode)))
+    except BaseException:
+        parsed.cancel()
+        raise
+    finally:
+        out_q.put(None)
+        thread.join()
+    if writer_error:
+        raise writer_error[0]

@@ -8,7 +8,7 @@ which now builds the graph the reference's own test uses for that mode
 """
 import numpy as np
 
-from .square_splitter import SquareSplitter
+from .square_splitter import SquareSplitter, _identity, _revlog
 from .nop_splitter import NopSplitter
 from .constants_reducer import NotConstantReducer, NotZeroReducer
 from .sliding_window_reducer import SlidingWindowReducer
@@ -17,9 +17,11 @@ from .reducer_combiner import ReducerCombiner
 from ..dto.sliding_window import SlidingWindow
 from ..log_marginal_likelyhood import ScorerFactory
 
+# module-level functions (not lambdas): splitters must pickle for the per-GPU worker processes, and the device
+# version of the regularised DP recognises exactly these two
 REGULARIZATION_FUNCTIONS = {
-    'none': lambda x: x,
-    'revlog': lambda x: 1 / np.log(x + 1),
+    'none': _identity,
+    'revlog': _revlog,
 }
 
 

@@ -21,6 +21,11 @@ def _identity(x):
     return x
 
 
+def _revlog(x):
+    """the `revlog` length penalty of the CLI: 1 / log(1 + l) (reference default_splitters.py:38, cli.py:49-53)"""
+    return 1 / np.log(x + 1)
+
+
 class SquareSplitter(object):
     def __init__(self, scorer_factory,
                  length_regularization_multiplier=0,

@@ -446,6 +446,19 @@ def test_load_and_round_asserts_and_table_growth(eng):
     bad[1234] = -1
     with pytest.raises(AssertionError):
         eng.load_and_round(bad, 2500, 1250, 'constants')
+    # a LARGE negative count: prefix sums stop being monotone, so no window may be processed after the scan saw it
+    # (table indices would be far out of range); the context must stay usable afterwards
+    for n, at in [(300000, 150000), (40000000, 39000000)]:
+        big = synth.dnase_like(n, 3, hotspot_share=0.3)
+        big[at] = -10 ** 9
+        with pytest.raises(AssertionError):
+            eng.load_and_round(big, 2500, 1250, 'constants')
+        with pytest.raises(AssertionError):
+            eng.load(big)
+    ok = synth.dnase_like(50000, 4, hotspot_share=0.3)
+    first_ok = eng.load_and_round(ok, 2500, 1250, 'constants')
+    want_ok, cells_ok = c_oracle.FlatOracle(ok, 1.0, 1.0).round(np.arange(len(ok) + 1, dtype=np.int64), 2500, 1250, 'constants')
+    assert np.array_equal(eng.candidates(), want_ok) and first_ok[2] == cells_ok
     deep = np.repeat(np.random.RandomState(3).poisson(900, 4000), 25).astype(np.int64)      # window counts > 2^20
     fo = c_oracle.FlatOracle(deep, 1.0, 1.0)
     first = eng.load_and_round(deep, 2500, 1250, 'constants')
