@@ -4,15 +4,25 @@
 A "step" is one pass of the default pasio pipeline (NotConstantReducer + RoundReducer over
 SlidingWindowReducer(2500, 1250) + SquareSplitter, then NopSplitter scoring) over one synthetic
 hg38-chr1-sized DNase-like contig (BASELINE.json configs[1]).  With N GPUs every rank segments
-its own chr1-sized contig (contigs are independent: no data-path collective; weak scaling).
+the SAME chr1-sized contig (contigs are independent: no data-path collective; weak scaling, so
+the N-GPU efficiency measures the machine, not the data).
 
   value : whole-job nt/s with the counts already resident in HBM when the timed region starts
   e2e   : the same through the public API (pasio_b200.segmentation.segment_on_device) from a
           PINNED HOST int64 buffer: H2D of the counts and D2H of splits / scores / means / logfac
           inside the timed region
   roofline : the dominant kernel (batched window DP), 4 FP64 ops per (i,j) cell against
-          the FP64-pipe instruction rate
+          the FP64-pipe instruction rate; `frac` counts ALGORITHMIC cells (what the reference
+          evaluates), `frac_evaluated` only the cells the kernel really evaluated (the rest is
+          proved irrelevant by the exact bound), `pipe_fp64_pct` is ncu's pipe utilisation
   cpu_baseline : oracle/ (numpy port of the reference) on a bounded prefix of the same contig
+  parity : the GPU's splits / score on that prefix against the oracle's, bit for bit; the line is
+          REFUSED (exit 1) if they differ
+  exact_dp : BASELINE configs[0] and configs[2] -- the whole-contig SquareSplitter DP (K3): kernel
+          time, ns per row of the dependent chain, FP64-roofline fractions (algorithmic / evaluated)
+  genome : BASELINE configs[3] -- the hg38 contig-size profile (195 contigs, 3.10e9 nt) partitioned
+          over the N ranks by longest-processing-time-first (pasio_b200.sharding), STRONG scaling:
+          resident and from-host throughput, per-rank ms / nt / rounds / segments
 
 `--impl reference` times the reference's CPU algorithm (oracle port; the reference is pure Python
 and /root/reference does not exist on the GPU box) on all host cores, same metric and config.
@@ -23,7 +33,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -35,6 +44,7 @@ if ROOT not in sys.path:
 CHR1 = 248956422
 WINDOW_SIZE, WINDOW_SHIFT, CONSTRAINT = 2500, 1250, 'constants'
 FP64_OPS_PER_CELL = 4            # DMUL s*Lg, DADD G-.., DADD +P_i, compare
+BIG_CONTIG = 16 << 20            # genome leg: shorter contigs share one batched launch sequence
 
 
 def measured_peaks():
@@ -107,22 +117,15 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
-def max_over_ranks(x, dist, device):
+def gather_rows(row, dist, device, world):
+    """every rank's list of floats -> list of lists on all ranks (timing control plane only)"""
     if dist is None:
-        return x
+        return [list(row)]
     import torch
-    t = torch.tensor([x], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
-def sum_over_ranks(x, dist, device):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    t = torch.tensor(row, dtype=torch.float64, device=device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
 
 
 def barrier(dist, torch):
@@ -131,8 +134,182 @@ def barrier(dist, torch):
     torch.cuda.synchronize()
 
 
+# ---- config 4: the genome profile, generated per rank before CUDA starts ------------------------
+_GEN = {}
+
+
+def _gen_one(job):
+    index, length, offset = job
+    from pasio_b200 import synth
+    arr = np.frombuffer(_GEN['raw'], dtype=np.int64)
+    arr[offset:offset + length] = synth.dnase_like(length, seed=index)      # config-2 generator, seed = contig index
+    return index
+
+
+def genome_generate(args):
+    """This rank's LPT share of the hg38 contig-size profile, as one int64 buffer: contigs of BIG_CONTIG positions or
+    more first (longest first), then the short ones contiguously (they go to the device as one batch)."""
+    if args.genome_scale <= 0:
+        return None
+    import multiprocessing as mp
+    from pasio_b200 import synth, sharding
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    sizes = synth.genome_profile(scale=args.genome_scale)
+    costs = [sharding.contig_cost(n) for _, n in sizes]
+    rank_of = sharding.lpt_assign(costs, world)
+    mine = [i for i in range(len(sizes)) if rank_of[i] == rank]
+    big = sorted([i for i in mine if sizes[i][1] >= BIG_CONTIG], key=lambda i: -sizes[i][1])
+    small = [i for i in mine if sizes[i][1] < BIG_CONTIG]
+    order = big + small
+    offsets, pos = {}, 0
+    for i in order:
+        offsets[i] = pos
+        pos += sizes[i][1]
+    raw = mp.RawArray('q', max(1, pos))
+    _GEN['raw'] = raw
+    procs = max(1, min(len(order), (os.cpu_count() or 1) // max(1, min(world, 8))))
+    t0 = time.perf_counter()
+    if order:
+        with mp.get_context('fork').Pool(procs) as pool:
+            pool.map(_gen_one, [(i, sizes[i][1], offsets[i]) for i in order], chunksize=1)
+    loads = [sum(costs[i] for i in range(len(sizes)) if rank_of[i] == r) for r in range(world)]
+    return dict(sizes=sizes, big=big, small=small, offsets=offsets, nt=pos, host=np.frombuffer(raw, dtype=np.int64)[:pos],
+                gen_s=time.perf_counter() - t0, lpt_max_over_mean=max(loads) / (sum(loads) / world),
+                total_nt=sum(n for _, n in sizes))
+
+
+def genome_leg(args, g, eng, plan, torch, dist, device, world):
+    """config 4, strong scaling: every rank segments its LPT share; the step time is the max over ranks."""
+    from pasio_b200.segmentation import segment_on_device
+    sizes, big, small, offs = g['sizes'], g['big'], g['small'], g['offsets']
+    resident = torch.from_numpy(g['host']).to(device) if g['nt'] else None
+    small_nt = sum(sizes[i][1] for i in small)
+    small_off = offs[small[0]] if small else 0
+    small_bounds = np.concatenate([[0], np.cumsum([sizes[i][1] for i in small])]).astype(np.int64) if small else None
+    stream = torch.cuda.ExternalStream(eng.stream_handle(), device=device)
+    stat = {}
+
+    def finish():
+        eng.segment_scores(scores=True, means=True)
+        return eng.candidate_count() - 1, float(eng.segment_scores_sum())
+
+    def step_resident():
+        nseg, rounds, cells = 0, 0, 0
+        for i in big:
+            eng.use_scorer(plan['factory'])
+            eng.load_device(resident.data_ptr() + 8 * offs[i], sizes[i][1], owner=resident)
+            eng.set_candidates(None)
+            sz, _, c = eng.rounds(WINDOW_SIZE, WINDOW_SHIFT, CONSTRAINT)
+            rounds += len(sz)
+            cells += c
+            nseg += finish()[0]
+        if small:
+            eng.use_scorer(plan['factory'])
+            eng.load_device(resident.data_ptr() + 8 * small_off, small_nt, owner=resident, offsets=small_bounds)
+            eng.set_candidates(None)
+            sz, _, c = eng.rounds(WINDOW_SIZE, WINDOW_SHIFT, CONSTRAINT)
+            rounds += len(sz)
+            cells += c
+            nseg += finish()[0]
+        stat.update(segments=nseg, rounds=rounds, cells=cells)
+
+    def step_e2e():
+        nseg = 0
+        for i in big:
+            eng.invalidate()
+            _, splits, means, _, _ = segment_on_device(g['host'][offs[i]:offs[i] + sizes[i][1]], plan, want_lmm=False)
+            nseg += len(splits) - 1
+        if small:
+            eng.invalidate()
+            eng.use_scorer(plan['factory'])
+            eng.load(g['host'][small_off:small_off + small_nt], offsets=small_bounds)
+            eng.set_candidates(None)
+            eng.rounds(WINDOW_SIZE, WINDOW_SHIFT, CONSTRAINT)
+            eng.candidates()
+            nseg += finish()[0]
+        return nseg
+
+    steps = max(1, args.genome_steps)
+    step_resident()
+    barrier(dist, torch)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step_resident()
+    ev1.record(stream)
+    ev1.synchronize()
+    my_ms = ev0.elapsed_time(ev1) / steps
+    barrier(dist, torch)
+    step_e2e()
+    barrier(dist, torch)
+    t0 = time.perf_counter()
+    nseg_e2e = step_e2e()
+    my_e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier(dist, torch)
+    assert nseg_e2e == stat['segments']
+    rows = gather_rows([my_ms, my_e2e_ms, float(g['nt']), float(len(big) + len(small)), float(stat['rounds']),
+                        float(stat['cells']), float(stat['segments'])], dist, device, world)
+    ms = max(r[0] for r in rows)
+    e2e_ms = max(r[1] for r in rows)
+    total_nt = g['total_nt']
+    return {
+        'workload': 'BASELINE configs[3]: hg38 contig-size profile (scale %g): %d contigs, %d nt, default pipeline, '
+                    'partitioned over %d GPU(s) by longest-processing-time-first; contigs under %d nt of a rank share one '
+                    'batched launch sequence' % (args.genome_scale, len(sizes), total_nt, world, BIG_CONTIG),
+        'scaling': 'strong', 'n_gpus': world, 'nt': total_nt, 'steps': steps,
+        'value': total_nt / (ms * 1e-3), 'unit': 'nt/s', 'ms_per_step': ms,
+        'e2e': {'value': total_nt / (e2e_ms * 1e-3), 'unit': 'nt/s', 'ms_per_step': e2e_ms,
+                'h2d_bytes_per_step': int(total_nt * 8), 'source': 'pageable host numpy arrays (staged upload)',
+                'note': 'per-rank results on the host; the ordered gather of the text is host-side (shard files, '
+                        'pasio_b200/device_pool.py) and not part of this number'},
+        'lpt_max_over_mean': g['lpt_max_over_mean'],
+        'per_rank': {'ms': [r[0] for r in rows], 'e2e_ms': [r[1] for r in rows], 'nt': [int(r[2]) for r in rows],
+                     'contigs': [int(r[3]) for r in rows], 'rounds': [int(r[4]) for r in rows],
+                     'cells': [int(r[5]) for r in rows], 'segments': [int(r[6]) for r in rows]},
+        'segments': int(sum(r[6] for r in rows)), 'dp_cells': int(sum(r[5] for r in rows)),
+        'host_generation_s': g['gen_s'],
+    }
+
+
+# ---- configs 1 and 3: the whole-contig exact DP --------------------------------------------------
+def exact_leg(eng, peak_nominal):
+    from pasio_b200 import synth
+    from pasio_b200.log_marginal_likelyhood import ScorerFactory
+    out = {}
+    eng.use_scorer(ScorerFactory(1.0, 1.0))
+    for name, counts, cands in [('config1', synth.piecewise_poisson(100000, 0), None),
+                                ('config3', synth.piecewise_poisson(2000000, 1), synth.random_candidates(2000000, 200000, 1))]:
+        N = len(counts) + 1 if cands is None else len(cands)
+        eng.invalidate()
+        eng.load(counts)
+        best = None
+        for rep in range(4):
+            eng.set_candidates(cands)
+            eng._cands_obj = None
+            eng.timing_reset(True)
+            score, splits = eng.square_split()
+            ms = eng.timing()['exact_dp'][0]
+            if rep > 0 and (best is None or ms < best):
+                best = ms
+        eng.timing_reset(False)
+        cells, skipped = eng.round_stats()
+        out[name] = {
+            'workload': 'BASELINE configs[%d]: exact SquareSplitter, N = %d candidates' % (0 if name == 'config1' else 2, N),
+            'cells': cells, 'cells_evaluated': cells - skipped, 'evaluated_frac': (cells - skipped) / cells,
+            'kernel_ms': best, 'cells_per_s': cells / (best * 1e-3), 'ns_per_row': best * 1e6 / N,
+            'roofline': {'bound': 'fp64 (algorithmic cells) / dependent chain of N rows', 'peak': peak_nominal / 1e12,
+                         'unit': 'TFLOP/s', 'achieved': cells * FP64_OPS_PER_CELL / (best * 1e-3) / 1e12,
+                         'frac': cells * FP64_OPS_PER_CELL / (best * 1e-3) / peak_nominal,
+                         'frac_evaluated': (cells - skipped) * FP64_OPS_PER_CELL / (best * 1e-3) / peak_nominal},
+            'splits': len(splits), 'score': float(score),
+        }
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
+    genome_host = genome_generate(args)          # host data of this rank's LPT share, before CUDA starts (fork pool)
     import torch
     from pasio_b200 import synth, _native
     from pasio_b200.splitters import configure_splitter, _fusion
@@ -145,10 +322,10 @@ def run_b200(args):
     n = args.nt
     peaks, peak_kind = measured_peaks()
 
-    # synthetic input, generated straight into pinned host memory (one chr1-sized contig per rank)
+    # synthetic input, generated straight into pinned host memory (the same chr1-sized contig on every rank)
     host = torch.empty(n, dtype=torch.int64, pin_memory=True)
     counts = host.numpy()
-    counts[:] = synth.dnase_like(n, seed=1000 + rank)
+    counts[:] = synth.dnase_like(n, seed=1000)
     resident = host.to(device, non_blocking=False)          # the HBM-resident copy for `value`
     torch.cuda.synchronize()
 
@@ -163,7 +340,7 @@ def run_b200(args):
         eng.load_device(resident.data_ptr(), n, owner=resident)
         eng.set_candidates(None)
         _run_device_pipeline(eng, plan)
-        scores, _, means, _ = eng.segment_scores(scores=True, means=True)
+        eng.segment_scores(scores=True, means=True)
         return eng.candidate_count(), float(eng.segment_scores_sum())
 
     def step_e2e():
@@ -192,15 +369,24 @@ def run_b200(args):
     dev_ms = ev0.elapsed_time(ev1)
     timing = eng.timing()
     eng.timing_reset(False)
-    step_ms = max_over_ranks(dev_ms / args.steps, dist, device)
-    total_nt = sum_over_ranks(float(n), dist, device)
+    rank_rows = gather_rows([dev_ms / args.steps], dist, device, world)
+    step_ms = max(r[0] for r in rank_rows)
+    total_nt = float(n) * world
     value = total_nt / (step_ms * 1e-3)
 
-    # cells of one step (same every step): one extra instrumented pass
+    # cells of one step (same every step): one extra instrumented pass, round by round
     eng.use_scorer(plan['factory'])
     eng.load_device(resident.data_ptr(), n, owner=resident)
     eng.set_candidates(None)
-    sizes, final, cells = eng.rounds(WINDOW_SIZE, WINDOW_SHIFT, CONSTRAINT)
+    sizes, cells, cells_skipped = [], 0, 0
+    while True:
+        n_in, n_out, c = eng.round(WINDOW_SIZE, WINDOW_SHIFT, CONSTRAINT)
+        sizes.append(n_in)
+        cells += c
+        cells_skipped += eng.round_stats()[1]
+        if n_in == n_out:
+            break
+    final = eng.candidate_count()
 
     # ---- end to end from pinned host memory ----------------------------------------------------
     for _ in range(min(args.warmup, 2)):
@@ -218,34 +404,68 @@ def run_b200(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_timing = eng.timing()
     eng.timing_reset(False)
-    e2e_s = max_over_ranks(e2e_s, dist, device)
+    e2e_rows = gather_rows([e2e_s * 1e3], dist, device, world)
+    e2e_s = max(r[0] for r in e2e_rows) * 1e-3
     e2e_value = total_nt / e2e_s
     assert m_e2e == m_final and abs(score_e2e - score) <= 1e-9 * abs(score)
+
+    # ---- parity gate: the GPU against the oracle on the cpu_baseline prefix (rank 0) -------------
+    cpu, parity = None, None
+    if rank == 0:
+        cpu, oracle_out = cpu_baseline_port(counts, args.cpu_sample_nt)
+        prefix = np.ascontiguousarray(counts[:args.cpu_sample_nt])
+        eng.invalidate()
+        g_score, g_splits, g_means, _, _ = segment_on_device(prefix, plan, want_lmm=False)
+        equal = bool(np.array_equal(np.asarray(g_splits), oracle_out['splits']))
+        rel = abs(float(g_score) - float(oracle_out['score'])) / max(1e-300, abs(float(oracle_out['score'])))
+        parity = {'prefix_nt': int(len(prefix)), 'splits_equal': equal, 'n_splits': int(len(oracle_out['splits'])),
+                  'means_equal': bool(np.array_equal(np.asarray(g_means), oracle_out['mean_counts'])),
+                  'score_rel': rel, 'oracle': 'oracle/pasio_oracle.default_pipeline (numpy restatement of the reference)'}
+
+    # ---- the other configs ------------------------------------------------------------------------
+    fp64_peak_nominal = 148 * 64 * peaks.get('sm_max_mhz', 1965.0) * 1e6
+    exact = exact_leg(eng, fp64_peak_nominal) if rank == 0 and not args.skip_exact else None
+    del resident, host, counts
+    torch.cuda.empty_cache()
+    barrier(dist, torch)
+    genome = genome_leg(args, genome_host, eng, plan, torch, dist, device, world) if genome_host is not None else None
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    if not (parity['splits_equal'] and parity['means_equal'] and parity['score_rel'] <= 1e-9):
+        print(json.dumps({'error': 'PARITY FAILED: the GPU path disagrees with the oracle on the cpu_baseline prefix; '
+                                   'no throughput is reported', 'parity': parity}))
+        sys.exit(1)
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     wd_ms, wd_launches = timing['window_dp']
     scan_ms, scan_launches = timing['scan']
-    fp64_peak_nominal = 148 * 64 * peaks.get('sm_max_mhz', 1965.0) * 1e6
     cells_per_launch = cells / max(1, len(sizes))
     # one timed span per round: the CTA-per-window kernel and the two warp-per-window kernels of a round overlap
     # (side stream), so the per-round span is the unit; wd_launches counts the kernels themselves
     wd_rounds = max(1, len(sizes) * args.steps)
     wd_avg_s = (wd_ms / wd_rounds) * 1e-3
     achieved = cells_per_launch * FP64_OPS_PER_CELL / wd_avg_s
-    traffic = None
+    evaluated = cells - cells_skipped
+    traffic, pipe = None, None
     prof = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(prof):
-        traffic = json.load(open(prof)).get('window_dp_dram_bytes_per_launch')
+        pj = json.load(open(prof))
+        traffic = pj.get('window_dp_dram_bytes_per_launch')
+        pipe = pj.get('window_dp_pipe_fp64_pct')
     roofline = {
         'kernel': 'window DP of one round: window_dp_kernel (CTA per window) + small_window_dp_kernel x2 (warp per window, '
                   'side stream), timed as one span per round',
         'bound': 'fp64', 'achieved': achieved / 1e12, 'peak': fp64_peak_nominal / 1e12, 'unit': 'TFLOP/s',
         'frac': achieved / fp64_peak_nominal, 'traffic': traffic,
+        'cells_algorithmic': cells, 'cells_evaluated': evaluated, 'evaluated_frac': evaluated / max(1, cells),
+        'frac_evaluated': (evaluated / max(1, len(sizes))) * FP64_OPS_PER_CELL / wd_avg_s / fp64_peak_nominal,
+        'pipe_fp64_pct': pipe,
+        'note': '`frac` counts the cells the reference evaluates (N(N-1)/2 per window); the kernel proves most of them '
+                'irrelevant with an exact bound and evaluates `cells_evaluated`; pipe_fp64_pct is ncu '
+                'sm__inst_executed_pipe_fp64 of window_dp_kernel (profiles/)',
         'peak_source': '148 SM x 64 FP64 lanes x sm_max_mhz (%s MEASURED_PEAKS.json has no FP64 entry); '
                        'DFMA micro-benchmark on this box: %.3g instr/s' % (peak_kind, fp64_peak_measured),
         'algorithmic_ops_per_cell': FP64_OPS_PER_CELL, 'cells_per_launch': cells_per_launch,
@@ -257,9 +477,6 @@ def run_b200(args):
                         'peak_source': peak_kind},
     }
 
-    # ---- CPU baseline: the oracle port on a bounded prefix of the same contig ------------------
-    cpu = cpu_baseline_port(counts, args.cpu_sample_nt)
-
     gpu_launches = int(sum(timing[k][1] for k in ['scan', 'window_dp', 'compact', 'exact_dp', 'score']))
     line = {
         'metric': 'whole-contig segmentation throughput, default pasio pipeline (nt/s); DP cell updates/s in dp_cells_per_s',
@@ -268,24 +485,26 @@ def run_b200(args):
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'BASELINE configs[1]: default pasio pipeline (constants + rounds over sliding window '
                                '2500/1250 + SquareSplitter, alpha=beta=1) on one synthetic chr1-sized (%d nt) DNase-like '
-                               'contig per GPU' % n,
+                               'contig per GPU (the same contig on every GPU)' % n,
                    'nt_per_gpu': n, 'window_size': WINDOW_SIZE, 'window_shift': WINDOW_SHIFT,
                    'split_constraints': CONSTRAINT, 'rounds': len(sizes), 'candidates_per_round': sizes,
                    'segments': final - 1, 'l2_policy': 'inputs larger than L2 (2 GB counts + 2 GB prefix sums per step)',
-                   'parallelism': 'contigs sharded over %d GPU(s), LPT, no collective' % world},
+                   'parallelism': 'one replica of the contig per GPU (%d), no collective; the LPT partition of a whole '
+                                  'genome over the GPUs is the `genome` key' % world},
+        'per_rank_ms_per_step': [r[0] for r in rank_rows],
         'dp_cells_per_step': cells, 'dp_cells_per_s': cells * world / (step_ms * 1e-3),
         'window_dp_cells_per_s_kernel_only': cells / (wd_ms / args.steps * 1e-3),
         'e2e': {'value': e2e_value, 'unit': 'nt/s', 'h2d_bytes_per_step': int(n * 8),
                 'd2h_bytes_per_step': int(final * 8 * 4), 'ms_per_step': e2e_s * 1e3,
                 'api': 'pasio_b200.segmentation.segment_on_device(counts_pinned_host, plan)',
                 'device_ms_per_step': {k: e2e_timing[k][0] / e2e_steps for k in e2e_timing},
-                'ms_each_step': e2e_each},
+                'ms_each_step': e2e_each, 'per_rank_ms_per_step': [r[0] for r in e2e_rows]},
         'gpu_launches': gpu_launches,
         'kernel_ms_per_step': {k: timing[k][0] / args.steps for k in timing},
         'wall_ms_per_step': wall / args.steps * 1e3,
         'clocks': {'sm_mhz': clocks['sm_mhz'], 'sm_max_mhz': clocks['sm_max_mhz'], 'reasons': clocks['reasons'],
                    'samples': clocks['samples']},
-        'roofline': roofline, 'cpu_baseline': cpu,
+        'roofline': roofline, 'cpu_baseline': cpu, 'parity': parity, 'exact_dp': exact, 'genome': genome,
     }
     print(json.dumps(line))
     if dist is not None:
@@ -294,7 +513,7 @@ def run_b200(args):
 
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline_port(counts, sample_nt):
-    """oracle/pasio_oracle.py (numpy restatement, one core) on the first sample_nt nt."""
+    """oracle/pasio_oracle.py (numpy restatement, one core) on the first sample_nt nt -> (cpu_baseline, oracle output)."""
     from oracle import pasio_oracle as po
     sample = np.ascontiguousarray(counts[:sample_nt])
     tables = po.Tables(1, 1.0)
@@ -303,7 +522,7 @@ def cpu_baseline_port(counts, sample_nt):
     dt = time.perf_counter() - t0
     return {'value': len(sample) / dt, 'unit': 'nt/s', 'cores': 1, 'kind': 'port',
             'sample': 'first %d nt of the rank-0 workload contig through oracle/pasio_oracle.default_pipeline '
-                      '(numpy port of the reference, %d segments, %.1f s)' % (len(sample), len(out['splits']) - 1, dt)}
+                      '(numpy port of the reference, %d segments, %.1f s)' % (len(sample), len(out['splits']) - 1, dt)}, out
 
 
 _REF_COUNTS = None      # set in the parent before the pool forks
@@ -344,7 +563,7 @@ def run_reference(args):
             jobs.append((lo, lo + slice_nt))
             k += 1
         t0 = time.perf_counter()
-        res = pool.map(_ref_worker, jobs)
+        pool.map(_ref_worker, jobs)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             step_times.append(dt)
@@ -379,6 +598,10 @@ def main():
     ap.add_argument('--nt', type=int, default=CHR1, help='contig length per GPU (default: hg38 chr1)')
     ap.add_argument('--cpu-sample-nt', type=int, default=2000000)
     ap.add_argument('--ref-slice-nt', type=int, default=500000)
+    ap.add_argument('--genome-scale', type=float, default=1.0,
+                    help='scale of the hg38 contig-size profile of the `genome` leg (configs[3]); 0 skips the leg')
+    ap.add_argument('--genome-steps', type=int, default=2)
+    ap.add_argument('--skip-exact', action='store_true', help='skip the `exact_dp` leg (configs[0], configs[2])')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -54,7 +54,10 @@ enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (defaul
        PASIO_TUNE_WINDOW_PHASES = 1,  /* 1: windows whose candidates all survived already are skipped      */
        PASIO_TUNE_EXACT_PRUNE = 2,    /* 1: whole-contig exact DP bounds far columns (csrc/exact_pruned.cu) */
        PASIO_TUNE_EXACT_LAG = 3,      /* far columns start this many 128-row blocks behind the diagonal (3 or 4) */
-       PASIO_TUNE_COUNT = 4 };
+       PASIO_TUNE_EXACT_RING = 4,     /* 1: self-score slabs in a 64-block ring (the layout of very long lists) even when short */
+       PASIO_TUNE_LOGFAC_EXACT = 5,   /* 1 (default): logfac_cumsum summed sequentially like np.cumsum (bit-identical LMM column);
+                                         0: three-pass parallel scan (1e-9 relative, faster on dense coverage) */
+       PASIO_TUNE_COUNT = 6 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int pasio_ctx_create(int device, pasio_ctx **out);
@@ -153,6 +156,16 @@ int pasio_rounds(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int 
  * prefix_scores / previous_splits (optional, N entries each) expose the DP arrays. */
 int pasio_square_split(pasio_ctx *ctx, int64_t *out_splits, int64_t cap, int64_t *n_splits,
                        double *score, double *prefix_scores, int64_t *previous_splits);
+/* SquareSplitter.split_with_normalizations (square_splitter.py:29-65) for element-wise penalty functions: per cell
+ *   t = self_score + P_i - split_number_penalty[num_splits_i] (+ first_column_refund for i = 0) - length_penalty[L_j - L_i],
+ * in that order, first arg-max, num_splits_j = prev_j ? num_splits[prev_j] + 1 : 0.  The caller builds the tables with
+ * the reference's own expressions: length_penalty[len] = multiplier * function(len) for len = 0 .. contig length,
+ * split_number_penalty[k] = multiplier * function(k + 1) for k = 0 .. candidates - 1, first_column_refund =
+ * multiplier * function(1) (square_splitter.py:46-54); NULL switches a term off.  Other arguments as pasio_square_split. */
+int pasio_square_split_regularized(pasio_ctx *ctx, const double *length_penalty, int64_t n_length_penalty,
+                                   const double *split_number_penalty, int64_t n_split_number_penalty,
+                                   double first_column_refund, int64_t *out_splits, int64_t cap, int64_t *n_splits,
+                                   double *score, double *prefix_scores, int64_t *previous_splits);
 /* LogMarginalLikelyhood*AlphaComputer.all_suffixes_self_score(stop)
  * (log_marginal_likelyhood.py:105-115, :121-132) over the current candidates:
  * out[0..stop). */

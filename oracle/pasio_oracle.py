@@ -337,3 +337,28 @@ def parse_bedgraph_text(text, split_at_gaps=False):
                 data.extend([cov] * (stop - start))
             contigs.append((part[0][0], np.array(data, dtype=int), part[0][1]))
     return contigs
+
+
+def split_bedgraph_text(text, tables, window_size=2500, window_shift=1250, constraint='constants', num_rounds=None,
+                        split_at_gaps=False, output_mode='bedgraph', threads=1):
+    """process_bedgraph.py:67-92 with the default splitter graph: bedgraph text in, the reference's output text out.
+    The rounds run through the flat C restatement (oracle/c_oracle.py) so that hundreds of contigs take seconds;
+    scoring and the '%' formatting are the reference's (process_bedgraph.py:71-89, log_marginal_likelyhood.py:67-83)."""
+    from . import c_oracle
+    out = []
+    for chrom, counts, chrom_start in parse_bedgraph_text(text, split_at_gaps):
+        fo = c_oracle.FlatOracle(counts, tables.alpha, tables.beta, threads=threads)
+        splits, _, _ = fo.rounds(window_size, window_shift, constraint, num_rounds)
+        sc = Scorer(counts, splits, tables)
+        means, lmm = sc.mean_counts(), sc.log_marginal_likelyhoods()
+        for k in range(len(splits) - 1):
+            a, b = splits[k] + chrom_start, splits[k + 1] + chrom_start
+            if output_mode == 'bedgraph':
+                out.append('%s\t%d\t%d\t%f\n' % (chrom, a, b, means[k]))
+            elif output_mode == 'bed':
+                out.append('%s\t%d\t%d\n' % (chrom, a, b))
+            elif output_mode == 'bedgraph+length+LMM':
+                out.append('%s\t%d\t%d\t%f\t%d\t%f\n' % (chrom, a, b, means[k], splits[k + 1] - splits[k], lmm[k]))
+            else:
+                raise ValueError('Unknown output mode `%s`' % output_mode)
+    return ''.join(out)

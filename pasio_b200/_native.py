@@ -17,7 +17,7 @@ OK = 0
 E_CUDA, E_ARG, E_COUNTS, E_CANDIDATES, E_TABLE_TOO_SHORT, E_STATE, E_TOO_LARGE, E_NOMEM = range(-1, -9, -1)
 TAB_LOG, TAB_LGAMMA, TAB_LGAMMA_ALPHA = 0, 1, 2
 CONSTRAINTS = {'none': 0, 'zeros': 1, 'constants': 2}
-TUNE = {'window_prune': 0, 'window_phases': 1, 'exact_prune': 2, 'exact_lag': 3}
+TUNE = {'window_prune': 0, 'window_phases': 1, 'exact_prune': 2, 'exact_lag': 3, 'exact_ring': 4, 'logfac_exact': 5}
 TIMING_FAMILIES = ['scan', 'window_dp', 'compact', 'exact_dp', 'score', 'h2d', 'd2h']
 
 _i64 = ctypes.c_int64
@@ -49,6 +49,8 @@ SIGNATURES = {
     'pasio_set_tuning': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     'pasio_rounds': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64, _i64p, _i64p, _i64p, _i64p, _i64]),
     'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
+    'pasio_square_split_regularized': (ctypes.c_int, [_vp, _f64p, _i64, _f64p, _i64, ctypes.c_double, _i64p, _i64, _i64p, _f64p,
+                                                     _f64p, _i64p]),
     'pasio_suffix_scores': (ctypes.c_int, [_vp, _i64, _f64p]),
     'pasio_segment_scores': (ctypes.c_int, [_vp, _f64p, _i64p, _f64p, _f64p, _i64, _i64p]),
     'pasio_segment_scores_sum': (ctypes.c_int, [_vp, _f64p]),
@@ -410,6 +412,22 @@ class Engine(object):
         self._cands_obj = out
         if want_arrays:
             return np.float64(score.value), out, P, prev
+        return np.float64(score.value), out
+
+    def square_split_regularized(self, length_penalty=None, split_number_penalty=None, first_column_refund=0.0):
+        """split_with_normalizations over the current candidates on the device; penalty tables as in include/pasio_b200.h"""
+        m = self.candidate_count()
+        splits = np.empty(m, dtype=np.int64)
+        n_splits, score = _i64(0), ctypes.c_double(0.0)
+        lp = None if length_penalty is None else np.ascontiguousarray(length_penalty, dtype=np.float64)
+        sp = None if split_number_penalty is None else np.ascontiguousarray(split_number_penalty, dtype=np.float64)
+        self._cands_obj = None
+        self._retry(lambda: self.lib.pasio_square_split_regularized(
+            self.ctx, None if lp is None else _ptr(lp, ctypes.c_double), 0 if lp is None else len(lp),
+            None if sp is None else _ptr(sp, ctypes.c_double), 0 if sp is None else len(sp), float(first_column_refund),
+            _ptr(splits, ctypes.c_int64), m, ctypes.byref(n_splits), ctypes.byref(score), None, None))
+        out = splits[:n_splits.value].copy()
+        self._cands_obj = out
         return np.float64(score.value), out
 
     def suffix_scores(self, stop):

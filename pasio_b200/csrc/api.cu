@@ -221,6 +221,8 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->tune[PASIO_TUNE_WINDOW_PHASES] = env_int("PASIO_WD_PHASES", 1);
     ctx->tune[PASIO_TUNE_EXACT_PRUNE] = env_int("PASIO_XD_PRUNE", 1);
     ctx->tune[PASIO_TUNE_EXACT_LAG] = env_int("PASIO_XD_LAG", 3);
+    ctx->tune[PASIO_TUNE_EXACT_RING] = env_int("PASIO_XD_RING", 0);
+    ctx->tune[PASIO_TUNE_LOGFAC_EXACT] = env_int("PASIO_B200_EXACT_LMM", 1);
     if (ctx->tune[PASIO_TUNE_EXACT_LAG] < 3 || ctx->tune[PASIO_TUNE_EXACT_LAG] > 4) ctx->tune[PASIO_TUNE_EXACT_LAG] = 3;
     *out = ctx;
     return PASIO_OK;
@@ -236,7 +238,7 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
                       &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large, &ctx->win_flags,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
                       &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full,
-                      &ctx->xpRing, &ctx->xpRec, &ctx->xpTasks};
+                      &ctx->xpRing, &ctx->xpRec, &ctx->xpTasks, &ctx->regLR, &ctx->regNR, &ctx->lxPos, &ctx->lxSum, &ctx->lxFirst};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -786,21 +788,16 @@ extern "C" int pasio_set_tuning(pasio_ctx *ctx, int key, int value)
     if (key < 0 || key >= PASIO_TUNE_COUNT) return pasio_fail(ctx, PASIO_E_ARG, "unknown tuning key %d", key);
     if (key == PASIO_TUNE_EXACT_LAG && (value < 3 || value > 4)) return pasio_fail(ctx, PASIO_E_ARG, "exact lag must be 3 or 4");
     ctx->tune[key] = value;
+    if (key == PASIO_TUNE_LOGFAC_EXACT) ctx->logfac_ready = false;
     return PASIO_OK;
 }
 
 // ---- exact DP -----------------------------------------------------------------------------------
-extern "C" int pasio_square_split(pasio_ctx *ctx, int64_t *out_splits, int64_t cap, int64_t *n_splits,
-                                  double *score, double *prefix_scores, int64_t *previous_splits)
+// shared tail of the two exact-DP entry points: results of the DP over the current candidates -> caller, back-trace, the
+// splits become the current candidates
+static int finish_square_split(pasio_ctx *ctx, i64 N, int64_t *out_splits, int64_t cap, int64_t *n_splits, double *score,
+                               double *prefix_scores, int64_t *previous_splits)
 {
-    NEED_CTX(ctx);
-    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
-    if (ctx->n_contigs != 1) return pasio_fail(ctx, PASIO_E_STATE, "pasio_square_split works on a single-contig context");
-    const i64 N = ctx->m;
-    // candidates span the whole contig: first = 0, last = n
-    PASIO_TRY(check_dp_tables(ctx, ctx->n, ctx->total));
-    PASIO_TRY(launch_gather_candidates(ctx));
-    PASIO_TRY(launch_exact_dp(ctx, N));
     if (score) PASIO_TRY(d2h(ctx, score, ctx->dpP.as<double>() + (N - 1), 8));
     if (prefix_scores) PASIO_TRY(d2h(ctx, prefix_scores, ctx->dpP.p, (size_t)N * 8));
     if (previous_splits) {
@@ -823,6 +820,51 @@ extern "C" int pasio_square_split(pasio_ctx *ctx, int64_t *out_splits, int64_t c
         return pasio_candidates_download(ctx, out_splits, cap, nullptr);
     }
     return PASIO_OK;
+}
+
+extern "C" int pasio_square_split(pasio_ctx *ctx, int64_t *out_splits, int64_t cap, int64_t *n_splits,
+                                  double *score, double *prefix_scores, int64_t *previous_splits)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (ctx->n_contigs != 1) return pasio_fail(ctx, PASIO_E_STATE, "pasio_square_split works on a single-contig context");
+    const i64 N = ctx->m;
+    // candidates span the whole contig: first = 0, last = n
+    PASIO_TRY(check_dp_tables(ctx, ctx->n, ctx->total));
+    PASIO_TRY(launch_gather_candidates(ctx));
+    PASIO_TRY(launch_exact_dp(ctx, N));
+    return finish_square_split(ctx, N, out_splits, cap, n_splits, score, prefix_scores, previous_splits);
+}
+
+extern "C" int pasio_square_split_regularized(pasio_ctx *ctx, const double *length_penalty, int64_t n_length_penalty,
+                                              const double *split_number_penalty, int64_t n_split_number_penalty,
+                                              double first_column_refund, int64_t *out_splits, int64_t cap, int64_t *n_splits,
+                                              double *score, double *prefix_scores, int64_t *previous_splits)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (ctx->n_contigs != 1) return pasio_fail(ctx, PASIO_E_STATE, "pasio_square_split_regularized works on a single-contig context");
+    const i64 N = ctx->m;
+    if (length_penalty && n_length_penalty < ctx->n + 1)
+        return pasio_fail(ctx, PASIO_E_ARG, "length penalty table needs %lld entries (0 .. contig length)", (long long)(ctx->n + 1));
+    if (split_number_penalty && n_split_number_penalty < N)
+        return pasio_fail(ctx, PASIO_E_ARG, "split-number penalty table needs %lld entries (one per candidate)", (long long)N);
+    PASIO_TRY(check_dp_tables(ctx, ctx->n, ctx->total));
+    PASIO_TRY(launch_gather_candidates(ctx));
+    const double *d_lr = nullptr, *d_nr = nullptr;
+    if (length_penalty) {
+        PASIO_TRY(pasio_reserve(ctx, ctx->regLR, (size_t)(ctx->n + 1) * 8));
+        PASIO_TRY(h2d(ctx, ctx->regLR.p, length_penalty, (size_t)(ctx->n + 1) * 8));
+        d_lr = ctx->regLR.as<double>();
+    }
+    if (split_number_penalty) {
+        PASIO_TRY(pasio_reserve(ctx, ctx->regNR, (size_t)N * 8));
+        PASIO_TRY(h2d(ctx, ctx->regNR.p, split_number_penalty, (size_t)N * 8));
+        d_nr = ctx->regNR.as<double>();
+    }
+    PASIO_TRY(launch_regularized_dp(ctx, N, d_lr, d_nr, first_column_refund));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the caller's tables were read by the copies above
+    return finish_square_split(ctx, N, out_splits, cap, n_splits, score, prefix_scores, previous_splits);
 }
 
 extern "C" int pasio_suffix_scores(pasio_ctx *ctx, int64_t stop, double *out)
@@ -857,9 +899,14 @@ extern "C" int pasio_suffix_scores(pasio_ctx *ctx, int64_t stop, double *out)
 static int ensure_logfac(pasio_ctx *ctx)
 {
     if (ctx->logfac_ready) return PASIO_OK;
-    PASIO_TRY(pasio_reserve(ctx, ctx->logfac_full, (size_t)(ctx->n + 1) * 8));
-    PASIO_TRY(launch_logfac_scan(ctx, ctx->logfac_full.as<double>()));
+    if (ctx->tune[PASIO_TUNE_LOGFAC_EXACT]) {
+        PASIO_TRY(launch_logfac_exact(ctx));              // the reference's sequential sum, bit for bit (logfac_exact.cu)
+    } else {
+        PASIO_TRY(pasio_reserve(ctx, ctx->logfac_full, (size_t)(ctx->n + 1) * 8));
+        PASIO_TRY(launch_logfac_scan(ctx, ctx->logfac_full.as<double>()));
+    }
     ctx->logfac_ready = true;
+    ctx->logfac_is_exact = ctx->tune[PASIO_TUNE_LOGFAC_EXACT] != 0;
     return PASIO_OK;
 }
 
@@ -899,7 +946,8 @@ extern "C" int pasio_segment_scores(pasio_ctx *ctx, double *scores, int64_t *seg
         // n+1 doubles of scratch, kept for the next call (a 2 GB cudaMalloc/cudaFree per contig is not free)
         PASIO_TRY(ensure_logfac(ctx));
         PASIO_TRY(pasio_reserve(ctx, ctx->dpP, (size_t)ctx->m * 8));
-        PASIO_TRY(launch_gather_f64_at_cands(ctx, ctx->logfac_full.as<double>(), ctx->dpP.as<double>()));
+        if (ctx->logfac_is_exact) PASIO_TRY(launch_logfac_at_candidates_exact(ctx, ctx->dpP.as<double>()));
+        else PASIO_TRY(launch_gather_f64_at_cands(ctx, ctx->logfac_full.as<double>(), ctx->dpP.as<double>()));
         PASIO_TRY(d2h(ctx, logfac_cumsum, ctx->dpP.p, (size_t)ctx->m * 8));
     }
     return PASIO_OK;
@@ -987,9 +1035,13 @@ extern "C" int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, 
     PASIO_TRY(launch_segment_scores(ctx, ctx->dpP.as<double>(), nullptr, nullptr));
     PASIO_TRY(ensure_logfac(ctx));
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, (size_t)nseg * 8));
-    PASIO_TRY(launch_lmm(ctx, ctx->dpP.as<double>(), ctx->logfac_full.as<double>(), ctx->dpPart.as<double>()));
+    if (ctx->logfac_is_exact) PASIO_TRY(launch_lmm_exact(ctx, ctx->dpP.as<double>(), ctx->dpPart.as<double>()));
+    else PASIO_TRY(launch_lmm(ctx, ctx->dpP.as<double>(), ctx->logfac_full.as<double>(), ctx->dpPart.as<double>()));
     if (lmm) PASIO_TRY(d2h(ctx, lmm, ctx->dpPart.p, (size_t)nseg * 8));
-    if (sum_logfac) PASIO_TRY(d2h(ctx, sum_logfac, ctx->logfac_full.as<double>() + ctx->n, 8));
+    if (sum_logfac) {
+        if (ctx->logfac_is_exact) PASIO_TRY(logfac_exact_total(ctx, sum_logfac));     // (a batch: the last contig's total)
+        else PASIO_TRY(d2h(ctx, sum_logfac, ctx->logfac_full.as<double>() + ctx->n, 8));
+    }
     return PASIO_OK;
 }
 

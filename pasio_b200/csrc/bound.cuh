@@ -24,22 +24,43 @@ struct __align__(16) CoarseRec {
 };
 static_assert(sizeof(CoarseRec) == 80, "CoarseRec layout");
 
+// The four table values a box bound needs, separated from the arithmetic so that a caller can have the gathers of many
+// boxes in flight before it consumes any (exact_pruned.cu).
+struct BoxCorners { double g_lo, g_hi, l_lo, l_hi; };
+
+template <bool AI>
+__device__ __forceinline__ BoxCorners box_corner_loads(int u_lo, int u_hi, int len_lo, int len_hi,
+                                                       const double *__restrict__ gtab, const double *__restrict__ ltab, int alpha_int)
+{
+    BoxCorners c;
+    c.g_lo = __ldg(gtab + (AI ? u_lo + alpha_int : u_lo));
+    c.g_hi = __ldg(gtab + (AI ? u_hi + alpha_int : u_hi));
+    c.l_lo = __ldg(ltab + len_lo);
+    c.l_hi = __ldg(ltab + len_hi);
+    return c;
+}
+
+__device__ __forceinline__ double tilted_box_max_of(const BoxCorners &c, int u_lo, int u_hi, int len_lo, int len_hi, double a, double b,
+                                                    double alpha)
+{
+    const double ud_lo = u32_to_double(u_lo), ud_hi = u32_to_double(u_hi);
+    const double s_lo = ud_lo + alpha, s_hi = ud_hi + alpha;
+    const double ta_lo = a * ud_lo, ta_hi = a * ud_hi;
+    const double tb_lo = b * u32_to_double(len_lo), tb_hi = b * u32_to_double(len_hi);
+    const double f00 = (c.g_lo - s_lo * c.l_lo) + (ta_lo + tb_lo);
+    const double f01 = (c.g_lo - s_lo * c.l_hi) + (ta_lo + tb_hi);
+    const double f10 = (c.g_hi - s_hi * c.l_lo) + (ta_hi + tb_lo);
+    const double f11 = (c.g_hi - s_hi * c.l_hi) + (ta_hi + tb_hi);
+    return fmax(fmax(f00, f01), fmax(f10, f11));
+}
+
 template <bool AI>
 __device__ __forceinline__ double tilted_box_max(int u_lo, int u_hi, int len_lo, int len_hi, double a, double b,
                                                  const double *__restrict__ gtab, const double *__restrict__ ltab,
                                                  int alpha_int, double alpha)
 {
-    const double g_lo = __ldg(gtab + (AI ? u_lo + alpha_int : u_lo)), g_hi = __ldg(gtab + (AI ? u_hi + alpha_int : u_hi));
-    const double l_lo = __ldg(ltab + len_lo), l_hi = __ldg(ltab + len_hi);
-    const double ud_lo = u32_to_double(u_lo), ud_hi = u32_to_double(u_hi);
-    const double s_lo = ud_lo + alpha, s_hi = ud_hi + alpha;
-    const double ta_lo = a * ud_lo, ta_hi = a * ud_hi;
-    const double tb_lo = b * u32_to_double(len_lo), tb_hi = b * u32_to_double(len_hi);
-    const double f00 = (g_lo - s_lo * l_lo) + (ta_lo + tb_lo);
-    const double f01 = (g_lo - s_lo * l_hi) + (ta_lo + tb_hi);
-    const double f10 = (g_hi - s_hi * l_lo) + (ta_hi + tb_lo);
-    const double f11 = (g_hi - s_hi * l_hi) + (ta_hi + tb_hi);
-    return fmax(fmax(f00, f01), fmax(f10, f11));
+    const BoxCorners c = box_corner_loads<AI>(u_lo, u_hi, len_lo, len_hi, gtab, ltab, alpha_int);
+    return tilted_box_max_of(c, u_lo, u_hi, len_lo, len_hi, a, b, alpha);
 }
 
 __device__ __forceinline__ double warp_sum(double v)

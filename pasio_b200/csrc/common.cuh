@@ -57,7 +57,8 @@ struct pasio_ctx {
     i64 n = 0;                   // total nt
     i64 total = 0;               // total count
     i64 max_count = 0;           // largest count
-    bool logfac_ready = false;   // logfac_full holds the prefix sums of the loaded contig
+    bool logfac_ready = false;   // the log-factorial prefix sums of the loaded contig are computed (logfac_full, or lxPos / lxSum)
+    bool logfac_is_exact = false;
     i64 n_contigs = 0;
     std::vector<int32_t> h_bounds;   // n_contigs+1 boundary positions (host copy)
     DevBuf counts;               // int64[n]
@@ -84,7 +85,9 @@ struct pasio_ctx {
 
     // scratch
     DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan, logfac_full;
-    DevBuf xpRing, xpRec, xpTasks;   // exact_pruned.cu: self-score ring, column-block records, task list
+    DevBuf xpRing, xpRec, xpTasks, regLR, regNR;
+    DevBuf lxPos, lxSum, lxFirst;    // logfac_exact.cu: positions / running sums of the non-zero log-factorial terms, first term per contig
+    i64 lx_terms = 0;   // exact_pruned.cu: self-score ring, column-block records, task list
 
     // tuning switches (pasio_set_tuning; defaults from the PASIO_WD_* / PASIO_XD_* environment variables)
     int tune[PASIO_TUNE_COUNT];
@@ -156,7 +159,8 @@ int window_dp_max_candidates(pasio_ctx *ctx);
 
 // exact_dp.cu
 int launch_exact_dp(pasio_ctx *ctx, i64 N);                   // over ctx->dpL/dpC -> dpP/dpPrev
-int launch_exact_dp_pruned(pasio_ctx *ctx, i64 N, int lag);   // exact_pruned.cu: the same result, far columns bounded
+int launch_exact_dp_pruned(pasio_ctx *ctx, i64 N, int lag);
+int launch_regularized_dp(pasio_ctx *ctx, i64 N, const double *d_lr, const double *d_nr, double add0);   // regularized_dp.cu   // exact_pruned.cu: the same result, far columns bounded
 int launch_gather_candidates(pasio_ctx *ctx);                 // current candidates -> dpL/dpC (rebased)
 int launch_backtrace_mark(pasio_ctx *ctx, i64 N);             // dpPrev -> keepbits (positions on the optimal path)
 int launch_suffix_row(pasio_ctx *ctx, i64 stop, double *d_out);
@@ -167,6 +171,12 @@ int launch_pairwise_leaves(pasio_ctx *ctx, const double *d_values, const i64 *d_
 int launch_gather_i64(pasio_ctx *ctx, const i64 *d_src, const int32_t *d_idx32, const i64 *d_idx64, i64 m, i64 *d_out);
 int launch_gather_f64_at_cands(pasio_ctx *ctx, const double *d_src, double *d_out);
 int launch_lmm(pasio_ctx *ctx, const double *d_scores, const double *d_logfac_full, double *d_lmm);
+
+// logfac_exact.cu: logfac_cumsum with the reference's sequential rounding
+int launch_logfac_exact(pasio_ctx *ctx);
+int launch_lmm_exact(pasio_ctx *ctx, const double *d_scores, double *d_lmm);
+int launch_logfac_at_candidates_exact(pasio_ctx *ctx, double *d_out);
+int logfac_exact_total(pasio_ctx *ctx, double *h_out);
 
 static inline const int32_t *cur_cand(const pasio_ctx *ctx) {
     return ctx->implicit_all ? nullptr : ctx->cand[ctx->cur].as<int32_t>();

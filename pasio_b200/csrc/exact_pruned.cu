@@ -24,24 +24,47 @@
 //   Task order makes every wait depend on tasks earlier in the list, and all CTAs are co-resident: no deadlock.
 #include "bound.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace {
 
 constexpr int XP_RB = 128;            // rows per block
 constexpr int XP_THREADS = 256;
-constexpr int XP_HELP = 7;            // helper warps of the diagonal CTA
+constexpr int XP_HELP = 7;            // helper warps of the diagonal CTA: six sweep the mid columns, one (warp 4) keeps the books
+constexpr int XP_MIDW = 6;
 constexpr int XP_G = 8;               // far slices per row block
 constexpr int XP_SQ = 4;              // self-score sub-tasks per row block
 constexpr int XP_RING = 64;           // row blocks of self scores kept
 constexpr int XP_SAHEAD = 16;         // self scores are produced this many blocks ahead of the diagonal
 constexpr int XP_PRING = 1024;        // finished P kept in the diagonal's shared memory
 constexpr int XP_ST = 63;             // self-score tile of the chain warp: distances 1..63
-constexpr int XP_MB = 28;             // mid sweep: loads in flight per lane
+constexpr int XP_MB = 30;             // mid sweep: loads per batch and lane (a multiple of 3); two batches are prefetched
 constexpr int XP_LIST1 = 4096;
+constexpr int XP_L2CHUNK = 128;       // level-1 survivors refined per pass (<= 4096 fine rectangles listed)
+constexpr size_t XP_LINEAR_BYTES = (size_t)2 << 30;
+
+// record of 32 finished columns: the bound record plus the end points of its four 8-column sub-blocks (level 2)
+struct __align__(16) XpRec32 {
+    CoarseRec r;
+    int sub[4][4];              // c_first, c_last, l_first, l_last
+};
+// published with every finished block: its last row e and the arg-max columns of rows e, e-1, ..., e-6 (the recent
+// change points) -- the anchors whose exactly evaluated cells bound the maxima of the rows ahead from below
+struct __align__(16) XpAnchors {
+    int idx[8], L[8], C[8];
+    double P[8];
+};
+static_assert(sizeof(XpRec32) == 144 && sizeof(XpAnchors) == 160, "record layouts");
 
 struct XpParams {
     int N, nB, nSteps, lag, DB, n_tasks, npad;
+    int dbg;                    // PASIO_XD_DBG (timing experiments only, results become wrong): 1 no mid sweep, 2 no records,
+                                // 4 no waiting for far results, 8 no tile moves
+    int s_slots;                // row blocks of self scores held: nB (every block has its own slab: written once per launch,
+                                // so the diagonal may read it through L1) or XP_RING (slabs reused: L2-coherent loads only)
     const int32_t *L;
     const int32_t *C;
     double *P;
@@ -54,15 +77,23 @@ struct XpParams {
     const int2 *tasks;          // x = type | block << 1, y = sub index
     double *farV;               // [XP_G][npad]
     int *farA;
-    CoarseRec *rec32;           // per 32 finished columns [1 + 32q, 33 + 32q)
+    XpRec32 *rec32;             // per 32 finished columns [1 + 32q, 33 + 32q)
     CoarseRec *rec128;          // per finished block
+    XpAnchors *anchors;         // per finished block
     double *pmax;               // running max |P|
     u64 *far_cells;             // far cells evaluated exactly
+    u64 *prof;                  // [32] cycle counters (see XP_PROF_NAMES)
     const double *gtab;
     const double *ltab;
     int alpha_int;
     double alpha, pen;
 };
+
+// cycle counters kept by one thread per role (negligible cost: a few clock reads per 32-row step / per task)
+enum { XQ_CHAIN = 0, XQ_CHAIN_BAR, XQ_H6_REC, XQ_H6_MID, XQ_H6_TILE, XQ_H6_SWAIT, XQ_H6_FAR, XQ_H6_BAR,
+       XQ_H0_MID, XQ_H0_TILE, XQ_H0_SWAIT, XQ_H0_FAR, XQ_H0_BAR, XQ_DIAG_TOTAL,
+       XQ_S_WORK = 16, XQ_S_WAIT, XQ_S_COUNT, XQ_F_WORK, XQ_F_WAIT, XQ_F_COUNT, XQ_F_MAX, XQ_F_L0, XQ_F_L1, XQ_F_L23, XQ_F_HEAD };
+__device__ __forceinline__ long long xp_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
 
 __device__ __forceinline__ int xp_ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 
@@ -74,45 +105,152 @@ __device__ __forceinline__ void xp_wait_cta(const int *flag, int target)     // 
     }
     __syncthreads();
 }
-__device__ __forceinline__ void xp_wait_helpers(const int *flag, int target)  // every helper thread (warps 1..7) calls
+// Self scores are written by worker CTAs and read by the diagonal after an acquire.  A slab that is written only once
+// per launch cannot be stale in the reader's L1 (L1 is invalidated at kernel boundaries), so ordinary loads are safe;
+// ring slabs are rewritten during the launch and must be read from L2 (ld.cg).
+template <bool RING, typename T>
+__device__ __forceinline__ T xp_ld_s(const T *p) { return RING ? __ldcg(p) : *p; }
+
+// Helpers: make sure the self scores of block `need` are complete.  One warp looks at the flags of 32 consecutive blocks
+// at once (they are produced far ahead of the diagonal), so the round trip to L2 is paid once per ~32 blocks.
+// *known: highest block index known complete (kept per thread, uniform over the helpers).
+__device__ __forceinline__ void xp_wait_s_blocks(const XpParams &p, int need, int *known, int *sKnown)
 {
-    if (threadIdx.x == 32) {
-        while (xp_ld_flag(flag) < target) __nanosleep(20);
+    if (need <= *known) return;
+    if ((threadIdx.x >> 5) == 4) {
+        const int lane = threadIdx.x & 31;
+        unsigned ok;
+        while (true) {
+            const int bq = need + lane;
+            const bool ready = bq < p.nB && xp_ld_flag(p.s_ready + bq) >= XP_SQ;
+            ok = __ballot_sync(0xffffffffu, ready);
+            if (ok & 1u) break;
+            __nanosleep(20);
+        }
         __threadfence();
+        if (lane == 0) *sKnown = need + __ffs(~ok | 0x80000000u) - 2 + ((ok == 0xffffffffu) ? 1 : 0);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(XP_HELP * 32) : "memory");
+    *known = *sKnown;
 }
 
 __device__ __forceinline__ int xp_far_bound(int b, int lag) { return b >= lag - 1 ? 1 + XP_RB * (b - lag + 1) : 0; }
 
 __host__ __device__ inline size_t xp_diag_smem()
 {
-    return (size_t)XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64;
+    return (size_t)XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + 64 * 4 + 16;
 }
 __host__ __device__ inline size_t xp_worker_smem()
 {
-    return (size_t)XP_RB * (8 + 8 + 8 + 8)              // rows: (L, C), LB, C and L as doubles
+    return (size_t)XP_RB * (8 + 16 + 8 + 8 + 8)         // rows: (L, C), float record, LB, C and L as doubles
            + 2 * XP_RB * 8                              // LB halves
            + 8 * XP_RB * 12                             // per-warp far results
-           + 256 * 4 + XP_LIST1 * 4                     // level-0 / level-1 survivor lists
-           + 8 * (4 + 8 + 8) + 16 * 8 + 64;             // anchors, scalars
+           + sizeof(XpAnchors)
+           + 256 * 4 + XP_LIST1 * 4 + XP_L2CHUNK * 32 * 2   // level-0 / level-1 / fine-rectangle lists
+           + 16 * 8 + 64;                               // scalars
 }
 
 // ---- diagonal CTA -----------------------------------------------------------------------------
+template <bool RING>
 __device__ __forceinline__ void xp_load_s_tile(const XpParams &p, int step, double *dst, int t, int nthreads)
 {
     const int jb = 1 + 32 * step;
     if (jb >= p.N) return;
     const int b = step >> 2;
-    const double *src = p.Sring + (size_t)(b % XP_RING) * p.DB * XP_RB + (step & 3) * 32;
-    for (int c = t; c < XP_ST * 16; c += nthreads) {
-        const int d1 = c >> 4, x = (c & 15) * 2;
-        const double2 v = __ldcg(reinterpret_cast<const double2 *>(src + (size_t)d1 * XP_RB + x));
-        *reinterpret_cast<double2 *>(dst + d1 * 32 + x) = v;
+    const double *src = p.Sring + (size_t)(b % p.s_slots) * p.DB * XP_RB + (step & 3) * 32;
+    constexpr int NV = (XP_ST * 16 + XP_HELP * 32 - 1) / (XP_HELP * 32);      // chunks per thread with 224 threads (5)
+    double2 v[NV];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {                                            // all loads in flight, then the stores
+        const int c = t + u * nthreads;
+        if (c < XP_ST * 16) v[u] = xp_ld_s<RING>(reinterpret_cast<const double2 *>(src + (size_t)(c >> 4) * XP_RB + (c & 15) * 2));
+    }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+        const int c = t + u * nthreads;
+        if (c < XP_ST * 16) *reinterpret_cast<double2 *>(dst + (c >> 4) * 32 + (c & 15) * 2) = v[u];
     }
 }
 
-template <bool AI>
+// Mid columns of the rows of one step, for one helper warp: the distances this warp sweeps and this lane's valid range.
+struct XpMid {
+    const double *Sb;      // self scores of this lane's row: Sb[(d - 1) * XP_RB]
+    int j, dlo, dhi, lane_lo, lane_hi;
+};
+__device__ __forceinline__ XpMid xp_mid_geometry(const XpParams &p, int step, int hw, int lane)
+{
+    XpMid g;
+    const int jbn = 1 + 32 * step, bn = step >> 2;
+    const int F = xp_far_bound(bn, p.lag);
+    g.j = jbn + lane;
+    g.Sb = p.Sring + (size_t)(bn % p.s_slots) * p.DB * XP_RB + (step & 3) * 32 + lane;
+    const int nd = jbn - F - 1;                          // distances 33 .. jbn + 31 - F over the warp
+    const int unit = (nd + XP_MIDW - 1) / XP_MIDW;       // six equal chunks (59 distances at lag 3: two batches)
+    g.dlo = 33 + hw * unit;
+    g.dhi = min(g.dlo + unit, 33 + nd);
+    g.lane_lo = max(g.dlo, 33 + lane);
+    g.lane_hi = (g.j < p.N) ? min(g.dhi - 1, g.j - F) : -1;      // this row's distances
+    return g;
+}
+// entries u = 0 .. XP_MB-1 of a batch are the distances d, d-1, ...; outside this row's range they hold -inf and never win
+template <bool RING>
+__device__ __forceinline__ void xp_mid_load(const XpMid &g, int d, double (&v)[XP_MB])
+{
+#pragma unroll
+    for (int u = 0; u < XP_MB; ++u) {
+        const int dd = d - u;
+        v[u] = (dd >= g.lane_lo && dd <= g.lane_hi) ? xp_ld_s<RING>(g.Sb + (size_t)(dd - 1) * XP_RB) : -INFINITY;
+    }
+}
+// Three independent (max, first arg-max) chains over consecutive thirds of the batch, merged in column order (a later
+// column wins only when strictly greater) = the sequential first maximum.
+__device__ __forceinline__ void xp_mid_fold(const XpMid &g, int d, const double (&v)[XP_MB], const double *sP, double &best, int &arg)
+{
+    constexpr int NCH = 3;
+    double qb[NCH];
+    int qa[NCH];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+        qb[q] = -INFINITY;
+        qa[q] = 0;
+#pragma unroll
+        for (int u = q * (XP_MB / NCH); u < (q + 1) * (XP_MB / NCH); ++u) {
+            const int col = g.j - (d - u);
+            const double t = __dadd_rn(v[u], sP[col & (XP_PRING - 1)]);
+            const bool w = t > qb[q];
+            qb[q] = w ? t : qb[q];
+            qa[q] = w ? col : qa[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+        if (qb[q] > best) { best = qb[q]; arg = qa[q]; }
+}
+
+// the chain warp's self-score tile of a step (distances 1..63 of its 32 rows): global -> registers, registers -> shared
+constexpr int XP_TILE_NV = (XP_ST * 16 + XP_MIDW * 32 - 1) / (XP_MIDW * 32);      // double2 chunks per sweeping thread (6)
+template <bool RING>
+__device__ __forceinline__ void xp_tile_load(const XpParams &p, int step, int t, int nthreads, double2 (&v)[XP_TILE_NV])
+{
+    if (1 + 32 * step >= p.N) return;
+    const double *src = p.Sring + (size_t)((step >> 2) % p.s_slots) * p.DB * XP_RB + (step & 3) * 32;
+#pragma unroll
+    for (int u = 0; u < XP_TILE_NV; ++u) {
+        const int c = t + u * nthreads;
+        if (c < XP_ST * 16) v[u] = xp_ld_s<RING>(reinterpret_cast<const double2 *>(src + (size_t)(c >> 4) * XP_RB + (c & 15) * 2));
+    }
+}
+__device__ __forceinline__ void xp_tile_store(const XpParams &p, int step, double *dst, int t, int nthreads, const double2 (&v)[XP_TILE_NV])
+{
+    if (1 + 32 * step >= p.N) return;
+#pragma unroll
+    for (int u = 0; u < XP_TILE_NV; ++u) {
+        const int c = t + u * nthreads;
+        if (c < XP_ST * 16) *reinterpret_cast<double2 *>(dst + (c >> 4) * 32 + (c & 15) * 2) = v[u];
+    }
+}
+
+template <bool AI, bool RING>
 __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
 {
     double *sP = reinterpret_cast<double *>(smem);              // [XP_PRING] finished P, ring by column index
@@ -122,6 +260,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     int *sMidA = reinterpret_cast<int *>(sFarV + 2 * XP_RB);    // [2][XP_HELP][32]
     int *sFarA = sMidA + 2 * XP_HELP * 32;                      // [2][128]
     double *sScal = reinterpret_cast<double *>(sFarA + 2 * XP_RB);   // [0] running max |P|
+    int *sPrevStep = reinterpret_cast<int *>(sScal + 8);             // [2][32] arg-max columns of the rows of a step (by step parity)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, lag = p.lag;
 
@@ -133,8 +272,8 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     }
     for (int k = tid; k < 2 * XP_HELP * 32; k += XP_THREADS) { sMidV[k] = -INFINITY; sMidA[k] = 0; }
     xp_wait_cta(p.s_ready, XP_SQ);
-    xp_load_s_tile(p, 0, sS, tid, XP_THREADS);
-    xp_load_s_tile(p, 1, sS + XP_ST * 32, tid, XP_THREADS);
+    xp_load_s_tile<RING>(p, 0, sS, tid, XP_THREADS);
+    xp_load_s_tile<RING>(p, 1, sS + XP_ST * 32, tid, XP_THREADS);
     __syncthreads();
 
     // chain warp state: accumulator of the NEXT step's rows over the columns being chained now
@@ -145,9 +284,27 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
         arg2 = 0;
     }
     const double tilt_c = (double)__ldg(p.C + N - 1) + p.alpha, tilt_l = (double)__ldg(p.L + N - 1);
-
+    // helper state carried from step to step: the self scores of the NEXT mid sweep and of the next tile are loaded
+    // one step ahead (they do not depend on P), so a step only adds the finished P to values that have already arrived
+    const int hw_mine = warp < 4 ? warp - 1 : (warp == 4 ? XP_MIDW : warp - 2);       // 0..5 sweep, 6 = the book-keeping warp
+    const int hidx = hw_mine * 32 + lane;                // index among the 192 sweeping threads
+    double pre0[XP_MB], pre1[XP_MB];
+    double2 tile_regs[XP_TILE_NV];
+    int s_known = 0;                                     // block 0 is complete (waited above)
+    int *sKnown = sPrevStep + 64;
+    if (warp > 0 && hw_mine < XP_MIDW) {
+        if (2 < p.nSteps) xp_tile_load<RING>(p, 2, hidx, XP_MIDW * 32, tile_regs);
+        if (1 < p.nSteps) {
+            const XpMid g = xp_mid_geometry(p, 1, hw_mine, lane);
+            xp_mid_load<RING>(g, g.dhi - 1, pre0);
+            xp_mid_load<RING>(g, g.dhi - 1 - XP_MB, pre1);
+        }
+    }
+    long long pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // per-thread phase cycles (only threads 0, 32 and 224 report)
+    const long long t_begin = xp_clock();
     for (int k = 0; k < p.nSteps; ++k) {
         const int jb = 1 + 32 * k, b = k >> 2, s = k & 3;
+        long long tq = xp_clock();
         if (warp == 0) {
             // ---------------- chain warp: rows [jb, jb + 32) ----------------
             const int j = jb + lane;
@@ -158,7 +315,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 arg = sFarA[(b & 1) * XP_RB + s * 32 + lane];
             }
 #pragma unroll
-            for (int w = XP_HELP - 1; w >= 0; --w) {             // mid columns: helper w swept the w-th distance chunk
+            for (int w = XP_MIDW - 1; w >= 0; --w) {             // mid columns: helper w swept the w-th distance chunk
                 const double v = sMidV[((k & 1) * XP_HELP + w) * 32 + lane];
                 if (v > best) { best = v; arg = sMidA[((k & 1) * XP_HELP + w) * 32 + lane]; }
             }
@@ -167,21 +324,34 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             arg2 = 0;
             const double *tri = sS + (k % 3) * XP_ST * 32;
             const double *nxt = sS + ((k + 1) % 3) * XP_ST * 32;
-            const int rows = min(32, N - jb);
             const bool valid2 = jb + 32 + lane < N;
             double mine = 0.0;
-#pragma unroll 8
-            for (int kk = 0; kk < rows; ++kk) {
-                const double pf = __dadd_rn(best, p.pen);       // prefix_scores[j] = max + segment_creation_cost
-                const double pk = __shfl_sync(0xffffffffu, pf, kk);
-                if (lane == kk) mine = pf;
-                if (lane > kk) {
-                    const double t = __dadd_rn(tri[(lane - kk - 1) * 32 + lane], pk);
-                    if (t > best) { best = t; arg = jb + kk; }
+            // Always 32 iterations: in the last (partial) step the lanes past the end only produce values nobody reads.
+            // The operands of 8 iterations are fetched from shared memory ahead of the dependent chain; a lane that
+            // must not take part in an update holds -inf there, so the updates need no branches.
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 8) {
+                double tv[8], nv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int kk = k0 + u;
+                    tv[u] = lane > kk ? tri[(lane - kk - 1) * 32 + lane] : -INFINITY;
+                    nv[u] = valid2 ? nxt[(31 + lane - kk) * 32 + lane] : -INFINITY;
                 }
-                if (valid2) {
-                    const double t2 = __dadd_rn(nxt[(31 + lane - kk) * 32 + lane], pk);
-                    if (t2 > best2) { best2 = t2; arg2 = jb + kk; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int kk = k0 + u;
+                    const double pf = __dadd_rn(best, p.pen);       // prefix_scores[j] = max + segment_creation_cost
+                    const double pk = __shfl_sync(0xffffffffu, pf, kk);
+                    mine = lane == kk ? pf : mine;
+                    const double t = __dadd_rn(tv[u], pk);
+                    const bool w = t > best;
+                    best = w ? t : best;
+                    arg = w ? jb + kk : arg;
+                    const double t2 = __dadd_rn(nv[u], pk);
+                    const bool w2 = t2 > best2;
+                    best2 = w2 ? t2 : best2;
+                    arg2 = w2 ? jb + kk : arg2;
                 }
             }
             double pm = 0.0;
@@ -191,95 +361,132 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 __stcg(p.prev + j, arg);
                 pm = fabs(mine);
             }
+            sPrevStep[(k & 1) * 32 + lane] = arg;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, off));
             pmax = fmax(pmax, pm);
             if (lane == 0) sScal[0] = pmax;
+            { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
         } else {
             // ---------------- helper warps ----------------
-            const int hw = warp - 1, ht = tid - 32;
-            if (hw == XP_HELP - 1 && k > 0) {
-                // records of the columns finished in step k-1 (and of the block they complete), then publish
-                const int jbp = jb - 32;
-                fit_column_record(__ldg(p.C + jbp + lane), __ldg(p.L + jbp + lane), sP[(jbp + lane) & (XP_PRING - 1)],
-                                  p.rec32 + (k - 1), tilt_c, tilt_l);
-                if (s == 0) {
-                    const int c0 = 1 + XP_RB * (b - 1);
-                    int cc[4], ll[4];
-                    double pp[4];
+            // warps 1,2,3,5,6,7 sweep the mid columns (six distance chunks, in this order) and move the tiles; warp 4 -- which
+            // shares its scheduler with the chain warp -- keeps the books: records, anchors, publishing, the far results
+            const int hw = hw_mine;
+            if (hw == XP_MIDW) {
+                if (k > 0) {
+                    // records of the columns finished in step k-1 (and of the block they complete), then publish
+                    const int jbp = jb - 32;
+                    const int cme = __ldg(p.C + jbp + lane), lme = __ldg(p.L + jbp + lane);
+                    XpRec32 *rec = p.rec32 + (k - 1);
+                    if (!(p.dbg & 2)) fit_column_record(cme, lme, sP[(jbp + lane) & (XP_PRING - 1)], &rec->r, tilt_c, tilt_l);
+                    if ((lane & 7) == 0) { rec->sub[lane >> 3][0] = cme; rec->sub[lane >> 3][2] = lme; }
+                    if ((lane & 7) == 7) { rec->sub[lane >> 3][1] = cme; rec->sub[lane >> 3][3] = lme; }
+                    if (s == 0) {
+                        const int c0 = 1 + XP_RB * (b - 1);
+                        int cc[4], ll[4];
+                        double pp[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            cc[q] = __ldg(p.C + c0 + lane + 32 * q);
+                            ll[q] = __ldg(p.L + c0 + lane + 32 * q);
+                            pp[q] = sP[(c0 + lane + 32 * q) & (XP_PRING - 1)];
+                        }
+                        if (!(p.dbg & 2)) fit_column_record128(cc, ll, pp, p.rec128 + (b - 1), tilt_c, tilt_l);
+                        // anchors of the block that just finished: its last row e and the last seven split points of the best
+                        // segmentation ending there (e -> prev[e] -> prev[prev[e]] ...): the rows ahead most likely continue
+                        // one of these, so "best up to the anchor, then one segment" bounds their maxima from below tightly
+                        const int e = jb - 1;
+                        int a = e, mine = e;
+                        for (int t = 1; t < 8; ++t) {                  // (every lane walks the same chain: uniform loads)
+                            a = a > 0 ? __ldcg(p.prev + a) : 0;
+                            if (lane == t) mine = a;
+                        }
+                        if (lane < 8) {
+                            mine = min(max(mine, 0), e);
+                            XpAnchors *an = p.anchors + (b - 1);
+                            an->idx[lane] = mine;
+                            an->L[lane] = __ldg(p.L + mine);
+                            an->C[lane] = __ldg(p.C + mine);
+                            an->P[lane] = mine > 0 ? __ldcg(p.P + mine) : 0.0;
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            __stcg(p.pmax, sScal[0]);
+                            __threadfence();
+                            *reinterpret_cast<volatile int *>(p.done_block) = b;
+                        }
+                    }
+                }
+                { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
+                if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
+                { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
+                // far results of the next block: four rows per lane, the eight slices merged by column index
+                if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
+                    if (lane == 0 && !(p.dbg & 4)) {
+                        while (xp_ld_flag(p.far_ready + (b + 1)) < XP_G) __nanosleep(20);
+                        __threadfence();
+                    }
+                    __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        cc[q] = __ldg(p.C + c0 + lane + 32 * q);
-                        ll[q] = __ldg(p.L + c0 + lane + 32 * q);
-                        pp[q] = sP[(c0 + lane + 32 * q) & (XP_PRING - 1)];
+                        const int row = lane + 32 * q, j = 1 + XP_RB * (b + 1) + row;
+                        double best = -INFINITY;
+                        int arg = 0x7fffffff;
+                        if (j < N) {
+                            double v[XP_G];
+                            int a[XP_G];
+#pragma unroll
+                            for (int g = 0; g < XP_G; ++g) {
+                                v[g] = __ldcg(p.farV + (size_t)g * p.npad + j);
+                                a[g] = __ldcg(p.farA + (size_t)g * p.npad + j);
+                            }
+#pragma unroll
+                            for (int g = 0; g < XP_G; ++g)
+                                if (v[g] > best || (v[g] == best && a[g] < arg)) { best = v[g]; arg = a[g]; }
+                        }
+                        sFarV[((b + 1) & 1) * XP_RB + row] = best;
+                        sFarA[((b + 1) & 1) * XP_RB + row] = arg;
                     }
-                    fit_column_record128(cc, ll, pp, p.rec128 + (b - 1), tilt_c, tilt_l);
-                    __syncwarp();
-                    if (lane == 0) {
-                        __stcg(p.pmax, sScal[0]);
-                        __threadfence();
-                        *reinterpret_cast<volatile int *>(p.done_block) = b;
-                    }
+                    { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
                 }
-            }
-            // mid columns of the next step's rows: [F, jb), by distance, descending (= ascending column)
-            if (k + 1 < p.nSteps) {
-                const int jbn = jb + 32, bn = (k + 1) >> 2;
-                const int F = xp_far_bound(bn, lag);
-                const int j = jbn + lane;
-                const double *Sb = p.Sring + (size_t)(bn % XP_RING) * p.DB * XP_RB + ((k + 1) & 3) * 32 + lane;
-                const int nd = jbn - F - 1;                      // distances 33 .. jbn + 31 - F over the warp
-                const int cs = (nd + XP_HELP - 1) / XP_HELP;
-                const int dlo = 33 + hw * cs, dhi = min(dlo + cs, 33 + nd);
-                const int lane_lo = max(dlo, 33 + lane), lane_hi = (j < N) ? min(dhi - 1, j - F) : -1;   // this row's distances
+            } else {
+                // self scores of block (k+3)/4 must be complete before anything of step k+3 is prefetched below
+                if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
+                { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
+                // mid columns of the next step's rows: [F, jb), by distance, descending (= ascending column).  The two
+                // batches were loaded during the previous step; as soon as a batch is folded its registers take the loads
+                // of the step after, so the transfers run under the arithmetic
+                const bool have1 = k + 1 < p.nSteps && !(p.dbg & 1), have2 = k + 2 < p.nSteps && !(p.dbg & 1);
+                const XpMid g1 = xp_mid_geometry(p, have1 ? k + 1 : k, hw, lane);
+                const XpMid g2 = xp_mid_geometry(p, have2 ? k + 2 : k, hw, lane);
                 double best = -INFINITY;
                 int arg = 0;
-                for (int d = dhi - 1; d >= dlo; d -= XP_MB) {
-                    double v[XP_MB];
-#pragma unroll
-                    for (int u = 0; u < XP_MB; ++u) {
-                        const int dd = d - u;
-                        v[u] = (dd >= lane_lo && dd <= lane_hi) ? __ldcg(Sb + (size_t)(dd - 1) * XP_RB) : 0.0;
+                if (have1) xp_mid_fold(g1, g1.dhi - 1, pre0, sP, best, arg);
+                if (have2) xp_mid_load<RING>(g2, g2.dhi - 1, pre0);
+                if (have1) {
+                    xp_mid_fold(g1, g1.dhi - 1 - XP_MB, pre1, sP, best, arg);
+                    for (int d = g1.dhi - 1 - 2 * XP_MB; d >= g1.dlo; d -= XP_MB) {    // (lag 4: further batches, loaded here)
+                        double v[XP_MB];
+                        xp_mid_load<RING>(g1, d, v);
+                        xp_mid_fold(g1, d, v, sP, best, arg);
                     }
-#pragma unroll
-                    for (int u = 0; u < XP_MB; ++u) {
-                        const int dd = d - u;
-                        if (dd >= lane_lo && dd <= lane_hi) {
-                            const double t = __dadd_rn(v[u], sP[(j - dd) & (XP_PRING - 1)]);
-                            if (t > best) { best = t; arg = j - dd; }
-                        }
-                    }
+                    sMidV[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = best;
+                    sMidA[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = arg;
                 }
-                sMidV[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = best;
-                sMidA[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = arg;
-            }
-            // self-score tile of step k+2
-            if (k + 2 < p.nSteps) {
-                if (((k + 2) & 3) == 0) xp_wait_helpers(p.s_ready + ((k + 2) >> 2), XP_SQ);
-                xp_load_s_tile(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, ht, XP_HELP * 32);
-            }
-            // far results of the next block
-            if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
-                xp_wait_helpers(p.far_ready + (b + 1), XP_G);
-                if (ht < XP_RB) {
-                    const int j = 1 + XP_RB * (b + 1) + ht;
-                    double best = -INFINITY;
-                    int arg = 0x7fffffff;
-                    if (j < N) {
-#pragma unroll
-                        for (int g = 0; g < XP_G; ++g) {
-                            const double v = __ldcg(p.farV + (size_t)g * p.npad + j);
-                            const int a = __ldcg(p.farA + (size_t)g * p.npad + j);
-                            if (v > best || (v == best && a < arg)) { best = v; arg = a; }
-                        }
-                    }
-                    sFarV[((b + 1) & 1) * XP_RB + ht] = best;
-                    sFarA[((b + 1) & 1) * XP_RB + ht] = arg;
-                }
+                if (have2) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
+                { const long long t1 = xp_clock(); pq[1] += t1 - tq; tq = t1; }
+                // the tile of step k+2 (loaded during the previous step) -> shared memory; then the loads of the next one
+                if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_tile_store(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, hidx, XP_MIDW * 32, tile_regs);
+                if (k + 3 < p.nSteps && !(p.dbg & 8)) xp_tile_load<RING>(p, k + 3, hidx, XP_MIDW * 32, tile_regs);
+                { const long long t1 = xp_clock(); pq[2] += t1 - tq; tq = t1; }
             }
         }
         __syncthreads();
+        pq[5] += xp_clock() - tq;
     }
+    if (tid == 0) { p.prof[XQ_CHAIN] = pq[0]; p.prof[XQ_CHAIN_BAR] = pq[5]; p.prof[XQ_DIAG_TOTAL] = xp_clock() - t_begin; }
+    if (tid == 32) { p.prof[XQ_H0_MID] = pq[1]; p.prof[XQ_H0_TILE] = pq[2]; p.prof[XQ_H0_SWAIT] = pq[3]; p.prof[XQ_H0_FAR] = pq[4]; p.prof[XQ_H0_BAR] = pq[5]; }
+    if (tid == 128) { p.prof[XQ_H6_REC] = pq[0]; p.prof[XQ_H6_MID] = pq[1]; p.prof[XQ_H6_TILE] = pq[2]; p.prof[XQ_H6_SWAIT] = pq[3]; p.prof[XQ_H6_FAR] = pq[4]; p.prof[XQ_H6_BAR] = pq[5]; }
 }
 
 // ---- worker CTAs -----------------------------------------------------------------------------
@@ -290,7 +497,9 @@ __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
     int2 *sLC = reinterpret_cast<int2 *>(smem);                 // (L, C) of candidates [F, r0 + nrows)
     const int tid = threadIdx.x;
     const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, p.N - r0), F = xp_far_bound(b, p.lag);
-    if (b >= XP_RING) xp_wait_cta(p.done_block, b - XP_RING + 1);      // the ring slot's previous block is finished
+    const long long ts0 = xp_clock();
+    if (b >= p.s_slots) xp_wait_cta(p.done_block, b - p.s_slots + 1);  // ring only: the slot's previous block is finished
+    const long long ts1 = xp_clock();
     const int cnt = r0 + nrows - F;
     for (int i = tid; i < cnt; i += XP_THREADS) sLC[i] = make_int2(__ldg(p.L + F + i), __ldg(p.C + F + i));
     __syncthreads();
@@ -299,7 +508,7 @@ __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
     if (r < nrows) {
         const int2 me = sLC[j - F];
         const RowConst<AI> row = make_row<AI>(me.y, me.x, p.alpha_int, p.alpha);
-        double *Sb = p.Sring + (size_t)(b % XP_RING) * p.DB * XP_RB + r;
+        double *Sb = p.Sring + (size_t)(b % p.s_slots) * p.DB * XP_RB + r;
         const int dmax = min(d1 - 1, j - F);                    // column j - d >= F
         constexpr int U = 4;
         for (int d = d0 + half; d <= dmax; d += 2 * U) {
@@ -328,6 +537,9 @@ __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
     if (tid == 0) {
         __threadfence();
         atomicAdd(p.s_ready + b, 1);
+        atomicAdd(p.prof + XQ_S_WAIT, (u64)(ts1 - ts0));
+        atomicAdd(p.prof + XQ_S_WORK, (u64)(xp_clock() - ts1));
+        atomicAdd(p.prof + XQ_S_COUNT, 1ull);
     }
 }
 
@@ -338,70 +550,119 @@ struct XpRows {
 // min over rows [ra, rb] of LB_r + a*C_r + b*L_r
 __device__ __forceinline__ double xp_row_min(const XpRows &R, int ra, int rb, double a, double b)
 {
-    double m = INFINITY;
-    for (int r = ra; r <= rb; ++r) m = fmin(m, R.lb[r] + (a * R.cd[r] + b * R.ld[r]));
-    return m;
+    double m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;      // four chains: the minimum is order-free
+    int r = ra;
+    for (; r + 3 <= rb; r += 4) {
+        m0 = fmin(m0, R.lb[r] + (a * R.cd[r] + b * R.ld[r]));
+        m1 = fmin(m1, R.lb[r + 1] + (a * R.cd[r + 1] + b * R.ld[r + 1]));
+        m2 = fmin(m2, R.lb[r + 2] + (a * R.cd[r + 2] + b * R.ld[r + 2]));
+        m3 = fmin(m3, R.lb[r + 3] + (a * R.cd[r + 3] + b * R.ld[r + 3]));
+    }
+    for (; r <= rb; ++r) m0 = fmin(m0, R.lb[r] + (a * R.cd[r] + b * R.ld[r]));
+    return fmin(fmin(m0, m1), fmin(m2, m3));
 }
 
-// F(b, g): far columns of row block b, column blocks c = g, g + 8, ... <= b - lag (slice 0 also column 0)
+// F(b, g): far columns of row block b that lie in the 32-column groups q = g, g + 8, ... (slice 0 also column 0): the
+// four groups of a column block belong to four slices, so the blocks next to the band -- where most survivors are --
+// are shared out evenly.
+// Written for LATENCY (the diagonal reaches block b two or three blocks after this task is released): every level
+// first issues all the loads of all its rectangles, then consumes them, so a level costs one or two round trips to
+// L2 whatever its size.
 template <bool AI>
 __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
 {
     int2 *sRowLC = reinterpret_cast<int2 *>(smem);                      // [128]
-    double *sLB = reinterpret_cast<double *>(sRowLC + XP_RB);           // [128]
+    float4 *sRowF = reinterpret_cast<float4 *>(sRowLC + XP_RB);         // [128] (LB, C, L) as floats: level-0 minima
+    double *sLB = reinterpret_cast<double *>(sRowF + XP_RB);            // [128]
     double *sCd = sLB + XP_RB, *sLd = sCd + XP_RB;                      // [128] each
     double *sHalf = sLd + XP_RB;                                        // [2][128]
     double *sWV = sHalf + 2 * XP_RB;                                    // [8][128]
-    double *sAncP = sWV + 8 * XP_RB;                                    // [8]
-    double *sRed = sAncP + 8;                                           // [8]
-    int *sWA = reinterpret_cast<int *>(sRed + 8);                       // [8][128]
-    int2 *sAncLC = reinterpret_cast<int2 *>(sWA + 8 * XP_RB);           // [8]
-    int *sList0 = reinterpret_cast<int *>(sAncLC + 8);                  // [256]
+    double *sRed = sWV + 8 * XP_RB;                                     // [8]
+    XpAnchors *sAnc = reinterpret_cast<XpAnchors *>(sRed + 8);
+    int *sWA = reinterpret_cast<int *>(sAnc + 1);                       // [8][128]
+    int *sList0 = sWA + 8 * XP_RB;                                      // [256]
     int *sList1 = sList0 + 256;                                         // [XP_LIST1]
     int *sCnt = sList1 + XP_LIST1;                                      // [4]
+    unsigned short *sList2 = reinterpret_cast<unsigned short *>(sCnt + 4);   // [XP_L2CHUNK * 32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, lag = p.lag;
     const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, N - r0);
-    const int F = xp_far_bound(b, lag), ncb = b - lag + 1;              // far column blocks 0 .. ncb-1
+    const int ncb = b - lag + 1;                                        // far column blocks 0 .. ncb-1
+    const long long tf0 = xp_clock();
     xp_wait_cta(p.done_block, ncb);
+    const long long tf1 = xp_clock();
+    long long tl0 = 0, tl1 = 0, tl2 = 0, thead = 0;
 
+    // ---- phase A: rows, anchors, this thread's first level-0 record, scalars: one round trip ----
     const int zC = __ldg(p.C + N - 1), zL = __ldg(p.L + N - 1);
-    const double scale0 = fabs(__ldg(p.gtab + zC + (AI ? p.alpha_int : 0))) + ((double)zC + p.alpha) * fabs(__ldg(p.ltab + zL)) + 1.0;
+    const double zg = __ldg(p.gtab + zC + (AI ? p.alpha_int : 0)), zl = __ldg(p.ltab + zL);
     const double pmax = __ldcg(p.pmax);
-    const double delta = (scale0 + pmax + fabs(p.pen) * XP_RB) * 5.684341886080802e-14;     // 2^-44
-    const double tilt_c = (double)zC + p.alpha, tilt_l = (double)zL;
-
+    int2 rowlc = make_int2(0, 0);
     if (tid < XP_RB) {
         const int j = min(r0 + tid, N - 1);
-        const int2 lc = make_int2(__ldg(p.L + j), __ldg(p.C + j));
-        sRowLC[tid] = lc;
-        sCd[tid] = (double)lc.y;
-        sLd[tid] = (double)lc.x;
+        rowlc = make_int2(__ldg(p.L + j), __ldg(p.C + j));
     }
-    if (tid < 8) {
-        // anchors: the last final row and the arg-max columns of the rows before it
-        const int e = F - 1;
-        int a = e;
-        if (tid > 0 && e > 0) a = __ldcg(p.prev + max(e - (tid - 1), 1));
-        a = min(max(a, 0), e);
-        sAncLC[tid] = make_int2(__ldg(p.L + a), __ldg(p.C + a));
-        sAncP[tid] = a > 0 ? __ldcg(p.P + a) : 0.0;
+    if (ncb >= 1) {
+        if (tid < (int)(sizeof(XpAnchors) / 4))
+            reinterpret_cast<int *>(sAnc)[tid] = __ldcg(reinterpret_cast<const int *>(p.anchors + (ncb - 1)) + tid);
+    } else if (tid < (int)(sizeof(XpAnchors) / 4)) {
+        reinterpret_cast<int *>(sAnc)[tid] = 0;                         // only column 0 is behind this block: P_0 = 0
+    }
+    int4 ends0 = make_int4(0, 0, 0, 0);
+    double a0 = 0.0, b0 = 0.0, mpt0 = 0.0;
+    static_assert(XP_G == 8, "slice g owns the 32-column groups q = g (mod 8): group g & 3 of every block c = g >> 2 (mod 2)");
+    const int c_first_chunk = (g >> 2) + 2 * tid;
+    if (c_first_chunk < ncb) {
+        const CoarseRec *rec = p.rec128 + c_first_chunk;
+        ends0 = __ldcg(reinterpret_cast<const int4 *>(rec));            // c_first, c_last, l_first, l_last
+        a0 = __ldcg(&rec->a);
+        b0 = __ldcg(&rec->b);
+        mpt0 = __ldcg(&rec->mpt);
     }
     for (int k = tid; k < 8 * XP_RB; k += XP_THREADS) { sWV[k] = -INFINITY; sWA[k] = 0x7fffffff; }
+    if (tid < XP_RB) {
+        sRowLC[tid] = rowlc;
+        sCd[tid] = (double)rowlc.y;
+        sLd[tid] = (double)rowlc.x;
+    }
+    const double scale0 = fabs(zg) + ((double)zC + p.alpha) * fabs(zl) + 1.0;
+    const double delta = (scale0 + pmax + fabs(p.pen) * XP_RB) * 5.684341886080802e-14;     // 2^-44
+    const double tilt_c = (double)zC + p.alpha, tilt_l = (double)zL;
     __syncthreads();
+
+    // ---- phase B: gathers of the lower bounds (rows x anchors), of column 0 and of this thread's level-0 box ----
+    const int2 rowF = sRowLC[0], rowE = sRowLC[nrows - 1];
+    BoxCorners box0 = {0.0, 0.0, 0.0, 0.0};
+    if (c_first_chunk < ncb)
+        box0 = box_corner_loads<AI>(rowF.y - ends0.y, rowE.y - ends0.x, rowF.x - ends0.w, rowE.x - ends0.z, p.gtab, p.ltab, p.alpha_int);
     {
         const int r = tid & (XP_RB - 1), h = tid >> 7;
         const int2 me = sRowLC[r];
         const RowConst<AI> row = make_row<AI>(me.y, me.x, p.alpha_int, p.alpha);
+        double gq[4], lq[4], g00 = 0.0, l00 = 0.0;
+        int ci[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ci[q] = sAnc->C[4 * h + q];
+            gq[q] = __ldg(p.gtab + (row.cjx - ci[q]));
+            lq[q] = __ldg(p.ltab + (row.lj - sAnc->L[4 * h + q]));
+        }
+        const bool col0 = g == 0 && h == 0 && r < nrows;     // column 0 belongs to no record: always evaluated (P_0 = 0)
+        const int c00 = __ldg(p.C), l00i = __ldg(p.L);
+        if (col0) {
+            g00 = __ldg(p.gtab + (row.cjx - c00));
+            l00 = __ldg(p.ltab + (row.lj - l00i));
+        }
         double lb = -INFINITY;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int2 a = sAncLC[4 * h + q];
-            lb = fmax(lb, __dadd_rn(self_score<AI>(a.y, a.x, row, p.gtab, p.ltab), sAncP[4 * h + q]));
+            const double sx = AI ? u32_to_double(row.cjx - ci[q]) : __dsub_rn(row.aj, u32_to_double(ci[q]));
+            lb = fmax(lb, __dadd_rn(__dsub_rn(gq[q], __dmul_rn(sx, lq[q])), sAnc->P[4 * h + q]));
         }
         sHalf[h * XP_RB + r] = lb;
-        if (g == 0 && h == 0 && r < nrows) {            // column 0 belongs to no record: always evaluated (P_0 = 0)
-            sWV[r] = __dadd_rn(self_score<AI>(__ldg(p.C), __ldg(p.L), row, p.gtab, p.ltab), 0.0);
+        if (col0) {
+            const double sx = AI ? u32_to_double(row.cjx - c00) : __dsub_rn(row.aj, u32_to_double(c00));
+            sWV[r] = __dadd_rn(__dsub_rn(g00, __dmul_rn(sx, l00)), 0.0);
             sWA[r] = 0;
         }
     }
@@ -413,103 +674,227 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
         if (tid >= nrows) lb = INFINITY;                 // rows past the end never lower a minimum
         else if (lb > -INFINITY) lbabs = fabs(lb);
         sLB[tid] = lb;
+        // float copy for the coarsest level: rounded DOWN so that it stays a lower bound of the double value
+        float lf = (float)lb;
+        if ((double)lf > lb) lf = nextafterf(lf, -INFINITY);
+        sRowF[tid] = make_float4(lf, (float)sRowLC[tid].y, (float)sRowLC[tid].x, 0.f);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) lbabs = fmax(lbabs, __shfl_xor_sync(0xffffffffu, lbabs, off));
     if (lane == 0) sRed[warp] = lbabs;
+    if (tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
     __syncthreads();
     lbabs = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) lbabs = fmax(lbabs, sRed[w]);
     const XpRows R = {sRowLC, sLB, sCd, sLd};
-    const int2 rowF = sRowLC[0], rowE = sRowLC[nrows - 1];
-    auto row_slack = [&](double a, double bb) { return (lbabs + fabs(a) * tilt_c + fabs(bb) * tilt_l) * 5.684341886080802e-14; };
+    auto row_slack = [&](double a, double bb) { return (lbabs + fabs(a) * tilt_c + fabs(bb) * tilt_l) * 5.684341886080802e-14; };   // 2^-44
     u64 evaluated = 0;
+    thead = xp_clock() - tf1;
 
-    for (int cbase = g; cbase < ncb; cbase += XP_THREADS * XP_G) {
-        __syncthreads();
-        if (tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
-        __syncthreads();
-        // ---- level 0: 128 rows x 128 columns, one thread per column block ----
+    for (int cbase = g >> 2; cbase < ncb; cbase += XP_THREADS * 2) {
+        long long tq = xp_clock();
+        // ---- level 0: 128 rows x 128 columns, one thread per column block; row minima in float ----
         {
-            const int c = cbase + tid * XP_G;
+            const int c = cbase + tid * 2;
             if (c < ncb) {
-                const CoarseRec *rec = p.rec128 + c;
-                const int4 ends = __ldcg(reinterpret_cast<const int4 *>(rec));        // c_first, c_last, l_first, l_last
-                const double a = __ldcg(&rec->a), bb = __ldcg(&rec->b);
-                const double ub = __ldcg(&rec->mpt) + tilted_box_max<AI>(rowF.y - ends.y, rowE.y - ends.x, rowF.x - ends.w, rowE.x - ends.z,
-                                                                          a, bb, p.gtab, p.ltab, p.alpha_int, p.alpha);
-                const double rmin = xp_row_min(R, 0, nrows - 1, a, bb) - row_slack(a, bb);
+                int4 ends = ends0;
+                double a = a0, bb = b0, mpt = mpt0;
+                BoxCorners box = box0;
+                if (cbase != (g >> 2)) {                 // (beyond 512 column blocks: later chunks load here)
+                    const CoarseRec *rec = p.rec128 + c;
+                    ends = __ldcg(reinterpret_cast<const int4 *>(rec));
+                    a = __ldcg(&rec->a);
+                    bb = __ldcg(&rec->b);
+                    mpt = __ldcg(&rec->mpt);
+                    box = box_corner_loads<AI>(rowF.y - ends.y, rowE.y - ends.x, rowF.x - ends.w, rowE.x - ends.z, p.gtab, p.ltab, p.alpha_int);
+                }
+                const double ub = mpt + tilted_box_max_of(box, rowF.y - ends.y, rowE.y - ends.x, rowF.x - ends.w, rowE.x - ends.z, a, bb, p.alpha);
+                const float af = (float)a, bf = (float)bb;
+                float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+                for (int r = 0; r < XP_RB; r += 4) {     // rows past the end hold +inf
+                    const float4 q0 = sRowF[r], q1 = sRowF[r + 1], q2 = sRowF[r + 2], q3 = sRowF[r + 3];
+                    m0 = fminf(m0, fmaf(af, q0.y, fmaf(bf, q0.z, q0.x)));
+                    m1 = fminf(m1, fmaf(af, q1.y, fmaf(bf, q1.z, q1.x)));
+                    m2 = fminf(m2, fmaf(af, q2.y, fmaf(bf, q2.z, q2.x)));
+                    m3 = fminf(m3, fmaf(af, q3.y, fmaf(bf, q3.z, q3.x)));
+                }
+                // float error: conversions of a, b, C, L and two fused roundings, each <= 2^-24 of the magnitudes involved
+                const double err = (lbabs + fabs(a) * tilt_c + fabs(bb) * tilt_l) * 9.5367431640625e-07;      // 2^-20
+                const double rmin = (double)fminf(fminf(m0, m1), fminf(m2, m3)) - err;
                 if (!(ub - rmin + delta < 0.0)) sList0[atomicAdd(sCnt, 1)] = c;      // NaN keeps the block
             }
         }
         __syncthreads();
+        { const long long t1 = xp_clock(); tl0 += t1 - tq; tq = t1; }
         const int n0 = sCnt[0];
-        // ---- level 1: 32 rows x 32 columns, one thread per rectangle ----
-        for (int e = tid; e < n0 * 16; e += XP_THREADS) {
-            const int c = sList0[e >> 4], rg = (e >> 2) & 3, cq = e & 3;
-            if (32 * rg < nrows) {
-                const int q32 = 4 * c + cq;
-                const CoarseRec *rec = p.rec32 + q32;
-                const int4 ends = __ldcg(reinterpret_cast<const int4 *>(rec));
-                const double a = __ldcg(&rec->a), bb = __ldcg(&rec->b);
-                const int ra = 32 * rg, rb = min(ra + 31, nrows - 1);
-                const int2 fa = sRowLC[ra], fb = sRowLC[rb];
-                const double ub = __ldcg(&rec->mpt) + tilted_box_max<AI>(fa.y - ends.y, fb.y - ends.x, fa.x - ends.w, fb.x - ends.z,
-                                                                          a, bb, p.gtab, p.ltab, p.alpha_int, p.alpha);
-                const double rmin = xp_row_min(R, ra, rb, a, bb) - row_slack(a, bb);
-                if (!(ub - rmin + delta < 0.0)) {
-                    const int slot = atomicAdd(sCnt + 1, 1);
-                    if (slot < XP_LIST1) sList1[slot] = q32 * 4 + rg;
+        // ---- level 1: 32 rows x 32 columns (this slice's column group of every surviving block), one thread per
+        //      rectangle, two rectangles in flight per thread ----
+        for (int e0 = tid; e0 < n0 * 4; e0 += 2 * XP_THREADS) {
+            int4 ends[2];
+            double a[2], bb[2], mpt[2];
+            BoxCorners box[2];
+            int ra[2], rb[2], ent[2];
+            bool act[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = e0 + u * XP_THREADS;
+                act[u] = false;
+                ent[u] = 0;
+                if (e < n0 * 4) {
+                    const int c = sList0[e >> 2], rg = e & 3, cq = g & 3;
+                    if (32 * rg < nrows) {
+                        act[u] = true;
+                        ent[u] = (4 * c + cq) * 4 + rg;
+                        ra[u] = 32 * rg;
+                        rb[u] = min(ra[u] + 31, nrows - 1);
+                        const CoarseRec *rec = &p.rec32[4 * c + cq].r;
+                        ends[u] = __ldcg(reinterpret_cast<const int4 *>(rec));
+                        a[u] = __ldcg(&rec->a);
+                        bb[u] = __ldcg(&rec->b);
+                        mpt[u] = __ldcg(&rec->mpt);
+                    }
                 }
             }
-        }
-        __syncthreads();
-        const int n1 = min(sCnt[1], XP_LIST1);       // n0 <= 256 blocks x 16 = 4096: never overflows
-        // ---- level 2 (4 rows x 8 columns, one lane per rectangle) and exact evaluation, one warp per 32 x 32 ----
-        for (int e = warp; e < n1; e += 8) {
-            const int ent = sList1[e], q32 = ent >> 2, rg = ent & 3;
-            const CoarseRec *rec = p.rec32 + q32;
-            const double a = __ldcg(&rec->a), bb = __ldcg(&rec->b);
-            const int sub = lane & 3, ra = 32 * rg + 4 * (lane >> 2);
-            bool surv = false;
-            if (ra < nrows) {
-                const int rb = min(ra + 3, nrows - 1);
-                const int i0 = 1 + 32 * q32 + 8 * sub;
-                const int2 cF = make_int2(__ldg(p.L + i0), __ldg(p.C + i0)), cL = make_int2(__ldg(p.L + i0 + 7), __ldg(p.C + i0 + 7));
-                const int2 fa = sRowLC[ra], fb = sRowLC[rb];
-                const double m2 = tilted_box_max<AI>(fa.y - cL.y, fb.y - cF.y, fa.x - cL.x, fb.x - cF.x, a, bb,
-                                                     p.gtab, p.ltab, p.alpha_int, p.alpha);
-                const double m3 = xp_row_min(R, ra, rb, a, bb) - row_slack(a, bb);
-                surv = !(__ldcg(&rec->mpt8[sub]) + m2 - m3 + delta < 0.0);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, surv);
-            evaluated += (u64)__popc(mask) * 32;
-            const int er = lane >> 3, ec = lane & 7;
-            while (mask) {
-                const int l2 = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int row = 32 * rg + 4 * (l2 >> 2) + er, col = 1 + 32 * q32 + 8 * (l2 & 3) + ec;
-                double t = -INFINITY;
-                int ta = 0x7fffffff;
-                if (row < nrows) {
-                    const int2 me = sRowLC[row];
-                    const RowConst<AI> rc = make_row<AI>(me.y, me.x, p.alpha_int, p.alpha);
-                    t = __dadd_rn(self_score<AI>(__ldg(p.C + col), __ldg(p.L + col), rc, p.gtab, p.ltab), __ldcg(p.P + col));
-                    ta = col;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (act[u]) {
+                    const int2 fa = sRowLC[ra[u]], fb = sRowLC[rb[u]];
+                    box[u] = box_corner_loads<AI>(fa.y - ends[u].y, fb.y - ends[u].x, fa.x - ends[u].w, fb.x - ends[u].z, p.gtab, p.ltab, p.alpha_int);
                 }
 #pragma unroll
-                for (int off = 1; off < 8; off <<= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, t, off);
-                    const int oa = __shfl_xor_sync(0xffffffffu, ta, off);
-                    if (ob > t || (ob == t && oa < ta)) { t = ob; ta = oa; }
+            for (int u = 0; u < 2; ++u)
+                if (act[u]) {
+                    const int2 fa = sRowLC[ra[u]], fb = sRowLC[rb[u]];
+                    const double ub = mpt[u] + tilted_box_max_of(box[u], fa.y - ends[u].y, fb.y - ends[u].x, fa.x - ends[u].w, fb.x - ends[u].z,
+                                                                 a[u], bb[u], p.alpha);
+                    const double rmin = xp_row_min(R, ra[u], rb[u], a[u], bb[u]) - row_slack(a[u], bb[u]);
+                    if (!(ub - rmin + delta < 0.0)) {
+                        const int slot = atomicAdd(sCnt + 1, 1);
+                        if (slot < XP_LIST1) sList1[slot] = ent[u];
+                    }
                 }
-                if (ec == 0 && row < nrows) {
-                    const double cur = sWV[warp * XP_RB + row];
-                    if (t > cur || (t == cur && ta < sWA[warp * XP_RB + row])) { sWV[warp * XP_RB + row] = t; sWA[warp * XP_RB + row] = ta; }
+        }
+        __syncthreads();
+        { const long long t1 = xp_clock(); tl1 += t1 - tq; tq = t1; }
+        const int n1 = min(sCnt[1], XP_LIST1);       // n0 <= 256 blocks x 16 = 4096: never overflows
+        // ---- level 2 (4 rows x 8 columns, one lane per rectangle) then exact evaluation, XP_L2CHUNK level-1 survivors per pass ----
+        for (int base = 0; base < n1; base += XP_L2CHUNK) {
+            if (tid == 0) sCnt[2] = 0;
+            __syncthreads();
+            const int nhere = min(XP_L2CHUNK, n1 - base);
+            constexpr int UE = 4;                        // level-1 survivors in flight per warp
+            for (int i0 = warp * UE; i0 < nhere; i0 += 8 * UE) {
+                double a[UE], bb[UE], m8[UE];
+                int4 sub[UE];
+                BoxCorners box[UE];
+                int ra[UE], rb[UE];
+                bool act[UE];
+#pragma unroll
+                for (int u = 0; u < UE; ++u) {
+                    act[u] = false;
+                    if (i0 + u < nhere) {
+                        const int ent = sList1[base + i0 + u], q32 = ent >> 2, rg = ent & 3;
+                        ra[u] = 32 * rg + 4 * (lane >> 2);
+                        if (ra[u] < nrows) {
+                            act[u] = true;
+                            rb[u] = min(ra[u] + 3, nrows - 1);
+                            const XpRec32 *rec = p.rec32 + q32;
+                            a[u] = __ldcg(&rec->r.a);
+                            bb[u] = __ldcg(&rec->r.b);
+                            m8[u] = __ldcg(&rec->r.mpt8[lane & 3]);
+                            sub[u] = __ldcg(reinterpret_cast<const int4 *>(rec->sub[lane & 3]));      // c_first, c_last, l_first, l_last
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UE; ++u)
+                    if (act[u]) {
+                        const int2 fa = sRowLC[ra[u]], fb = sRowLC[rb[u]];
+                        box[u] = box_corner_loads<AI>(fa.y - sub[u].y, fb.y - sub[u].x, fa.x - sub[u].w, fb.x - sub[u].z, p.gtab, p.ltab, p.alpha_int);
+                    }
+#pragma unroll
+                for (int u = 0; u < UE; ++u) {
+                    bool surv = false;
+                    if (act[u]) {
+                        const int2 fa = sRowLC[ra[u]], fb = sRowLC[rb[u]];
+                        const double m2 = tilted_box_max_of(box[u], fa.y - sub[u].y, fb.y - sub[u].x, fa.x - sub[u].w, fb.x - sub[u].z, a[u], bb[u], p.alpha);
+                        const double m3 = xp_row_min(R, ra[u], rb[u], a[u], bb[u]) - row_slack(a[u], bb[u]);
+                        surv = !(m8[u] + m2 - m3 + delta < 0.0);
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, surv);
+                    if (mask) {
+                        int slot = 0;
+                        if (lane == 0) slot = atomicAdd(sCnt + 2, __popc(mask));
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                        if (surv) sList2[slot + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)(((i0 + u) << 5) | lane);
+                    }
                 }
             }
+            __syncthreads();
+            // exact evaluation of the listed 4 x 8 rectangles: a warp per rectangle, four in flight
+            const int n2 = sCnt[2];
+            evaluated += (warp == 0 && lane == 0) ? (u64)n2 * 32 : 0;
+            constexpr int UX = 4;
+            const int er = lane >> 3, ec = lane & 7;
+            for (int f0 = warp * UX; f0 < n2; f0 += 8 * UX) {
+                int row[UX], col[UX], cc[UX], ll[UX];
+                double pc[UX], gg[UX], lg[UX];
+                RowConst<AI> rc[UX];
+                bool act[UX];
+#pragma unroll
+                for (int u = 0; u < UX; ++u) {
+                    act[u] = false;
+                    row[u] = 0;
+                    col[u] = 0x7fffffff;
+                    if (f0 + u < n2) {
+                        const int code = sList2[f0 + u], l2 = code & 31;
+                        const int ent = sList1[base + (code >> 5)], q32 = ent >> 2, rg = ent & 3;
+                        row[u] = 32 * rg + 4 * (l2 >> 2) + er;
+                        if (row[u] < nrows) {
+                            act[u] = true;
+                            col[u] = 1 + 32 * q32 + 8 * (l2 & 3) + ec;
+                            cc[u] = __ldg(p.C + col[u]);
+                            ll[u] = __ldg(p.L + col[u]);
+                            pc[u] = __ldcg(p.P + col[u]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UX; ++u)
+                    if (act[u]) {
+                        const int2 me = sRowLC[row[u]];
+                        rc[u] = make_row<AI>(me.y, me.x, p.alpha_int, p.alpha);
+                        gg[u] = __ldg(p.gtab + (rc[u].cjx - cc[u]));
+                        lg[u] = __ldg(p.ltab + (rc[u].lj - ll[u]));
+                    }
+#pragma unroll
+                for (int u = 0; u < UX; ++u) {
+                    double t = -INFINITY;
+                    int ta = 0x7fffffff;
+                    if (act[u]) {
+                        const double sx = AI ? u32_to_double(rc[u].cjx - cc[u]) : __dsub_rn(rc[u].aj, u32_to_double(cc[u]));
+                        t = __dadd_rn(__dsub_rn(gg[u], __dmul_rn(sx, lg[u])), pc[u]);
+                        ta = col[u];
+                    }
+#pragma unroll
+                    for (int off = 1; off < 8; off <<= 1) {
+                        const double ob = __shfl_xor_sync(0xffffffffu, t, off);
+                        const int oa = __shfl_xor_sync(0xffffffffu, ta, off);
+                        if (ob > t || (ob == t && oa < ta)) { t = ob; ta = oa; }
+                    }
+                    if (ec == 0 && act[u]) {
+                        const double cur = sWV[warp * XP_RB + row[u]];
+                        if (t > cur || (t == cur && ta < sWA[warp * XP_RB + row[u]])) { sWV[warp * XP_RB + row[u]] = t; sWA[warp * XP_RB + row[u]] = ta; }
+                    }
+                    __syncwarp();            // two rectangles in flight may belong to the same rows
+                }
+            }
+            __syncthreads();
         }
+        tl2 += xp_clock() - tq;
+        if (tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
+        __syncthreads();
     }
     __syncthreads();
     if (tid < nrows) {
@@ -524,22 +909,31 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
         __stcg(p.farV + (size_t)g * p.npad + r0 + tid, best);
         __stcg(p.farA + (size_t)g * p.npad + r0 + tid, arg);
     }
-    if (lane == 0 && evaluated) atomicAdd(p.far_cells, evaluated);
+    if (tid == 0 && evaluated) atomicAdd(p.far_cells, evaluated);
     __syncthreads();
     if (tid == 0) {
         __threadfence();
         atomicAdd(p.far_ready + b, 1);
+        const u64 work = (u64)(xp_clock() - tf1);
+        atomicAdd(p.prof + XQ_F_WAIT, (u64)(tf1 - tf0));
+        atomicAdd(p.prof + XQ_F_WORK, work);
+        atomicAdd(p.prof + XQ_F_COUNT, 1ull);
+        atomicMax(p.prof + XQ_F_MAX, work);
+        atomicAdd(p.prof + XQ_F_L0, (u64)tl0);
+        atomicAdd(p.prof + XQ_F_L1, (u64)tl1);
+        atomicAdd(p.prof + XQ_F_L23, (u64)tl2);
+        atomicAdd(p.prof + XQ_F_HEAD, (u64)thead);
     }
 }
 
-template <bool AI>
+template <bool AI, bool RING>
 __global__ void __launch_bounds__(XP_THREADS, 1)
 exact_pruned_kernel(XpParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int sTask;
     if (blockIdx.x == 0) {
-        xp_diagonal<AI>(p, smem);
+        xp_diagonal<AI, RING>(p, smem);
         return;
     }
     while (true) {
@@ -576,16 +970,20 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.nB = (int)((N - 1 + XP_RB - 1) / XP_RB);
     p.nSteps = (int)((N - 1 + 31) / 32);
     p.lag = lag;
+    p.dbg = getenv("PASIO_XD_DBG") ? atoi(getenv("PASIO_XD_DBG")) : 0;
     p.DB = XP_RB * lag;
     p.npad = (int)((N + 127) & ~(i64)127);
     const std::vector<int2> tasks = build_tasks(p.nB, lag);
     p.n_tasks = (int)tasks.size();
 
-    const int slots = p.nB < XP_RING ? p.nB : XP_RING;
+    // every row block its own slab of self scores while that fits XP_LINEAR_BYTES (2 GB: N <= 680 000 at lag 3), else a ring
+    const bool ring = (size_t)p.nB * p.DB * XP_RB * 8 > XP_LINEAR_BYTES;
+    const int slots = ring ? XP_RING : p.nB;
+    p.s_slots = slots;
     const size_t ring_bytes = (size_t)slots * p.DB * XP_RB * 8;
     const size_t far_bytes = (size_t)XP_G * p.npad * 12;
-    const size_t rec_bytes = ((size_t)p.nSteps + p.nB + 2) * sizeof(CoarseRec);
-    const size_t flag_ints = (size_t)2 * p.nB + 8;
+    const size_t rec_bytes = ((size_t)p.nSteps + 1) * sizeof(XpRec32) + ((size_t)p.nB + 1) * (sizeof(CoarseRec) + sizeof(XpAnchors));
+    const size_t flag_ints = (size_t)2 * p.nB + 8 + 64;          // + 32 u64 profile counters
     PASIO_TRY(pasio_reserve(ctx, ctx->xpRing, ring_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, far_bytes > rec_bytes ? far_bytes : rec_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->xpRec, rec_bytes));
@@ -605,13 +1003,15 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.far_cells = reinterpret_cast<u64 *>(flags + 2);           // 8 bytes
     p.done_block = flags + 4;
     p.task_counter = reinterpret_cast<unsigned *>(flags + 5);
-    p.s_ready = flags + 8;
+    p.prof = reinterpret_cast<u64 *>(flags + 8);                // 32 x 8 bytes
+    p.s_ready = flags + 8 + 64;
     p.far_ready = p.s_ready + p.nB;
     p.tasks = ctx->xpTasks.as<int2>();
     p.farV = ctx->dpPart.as<double>();
     p.farA = reinterpret_cast<int *>(p.farV + (size_t)XP_G * p.npad);
-    p.rec32 = ctx->xpRec.as<CoarseRec>();
-    p.rec128 = p.rec32 + p.nSteps + 1;
+    p.rec32 = ctx->xpRec.as<XpRec32>();
+    p.rec128 = reinterpret_cast<CoarseRec *>(p.rec32 + p.nSteps + 1);
+    p.anchors = reinterpret_cast<XpAnchors *>(p.rec128 + p.nB + 1);
     p.gtab = ctx->tab[AI ? PASIO_TAB_LGAMMA : PASIO_TAB_LGAMMA_ALPHA].as<double>();
     p.ltab = ctx->tab[PASIO_TAB_LOG].as<double>();
     p.alpha_int = (int)ctx->alpha_int;
@@ -619,10 +1019,21 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.pen = ctx->pen;
 
     const size_t smem = xp_diag_smem() > xp_worker_smem() ? xp_diag_smem() : xp_worker_smem();
-    CUDA_TRY(ctx, cudaFuncSetAttribute(exact_pruned_kernel<AI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(XpParams) = ring ? exact_pruned_kernel<AI, true> : exact_pruned_kernel<AI, false>;
+    if (ctx->tune[PASIO_TUNE_EXACT_RING] && p.nB > XP_RING) {                // (tests: exercise the ring on short lists)
+        kern = exact_pruned_kernel<AI, true>;
+        p.s_slots = XP_RING;
+    }
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exact_pruned_kernel<AI>, XP_THREADS, smem));
-    if (per_sm < 1) return pasio_fail(ctx, PASIO_E_CUDA, "pruned exact DP kernel cannot be resident");
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XP_THREADS, smem));
+    if (per_sm < 1) {
+        cudaFuncAttributes fa;
+        memset(&fa, 0, sizeof fa);
+        cudaFuncGetAttributes(&fa, kern);
+        return pasio_fail(ctx, PASIO_E_CUDA, "pruned exact DP kernel cannot be resident (smem %zu, regs %d, static smem %zu, max dynamic %d, "
+                          "ring %d, N %d)", smem, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, (int)ring, p.N);
+    }
     int workers = ctx->sm_count - 1;                            // one CTA per SM: the diagonal has an SM to itself
     if (workers > p.n_tasks) workers = p.n_tasks;
     if (workers < 1) workers = 1;
@@ -630,8 +1041,7 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     {
         TimingScope ts(ctx, TF_EXACT_DP);
         // cooperative launch = all CTAs co-resident, which the flag waits rely on
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)exact_pruned_kernel<AI>, dim3(1 + workers), dim3(XP_THREADS), args, smem,
-                                                  ctx->stream));
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)kern, dim3(1 + workers), dim3(XP_THREADS), args, smem, ctx->stream));
     }
     // cells that were evaluated: the band the diagonal adds up + the far cells that survived the bounds
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 8, p.far_cells, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -644,6 +1054,21 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     }
     ctx->last_cells = N * (N - 1) / 2;
     ctx->last_cells_skipped = ctx->last_cells - band - ctx->h_scalars[8];
+    static const bool prof = getenv("PASIO_XD_PROF") != nullptr;
+    if (prof) {
+        u64 h[32];
+        cudaMemcpy(h, p.prof, sizeof h, cudaMemcpyDeviceToHost);
+        const double st = (double)p.nSteps;
+        fprintf(stderr, "[xp_prof] N=%d steps=%d lag=%d workers=%d | cycles/step: diag %.0f = chain %.0f + barrier wait %.0f | book-keeping warp: rec %.0f mid %.0f tile %.0f "
+                        "s-wait %.0f far %.0f bar %.0f | sweeping warp: mid %.0f tile %.0f s-wait %.0f far %.0f bar %.0f\n",
+                p.N, p.nSteps, lag, workers, h[XQ_DIAG_TOTAL] / st, h[XQ_CHAIN] / st, h[XQ_CHAIN_BAR] / st, h[XQ_H6_REC] / st, h[XQ_H6_MID] / st,
+                h[XQ_H6_TILE] / st, h[XQ_H6_SWAIT] / st, h[XQ_H6_FAR] / st, h[XQ_H6_BAR] / st, h[XQ_H0_MID] / st, h[XQ_H0_TILE] / st,
+                h[XQ_H0_SWAIT] / st, h[XQ_H0_FAR] / st, h[XQ_H0_BAR] / st);
+        const double ns = (double)(h[XQ_S_COUNT] ? h[XQ_S_COUNT] : 1), nf = (double)(h[XQ_F_COUNT] ? h[XQ_F_COUNT] : 1);
+        fprintf(stderr, "[xp_prof] S tasks %llu: work %.0f cyc, wait %.0f | F tasks %llu: wait %.0f, work %.0f (max %llu) = head %.0f + L0 %.0f + L1 %.0f + L2/3 %.0f\n",
+                (unsigned long long)h[XQ_S_COUNT], h[XQ_S_WORK] / ns, h[XQ_S_WAIT] / ns, (unsigned long long)h[XQ_F_COUNT], h[XQ_F_WAIT] / nf,
+                h[XQ_F_WORK] / nf, (unsigned long long)h[XQ_F_MAX], h[XQ_F_HEAD] / nf, h[XQ_F_L0] / nf, h[XQ_F_L1] / nf, h[XQ_F_L23] / nf);
+    }
     return PASIO_OK;
 }
 

@@ -27,7 +27,8 @@ def _attach(name, n_runs):
 
 def _worker(device, jobs, shm_name, n_runs, splitter_blob, mode, tmpdir, done_q):
     try:
-        os.environ['PASIO_B200_DEVICE'] = str(device)
+        # (PASIO_B200_POOL_SAME_DEVICE: tests on a one-GPU box run both workers on device 0)
+        os.environ['PASIO_B200_DEVICE'] = '0' if os.environ.get('PASIO_B200_POOL_SAME_DEVICE') else str(device)
         from . import process_bedgraph
         from .splitters import _fusion
         splitter = pickle.loads(splitter_blob)

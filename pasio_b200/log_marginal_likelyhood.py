@@ -150,6 +150,10 @@ class LogMarginalLikelyhoodComputer(object):
         score, splits = self._bind().square_split()
         return score, splits
 
+    # regularised DP over this scorer's candidates (SquareSplitter.split_with_normalizations) with host-built penalty tables
+    def _square_split_regularized(self, length_penalty, split_number_penalty, first_column_refund):
+        return self._bind().square_split_regularized(length_penalty, split_number_penalty, first_column_refund)
+
 
 class LogMarginalLikelyhoodIntAlphaComputer(LogMarginalLikelyhoodComputer):
     pass

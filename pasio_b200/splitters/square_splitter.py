@@ -61,7 +61,35 @@ class SquareSplitter(object):
 
     def split_with_normalizations(self, counts, split_candidates):
         score_computer = self.scorer(counts, split_candidates)
+        tables = self._device_penalty_tables(score_computer, counts, split_candidates)
+        if tables is not None:
+            return score_computer._square_split_regularized(*tables)       # device DP (csrc/regularized_dp.cu)
         return self._scorer_protocol_dp(score_computer, split_candidates, regularized=True)
+
+    def _device_penalty_tables(self, score_computer, counts, split_candidates):
+        """Penalty tables for the device version of the regularised DP, or None when it does not apply: the scorer must be
+        a pasio_b200 LogML computer and the penalty functions the two the reference's CLI offers (identity and 1/log(1+l),
+        default_splitters.py:36-39) -- an arbitrary callable need not be element-wise, so it keeps the host route.
+        The tables are evaluated with the reference's own expressions (square_splitter.py:46-54)."""
+        if not isinstance(score_computer, LogMarginalLikelyhoodComputer):
+            return None
+        builtin = (_identity, _revlog)
+        if self.length_regularization_function not in builtin or self.split_number_regularization_function not in builtin:
+            return None
+        length_penalty = split_number_penalty = None
+        refund = 0.0
+        with np.errstate(all='ignore'):
+            if self.length_regularization_multiplier != 0:
+                lengths = np.arange(len(counts) + 1)                   # split_candidates[j] - split_candidates[:j] takes these values
+                length_penalty = np.asarray(self.length_regularization_multiplier * self.length_regularization_function(lengths),
+                                            dtype=np.float64)
+            if self.split_number_regularization_multiplier != 0:
+                num_splits = np.arange(len(split_candidates), dtype=np.float64)      # num_splits is a float array (:40)
+                split_number_penalty = np.asarray(
+                    self.split_number_regularization_multiplier * self.split_number_regularization_function(num_splits + 1),
+                    dtype=np.float64)
+                refund = float(self.split_number_regularization_multiplier * self.split_number_regularization_function(1))
+        return length_penalty, split_number_penalty, refund
 
     def _scorer_protocol_dp(self, score_computer, split_candidates, regularized):
         """Row-by-row recurrence through an arbitrary scorer object.

@@ -100,9 +100,10 @@ def test_scorer_attributes_match_oracle():
         assert sc.segment_creation_cost == ref.pen
         assert np.array_equal(sc.scores(), ref.scores())
         assert np.array_equal(sc.mean_counts(), ref.mean_counts())
-        assert np.allclose(sc.logfac_cumsum, ref.logfac_cumsum, rtol=1e-12, atol=1e-9)
-        assert np.allclose(sc.log_marginal_likelyhoods(), ref.log_marginal_likelyhoods(), rtol=1e-9, atol=1e-9)
-        assert abs(sc.total_sum_logfac() - ref.total_sum_logfac()) <= 1e-9 * abs(ref.total_sum_logfac())
+        # logfac_cumsum is summed sequentially like np.cumsum (csrc/logfac_exact.cu): bit for bit
+        assert np.array_equal(sc.logfac_cumsum, ref.logfac_cumsum)
+        assert np.array_equal(sc.log_marginal_likelyhoods(), ref.log_marginal_likelyhoods())
+        assert sc.total_sum_logfac() == ref.total_sum_logfac()
         assert sc.score(3, 17) == ref.row(17)[3] + ref.pen
         assert sc.score_no_splits() == ref.row(len(cands) - 1)[0] + ref.pen
 
@@ -181,8 +182,8 @@ def test_segments_with_scores_vs_reference_fixture(golden, name, kwargs):
     assert np.array_equal(splits[:-1], starts)
     if g.bit_exact(name):
         assert np.array_equal(means, g[name + '.mean'])
-        # logfac_cumsum is a parallel scan here and a sequential sum in the reference: tolerance only
-        assert np.allclose(lmm, g[name + '.lmm'], rtol=1e-9, atol=1e-7)
+        # logfac_cumsum is summed in the reference's order (csrc/logfac_exact.cu): the LMM column is bit-identical
+        assert np.array_equal(lmm, g[name + '.lmm'])
 
 
 def test_split_bedgraph_text_vs_reference_fixture(golden):
@@ -197,15 +198,7 @@ def test_split_bedgraph_text_vs_reference_fixture(golden):
             if not g.bit_exact('bedgraph text %s gaps=%d' % (mode, gaps)):
                 pytest.skip('host np.log/gammaln tables differ from the fixtures\' (see the pytest header): the text '
                             'comparison with the reference fixture cannot be made on this host')
-            if mode != 'bedgraph+length+LMM':
-                assert out.getvalue() == want, (mode, gaps)
-            else:
-                a = [ln.split('\t') for ln in out.getvalue().splitlines()]
-                b = [ln.split('\t') for ln in want.splitlines()]
-                assert len(a) == len(b)
-                for x, y in zip(a, b):
-                    assert x[:5] == y[:5]
-                    assert abs(float(x[5]) - float(y[5])) <= 2e-6 + 1e-9 * abs(float(y[5]))
+            assert out.getvalue() == want, (mode, gaps)          # all three modes byte for byte, the LMM column included
 
 
 def test_slidingwindow_algorithm_graph():
@@ -234,6 +227,47 @@ def test_regularized_split_uses_device_rows():
                         length_regularization_function=lambda x: 1 / np.log(1 + x))
     score, splits = sp.split(counts, cands)
     o = po.square_split_regularized(counts, cands, po.Tables(1, 1.0), len_mult=1.5, len_fn=lambda x: 1 / np.log(1 + x))
+    assert score == o[0] and np.array_equal(splits, o[1])
+
+
+def test_regularized_dp_on_device_vs_oracle(monkeypatch):
+    """--split-number-regularization / --length-regularization run as ONE kernel per candidate list
+    (csrc/regularized_dp.cu), no per-row launches, bit-equal to the reference recurrence at N = 20 001"""
+    from pasio_b200 import _native
+    from pasio_b200.splitters.square_splitter import _revlog
+
+    def no_rows(self, stop):
+        raise AssertionError('the regularised DP fetched a row from the device: the host loop is still in use')
+    monkeypatch.setattr(_native.Engine, 'suffix_scores', no_rows)
+    counts = synth.piecewise_poisson(20000, 4)
+    allpos = np.arange(len(counts) + 1)
+    sparse = synth.random_candidates(len(counts), 3000, 8)
+    revlog = lambda x: 1 / np.log(x + 1)                                        # noqa: E731
+    cases = [
+        (allpos, (1.0, 1.0), dict(split_number_regularization_multiplier=3.0), dict(num_mult=3.0)),
+        (allpos, (1.0, 1.0), dict(length_regularization_multiplier=1.5, length_regularization_function=_revlog),
+         dict(len_mult=1.5, len_fn=revlog)),
+        (sparse, (2.5, 3.0), dict(length_regularization_multiplier=40.0, length_regularization_function=_revlog,
+                                  split_number_regularization_multiplier=0.75), dict(len_mult=40.0, len_fn=revlog, num_mult=0.75)),
+        (sparse, (1.0, 1.0), dict(length_regularization_multiplier=0.001), dict(len_mult=0.001)),      # identity length penalty
+        (allpos[:302], (1.0, 1.0), dict(split_number_regularization_multiplier=2), dict(num_mult=2)),  # integer multiplier
+    ]
+    for cands, ab, kw, okw in cases:
+        c = counts[:cands[-1]]
+        score, splits = SquareSplitter(ScorerFactory(*ab), **kw).split(c, cands)
+        o = po.square_split_regularized(c, cands, po.Tables(po.normalise_alpha(ab[0]), ab[1]), **okw)
+        assert score == o[0] and np.array_equal(splits, o[1]), kw
+    # through configure_splitter, as the CLI builds it (the regularised splitter is also the windows' base reducer)
+    splitter = configure_splitter(algorithm='exact', length_regularization=1.5, length_regularization_function='revlog',
+                                  split_number_regularization=0.5)
+    score, splits = splitter.split(counts[:5000], np.arange(5001))
+    o = po.square_split_regularized(counts[:5000], np.arange(5001), po.Tables(1, 1.0), len_mult=1.5, len_fn=revlog, num_mult=0.5)
+    assert score == o[0] and np.array_equal(splits, o[1])
+    # an arbitrary callable need not be element-wise: host route (rows from the device)
+    monkeypatch.undo()
+    sp = SquareSplitter(ScorerFactory(1.0, 1.0), length_regularization_multiplier=1.5, length_regularization_function=revlog)
+    score, splits = sp.split(counts[:400], np.arange(401))
+    o = po.square_split_regularized(counts[:400], np.arange(401), po.Tables(1, 1.0), len_mult=1.5, len_fn=revlog)
     assert score == o[0] and np.array_equal(splits, o[1])
 
 
@@ -361,3 +395,192 @@ def test_split_bedgraph_batches_short_contigs():
     out = io.StringIO()
     split_bedgraph_stream(io.StringIO(short_text), out, exact)
     assert out.getvalue().startswith('tx3\t')
+
+
+def _subsampled_text(kind, n_contigs, seed):
+    """a sub-sample of BASELINE config 4 (hg38 contig-size profile, scaled) / config 5 (transcript-like stream) as
+    run-length bedgraph text"""
+    rs = np.random.RandomState(seed)
+    lines = []
+    if kind == 'genome':
+        sizes = synth.genome_profile(scale=0.004)                    # 195 contigs, 1 kb .. 1 Mb
+        pick = sorted(rs.choice(len(sizes), size=n_contigs, replace=False))
+        for i in pick:
+            name, n = sizes[i]
+            lines.extend(synth.to_bedgraph_lines(name, synth.dnase_like(n, seed=i), chrom_start=int(rs.randint(0, 1000))))
+    else:
+        lens = synth.transcript_lengths(n_contigs, seed=seed)
+        for c, n in enumerate(lens):
+            lines.extend(synth.to_bedgraph_lines('tx%05d' % c, synth.dnase_like(int(n), seed=5000 + c, hotspot_share=0.3)))
+    return ''.join(lines)
+
+
+@pytest.mark.parametrize('kind,n_contigs', [('genome', 120), ('transcripts', 1000)])
+def test_configs_4_and_5_subsample_text_vs_oracle(kind, n_contigs):
+    """BASELINE configs 4 / 5 at sub-sampled shape through the text boundary (split_bedgraph_stream: chunked reader,
+    batched launches, C++ formatter) against the oracle's parser + pipeline + '%' formatting, byte for byte."""
+    import io
+    from pasio_b200 import process_bedgraph as pb
+    text = _subsampled_text(kind, n_contigs, 77)
+    want = po.split_bedgraph_text(text, po.Tables(1, 1.0), threads=8)
+    old = pb.CHUNK_BYTES
+    pb.CHUNK_BYTES = 1 << 20                                          # many pieces: contigs straddle the seams
+    try:
+        out = io.StringIO()
+        split_bedgraph_stream(io.StringIO(text), out, configure_splitter())
+        got = out.getvalue()
+    finally:
+        pb.CHUNK_BYTES = old
+    assert got.count('\n') == want.count('\n')
+    assert got == want
+    for mode in ['bed', 'bedgraph+length+LMM']:        # the LMM column: every contig of a batch restarts its log-factorial sum
+        out = io.StringIO()
+        split_bedgraph_stream(io.StringIO(text), out, configure_splitter(), output_mode=mode)
+        assert out.getvalue() == po.split_bedgraph_text(text, po.Tables(1, 1.0), output_mode=mode, threads=8), mode
+
+
+def test_split_bedgraph_devices_pool_equals_single_process():
+    """devices=N: one worker process per GPU, LPT over the batches, shard files gathered in input order -- the same text
+    (with one GPU in the box both workers share it; the partition, the spawn path and the gather are the same)"""
+    import io
+    import ctypes
+    from pasio_b200 import _native, device_pool
+    text = _subsampled_text('genome', 40, 5)
+    single = io.StringIO()
+    split_bedgraph_stream(io.StringIO(text), single, configure_splitter(window_size=800, window_shift=400),
+                          output_mode='bedgraph+length+LMM')
+    import torch
+    n_dev = max(1, min(2, torch.cuda.device_count()))
+    old_worker = device_pool._worker
+    multi = io.StringIO()
+    if n_dev == 1:                                                    # two workers on the one GPU
+        import os
+        os.environ['PASIO_B200_POOL_SAME_DEVICE'] = '1'
+    try:
+        split_bedgraph_stream(io.StringIO(text), multi, configure_splitter(window_size=800, window_shift=400),
+                              output_mode='bedgraph+length+LMM', devices=2)
+    finally:
+        import os
+        os.environ.pop('PASIO_B200_POOL_SAME_DEVICE', None)
+    assert multi.getvalue() == single.getvalue()
+    assert single.getvalue().count('\n') > 40
+
+
+def test_contig_load_device_equals_host_load():
+    """pasio_contig_load_device (counts already in HBM: the entry point bench.py's `value` runs through) == pasio_contig_load
+    of the same counts: prefix sums, rounds, scores; single contig and a batch with offsets; alignment is checked"""
+    import torch
+    from pasio_b200 import _native
+    from pasio_b200.log_marginal_likelyhood import ScorerFactory
+    eng = _native.engine()
+    f = ScorerFactory(1.0, 1.0)
+    eng.use_scorer(f)
+    counts = synth.dnase_like(3000000, 21, hotspot_share=0.2)
+    dev = torch.from_numpy(counts).cuda()
+    for offsets in [None, np.array([0, 1000000, 1000001, 2500000, 3000000], dtype=np.int64)]:
+        eng.invalidate()
+        eng.load(counts, offsets=offsets)
+        eng.set_candidates(None)
+        sizes_a, final_a, cells_a = eng.rounds(2500, 1250, 'constants')
+        splits_a = eng.candidates().copy()
+        scores_a = eng.segment_scores(scores=True)[0].copy()
+        cum_a = eng.cumsum_at_candidates()
+        eng.invalidate()
+        eng.load_device(dev.data_ptr(), len(counts), owner=dev, offsets=offsets)
+        assert eng.info()[0] == len(counts) and eng.info()[1] == int(counts.sum())
+        eng.set_candidates(None)
+        sizes_b, final_b, cells_b = eng.rounds(2500, 1250, 'constants')
+        assert (sizes_b, final_b, cells_b) == (sizes_a, final_a, cells_a)
+        assert np.array_equal(eng.candidates(), splits_a)
+        assert np.array_equal(eng.segment_scores(scores=True)[0], scores_a)
+        assert np.array_equal(eng.cumsum_at_candidates(), cum_a)
+    want, _, _ = c_oracle.FlatOracle(counts, 1.0, 1.0, threads=8).rounds(2500, 1250, 'constants')
+    eng.invalidate()
+    eng.load_device(dev.data_ptr(), len(counts), owner=dev)
+    eng.set_candidates(None)
+    eng.rounds(2500, 1250, 'constants')
+    assert np.array_equal(eng.candidates(), want)
+    with pytest.raises(ValueError):
+        eng.load_device(dev.data_ptr() + 8, len(counts) - 1, owner=dev)          # not 16-byte aligned
+    neg = dev.clone()
+    neg[12345] = -5
+    with pytest.raises(AssertionError):
+        eng.load_device(neg.data_ptr(), len(counts), owner=neg)
+
+
+def test_window_prune_switch_gives_identical_rounds():
+    """the far-column bound of the window kernel and the skipping of covered windows are exact: with both switched off
+    (every cell of every window evaluated) every round of a bench-like contig gives the same candidates"""
+    from pasio_b200 import _native
+    from pasio_b200.log_marginal_likelyhood import ScorerFactory
+    eng = _native.engine()
+    eng.use_scorer(ScorerFactory(1.0, 1.0))
+    counts = synth.dnase_like(30000000, 1000)                        # the first 30 Mb of the bench contig
+    eng.invalidate()
+    eng.load(counts)
+    per_round = {}
+    try:
+        for prune in (1, 0):
+            eng.set_tuning('window_prune', prune)
+            eng.set_tuning('window_phases', prune)
+            eng.set_candidates(None)
+            rounds = []
+            while True:
+                n_in, n_out, cells = eng.round(2500, 1250, 'constants')
+                rounds.append((n_in, n_out, cells, eng.round_stats()[1], eng.candidates().copy()))
+                if n_in == n_out:
+                    break
+            per_round[prune] = rounds
+    finally:
+        eng.set_tuning('window_prune', 1)
+        eng.set_tuning('window_phases', 1)
+    assert len(per_round[0]) == len(per_round[1])
+    for a, b in zip(per_round[1], per_round[0]):
+        assert a[:3] == b[:3] and np.array_equal(a[4], b[4])
+        assert b[3] == 0                                              # nothing skipped with the switches off
+    assert sum(a[3] for a in per_round[1]) > 0
+
+
+def test_logfac_exact_and_parallel_modes():
+    """logfac_cumsum: the default reproduces np.cumsum's sequential float64 sum bit for bit (sparse and dense coverage, a
+    batch of contigs: every contig's sum restarts at 0); PASIO_TUNE_LOGFAC_EXACT = 0 (parallel scan) agrees to 1e-9"""
+    from pasio_b200 import _native
+    eng = _native.engine()
+    f = ScorerFactory(1.0, 1.0)
+    t = po.Tables(1, 1.0)
+    for counts in [synth.dnase_like(400000, 3, hotspot_share=0.3), synth.two_level_poisson(60000, seed=5),
+                   np.zeros(5000, dtype=np.int64), np.ones(777, dtype=np.int64)]:
+        cands = synth.random_candidates(len(counts), min(3000, len(counts) // 2), 9)
+        ref = po.Scorer(counts, cands, t)
+        eng.use_scorer(f)
+        eng.invalidate()
+        eng.load(counts)
+        eng.set_candidates(cands)
+        try:
+            for exact in (1, 0):
+                eng.set_tuning('logfac_exact', exact)
+                lmm, total = eng.segment_lmm()
+                lf = eng.segment_scores(scores=False, logfac=True)[3]
+                if exact:
+                    assert np.array_equal(lf, ref.logfac_cumsum) and np.array_equal(lmm, ref.log_marginal_likelyhoods())
+                    assert total == ref.total_sum_logfac()
+                else:
+                    assert np.allclose(lf, ref.logfac_cumsum, rtol=1e-12, atol=1e-9)
+                    assert np.allclose(lmm, ref.log_marginal_likelyhoods(), rtol=1e-9, atol=1e-7)
+        finally:
+            eng.set_tuning('logfac_exact', 1)
+    # a batch: three contigs as one super-contig with boundaries
+    parts = [synth.dnase_like(50000, 11, hotspot_share=0.4), synth.two_level_poisson(4000, seed=6), synth.dnase_like(20000, 12)]
+    batch = np.concatenate(parts)
+    offsets = np.concatenate([[0], np.cumsum([len(x) for x in parts])]).astype(np.int64)
+    eng.invalidate()
+    eng.load(batch, offsets=offsets)
+    eng.set_candidates(None)
+    eng.rounds(500, 250, 'constants')
+    splits = eng.candidates()
+    lmm, _ = eng.segment_lmm()
+    want = []
+    for k, part in enumerate(parts):
+        local = splits[(splits >= offsets[k]) & (splits <= offsets[k + 1])] - offsets[k]
+        want.append(po.Scorer(part, local, t).log_marginal_likelyhoods())
+    assert np.array_equal(lmm, np.concatenate(want))

@@ -135,7 +135,7 @@ def test_rounds_vs_reference_fixture(eng, golden, name):
     assert np.array_equal(scores, sc.scores())
     assert np.array_equal(means, sc.mean_counts())
     assert np.array_equal(segc, np.diff(sc.cumsum))
-    assert np.allclose(logfac, sc.logfac_cumsum, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(logfac, sc.logfac_cumsum)            # sequential sum, like np.cumsum (csrc/logfac_exact.cu)
     g.check_splits(cands, g[name + '.splits'], np.sum(scores), g[name + '.score'], name)
 
 
@@ -283,9 +283,10 @@ def test_exact_pruned_vs_oracle_and_unpruned(eng, case, ab):
         cands = np.arange(len(counts) + 1, dtype=np.int64)
     o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, *ab, threads=_oracle_threads()).square_split(cands)
     try:
-        for prune, lag in [(1, 3), (1, 4), (0, 3)]:
+        for prune, lag, ring in [(1, 3, 0), (1, 4, 0), (1, 3, 1), (0, 3, 0)]:
             eng.set_tuning('exact_prune', prune)
             eng.set_tuning('exact_lag', lag)
+            eng.set_tuning('exact_ring', ring)       # ring = the self-score layout of very long lists (slabs reused)
             score, splits, P, prev = gpu_exact(eng, counts, cands, *ab)
             assert np.array_equal(P, o_P), (case, prune, lag)
             assert np.array_equal(prev, o_prev), (case, prune, lag)
@@ -293,6 +294,7 @@ def test_exact_pruned_vs_oracle_and_unpruned(eng, case, ab):
     finally:
         eng.set_tuning('exact_prune', 1)
         eng.set_tuning('exact_lag', 3)
+        eng.set_tuning('exact_ring', 0)
 
 
 def test_config3_prefix_property(eng):

@@ -149,3 +149,50 @@ def test_config3_oracle_vs_reference_fixture(golden):
     fo = c_oracle.FlatOracle(counts, 1.0, 1.0, threads=max(1, min(32, os.cpu_count() or 1)))
     score, splits, _, _ = fo.square_split(cands)
     g.check_splits(splits, g['config3.splits'], score, g['config3.score'], 'config3')
+
+
+def test_oracle_text_pipeline_vs_reference_fixture(golden):
+    """po.split_bedgraph_text (parser + flat C rounds + reference scoring + '%' formatting) reproduces the reference's
+    split_bedgraph_stream output byte for byte: three output modes, gaps filled and split"""
+    g = golden('pipeline.npz')
+    text = str(g['bg.input'])
+    t = po.Tables(1, 1.0)
+    for mode in ['bedgraph', 'bed', 'bedgraph+length+LMM']:
+        for gaps in [False, True]:
+            got = po.split_bedgraph_text(text, t, 500, 250, split_at_gaps=gaps, output_mode=mode)
+            if g.bit_exact('oracle text %s %d' % (mode, gaps)):
+                assert got == str(g['bg.%s.%d' % (mode, int(gaps))]), (mode, gaps)
+
+
+def test_chunked_bedgraph_reader_equals_whole_input():
+    """the streaming reader (pieces cut at line starts, the contig in progress carried over) yields the same contigs as
+    one pass over the whole text -- any piece size, gaps filled or split, blank lines, a contig spanning many pieces"""
+    import io
+    from pasio_b200 import process_bedgraph as pb, synth
+    rs = np.random.RandomState(3)
+    lines = []
+    for c in range(30):
+        n = int(rs.randint(50, 4000)) if c != 7 else 60000
+        lines.extend(synth.to_bedgraph_lines('c%d' % (c % 11), synth.dnase_like(n, 100 + c, hotspot_share=0.5),
+                                             chrom_start=int(rs.randint(0, 9))))
+        if c % 5 == 0:
+            lines.append('\n')
+    lines = [ln for k, ln in enumerate(lines) if k % 13 != 5]         # gaps
+    text = ''.join(lines)
+    for gaps in (False, True):
+        want = [(c, a.tolist(), s) for c, a, s in po.parse_bedgraph_text(text, gaps)]
+        for chunk in (64, 1000, 7777, 1 << 20):
+            old = pb.CHUNK_BYTES
+            pb.CHUNK_BYTES = chunk
+            try:
+                got = [(c, a.tolist(), s) for c, a, s in pb.parse_bedgraph_stream(io.StringIO(text), gaps)]
+                got_b = [(c, a.tolist(), s) for c, a, s in pb.parse_bedgraph_stream(io.TextIOWrapper(io.BytesIO(text.encode())), gaps)]
+            finally:
+                pb.CHUNK_BYTES = old
+            assert got == want, (gaps, chunk)
+            assert got_b == want, (gaps, chunk)
+    # a text stream the caller already read a line from: the binary layer is repositioned, nothing is lost
+    stream = io.TextIOWrapper(io.BytesIO(text.encode()))
+    first = stream.readline()
+    rest = [(c, a.tolist(), s) for c, a, s in pb.parse_bedgraph_stream(stream)]
+    assert rest == [(c, a.tolist(), s) for c, a, s in po.parse_bedgraph_text(text[len(first):])]

@@ -27,13 +27,17 @@ def _worker(rank, world, port, out_dir):
 
     mine = sharding.shard_indices([len(c[1]) for c in contigs], rank, world)
     res = sharding.segment_contigs(contigs, segment, rank=rank, world_size=world, dist=dist)
+    shard_dir = os.path.join(out_dir, 'shards')
+    os.makedirs(shard_dir, exist_ok=True)
+    res_files = sharding.segment_contigs(contigs, segment, rank=rank, world_size=world, dist=dist, shard_dir=shard_dir)
     if rank == 0:
         serial = [segment(*c) for c in contigs]
         assert res == serial
+        assert res_files == serial            # the same through per-rank shard files
         with open(os.path.join(out_dir, 'ok'), 'w') as f:
             f.write(','.join(map(str, mine)))
     else:
-        assert res is None
+        assert res is None and res_files is None
     dist.barrier()
     dist.destroy_process_group()
 

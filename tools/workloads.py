@@ -35,6 +35,7 @@ def exact(args, which):
     eng.load(counts)
     eng.set_tuning('exact_prune', args.prune)
     eng.set_tuning('exact_lag', args.lag)
+    eng.set_tuning('exact_ring', args.ring)
     times = []
     for rep in range(args.reps + 1):
         eng.set_candidates(cands)
@@ -66,7 +67,7 @@ def genome(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
-        dist.init_process_group('nccl')
+        dist.init_process_group("gloo")      # control plane and the host-side gather only: contigs are partitioned, never exchanged
     sizes = synth.genome_profile(scale=args.scale)
     costs = [sharding.contig_cost(n) for _, n in sizes]
     mine = sharding.shard_indices(costs, rank, world)
@@ -98,9 +99,9 @@ def genome(args):
     total_nt = sum(n for _, n in sizes)
     if dist is not None:
         import torch
-        t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        t = torch.tensor([dt], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([float(nseg)], dtype=torch.float64, device='cuda')
+        s = torch.tensor([float(nseg)], dtype=torch.float64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         dt, nseg = float(t.item()), int(s.item())
     if rank == 0:
@@ -153,6 +154,7 @@ if __name__ == '__main__':
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--contigs', type=int, default=100000)
     ap.add_argument('--prune', type=int, default=1, help='exact DP: 1 = bounded far columns (default), 0 = every cell')
+    ap.add_argument('--ring', type=int, default=0, help='exact DP: 1 = self scores in the ring layout of very long lists')
     ap.add_argument('--lag', type=int, default=3, help='exact DP: far columns start this many blocks behind (3 or 4)')
     a = ap.parse_args()
     if a.what == 'exact1':
