@@ -164,6 +164,8 @@ def genome_generate(args):
     order = big + small
     offsets, pos = {}, 0
     for i in order:
+        if i in big or (small and i == small[0]):
+            pos += pos & 1                       # device pointers handed to pasio_contig_load_device are 16-byte aligned
         offsets[i] = pos
         pos += sizes[i][1]
     raw = mp.RawArray('q', max(1, pos))

@@ -191,6 +191,10 @@ int pasio_segment_scores_sum(pasio_ctx *ctx, double *total);
  * device: lmm[k] = score[k] - (logfac_cumsum[k+1] - logfac_cumsum[k]), same two roundings as numpy.
  * sum_logfac = total_sum_logfac() (:64-65).  lmm has m-1 entries. */
 int pasio_segment_lmm(pasio_ctx *ctx, double *lmm, int64_t capacity, double *sum_logfac);
+/* Start computing the log-factorial prefix sums of the loaded batch (what pasio_segment_lmm and the logfac_cumsum output
+ * of pasio_segment_scores need) on a side stream, so that the sequential sum (one thread per contig) runs beside the
+ * rounds instead of after them.  Optional: the consumers compute the sums themselves when nothing was prefetched. */
+int pasio_logfac_prefetch(pasio_ctx *ctx);
 
 /* ---- pinned host buffers --------------------------------------------------------------------------
  * Page-locked host memory for callers that want full-rate PCIe copies (any host pointer works, pinned

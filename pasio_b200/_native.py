@@ -55,6 +55,7 @@ SIGNATURES = {
     'pasio_segment_scores': (ctypes.c_int, [_vp, _f64p, _i64p, _f64p, _f64p, _i64, _i64p]),
     'pasio_segment_scores_sum': (ctypes.c_int, [_vp, _f64p]),
     'pasio_segment_lmm': (ctypes.c_int, [_vp, _f64p, _i64, _f64p]),
+    'pasio_logfac_prefetch': (ctypes.c_int, [_vp]),
     'pasio_host_alloc': (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     'pasio_host_free': (ctypes.c_int, [_vp]),
     'pasio_bedgraph_count_lines': (_i64, [ctypes.c_char_p, _i64]),
@@ -461,6 +462,10 @@ class Engine(object):
         total = ctypes.c_double(0.0)
         self._retry(lambda: self.lib.pasio_segment_scores_sum(self.ctx, ctypes.byref(total)))
         return np.float64(total.value)
+
+    def logfac_prefetch(self):
+        """start the sequential log-factorial sums of the loaded batch beside whatever runs next (segment_lmm uses them)"""
+        self._check(self.lib.pasio_logfac_prefetch(self.ctx))
 
     def segment_lmm(self):
         """(log_marginal_likelyhoods per segment, total_sum_logfac), formed on the device"""

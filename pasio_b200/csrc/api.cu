@@ -71,6 +71,7 @@ static int resolve_spans(pasio_ctx *ctx)
 {
     if (ctx->spans.empty()) return PASIO_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream_lx) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_lx));
     if (ctx->stream_copy) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_copy));
     if (ctx->stream2) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream2));
     for (auto &s : ctx->spans) {
@@ -207,6 +208,9 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, 0) != cudaSuccess ||      // (lowest priority)
         cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream_lx, cudaStreamNonBlocking, 0) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_lx0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_lx1, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void **)&ctx->h_scalars, 16 * sizeof(i64)) != cudaSuccess ||
@@ -235,7 +239,7 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     drop_borrowed_counts(ctx);
     DevBuf *bufs[] = {&ctx->tab[0], &ctx->tab[1], &ctx->tab[2], &ctx->counts, &ctx->cg, &ctx->cpbits, &ctx->keepbits,
-                      &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large, &ctx->win_flags,
+                      &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->candC[0], &ctx->candC[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large, &ctx->win_flags,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
                       &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full,
                       &ctx->xpRing, &ctx->xpRec, &ctx->xpTasks, &ctx->regLR, &ctx->regNR, &ctx->lxPos, &ctx->lxSum, &ctx->lxFirst};
@@ -251,6 +255,9 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
+    if (ctx->stream_lx) { cudaStreamSynchronize(ctx->stream_lx); cudaStreamDestroy(ctx->stream_lx); }
+    if (ctx->ev_lx0) cudaEventDestroy(ctx->ev_lx0);
+    if (ctx->ev_lx1) cudaEventDestroy(ctx->ev_lx1);
     for (auto e : ctx->chunk_events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -354,6 +361,10 @@ static int finish_load(pasio_ctx *ctx, const int64_t *offsets, int64_t n_contigs
 
 static int check_load_args(pasio_ctx *ctx, int64_t n, const int64_t *offsets, int64_t n_contigs)
 {
+    if (ctx->logfac_pending) {                 // a prefetch nobody consumed still reads the buffers that are about to change
+        cudaStreamSynchronize(ctx->stream_lx);
+        ctx->logfac_pending = false;
+    }
     ctx->logfac_ready = false;
     ctx->have_contig = false;
     if (n < 1) return pasio_fail(ctx, PASIO_E_COUNTS, "contig is empty");            // len(counts) > 0
@@ -528,7 +539,7 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
     const int nxt = 1 - ctx->cur;
     PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)ctx->m * 4));
     i64 m_new = 0;
-    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    PASIO_TRY(launch_compact_keepbits(ctx, nxt, &m_new));
     PASIO_TRY(d2h(ctx, ctx->h_scalars + 10, ctx->scalars.as<i64>() + 10, 24));
     if (cells) *cells = ctx->h_scalars[10];
     ctx->last_cells = ctx->h_scalars[10];
@@ -611,6 +622,8 @@ extern "C" int pasio_candidates_set(pasio_ctx *ctx, const int64_t *cands, int64_
     if (ctx->h_scalars[5]) { ctx->implicit_all = true; ctx->m = ctx->n + 1; return pasio_fail(ctx, PASIO_E_CANDIDATES, "candidate out of range"); }
     ctx->implicit_all = false;
     ctx->m = m;
+    PASIO_TRY(pasio_reserve(ctx, ctx->candC[ctx->cur], (size_t)m * 8));
+    PASIO_TRY(launch_gather_i64(ctx, ctx->cg.as<i64>(), ctx->cand[ctx->cur].as<int32_t>(), nullptr, m, ctx->candC[ctx->cur].as<i64>()));
     PASIO_TRY(refresh_boundary_ranks(ctx));
     i64 bad = 0;
     PASIO_TRY(launch_validate_candidates(ctx, &bad));
@@ -661,7 +674,7 @@ extern "C" int pasio_filter_candidates(pasio_ctx *ctx, int constraint, int64_t *
     const int nxt = 1 - ctx->cur;
     PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)ctx->m * 4));
     i64 m_new = 0;
-    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    PASIO_TRY(launch_compact_keepbits(ctx, nxt, &m_new));
     ctx->cur = nxt;
     ctx->implicit_all = false;
     ctx->m = m_new;
@@ -736,7 +749,7 @@ extern "C" int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_s
     const int nxt = 1 - ctx->cur;
     PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)ctx->m * 4));
     i64 m_new = 0;
-    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    PASIO_TRY(launch_compact_keepbits(ctx, nxt, &m_new));
     PASIO_TRY(d2h(ctx, ctx->h_scalars + 10, ctx->scalars.as<i64>() + 10, 24));
     if (cells) *cells = ctx->h_scalars[10];
     ctx->last_cells = ctx->h_scalars[10];
@@ -788,7 +801,10 @@ extern "C" int pasio_set_tuning(pasio_ctx *ctx, int key, int value)
     if (key < 0 || key >= PASIO_TUNE_COUNT) return pasio_fail(ctx, PASIO_E_ARG, "unknown tuning key %d", key);
     if (key == PASIO_TUNE_EXACT_LAG && (value < 3 || value > 4)) return pasio_fail(ctx, PASIO_E_ARG, "exact lag must be 3 or 4");
     ctx->tune[key] = value;
-    if (key == PASIO_TUNE_LOGFAC_EXACT) ctx->logfac_ready = false;
+    if (key == PASIO_TUNE_LOGFAC_EXACT) {
+        if (ctx->logfac_pending) { cudaStreamSynchronize(ctx->stream_lx); ctx->logfac_pending = false; }
+        ctx->logfac_ready = false;
+    }
     return PASIO_OK;
 }
 
@@ -809,7 +825,7 @@ static int finish_square_split(pasio_ctx *ctx, i64 N, int64_t *out_splits, int64
     const int nxt = 1 - ctx->cur;
     PASIO_TRY(pasio_reserve(ctx, ctx->cand[nxt], (size_t)N * 4));
     i64 m_new = 0;
-    PASIO_TRY(launch_compact_keepbits(ctx, ctx->cand[nxt].as<int32_t>(), &m_new));
+    PASIO_TRY(launch_compact_keepbits(ctx, nxt, &m_new));
     ctx->cur = nxt;
     ctx->implicit_all = false;
     ctx->m = m_new;
@@ -898,6 +914,10 @@ extern "C" int pasio_suffix_scores(pasio_ctx *ctx, int64_t stop, double *out)
 // the bandwidth-bound scan and the latency-bound window kernels slow each other down by as much as is hidden.)
 static int ensure_logfac(pasio_ctx *ctx)
 {
+    if (ctx->logfac_pending) {                 // prefetched on the side stream: order the consumers behind it
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lx1, 0));
+        ctx->logfac_pending = false;
+    }
     if (ctx->logfac_ready) return PASIO_OK;
     if (ctx->tune[PASIO_TUNE_LOGFAC_EXACT]) {
         PASIO_TRY(launch_logfac_exact(ctx));              // the reference's sequential sum, bit for bit (logfac_exact.cu)
@@ -907,6 +927,24 @@ static int ensure_logfac(pasio_ctx *ctx)
     }
     ctx->logfac_ready = true;
     ctx->logfac_is_exact = ctx->tune[PASIO_TUNE_LOGFAC_EXACT] != 0;
+    return PASIO_OK;
+}
+
+// Start the sequential log-factorial sums of the loaded batch on a side stream, so that they run (one thread per contig:
+// no SM is taken away) beside the rounds that follow; pasio_segment_lmm / pasio_segment_scores then find them done.
+extern "C" int pasio_logfac_prefetch(pasio_ctx *ctx)
+{
+    NEED_CTX(ctx);
+    if (!ctx->have_contig) return pasio_fail(ctx, PASIO_E_STATE, "no contig loaded");
+    if (ctx->logfac_ready || ctx->logfac_pending || !ctx->tune[PASIO_TUNE_LOGFAC_EXACT]) return PASIO_OK;
+    if (ctx->max_count + 2 > ctx->ntab[PASIO_TAB_LGAMMA]) return PASIO_OK;     // the table must grow first: left to the consumer
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_lx0, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_lx, ctx->ev_lx0, 0));
+    PASIO_TRY(launch_logfac_exact(ctx, ctx->stream_lx));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_lx1, ctx->stream_lx));
+    ctx->logfac_ready = true;
+    ctx->logfac_is_exact = true;
+    ctx->logfac_pending = true;
     return PASIO_OK;
 }
 

@@ -34,6 +34,9 @@ struct pasio_ctx {
     cudaStream_t stream2 = nullptr;      // side stream: the warp-per-window kernels run beside the CTA-per-window kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream_copy = nullptr;  // host->device chunks of pasio_contig_load_round
+    cudaStream_t stream_lx = nullptr;    // log-factorial sums prefetched beside the rounds (pasio_logfac_prefetch)
+    cudaEvent_t ev_lx0 = nullptr, ev_lx1 = nullptr;
+    bool logfac_pending = false;         // the prefetch is in flight: consumers wait for ev_lx1 first
     std::vector<cudaEvent_t> chunk_events;
     void *stage[3] = {nullptr, nullptr, nullptr};   // page-locked staging ring for uploads from pageable memory
     cudaEvent_t stage_free[3] = {nullptr, nullptr, nullptr};
@@ -72,6 +75,7 @@ struct pasio_ctx {
     // candidates (positions, int32, ascending); implicit_all: cand[q] == q
     bool implicit_all = true;
     DevBuf cand[2];
+    DevBuf candC[2];             // int64 prefix sums at the candidates (cg[cand[k]]), written with the list
     int cur = 0;
     i64 m = 0;
 
@@ -87,7 +91,8 @@ struct pasio_ctx {
     DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan, logfac_full;
     DevBuf xpRing, xpRec, xpTasks, regLR, regNR;
     DevBuf lxPos, lxSum, lxFirst;    // logfac_exact.cu: positions / running sums of the non-zero log-factorial terms, first term per contig
-    i64 lx_terms = 0;   // exact_pruned.cu: self-score ring, column-block records, task list
+    i64 lx_terms = 0;
+    i64 scan_tiles_done = 0;     // tiles of the loaded contig already scanned (pasio_contig_load_round scans chunk by chunk)   // exact_pruned.cu: self-score ring, column-block records, task list
 
     // tuning switches (pasio_set_tuning; defaults from the PASIO_WD_* / PASIO_XD_* environment variables)
     int tune[PASIO_TUNE_COUNT];
@@ -142,7 +147,7 @@ int launch_expand_rle(pasio_ctx *ctx, const i64 *d_starts, const i64 *d_values, 
 int launch_logfac_scan(pasio_ctx *ctx, double *d_out, cudaStream_t stream = nullptr);   // float64 prefix sums of G[counts+1], n+1 entries
 
 // compact.cu
-int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count);  // keepbits -> sorted positions; syncs
+int launch_compact_keepbits(pasio_ctx *ctx, int slot, i64 *h_count);  // keepbits -> cand[slot] (sorted positions) + candC[slot]; syncs
 int launch_boundary_ranks(pasio_ctx *ctx);                    // brank from current candidates
 // classify_constraint >= 0: also sort the windows into ctx->win_small / win_large (n_small, n_large) for launch_window_dp
 int launch_window_prepass(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, i64 *h_max_span, i64 *h_max_cnt,
@@ -173,13 +178,16 @@ int launch_gather_f64_at_cands(pasio_ctx *ctx, const double *d_src, double *d_ou
 int launch_lmm(pasio_ctx *ctx, const double *d_scores, const double *d_logfac_full, double *d_lmm);
 
 // logfac_exact.cu: logfac_cumsum with the reference's sequential rounding
-int launch_logfac_exact(pasio_ctx *ctx);
+int launch_logfac_exact(pasio_ctx *ctx, cudaStream_t stream = nullptr);
 int launch_lmm_exact(pasio_ctx *ctx, const double *d_scores, double *d_lmm);
 int launch_logfac_at_candidates_exact(pasio_ctx *ctx, double *d_out);
 int logfac_exact_total(pasio_ctx *ctx, double *h_out);
 
 static inline const int32_t *cur_cand(const pasio_ctx *ctx) {
     return ctx->implicit_all ? nullptr : ctx->cand[ctx->cur].as<int32_t>();
+}
+static inline const i64 *cur_cand_cg(const pasio_ctx *ctx) {
+    return ctx->implicit_all ? nullptr : ctx->candC[ctx->cur].as<i64>();
 }
 
 // Window geometry of dto/sliding_window.py:9-15 over candidate indices: either the closed form

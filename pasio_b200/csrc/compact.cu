@@ -73,7 +73,7 @@ scan_block_sums(int *blocksum, i64 nblocks, i64 *total_out)
 
 __global__ void __launch_bounds__(CP_THREADS)
 scatter_bits(const uint32_t *__restrict__ bits, i64 nwords, const int *__restrict__ blockprefix,
-             int32_t *__restrict__ out)
+             int32_t *__restrict__ out, const i64 *__restrict__ cg, i64 *__restrict__ cg_out)
 {
     __shared__ int s_warp[CP_THREADS / 32];
     const i64 base = (i64)blockIdx.x * CP_TILE + (i64)threadIdx.x * CP_WORDS;
@@ -92,7 +92,9 @@ scatter_bits(const uint32_t *__restrict__ bits, i64 nwords, const int *__restric
         const int32_t pos0 = (int32_t)((base + k) << 5);
         while (x) {
             int b = __ffs(x) - 1;
-            out[off++] = pos0 + b;
+            out[off] = pos0 + b;
+            cg_out[off] = __ldg(cg + pos0 + b);       // the candidate's prefix sum travels with it: the window kernels read
+            ++off;                                    // both arrays coalesced instead of gathering 8 bytes per 32-byte sector
             x &= x - 1;
         }
     }
@@ -232,8 +234,10 @@ WinGeom make_geom(const pasio_ctx *ctx, int wsize, int wshift)
     return g;
 }
 
-int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count)
+int launch_compact_keepbits(pasio_ctx *ctx, int slot, i64 *h_count)
 {
+    int32_t *d_out = ctx->cand[slot].as<int32_t>();
+    PASIO_TRY(pasio_reserve(ctx, ctx->candC[slot], ctx->cand[slot].bytes * 2));
     const i64 nwords = (ctx->n + 1 + 31) / 32;
     const i64 nblocks = (nwords + CP_TILE - 1) / CP_TILE;
     PASIO_TRY(pasio_reserve(ctx, ctx->blocksum, (size_t)nblocks * sizeof(int)));
@@ -244,7 +248,7 @@ int launch_compact_keepbits(pasio_ctx *ctx, int32_t *d_out, i64 *h_count)
         TimingScope ts(ctx, TF_COMPACT, 3);
         popc_block_sums<<<(unsigned)nblocks, CP_THREADS, 0, ctx->stream>>>(bits, nwords, bs);
         scan_block_sums<<<1, CP_THREADS, 0, ctx->stream>>>(bs, nblocks, d_total);
-        scatter_bits<<<(unsigned)nblocks, CP_THREADS, 0, ctx->stream>>>(bits, nwords, bs, d_out);
+        scatter_bits<<<(unsigned)nblocks, CP_THREADS, 0, ctx->stream>>>(bits, nwords, bs, d_out, ctx->cg.as<i64>(), ctx->candC[slot].as<i64>());
     }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 4, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));

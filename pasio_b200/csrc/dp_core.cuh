@@ -40,14 +40,17 @@ __device__ __forceinline__ RowConst<AI> make_row(int cj, int lj, int alpha_int, 
 }
 
 // self score of segment [i, j): G[s] - s * Lg[len]
-template <bool AI>
+// LGS: ltab points to a copy of the first entries of the log table in SHARED memory (round 1 of the sliding-window
+// pipeline: every length is below the window size, and the lengths of one warp's gather spread over tens of cache
+// lines -- from shared memory the same gather costs a few bank conflicts instead)
+template <bool AI, bool LGS = false>
 __device__ __forceinline__ double self_score(int ci, int li, const RowConst<AI> &r,
                                              const double *__restrict__ gtab, const double *__restrict__ ltab)
 {
     const int idx = r.cjx - ci;
     const int len = r.lj - li;
     const double g = __ldg(gtab + idx);
-    const double lg = __ldg(ltab + len);
+    const double lg = LGS ? ltab[len] : __ldg(ltab + len);
     const double s = AI ? u32_to_double(idx) : __dsub_rn(r.aj, u32_to_double(ci));
     return __dsub_rn(g, __dmul_rn(s, lg));
 }
@@ -77,7 +80,7 @@ __device__ __forceinline__ void merge_column_phases(double &best, int &arg)
 // the first maximum among the lane's own (ascending) columns.  Every column record read from shared
 // memory feeds RPL cells.  The table gathers are the long-latency part: a batch of U columns first
 // issues all 2*U*RPL gathers, then does the arithmetic.
-template <bool AI, int U, int RPL>
+template <bool AI, int U, int RPL, bool LGS = false>
 __device__ __forceinline__ void sweep_columns(int i0, int i1, int phase, int stride, const ColRec *sCol,
                                               const RowConst<AI> (&r)[RPL],
                                               const double *__restrict__ gtab, const double *__restrict__ ltab,
@@ -95,7 +98,7 @@ __device__ __forceinline__ void sweep_columns(int i0, int i1, int phase, int str
             for (int k = 0; k < RPL; ++k) {
                 const int idx = r[k].cjx - a.C;
                 g[u][k] = __ldg(gtab + idx);
-                lg[u][k] = __ldg(ltab + (r[k].lj - a.L));
+                lg[u][k] = LGS ? ltab[r[k].lj - a.L] : __ldg(ltab + (r[k].lj - a.L));
                 sx[u][k] = AI ? idx : a.C;
             }
         }
@@ -112,7 +115,7 @@ __device__ __forceinline__ void sweep_columns(int i0, int i1, int phase, int str
         const ColRec a = sCol[i];
 #pragma unroll
         for (int k = 0; k < RPL; ++k) {
-            const double t = __dadd_rn(self_score<AI>(a.C, a.L, r[k], gtab, ltab), a.P);
+            const double t = __dadd_rn(self_score<AI, LGS>(a.C, a.L, r[k], gtab, ltab), a.P);
             if (t > best[k]) { best[k] = t; arg[k] = i; }
         }
     }

@@ -43,6 +43,9 @@ constexpr int XP_PRING = 1024;        // finished P kept in the diagonal's share
 constexpr int XP_ST = 63;             // self-score tile of the chain warp: distances 1..63
 constexpr int XP_MB = 30;             // mid sweep: loads per batch and lane (a multiple of 3); two batches are prefetched
 constexpr int XP_LIST1 = 4096;
+#ifndef XP_STREAM_LOADS
+#define XP_STREAM_LOADS 1      // every self score is read once: evict-first loads keep them from displacing the tables in L1
+#endif
 constexpr int XP_L2CHUNK = 128;       // level-1 survivors refined per pass (<= 4096 fine rectangles listed)
 constexpr size_t XP_LINEAR_BYTES = (size_t)2 << 30;
 
@@ -62,7 +65,7 @@ static_assert(sizeof(XpRec32) == 144 && sizeof(XpAnchors) == 160, "record layout
 struct XpParams {
     int N, nB, nSteps, lag, DB, n_tasks, npad;
     int dbg;                    // PASIO_XD_DBG (timing experiments only, results become wrong): 1 no mid sweep, 2 no records,
-                                // 4 no waiting for far results, 8 no tile moves
+                                // 4 no waiting for far results, 8 no tile moves, 16 mid: loads only, 32 mid: arithmetic only
     int s_slots;                // row blocks of self scores held: nB (every block has its own slab: written once per launch,
                                 // so the diagonal may read it through L1) or XP_RING (slabs reused: L2-coherent loads only)
     const int32_t *L;
@@ -75,7 +78,7 @@ struct XpParams {
     int *done_block;            // blocks finished and published (P, prev, records)
     unsigned *task_counter;
     const int2 *tasks;          // x = type | block << 1, y = sub index
-    double *farV;               // [XP_G][npad]
+    double *farV;               // [nB][XP_G][128]
     int *farA;
     XpRec32 *rec32;             // per 32 finished columns [1 + 32q, 33 + 32q)
     CoarseRec *rec128;          // per finished block
@@ -87,6 +90,7 @@ struct XpParams {
     const double *ltab;
     int alpha_int;
     double alpha, pen;
+    const double *consts;       // [0] scale of the bound's delta (largest |G| + s*Lg a cell can reach), [1], [2] tilt scales
 };
 
 // cycle counters kept by one thread per role (negligible cost: a few clock reads per 32-row step / per task)
@@ -109,7 +113,7 @@ __device__ __forceinline__ void xp_wait_cta(const int *flag, int target)     // 
 // per launch cannot be stale in the reader's L1 (L1 is invalidated at kernel boundaries), so ordinary loads are safe;
 // ring slabs are rewritten during the launch and must be read from L2 (ld.cg).
 template <bool RING, typename T>
-__device__ __forceinline__ T xp_ld_s(const T *p) { return RING ? __ldcg(p) : *p; }
+__device__ __forceinline__ T xp_ld_s(const T *p) { return RING ? __ldcg(p) : (XP_STREAM_LOADS ? __ldcs(p) : *p); }
 
 // Helpers: make sure the self scores of block `need` are complete.  One warp looks at the flags of 32 consecutive blocks
 // at once (they are produced far ahead of the diagonal), so the round trip to L2 is paid once per ~32 blocks.
@@ -138,7 +142,7 @@ __device__ __forceinline__ int xp_far_bound(int b, int lag) { return b >= lag - 
 
 __host__ __device__ inline size_t xp_diag_smem()
 {
-    return (size_t)XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + 64 * 4 + 16;
+    return (size_t)XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + XP_PRING * 4 + 16;
 }
 __host__ __device__ inline size_t xp_worker_smem()
 {
@@ -260,7 +264,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     int *sMidA = reinterpret_cast<int *>(sFarV + 2 * XP_RB);    // [2][XP_HELP][32]
     int *sFarA = sMidA + 2 * XP_HELP * 32;                      // [2][128]
     double *sScal = reinterpret_cast<double *>(sFarA + 2 * XP_RB);   // [0] running max |P|
-    int *sPrevStep = reinterpret_cast<int *>(sScal + 8);             // [2][32] arg-max columns of the rows of a step (by step parity)
+    int *sPrevRing = reinterpret_cast<int *>(sScal + 8);             // [XP_PRING] arg-max columns of the finished rows, ring by row index
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, lag = p.lag;
 
@@ -290,8 +294,10 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     const int hidx = hw_mine * 32 + lane;                // index among the 192 sweeping threads
     double pre0[XP_MB], pre1[XP_MB];
     double2 tile_regs[XP_TILE_NV];
+    int rec_c = 0, rec_l = 0, rec_c4[4] = {0, 0, 0, 0}, rec_l4[4] = {0, 0, 0, 0};     // book-keeping warp: (C, L) of the columns its next records cover
     int s_known = 0;                                     // block 0 is complete (waited above)
-    int *sKnown = sPrevStep + 64;
+    int *sKnown = sPrevRing + XP_PRING;
+    if (warp == 4 && 1 + lane < N) { rec_c = __ldg(p.C + 1 + lane); rec_l = __ldg(p.L + 1 + lane); }
     if (warp > 0 && hw_mine < XP_MIDW) {
         if (2 < p.nSteps) xp_tile_load<RING>(p, 2, hidx, XP_MIDW * 32, tile_regs);
         if (1 < p.nSteps) {
@@ -361,7 +367,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 __stcg(p.prev + j, arg);
                 pm = fabs(mine);
             }
-            sPrevStep[(k & 1) * 32 + lane] = arg;
+            if (j < N) sPrevRing[j & (XP_PRING - 1)] = arg;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, off));
             pmax = fmax(pmax, pm);
@@ -374,31 +380,27 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             const int hw = hw_mine;
             if (hw == XP_MIDW) {
                 if (k > 0) {
-                    // records of the columns finished in step k-1 (and of the block they complete), then publish
+                    // records of the columns finished in step k-1 (and of the block they complete), then publish; the
+                    // columns' (C, L) were loaded during the previous step
                     const int jbp = jb - 32;
-                    const int cme = __ldg(p.C + jbp + lane), lme = __ldg(p.L + jbp + lane);
+                    const int cme = rec_c, lme = rec_l;
                     XpRec32 *rec = p.rec32 + (k - 1);
                     if (!(p.dbg & 2)) fit_column_record(cme, lme, sP[(jbp + lane) & (XP_PRING - 1)], &rec->r, tilt_c, tilt_l);
                     if ((lane & 7) == 0) { rec->sub[lane >> 3][0] = cme; rec->sub[lane >> 3][2] = lme; }
                     if ((lane & 7) == 7) { rec->sub[lane >> 3][1] = cme; rec->sub[lane >> 3][3] = lme; }
                     if (s == 0) {
                         const int c0 = 1 + XP_RB * (b - 1);
-                        int cc[4], ll[4];
                         double pp[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            cc[q] = __ldg(p.C + c0 + lane + 32 * q);
-                            ll[q] = __ldg(p.L + c0 + lane + 32 * q);
-                            pp[q] = sP[(c0 + lane + 32 * q) & (XP_PRING - 1)];
-                        }
-                        if (!(p.dbg & 2)) fit_column_record128(cc, ll, pp, p.rec128 + (b - 1), tilt_c, tilt_l);
+                        for (int q = 0; q < 4; ++q) pp[q] = sP[(c0 + lane + 32 * q) & (XP_PRING - 1)];
+                        if (!(p.dbg & 2)) fit_column_record128(rec_c4, rec_l4, pp, p.rec128 + (b - 1), tilt_c, tilt_l);
                         // anchors of the block that just finished: its last row e and the last seven split points of the best
                         // segmentation ending there (e -> prev[e] -> prev[prev[e]] ...): the rows ahead most likely continue
                         // one of these, so "best up to the anchor, then one segment" bounds their maxima from below tightly
                         const int e = jb - 1;
                         int a = e, mine = e;
                         for (int t = 1; t < 8; ++t) {                  // (every lane walks the same chain: uniform loads)
-                            a = a > 0 ? __ldcg(p.prev + a) : 0;
+                            if (a > 0) a = a > e - (XP_PRING - 64) ? sPrevRing[a & (XP_PRING - 1)] : __ldcg(p.prev + a);
                             if (lane == t) mine = a;
                         }
                         if (lane < 8) {
@@ -407,7 +409,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                             an->idx[lane] = mine;
                             an->L[lane] = __ldg(p.L + mine);
                             an->C[lane] = __ldg(p.C + mine);
-                            an->P[lane] = mine > 0 ? __ldcg(p.P + mine) : 0.0;
+                            an->P[lane] = mine > e - (XP_PRING - 64) ? sP[mine & (XP_PRING - 1)] : (mine > 0 ? __ldcg(p.P + mine) : 0.0);
                         }
                         __syncwarp();
                         if (lane == 0) {
@@ -417,36 +419,28 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                         }
                     }
                 }
+                // inputs of the next step's records
+                if (jb + lane < N) { rec_c = __ldg(p.C + jb + lane); rec_l = __ldg(p.L + jb + lane); }
+                if (s == 3) {
+                    const int c0 = 1 + XP_RB * b;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = min(c0 + lane + 32 * q, N - 1);
+                        rec_c4[q] = __ldg(p.C + col);
+                        rec_l4[q] = __ldg(p.L + col);
+                    }
+                }
                 { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
                 { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
-                // far results of the next block: four rows per lane, the eight slices merged by column index
+                // the far results of the next block must have arrived: this warp waits for them, the sweeping warps fetch them
                 if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
                     if (lane == 0 && !(p.dbg & 4)) {
                         while (xp_ld_flag(p.far_ready + (b + 1)) < XP_G) __nanosleep(20);
                         __threadfence();
                     }
                     __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int row = lane + 32 * q, j = 1 + XP_RB * (b + 1) + row;
-                        double best = -INFINITY;
-                        int arg = 0x7fffffff;
-                        if (j < N) {
-                            double v[XP_G];
-                            int a[XP_G];
-#pragma unroll
-                            for (int g = 0; g < XP_G; ++g) {
-                                v[g] = __ldcg(p.farV + (size_t)g * p.npad + j);
-                                a[g] = __ldcg(p.farA + (size_t)g * p.npad + j);
-                            }
-#pragma unroll
-                            for (int g = 0; g < XP_G; ++g)
-                                if (v[g] > best || (v[g] == best && a[g] < arg)) { best = v[g]; arg = a[g]; }
-                        }
-                        sFarV[((b + 1) & 1) * XP_RB + row] = best;
-                        sFarA[((b + 1) & 1) * XP_RB + row] = arg;
-                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(XP_HELP * 32) : "memory");
                     { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
                 }
             } else {
@@ -461,10 +455,11 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 const XpMid g2 = xp_mid_geometry(p, have2 ? k + 2 : k, hw, lane);
                 double best = -INFINITY;
                 int arg = 0;
-                if (have1) xp_mid_fold(g1, g1.dhi - 1, pre0, sP, best, arg);
-                if (have2) xp_mid_load<RING>(g2, g2.dhi - 1, pre0);
+                const bool do_fold = !(p.dbg & 16), do_load = !(p.dbg & 32);
+                if (have1 && do_fold) xp_mid_fold(g1, g1.dhi - 1, pre0, sP, best, arg);
+                if (have2 && do_load) xp_mid_load<RING>(g2, g2.dhi - 1, pre0);
                 if (have1) {
-                    xp_mid_fold(g1, g1.dhi - 1 - XP_MB, pre1, sP, best, arg);
+                    if (do_fold) xp_mid_fold(g1, g1.dhi - 1 - XP_MB, pre1, sP, best, arg);
                     for (int d = g1.dhi - 1 - 2 * XP_MB; d >= g1.dlo; d -= XP_MB) {    // (lag 4: further batches, loaded here)
                         double v[XP_MB];
                         xp_mid_load<RING>(g1, d, v);
@@ -473,12 +468,38 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                     sMidV[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = best;
                     sMidA[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = arg;
                 }
-                if (have2) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
+                if (have2 && do_load) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
+                if (p.dbg & 16) { double acc = 0.0; for (int u = 0; u < XP_MB; ++u) acc += pre0[u] + pre1[u]; if (acc == 1.2345) sMidV[0] = acc; }   // (keeps the loads alive)
                 { const long long t1 = xp_clock(); pq[1] += t1 - tq; tq = t1; }
                 // the tile of step k+2 (loaded during the previous step) -> shared memory; then the loads of the next one
                 if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_tile_store(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, hidx, XP_MIDW * 32, tile_regs);
                 if (k + 3 < p.nSteps && !(p.dbg & 8)) xp_tile_load<RING>(p, k + 3, hidx, XP_MIDW * 32, tile_regs);
                 { const long long t1 = xp_clock(); pq[2] += t1 - tq; tq = t1; }
+                // far results of the next block (the book-keeping warp saw them arrive): one row per thread, the eight
+                // slices merged by column index
+                if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
+                    asm volatile("bar.sync 2, %0;" ::"n"(XP_HELP * 32) : "memory");
+                    if (hidx < XP_RB) {
+                        const int j = 1 + XP_RB * (b + 1) + hidx;
+                        double best = -INFINITY;
+                        int arg = 0x7fffffff;
+                        if (j < N) {
+                            double v[XP_G];
+                            int a[XP_G];
+#pragma unroll
+                            for (int g = 0; g < XP_G; ++g) {
+                                v[g] = __ldcg(p.farV + ((size_t)(b + 1) * XP_G + g) * XP_RB + hidx);
+                                a[g] = __ldcg(p.farA + ((size_t)(b + 1) * XP_G + g) * XP_RB + hidx);
+                            }
+#pragma unroll
+                            for (int g = 0; g < XP_G; ++g)
+                                if (v[g] > best || (v[g] == best && a[g] < arg)) { best = v[g]; arg = a[g]; }
+                        }
+                        sFarV[((b + 1) & 1) * XP_RB + hidx] = best;
+                        sFarA[((b + 1) & 1) * XP_RB + hidx] = arg;
+                    }
+                    { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
+                }
             }
         }
         __syncthreads();
@@ -594,8 +615,7 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
     long long tl0 = 0, tl1 = 0, tl2 = 0, thead = 0;
 
     // ---- phase A: rows, anchors, this thread's first level-0 record, scalars: one round trip ----
-    const int zC = __ldg(p.C + N - 1), zL = __ldg(p.L + N - 1);
-    const double zg = __ldg(p.gtab + zC + (AI ? p.alpha_int : 0)), zl = __ldg(p.ltab + zL);
+    const double scale0 = __ldg(p.consts), tilt_c = __ldg(p.consts + 1), tilt_l = __ldg(p.consts + 2);
     const double pmax = __ldcg(p.pmax);
     int2 rowlc = make_int2(0, 0);
     if (tid < XP_RB) {
@@ -625,9 +645,7 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
         sCd[tid] = (double)rowlc.y;
         sLd[tid] = (double)rowlc.x;
     }
-    const double scale0 = fabs(zg) + ((double)zC + p.alpha) * fabs(zl) + 1.0;
     const double delta = (scale0 + pmax + fabs(p.pen) * XP_RB) * 5.684341886080802e-14;     // 2^-44
-    const double tilt_c = (double)zC + p.alpha, tilt_l = (double)zL;
     __syncthreads();
 
     // ---- phase B: gathers of the lower bounds (rows x anchors), of column 0 and of this thread's level-0 box ----
@@ -832,62 +850,57 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
                 }
             }
             __syncthreads();
-            // exact evaluation of the listed 4 x 8 rectangles: a warp per rectangle, four in flight
+            // exact evaluation of the listed 4 x 8 rectangles, eight per warp pass: four lanes per rectangle, a lane owns one
+            // row and walks its eight columns in ascending order (strict '>': the first maximum), all sixteen table
+            // gathers of a lane in flight together
             const int n2 = sCnt[2];
             evaluated += (warp == 0 && lane == 0) ? (u64)n2 * 32 : 0;
-            constexpr int UX = 4;
-            const int er = lane >> 3, ec = lane & 7;
-            for (int f0 = warp * UX; f0 < n2; f0 += 8 * UX) {
-                int row[UX], col[UX], cc[UX], ll[UX];
-                double pc[UX], gg[UX], lg[UX];
-                RowConst<AI> rc[UX];
-                bool act[UX];
+            for (int f0 = warp * 8; f0 < n2; f0 += 64) {
+                const int f = f0 + (lane >> 2), er = lane & 3;
+                bool act = f < n2;
+                int row = 0, c0 = 0;
+                if (act) {
+                    const int code = sList2[f], l2 = code & 31;
+                    const int ent = sList1[base + (code >> 5)], q32 = ent >> 2, rg = ent & 3;
+                    row = 32 * rg + 4 * (l2 >> 2) + er;
+                    c0 = 1 + 32 * q32 + 8 * (l2 & 3);
+                    act = row < nrows;
+                }
+                double t = -INFINITY;
+                int ta = 0x7fffffff;
+                if (act) {
+                    const int2 me = sRowLC[row];
+                    const RowConst<AI> rc = make_row<AI>(me.y, me.x, p.alpha_int, p.alpha);
+                    int cc[8], ll[8];
+                    double pc[8], gg[8], lg[8];
 #pragma unroll
-                for (int u = 0; u < UX; ++u) {
-                    act[u] = false;
-                    row[u] = 0;
-                    col[u] = 0x7fffffff;
-                    if (f0 + u < n2) {
-                        const int code = sList2[f0 + u], l2 = code & 31;
-                        const int ent = sList1[base + (code >> 5)], q32 = ent >> 2, rg = ent & 3;
-                        row[u] = 32 * rg + 4 * (l2 >> 2) + er;
-                        if (row[u] < nrows) {
-                            act[u] = true;
-                            col[u] = 1 + 32 * q32 + 8 * (l2 & 3) + ec;
-                            cc[u] = __ldg(p.C + col[u]);
-                            ll[u] = __ldg(p.L + col[u]);
-                            pc[u] = __ldcg(p.P + col[u]);
-                        }
+                    for (int c = 0; c < 8; ++c) {
+                        cc[c] = __ldg(p.C + c0 + c);
+                        ll[c] = __ldg(p.L + c0 + c);
+                        pc[c] = __ldcg(p.P + c0 + c);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        gg[c] = __ldg(p.gtab + (rc.cjx - cc[c]));
+                        lg[c] = __ldg(p.ltab + (rc.lj - ll[c]));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const double sx = AI ? u32_to_double(rc.cjx - cc[c]) : __dsub_rn(rc.aj, u32_to_double(cc[c]));
+                        const double v = __dadd_rn(__dsub_rn(gg[c], __dmul_rn(sx, lg[c])), pc[c]);
+                        if (v > t) { t = v; ta = c0 + c; }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < UX; ++u)
-                    if (act[u]) {
-                        const int2 me = sRowLC[row[u]];
-                        rc[u] = make_row<AI>(me.y, me.x, p.alpha_int, p.alpha);
-                        gg[u] = __ldg(p.gtab + (rc[u].cjx - cc[u]));
-                        lg[u] = __ldg(p.ltab + (rc[u].lj - ll[u]));
+                // rectangles of one pass may share rows: lanes with the same row update it one after the other
+                const unsigned same = __match_any_sync(0xffffffffu, act ? row : -1 - lane);
+                const int turn = __popc(same & ((1u << lane) - 1u));
+                const int turns = __reduce_max_sync(0xffffffffu, turn);
+                for (int r = 0; r <= turns; ++r) {
+                    if (act && turn == r) {
+                        const double cur = sWV[warp * XP_RB + row];
+                        if (t > cur || (t == cur && ta < sWA[warp * XP_RB + row])) { sWV[warp * XP_RB + row] = t; sWA[warp * XP_RB + row] = ta; }
                     }
-#pragma unroll
-                for (int u = 0; u < UX; ++u) {
-                    double t = -INFINITY;
-                    int ta = 0x7fffffff;
-                    if (act[u]) {
-                        const double sx = AI ? u32_to_double(rc[u].cjx - cc[u]) : __dsub_rn(rc[u].aj, u32_to_double(cc[u]));
-                        t = __dadd_rn(__dsub_rn(gg[u], __dmul_rn(sx, lg[u])), pc[u]);
-                        ta = col[u];
-                    }
-#pragma unroll
-                    for (int off = 1; off < 8; off <<= 1) {
-                        const double ob = __shfl_xor_sync(0xffffffffu, t, off);
-                        const int oa = __shfl_xor_sync(0xffffffffu, ta, off);
-                        if (ob > t || (ob == t && oa < ta)) { t = ob; ta = oa; }
-                    }
-                    if (ec == 0 && act[u]) {
-                        const double cur = sWV[warp * XP_RB + row[u]];
-                        if (t > cur || (t == cur && ta < sWA[warp * XP_RB + row[u]])) { sWV[warp * XP_RB + row[u]] = t; sWA[warp * XP_RB + row[u]] = ta; }
-                    }
-                    __syncwarp();            // two rectangles in flight may belong to the same rows
+                    __syncwarp();
                 }
             }
             __syncthreads();
@@ -906,8 +919,8 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
             const int a = sWA[w * XP_RB + tid];
             if (v > best || (v == best && a < arg)) { best = v; arg = a; }
         }
-        __stcg(p.farV + (size_t)g * p.npad + r0 + tid, best);
-        __stcg(p.farA + (size_t)g * p.npad + r0 + tid, arg);
+        __stcg(p.farV + ((size_t)b * XP_G + g) * XP_RB + tid, best);
+        __stcg(p.farA + ((size_t)b * XP_G + g) * XP_RB + tid, arg);
     }
     if (tid == 0 && evaluated) atomicAdd(p.far_cells, evaluated);
     __syncthreads();
@@ -924,6 +937,17 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
         atomicAdd(p.prof + XQ_F_L23, (u64)tl2);
         atomicAdd(p.prof + XQ_F_HEAD, (u64)thead);
     }
+}
+
+// constants of the bound, once per launch (so that no far task starts with a chain of dependent loads)
+template <bool AI>
+__global__ void xp_consts_kernel(const int32_t *__restrict__ L, const int32_t *__restrict__ C, int N, const double *__restrict__ gtab,
+                                 const double *__restrict__ ltab, int alpha_int, double alpha, double *out)
+{
+    const int zC = C[N - 1], zL = L[N - 1];
+    out[0] = fabs(gtab[zC + (AI ? alpha_int : 0)]) + ((double)zC + alpha) * fabs(ltab[zL]) + 1.0;
+    out[1] = (double)zC + alpha;
+    out[2] = (double)zL;
 }
 
 template <bool AI, bool RING>
@@ -981,9 +1005,9 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     const int slots = ring ? XP_RING : p.nB;
     p.s_slots = slots;
     const size_t ring_bytes = (size_t)slots * p.DB * XP_RB * 8;
-    const size_t far_bytes = (size_t)XP_G * p.npad * 12;
+    const size_t far_bytes = (size_t)XP_G * XP_RB * p.nB * 12;
     const size_t rec_bytes = ((size_t)p.nSteps + 1) * sizeof(XpRec32) + ((size_t)p.nB + 1) * (sizeof(CoarseRec) + sizeof(XpAnchors));
-    const size_t flag_ints = (size_t)2 * p.nB + 8 + 64;          // + 32 u64 profile counters
+    const size_t flag_ints = (size_t)2 * p.nB + 8 + 64 + 8;      // + 32 u64 profile counters + 4 doubles of constants
     PASIO_TRY(pasio_reserve(ctx, ctx->xpRing, ring_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, far_bytes > rec_bytes ? far_bytes : rec_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->xpRec, rec_bytes));
@@ -1004,11 +1028,13 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.done_block = flags + 4;
     p.task_counter = reinterpret_cast<unsigned *>(flags + 5);
     p.prof = reinterpret_cast<u64 *>(flags + 8);                // 32 x 8 bytes
-    p.s_ready = flags + 8 + 64;
+    double *consts = reinterpret_cast<double *>(flags + 8 + 64);    // 4 x 8 bytes
+    p.consts = consts;
+    p.s_ready = flags + 8 + 64 + 8;
     p.far_ready = p.s_ready + p.nB;
     p.tasks = ctx->xpTasks.as<int2>();
     p.farV = ctx->dpPart.as<double>();
-    p.farA = reinterpret_cast<int *>(p.farV + (size_t)XP_G * p.npad);
+    p.farA = reinterpret_cast<int *>(p.farV + (size_t)XP_G * XP_RB * p.nB);
     p.rec32 = ctx->xpRec.as<XpRec32>();
     p.rec128 = reinterpret_cast<CoarseRec *>(p.rec32 + p.nSteps + 1);
     p.anchors = reinterpret_cast<XpAnchors *>(p.rec128 + p.nB + 1);
@@ -1018,6 +1044,7 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.alpha = ctx->alpha;
     p.pen = ctx->pen;
 
+    xp_consts_kernel<AI><<<1, 1, 0, ctx->stream>>>(p.L, p.C, p.N, p.gtab, p.ltab, p.alpha_int, p.alpha, consts);
     const size_t smem = xp_diag_smem() > xp_worker_smem() ? xp_diag_smem() : xp_worker_smem();
     void (*kern)(XpParams) = ring ? exact_pruned_kernel<AI, true> : exact_pruned_kernel<AI, false>;
     if (ctx->tune[PASIO_TUNE_EXACT_RING] && p.nB > XP_RING) {                // (tests: exercise the ring on short lists)

@@ -209,9 +209,11 @@ inline unsigned grid_for(pasio_ctx *ctx, i64 n)
 
 }  // namespace
 
-// steps 1 and 2 for the loaded batch; cached in the context until the next load
-int launch_logfac_exact(pasio_ctx *ctx)
+// steps 1 and 2 for the loaded batch; cached in the context until the next load.  stream: the context's main stream, or
+// its side stream when the sums are prefetched beside the rounds (pasio_logfac_prefetch)
+int launch_logfac_exact(pasio_ctx *ctx, cudaStream_t stream)
 {
+    if (!stream) stream = ctx->stream;
     const i64 n = ctx->n;
     if (ctx->max_count + 2 > ctx->ntab[PASIO_TAB_LGAMMA]) {
         ctx->need[PASIO_TAB_LGAMMA] = ctx->max_count + 2;
@@ -224,19 +226,19 @@ int launch_logfac_exact(pasio_ctx *ctx)
     PASIO_TRY(pasio_reserve(ctx, ctx->lxFirst, (size_t)ctx->n_contigs * 8));
     unsigned *d_tiles = ctx->fscan.as<unsigned>();
     i64 *d_total = ctx->scalars.as<i64>() + 9;
-    TimingScope ts(ctx, TF_SCORE, 4);
-    nonzero_count_kernel<<<(unsigned)tiles, LX_THREADS, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles);
-    tile_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_tiles, tiles, d_total);
+    TimingScope ts(ctx, TF_SCORE, 4, stream);
+    nonzero_count_kernel<<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles);
+    tile_offsets_kernel<<<1, 1024, 0, stream>>>(d_tiles, tiles, d_total);
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 9, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 9, d_total, 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
     const i64 n_terms = ctx->h_scalars[9];
     PASIO_TRY(pasio_reserve(ctx, ctx->lxPos, (size_t)(n_terms + 1) * 4));
     PASIO_TRY(pasio_reserve(ctx, ctx->lxSum, (size_t)(n_terms + 1) * 8));
-    nonzero_scatter_kernel<<<(unsigned)tiles, LX_THREADS, 0, ctx->stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles,
+    nonzero_scatter_kernel<<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles,
                                                                            ctx->lxPos.as<int32_t>(), ctx->lxSum.as<double>());
     const unsigned g = (unsigned)((ctx->n_contigs + 63) / 64);
-    sequential_sum_kernel<<<g < 1 ? 1 : g, 64, 0, ctx->stream>>>(ctx->lxPos.as<int32_t>(), ctx->lxSum.as<double>(), n_terms,
+    sequential_sum_kernel<<<g < 1 ? 1 : g, 64, 0, stream>>>(ctx->lxPos.as<int32_t>(), ctx->lxSum.as<double>(), n_terms,
                                                                  ctx->bounds.as<int32_t>(), ctx->n_contigs, ctx->lxFirst.as<i64>());
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->lx_terms = n_terms;

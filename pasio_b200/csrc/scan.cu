@@ -36,16 +36,22 @@ __device__ __forceinline__ u64 spread_bits(unsigned x)   // bit k of x -> bit 2k
 // bits of a slab come from two ballots interleaved into one 64-bit word.
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
-                   u64 *__restrict__ cpwords, u64 *tile_state, unsigned *tile_counter,
+                   u64 *__restrict__ cpwords, u64 *tile_state, unsigned *tile_counter, i64 first_tile, i64 n_tiles,
                    i64 *scalars /* [0]=total, [1]=negative seen, [2]=largest count */)
 {
     __shared__ unsigned s_tile;
     __shared__ i64 s_warp[SCAN_THREADS / 32];
     __shared__ i64 s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);   // tiles start in issue order: look-back never waits on an unscheduled tile
+    // Persistent CTAs (one resident wave) take tile numbers from a per-launch counter: tiles start in issue order, so the
+    // look-back never waits on an unscheduled tile, and a chr1-sized contig is 60 000 tiles but only a few hundred CTAs
+    // (the CTA launch rate, not HBM, bounded the one-tile-per-CTA version: profiles/r02_scan_*).
+    while (true) {
     __syncthreads();
-    const i64 tile = s_tile;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    if ((i64)s_tile >= n_tiles) break;
+    const i64 tile = first_tile + s_tile;
     const i64 wbase = tile * SCAN_TILE + (i64)warp * SCAN_WARP_ELEMS;     // first element of this warp's chunk
 
     i64 v0[SCAN_SLABS], v1[SCAN_SLABS];
@@ -161,6 +167,7 @@ scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
             if (e == n) scalars[0] = c0;
         }
     }
+    }   // next tile
 }
 
 // Expand run-length intervals (bedgraph form) to the dense int64 profile.
@@ -281,6 +288,7 @@ int launch_scan_prepare(pasio_ctx *ctx, i64 *n_tiles, i64 *tile_elems)
     PASIO_TRY(pasio_reserve(ctx, ctx->tilestate, (size_t)(tiles + 1) * 8 + 16));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->tilestate.p, 0, (size_t)(tiles + 1) * 8 + 16, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(i64), ctx->stream));
+    ctx->scan_tiles_done = 0;
     if (n_tiles) *n_tiles = tiles;
     if (tile_elems) *tile_elems = SCAN_TILE;
     return PASIO_OK;
@@ -293,12 +301,21 @@ int launch_scan_tiles(pasio_ctx *ctx, i64 tiles)
     if (tiles <= 0) return PASIO_OK;
     u64 *state = ctx->tilestate.as<u64>() + 2;
     unsigned *counter = ctx->tilestate.as<unsigned>();
+    static int per_sm = 0;
+    if (!per_sm) {
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_counts_kernel, SCAN_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    i64 grid = (i64)ctx->sm_count * per_sm;
+    if (grid > tiles) grid = tiles;
     {
         TimingScope ts(ctx, TF_SCAN);
-        scan_counts_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(
-            ctx->counts.as<i64>(), ctx->n, ctx->cg.as<i64>(), ctx->cpbits.as<u64>(), state, counter,
+        CUDA_TRY(ctx, cudaMemsetAsync(counter, 0, 4, ctx->stream));          // per-launch tile counter
+        scan_counts_kernel<<<(unsigned)grid, SCAN_THREADS, 0, ctx->stream>>>(
+            ctx->counts.as<i64>(), ctx->n, ctx->cg.as<i64>(), ctx->cpbits.as<u64>(), state, counter, ctx->scan_tiles_done, tiles,
             ctx->scalars.as<i64>());
     }
+    ctx->scan_tiles_done += tiles;
     CUDA_TRY(ctx, cudaGetLastError());
     return PASIO_OK;
 }

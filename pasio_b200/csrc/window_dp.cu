@@ -71,6 +71,7 @@ struct WinDpParams {
     i64 nwin;
     const int32_t *cand;        // nullptr: all positions
     const i64 *cg;
+    const i64 *cgc;             // cg at the candidates (cgc[q] == cg[cand[q]]); nullptr with all positions
     const uint32_t *cpbits;
     uint32_t *keepbits;
     const double *gtab;
@@ -92,6 +93,7 @@ struct WinDpParams {
     unsigned char *done_flags;  // [list_len], index = window number - w_begin
     int p1_stride;
     int skip_covered;           // 0: phase-2 windows neither wait nor get skipped (experiments)
+    int n_lg;                   // warp-per-window kernels with the log table in shared memory: entries copied
 };
 
 __host__ __device__ inline size_t window_smem_bytes(int cap)
@@ -500,8 +502,8 @@ window_dp_kernel(WinDpParams p)
         const int nq = (int)(en - st);
         const i64 first = p.cand ? (i64)__ldg(p.cand + st) : st;
         const i64 last = p.cand ? (i64)__ldg(p.cand + en - 1) : en - 1;
-        const i64 cg_first = __ldg(p.cg + first);
-        const bool all_zero = (p.constraint == PASIO_CONSTRAINT_ZEROS) && (__ldg(p.cg + last) == cg_first);
+        const i64 cg_first = p.cand ? __ldg(p.cgc + st) : __ldg(p.cg + first);
+        const bool all_zero = (p.constraint == PASIO_CONSTRAINT_ZEROS) && ((p.cand ? __ldg(p.cgc + en - 1) : __ldg(p.cg + last)) == cg_first);
         int count = 0;
         const bool by_words = !p.cand && p.constraint == PASIO_CONSTRAINT_CONSTANTS;
         if (by_words) {
@@ -570,7 +572,7 @@ window_dp_kernel(WinDpParams p)
             if (take) {
                 const int k = count + woff + __popc(bal & ((1u << lane) - 1u));
                 sCol[k].L = (int)(pos - first);
-                sCol[k].C = (int)(__ldg(p.cg + pos) - cg_first);
+                sCol[k].C = (int)((p.cand ? __ldg(p.cgc + st + q) : __ldg(p.cg + pos)) - cg_first);
             }
             count += tot;
             __syncthreads();
@@ -734,7 +736,7 @@ struct __align__(16) SmallWin {
     unsigned char mark[MAXN];
 };
 
-template <bool AI, int MAXN, int NWARPS, int CTAS, int U>
+template <bool AI, int MAXN, int NWARPS, int CTAS, int U, bool LGS>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
 small_window_dp_kernel(WinDpParams p)
 {
@@ -742,6 +744,15 @@ small_window_dp_kernel(WinDpParams p)
     const int lane = threadIdx.x & 31;
     SmallWin<MAXN> &W = reinterpret_cast<SmallWin<MAXN> *>(smem)[threadIdx.x >> 5];
     u64 my_cells = 0;
+    // LGS (all positions are candidates, i.e. round 1: no length exceeds the window size): the log table's first
+    // p.n_lg entries are copied to shared memory once per CTA and every Lg look-up of the DP reads that copy
+    const double *lgt = p.ltab;
+    if (LGS) {
+        double *sLg = reinterpret_cast<double *>(smem + sizeof(SmallWin<MAXN>) * NWARPS);
+        for (int k = threadIdx.x; k < p.n_lg; k += NWARPS * 32) sLg[k] = __ldg(p.ltab + k);
+        __syncthreads();
+        lgt = sLg;
+    }
 
     while (true) {
         unsigned widx = 0;
@@ -756,8 +767,8 @@ small_window_dp_kernel(WinDpParams p)
         const int nq = (int)(en - st);
         const i64 first = p.cand ? (i64)__ldg(p.cand + st) : st;
         const i64 last = p.cand ? (i64)__ldg(p.cand + en - 1) : en - 1;
-        const i64 cg_first = __ldg(p.cg + first);
-        const bool all_zero = (p.constraint == PASIO_CONSTRAINT_ZEROS) && (__ldg(p.cg + last) == cg_first);
+        const i64 cg_first = p.cand ? __ldg(p.cgc + st) : __ldg(p.cg + first);
+        const bool all_zero = (p.constraint == PASIO_CONSTRAINT_ZEROS) && ((p.cand ? __ldg(p.cgc + en - 1) : __ldg(p.cg + last)) == cg_first);
         int count = 0;
         if (!p.cand && p.constraint == PASIO_CONSTRAINT_CONSTANTS) {
             const i64 w0 = first >> 5, w1 = last >> 5;
@@ -803,7 +814,7 @@ small_window_dp_kernel(WinDpParams p)
                 if (take) {
                     const int k = count + __popc(bal & ((1u << lane) - 1u));
                     W.col[k].L = (int)(pos - first);
-                    W.col[k].C = (int)(__ldg(p.cg + pos) - cg_first);
+                    W.col[k].C = (int)((p.cand ? __ldg(p.cgc + st + q) : __ldg(p.cg + pos)) - cg_first);
                 }
                 count += __popc(bal);
             }
@@ -819,7 +830,7 @@ small_window_dp_kernel(WinDpParams p)
             RowConst<AI> rc[1] = {make_row<AI>(me.C, me.L, p.alpha_int, p.alpha)};
             double best[1] = {-INFINITY};
             int arg[1] = {ph};
-            sweep_columns<AI, U, 1>(0, jb, ph, 2, W.col, rc, p.gtab, p.ltab, best, arg);
+            sweep_columns<AI, U, 1, LGS>(0, jb, ph, 2, W.col, rc, p.gtab, lgt, best, arg);
             {   // the two column phases of a row: larger value, equal values keep the smaller column
                 const double ob = __shfl_xor_sync(0xffffffffu, best[0], 16);
                 const int oa = __shfl_xor_sync(0xffffffffu, arg[0], 16);
@@ -829,7 +840,7 @@ small_window_dp_kernel(WinDpParams p)
             for (int k = ph; k < r; k += 2)
                 if (jb + r < N) {
                     const ColRec a = W.col[jb + k];
-                    W.tri[k * SW_JB + r] = self_score<AI>(a.C, a.L, rc[0], p.gtab, p.ltab);
+                    W.tri[k * SW_JB + r] = self_score<AI, LGS>(a.C, a.L, rc[0], p.gtab, lgt);
                 }
             __syncwarp();
             double bst = best[0], mine = 0.0;
@@ -894,6 +905,7 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     p.nwin = nwin;
     p.cand = cur_cand(ctx);
     p.cg = ctx->cg.as<i64>();
+    p.cgc = cur_cand_cg(ctx);
     p.cpbits = ctx->cpbits.as<uint32_t>();
     p.keepbits = ctx->keepbits.as<uint32_t>();
     p.gtab = ctx->tab[ctx->alpha_is_int ? PASIO_TAB_LGAMMA : PASIO_TAB_LGAMMA_ALPHA].as<double>();
@@ -950,27 +962,37 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
         ps.n_p1 = n;
         ps.work_counter = counter;
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        int resident = ctas;                          // persistent CTAs: one resident wave (fewer fit with the log table on board)
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, nwarps * 32, smem_bytes));
+        if (resident < 1) resident = 1;
+        if (resident > ctas) resident = ctas;
         i64 g = (n + nwarps - 1) / nwarps;
-        if (g > (i64)ctx->sm_count * ctas) g = (i64)ctx->sm_count * ctas;
+        if (g > (i64)ctx->sm_count * resident) g = (i64)ctx->sm_count * resident;
         ctx->fam_launches[TF_WINDOW_DP] += 1;
         kern<<<(unsigned)g, nwarps * 32, smem_bytes, stream>>>(ps);
         CUDA_TRY(ctx, cudaGetLastError());
         return PASIO_OK;
     };
+    // round 1 (all positions are candidates): lengths stay below the window size, so the log table fits shared memory
+    static const int lgs_env = getenv("PASIO_WD_LGS") ? atoi(getenv("PASIO_WD_LGS")) : 0;   // measured slower (5.50 vs 5.19 ms for round 1 of chr1, profiles/r02_rounds_lgs*.txt): off
+    const bool lgs = lgs_env && p.cand == nullptr && (i64)wsize + 2 <= 4096 && ctx->ntab[PASIO_TAB_LOG] >= (i64)wsize + 2;
+    p.n_lg = lgs ? wsize + 2 : 0;
+    const size_t lg_bytes = (size_t)((p.n_lg + 1) & ~1) * 8;
     auto launch_small_kernels = [&](cudaStream_t stream) -> int {
         unsigned *c_small = ctx->scalars.as<unsigned>() + 2 * 15, *c_medium = c_small + 1;     // scalars[15]
-        const size_t sm_small = sizeof(SmallWin<SW_SMALL_N>) * SW_SMALL_WARPS, sm_medium = sizeof(SmallWin<SW_MEDIUM_N>) * SW_MEDIUM_WARPS;
+        const size_t sm_small = sizeof(SmallWin<SW_SMALL_N>) * SW_SMALL_WARPS + lg_bytes,
+                     sm_medium = sizeof(SmallWin<SW_MEDIUM_N>) * SW_MEDIUM_WARPS + lg_bytes;
+#define PASIO_SMALL_LAUNCH(AIV, LGV)                                                                                                          \
+        PASIO_TRY(launch_small(small_window_dp_kernel<AIV, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS, 4, LGV>, ctx->win_small.as<int32_t>(),   \
+                               n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small, stream));                                            \
+        PASIO_TRY(launch_small(small_window_dp_kernel<AIV, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, 8, LGV>, ctx->win_medium.as<int32_t>(), \
+                               n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium, stream));
         if (ctx->alpha_is_int) {
-            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS, 4>, ctx->win_small.as<int32_t>(),
-                                   n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small, stream));
-            PASIO_TRY(launch_small(small_window_dp_kernel<true, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, 8>, ctx->win_medium.as<int32_t>(),
-                                   n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium, stream));
+            if (lgs) { PASIO_SMALL_LAUNCH(true, true) } else { PASIO_SMALL_LAUNCH(true, false) }
         } else {
-            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_SMALL_N, SW_SMALL_WARPS, SW_SMALL_CTAS, 4>, ctx->win_small.as<int32_t>(),
-                                   n_small, SW_SMALL_WARPS, SW_SMALL_CTAS, sm_small, c_small, stream));
-            PASIO_TRY(launch_small(small_window_dp_kernel<false, SW_MEDIUM_N, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, 8>, ctx->win_medium.as<int32_t>(),
-                                   n_medium, SW_MEDIUM_WARPS, SW_MEDIUM_CTAS, sm_medium, c_medium, stream));
+            if (lgs) { PASIO_SMALL_LAUNCH(false, true) } else { PASIO_SMALL_LAUNCH(false, false) }
         }
+#undef PASIO_SMALL_LAUNCH
         return PASIO_OK;
     };
     if (serial_small) PASIO_TRY(launch_small_kernels(ctx->stream));

@@ -223,6 +223,8 @@ def _segment_runs_on_device(plan, contigs, want_lmm):
     else:
         starts = np.concatenate([[0], np.cumsum(np.concatenate([rl for rl, _ in contigs]))]).astype(np.int64)
         eng.load_rle(starts, np.concatenate([rv for _, rv in contigs]), offsets=offsets)
+    if want_lmm:
+        eng.logfac_prefetch()                     # the sequential log-factorial sums run beside the rounds
     _, splits, means, lmm, _ = run_loaded_pipeline(eng, plan, want_lmm=want_lmm)
     first_split = np.searchsorted(splits, offsets)           # every contig boundary is a split point
     assert np.array_equal(splits[first_split], offsets)

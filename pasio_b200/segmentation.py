@@ -63,9 +63,13 @@ def segment_on_device(counts, plan, want_lmm=True):
         _, factory, size, shift, constraint = steps[0][:5]
         eng.use_scorer(factory)
         first = eng.load_and_round(counts, size, shift, constraint)
+        if want_lmm:
+            eng.logfac_prefetch()                 # the sequential log-factorial sums run beside the remaining rounds
         return run_loaded_pipeline(eng, plan, want_lmm, first=first)
     eng.use_scorer(plan['factory'])
     eng.load(counts)
+    if want_lmm:
+        eng.logfac_prefetch()
     return run_loaded_pipeline(eng, plan, want_lmm)
 
 
