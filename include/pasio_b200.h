@@ -54,7 +54,8 @@ enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (defaul
        PASIO_TUNE_WINDOW_PHASES = 1,  /* 1: windows whose candidates all survived already are skipped      */
        PASIO_TUNE_EXACT_PRUNE = 2,    /* 1: whole-contig exact DP bounds far columns (csrc/exact_pruned.cu) */
        PASIO_TUNE_EXACT_LAG = 3,      /* far columns start this many 128-row blocks behind the diagonal (3 or 4) */
-       PASIO_TUNE_EXACT_RING = 4,     /* 1: self-score slabs in a 64-block ring (the layout of very long lists) even when short */
+       PASIO_TUNE_EXACT_RING = 4,     /* 1 (default): self scores in an L2-resident ring of 64 row blocks; 0: one slab per row block
+                                         while that fits 2 GB (measured slower: the slabs fall out of L2) */
        PASIO_TUNE_LOGFAC_EXACT = 5,   /* 1 (default): logfac_cumsum summed sequentially like np.cumsum (bit-identical LMM column);
                                          0: three-pass parallel scan (1e-9 relative, faster on dense coverage) */
        PASIO_TUNE_COUNT = 6 };

@@ -225,7 +225,7 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->tune[PASIO_TUNE_WINDOW_PHASES] = env_int("PASIO_WD_PHASES", 1);
     ctx->tune[PASIO_TUNE_EXACT_PRUNE] = env_int("PASIO_XD_PRUNE", 1);
     ctx->tune[PASIO_TUNE_EXACT_LAG] = env_int("PASIO_XD_LAG", 3);
-    ctx->tune[PASIO_TUNE_EXACT_RING] = env_int("PASIO_XD_RING", 0);
+    ctx->tune[PASIO_TUNE_EXACT_RING] = env_int("PASIO_XD_RING", 1);
     ctx->tune[PASIO_TUNE_LOGFAC_EXACT] = env_int("PASIO_B200_EXACT_LMM", 1);
     if (ctx->tune[PASIO_TUNE_EXACT_LAG] < 3 || ctx->tune[PASIO_TUNE_EXACT_LAG] > 4) ctx->tune[PASIO_TUNE_EXACT_LAG] = 3;
     *out = ctx;

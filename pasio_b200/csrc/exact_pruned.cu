@@ -142,7 +142,7 @@ __device__ __forceinline__ int xp_far_bound(int b, int lag) { return b >= lag - 
 
 __host__ __device__ inline size_t xp_diag_smem()
 {
-    return (size_t)XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + XP_PRING * 4 + 16;
+    return (size_t)2 * XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + XP_PRING * 4 + 16;
 }
 __host__ __device__ inline size_t xp_worker_smem()
 {
@@ -196,39 +196,53 @@ __device__ __forceinline__ XpMid xp_mid_geometry(const XpParams &p, int step, in
     g.lane_hi = (g.j < p.N) ? min(g.dhi - 1, g.j - F) : -1;      // this row's distances
     return g;
 }
-// entries u = 0 .. XP_MB-1 of a batch are the distances d, d-1, ...; outside this row's range they hold -inf and never win
+// entries u = 0 .. XP_MB-1 of a batch are the distances d, d-1, ...; outside this row's range they hold -inf and never win.
+// A batch that is valid for every lane of the warp (all but the first and the last of a sweep) is loaded without the
+// per-entry range test: the sweeping warps are bound by instruction issue, not by the loads.
 template <bool RING>
 __device__ __forceinline__ void xp_mid_load(const XpMid &g, int d, double (&v)[XP_MB])
 {
+    const double *top = g.Sb + (size_t)(d - 1) * XP_RB;              // entry u sits u * XP_RB doubles below
+    const int lo_all = __reduce_max_sync(0xffffffffu, g.lane_lo), hi_all = __reduce_min_sync(0xffffffffu, g.lane_hi);
+    if (d - (XP_MB - 1) >= lo_all && d <= hi_all) {
 #pragma unroll
-    for (int u = 0; u < XP_MB; ++u) {
-        const int dd = d - u;
-        v[u] = (dd >= g.lane_lo && dd <= g.lane_hi) ? xp_ld_s<RING>(g.Sb + (size_t)(dd - 1) * XP_RB) : -INFINITY;
-    }
-}
-// Three independent (max, first arg-max) chains over consecutive thirds of the batch, merged in column order (a later
-// column wins only when strictly greater) = the sequential first maximum.
-__device__ __forceinline__ void xp_mid_fold(const XpMid &g, int d, const double (&v)[XP_MB], const double *sP, double &best, int &arg)
-{
-    constexpr int NCH = 3;
-    double qb[NCH];
-    int qa[NCH];
+        for (int u = 0; u < XP_MB; ++u) v[u] = xp_ld_s<RING>(top - (size_t)u * XP_RB);
+    } else {
 #pragma unroll
-    for (int q = 0; q < NCH; ++q) {
-        qb[q] = -INFINITY;
-        qa[q] = 0;
-#pragma unroll
-        for (int u = q * (XP_MB / NCH); u < (q + 1) * (XP_MB / NCH); ++u) {
-            const int col = g.j - (d - u);
-            const double t = __dadd_rn(v[u], sP[col & (XP_PRING - 1)]);
-            const bool w = t > qb[q];
-            qb[q] = w ? t : qb[q];
-            qa[q] = w ? col : qa[q];
+        for (int u = 0; u < XP_MB; ++u) {
+            const int dd = d - u;
+            v[u] = (dd >= g.lane_lo && dd <= g.lane_hi) ? xp_ld_s<RING>(top - (size_t)u * XP_RB) : -INFINITY;
         }
     }
+}
+// Six independent (max, first arg-max) chains over consecutive sixths of the batch -- written interleaved, so that the
+// in-order issue finds an independent instruction every cycle -- merged in column order (a later column wins only when
+// strictly greater) = the sequential first maximum.  Column of entry u: j - d + u; its P sits at a fixed offset from
+// the first one in the mirrored ring.
+__device__ __forceinline__ void xp_mid_fold(const XpMid &g, int d, const double (&v)[XP_MB], const double *sP, double &best, int &arg)
+{
+    constexpr int NCH = 6, PER = XP_MB / NCH;
+    static_assert(XP_MB % NCH == 0, "batch must split into equal chains");
+    const int col0 = g.j - d;
+    const double *pc = sP + (col0 & (XP_PRING - 1));
+    double t[XP_MB];
+#pragma unroll
+    for (int u = 0; u < XP_MB; ++u) t[u] = __dadd_rn(v[u], pc[u]);
+    double qb[NCH];
+    int qu[NCH];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) { qb[q] = t[q * PER]; qu[q] = q * PER; }
+#pragma unroll
+    for (int k = 1; k < PER; ++k)
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            const bool w = t[q * PER + k] > qb[q];
+            qb[q] = w ? t[q * PER + k] : qb[q];
+            qu[q] = w ? q * PER + k : qu[q];
+        }
 #pragma unroll
     for (int q = 0; q < NCH; ++q)
-        if (qb[q] > best) { best = qb[q]; arg = qa[q]; }
+        if (qb[q] > best) { best = qb[q]; arg = col0 + qu[q]; }
 }
 
 // the chain warp's self-score tile of a step (distances 1..63 of its 32 rows): global -> registers, registers -> shared
@@ -257,8 +271,9 @@ __device__ __forceinline__ void xp_tile_store(const XpParams &p, int step, doubl
 template <bool AI, bool RING>
 __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
 {
-    double *sP = reinterpret_cast<double *>(smem);              // [XP_PRING] finished P, ring by column index
-    double *sS = sP + XP_PRING;                                 // [3][XP_ST][32] self-score tiles of three steps
+    double *sP = reinterpret_cast<double *>(smem);              // [2 * XP_PRING] finished P, ring by column index, every entry
+                                                                // mirrored XP_PRING further: a run of columns never wraps
+    double *sS = sP + 2 * XP_PRING;                                 // [3][XP_ST][32] self-score tiles of three steps
     double *sMidV = sS + 3 * XP_ST * 32;                        // [2][XP_HELP][32]
     double *sFarV = sMidV + 2 * XP_HELP * 32;                   // [2][128]
     int *sMidA = reinterpret_cast<int *>(sFarV + 2 * XP_RB);    // [2][XP_HELP][32]
@@ -270,6 +285,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
 
     if (tid == 0) {
         sP[0] = 0.0;                         // prefix_scores[0] = 0 (square_splitter.py:72)
+        sP[XP_PRING] = 0.0;
         __stcg(p.P, 0.0);
         __stcg(p.prev, 0);
         sScal[0] = 0.0;
@@ -363,6 +379,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             double pm = 0.0;
             if (j < N) {
                 sP[j & (XP_PRING - 1)] = mine;
+                sP[(j & (XP_PRING - 1)) + XP_PRING] = mine;
                 __stcg(p.P + j, mine);
                 __stcg(p.prev + j, arg);
                 pm = fabs(mine);
@@ -434,6 +451,8 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
                 { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
                 // the far results of the next block must have arrived: this warp waits for them, the sweeping warps fetch them
+                // (looking at the flag earlier -- every step, by this warp or by every thread -- and fetching early was
+                // measured slower: profiles/r02_exact_dp_v8_notes.txt)
                 if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
                     if (lane == 0 && !(p.dbg & 4)) {
                         while (xp_ld_flag(p.far_ready + (b + 1)) < XP_G) __nanosleep(20);
@@ -1001,8 +1020,10 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.n_tasks = (int)tasks.size();
 
     // every row block its own slab of self scores while that fits XP_LINEAR_BYTES (2 GB: N <= 680 000 at lag 3), else a ring
-    const bool ring = (size_t)p.nB * p.DB * XP_RB * 8 > XP_LINEAR_BYTES;
-    const int slots = ring ? XP_RING : p.nB;
+    // a ring of XP_RING slabs (25 MB at lag 3) stays in L2; one slab per block (307 / 614 MB for configs 1 / 3) was measured
+    // slower (profiles/r02_exact_dp_v7_*: 9.6 vs 8.9 ms): its slabs are written back to DRAM before the diagonal reads them
+    const bool ring = ctx->tune[PASIO_TUNE_EXACT_RING] != 0 || (size_t)p.nB * p.DB * XP_RB * 8 > XP_LINEAR_BYTES;
+    const int slots = ring && p.nB > XP_RING ? XP_RING : p.nB;
     p.s_slots = slots;
     const size_t ring_bytes = (size_t)slots * p.DB * XP_RB * 8;
     const size_t far_bytes = (size_t)XP_G * XP_RB * p.nB * 12;
@@ -1047,10 +1068,6 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     xp_consts_kernel<AI><<<1, 1, 0, ctx->stream>>>(p.L, p.C, p.N, p.gtab, p.ltab, p.alpha_int, p.alpha, consts);
     const size_t smem = xp_diag_smem() > xp_worker_smem() ? xp_diag_smem() : xp_worker_smem();
     void (*kern)(XpParams) = ring ? exact_pruned_kernel<AI, true> : exact_pruned_kernel<AI, false>;
-    if (ctx->tune[PASIO_TUNE_EXACT_RING] && p.nB > XP_RING) {                // (tests: exercise the ring on short lists)
-        kern = exact_pruned_kernel<AI, true>;
-        p.s_slots = XP_RING;
-    }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XP_THREADS, smem));

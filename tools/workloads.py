@@ -154,7 +154,7 @@ if __name__ == '__main__':
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--contigs', type=int, default=100000)
     ap.add_argument('--prune', type=int, default=1, help='exact DP: 1 = bounded far columns (default), 0 = every cell')
-    ap.add_argument('--ring', type=int, default=0, help='exact DP: 1 = self scores in the ring layout of very long lists')
+    ap.add_argument('--ring', type=int, default=1, help='exact DP: 1 = self scores in the ring layout of very long lists')
     ap.add_argument('--lag', type=int, default=3, help='exact DP: far columns start this many blocks behind (3 or 4)')
     a = ap.parse_args()
     if a.what == 'exact1':
