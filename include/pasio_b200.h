@@ -58,7 +58,10 @@ enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (defaul
                                          while that fits 2 GB (measured slower: the slabs fall out of L2) */
        PASIO_TUNE_LOGFAC_EXACT = 5,   /* 1 (default): logfac_cumsum summed sequentially like np.cumsum (bit-identical LMM column);
                                          0: three-pass parallel scan (1e-9 relative, faster on dense coverage) */
-       PASIO_TUNE_COUNT = 6 };
+       PASIO_TUNE_WINDOW_SPECULATE = 6, /* 1 (default): window DP first resolves a 32-row block assuming every row's arg-max is the
+                                         row before it (true for nearly all rows of the later rounds), verifies, and falls
+                                         back to the ordinary chain where the assumption fails */
+       PASIO_TUNE_COUNT = 7 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int pasio_ctx_create(int device, pasio_ctx **out);

@@ -17,7 +17,8 @@ OK = 0
 E_CUDA, E_ARG, E_COUNTS, E_CANDIDATES, E_TABLE_TOO_SHORT, E_STATE, E_TOO_LARGE, E_NOMEM = range(-1, -9, -1)
 TAB_LOG, TAB_LGAMMA, TAB_LGAMMA_ALPHA = 0, 1, 2
 CONSTRAINTS = {'none': 0, 'zeros': 1, 'constants': 2}
-TUNE = {'window_prune': 0, 'window_phases': 1, 'exact_prune': 2, 'exact_lag': 3, 'exact_ring': 4, 'logfac_exact': 5}
+TUNE = {'window_prune': 0, 'window_phases': 1, 'exact_prune': 2, 'exact_lag': 3, 'exact_ring': 4, 'logfac_exact': 5,
+        'window_speculate': 6}
 TIMING_FAMILIES = ['scan', 'window_dp', 'compact', 'exact_dp', 'score', 'h2d', 'd2h']
 
 _i64 = ctypes.c_int64
@@ -162,6 +163,8 @@ class Engine(object):
         self._tables = {}            # table id -> (computer object, uploaded length)
         self._scorer_source = None   # object providing the three computers
         self._loaded = None          # strong ref to the loaded counts array (identity cache)
+        self._loaded_print = None    # its sampled content fingerprint
+        self._cands_print = None
         self._loaded_offsets = None
         self._cands_obj = None       # array object the device candidates correspond to (identity cache)
         self._pool = _PinnedPool(self.lib)
@@ -225,9 +228,21 @@ class Engine(object):
             self._grow_tables()
 
     # -- contig ------------------------------------------------------------------------------
+    @staticmethod
+    def _fingerprint(arr):
+        """cheap content check behind the identity caches: length, both ends and a strided sample of <= 4096 elements.
+        (The reference recomputes from the array on every call; an array mutated in place between calls is re-uploaded
+        if the sample sees the change -- callers that mutate loaded arrays should call invalidate().)"""
+        n = len(arr)
+        if n == 0:
+            return (0,)
+        step = max(1, n // 4096)
+        return (n, int(arr[0]), int(arr[-1]), int(np.asarray(arr[::step]).sum()))
+
     def load(self, counts, offsets=None):
-        """H2D + prefix scan + change-point bitmap; cached by array identity."""
-        if self._loaded is counts and offsets is None and self._loaded_offsets is None:
+        """H2D + prefix scan + change-point bitmap; cached by array identity (+ a sampled content fingerprint)."""
+        if (self._loaded is counts and offsets is None and self._loaded_offsets is None
+                and self._loaded_print == self._fingerprint(counts)):
             return
         assert isinstance(counts, np.ndarray)
         assert counts.dtype == int
@@ -243,6 +258,7 @@ class Engine(object):
                                             len(off) - 1)
         self._check(rc)
         self._loaded = counts
+        self._loaded_print = self._fingerprint(counts)
         self._loaded_offsets = None if offsets is None else np.array(offsets, dtype=np.int64)
 
     def load_and_round(self, counts, window_size, window_shift, constraint):
@@ -261,6 +277,7 @@ class Engine(object):
         if rc != E_TABLE_TOO_SHORT:
             self._check(rc)
         self._loaded = counts
+        self._loaded_print = self._fingerprint(counts)
         self._loaded_offsets = None
         if rc == E_TABLE_TOO_SHORT:          # the contig is loaded; longer tables, then the round on its own
             self._grow_tables()
@@ -321,12 +338,13 @@ class Engine(object):
             self._check(self.lib.pasio_candidates_set(self.ctx, None, 0))
             self._cands_obj = None
             return
-        if self._cands_obj is cands:
+        if self._cands_obj is cands and self._cands_print == self._fingerprint(cands):
             return
         c = np.ascontiguousarray(cands, dtype=np.int64)
         self._cands_obj = None
         self._check(self.lib.pasio_candidates_set(self.ctx, _ptr(c, ctypes.c_int64), len(c)))
         self._cands_obj = cands
+        self._cands_print = self._fingerprint(cands)
 
     def candidates(self):
         m = _i64(0)
@@ -334,6 +352,7 @@ class Engine(object):
         out = self._pool.empty(m.value, np.int64)
         self._check(self.lib.pasio_candidates_download(self.ctx, _ptr(out, ctypes.c_int64), len(out), None))
         self._cands_obj = out
+        self._cands_print = self._fingerprint(out)
         return out
 
     def candidate_count(self):
@@ -397,8 +416,18 @@ class Engine(object):
                 break       # fixed point reached inside the library
         return sizes, self.candidate_count(), cells_total
 
+    def _check_exact_limits(self):
+        """The whole-contig DP indexes the lgamma table with the contig's TOTAL count (+ alpha) in 32 bits and needs the
+        table up to there: refuse clearly before any multi-GB table is built.  (The default rounds pipeline has no such
+        limit: its tables only reach the largest count inside one window.)"""
+        n, total, _ = self.info()
+        if total + (self._params[1] if self._params else 0) >= 2 ** 31 - 2:
+            raise PasioDeviceError('pasio_b200: the exact SquareSplitter DP over a whole contig needs the total count (%d) below '
+                                   '2^31; use the default `rounds` algorithm for deep-coverage contigs' % total)
+
     def square_split(self, want_arrays=False):
         """Exact DP over the current candidates; they are replaced by the splits."""
+        self._check_exact_limits()
         m = self.candidate_count()
         splits = np.empty(m, dtype=np.int64)
         n_splits, score = _i64(0), ctypes.c_double(0.0)
@@ -411,12 +440,14 @@ class Engine(object):
             _ptr(prev, ctypes.c_int64) if want_arrays else None))
         out = splits[:n_splits.value].copy()
         self._cands_obj = out
+        self._cands_print = self._fingerprint(out)
         if want_arrays:
             return np.float64(score.value), out, P, prev
         return np.float64(score.value), out
 
     def square_split_regularized(self, length_penalty=None, split_number_penalty=None, first_column_refund=0.0):
         """split_with_normalizations over the current candidates on the device; penalty tables as in include/pasio_b200.h"""
+        self._check_exact_limits()
         m = self.candidate_count()
         splits = np.empty(m, dtype=np.int64)
         n_splits, score = _i64(0), ctypes.c_double(0.0)
@@ -429,6 +460,7 @@ class Engine(object):
             _ptr(splits, ctypes.c_int64), m, ctypes.byref(n_splits), ctypes.byref(score), None, None))
         out = splits[:n_splits.value].copy()
         self._cands_obj = out
+        self._cands_print = self._fingerprint(out)
         return np.float64(score.value), out
 
     def suffix_scores(self, stop):

@@ -232,6 +232,49 @@ __device__ __forceinline__ void block_chain(int jb, int N, ColRec *sCol, unsigne
     }
 }
 
+// The same block under the hypothesis "the first maximum of row j is column j-1" for the rows after the block's
+// first -- what the later sliding-window rounds find for nearly every row, since nearly every candidate survives.
+// Then P_j = (self(j-1, j) + P_{j-1}) + pen is a sequential sum whose dependent path is two DADDs per row instead
+// of block_chain's DADD, shuffle, DADD, compare, select; every lane still folds all columns of its row with those P
+// (off the critical path) and the warp votes whether each first maximum is where assumed.  If so, by induction over
+// the rows every P used was the true one: P and prev are what block_chain writes, bit for bit (same operations in the
+// same order).  If not, nothing is written and the caller runs block_chain.
+template <int NQ>
+__device__ __forceinline__ bool block_chain_speculative(int jb, int N, ColRec *sCol, unsigned short *sPrev16,
+                                                        const double *sPartV, const int *sPartA, const double *sTri,
+                                                        double pen, double init_best, int init_arg)
+{
+    const int lane = threadIdx.x & 31;
+    double best = init_best;
+    int arg = init_arg;
+#pragma unroll
+    for (int w = 0; w < NQ; ++w) {
+        const double v = sPartV[w * 32 + lane];
+        if (v > best) { best = v; arg = sPartA[w * 32 + lane]; }
+    }
+    const int rows = min(DP_JB, N - jb);
+    const double below = (lane >= 1 && lane < rows) ? sTri[(lane - 1) * DP_JB + lane] : 0.0;   // self(j-1, j) of my row
+    double pk = __shfl_sync(0xffffffffu, __dadd_rn(best, pen), 0);        // the block's first row depends on no other
+    double mine = pk;
+#pragma unroll 8
+    for (int k = 0; k < rows; ++k) {
+        if (lane == k) mine = pk;
+        if (lane > k) {
+            const double t = __dadd_rn(sTri[k * DP_JB + lane], pk);
+            if (t > best) { best = t; arg = jb + k; }
+        }
+        const double dn = __shfl_sync(0xffffffffu, below, (k + 1) & 31);
+        pk = __dadd_rn(__dadd_rn(dn, pk), pen);
+    }
+    const bool as_assumed = lane == 0 || lane >= rows || arg == jb + lane - 1;
+    if (!__all_sync(0xffffffffu, as_assumed)) return false;
+    if (lane < rows) {
+        sCol[jb + lane].P = mine;
+        sPrev16[jb + lane] = (unsigned short)arg;
+    }
+    return true;
+}
+
 // One full block step: rectangle over [col0, jb), triangle, chain.  Requires col0 <= jb and
 // blockDim.x == NW*32.  Ends with a __syncthreads().
 template <bool AI, int NW, int U, int RPL>

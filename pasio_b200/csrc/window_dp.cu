@@ -93,6 +93,7 @@ struct WinDpParams {
     unsigned char *done_flags;  // [list_len], index = window number - w_begin
     int p1_stride;
     int skip_covered;           // 0: phase-2 windows neither wait nor get skipped (experiments)
+    int speculate;              // CTA kernel: try block_chain_speculative first (PASIO_TUNE_WINDOW_SPECULATE)
     int n_lg;                   // warp-per-window kernels with the log table in shared memory: entries copied
 };
 
@@ -636,6 +637,7 @@ window_dp_kernel(WinDpParams p)
             //   phase X(k): warp 0 turns block k-1 into a column block and prepares the row bounds of block k+1;
             //               warps 1..7 sweep the nearest 32 columns and the triangle of block k
             //   phase Y(k): warp 0 merges and resolves the chain of block k; warps 1..7 run the far pass of block k+1
+            int spec_wait = 0, spec_back = 1;       // warp 0: blocks to sit out before speculating again, and the next back-off
             if (warp == 0) prepare_rows(jb);
             __syncthreads();
             if (warp > 0) {
@@ -667,8 +669,19 @@ window_dp_kernel(WinDpParams p)
                         const int a = sFarA[(buf * WD_FARW + w2) * 32 + lane];
                         if (v > fbest || (v == fbest && a < farg)) { fbest = v; farg = a; }
                     }
-                    block_chain<NEAR_Q>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen,
-                                        jb + lane < N ? fbest : -INFINITY, jb + lane < N ? farg : 0, 0, nullptr);
+                    const double ib = jb + lane < N ? fbest : -INFINITY;
+                    const int ia = jb + lane < N ? farg : 0;
+                    // speculate unless it just failed: a failure costs a fifth of a chain, so back off (1, 2, 4, ... 16
+                    // blocks) where candidates are still being dropped and return to it where they are not
+                    bool resolved = false;
+                    if (p.speculate && spec_wait == 0) {
+                        resolved = block_chain_speculative<NEAR_Q>(jb, N, sCol, sPrev, sPartV, sPartA, sTri, p.pen, ib, ia);
+                        if (resolved) spec_back = 1;
+                        else { spec_wait = spec_back; spec_back = min(spec_back * 2, 16); }
+                    } else if (spec_wait > 0) {
+                        --spec_wait;
+                    }
+                    if (!resolved) block_chain<NEAR_Q>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen, ib, ia, 0, nullptr);
                 } else if (jb + DP_JB < N) {
                     skipped += far_pass<AI>(jb + DP_JB, N, k, sCol, sCoarse, sRow, sScal[4], sList, sList + capr, sListCount,
                                             sFarV + ((buf ^ 1) * WD_FARW + warp - 1) * 32,
@@ -942,6 +955,7 @@ int launch_window_dp(pasio_ctx *ctx, i64 nwin, int wsize, int wshift, int constr
     p.list_len = nwin;
     p.n_p1 = use_lists ? ctx->n_large_p1 : n_large;
     p.skip_covered = phase_env;                                       // PASIO_WD_PHASES=0 (experiments): no window is skipped
+    p.speculate = ctx->tune[PASIO_TUNE_WINDOW_SPECULATE];
     p.done_flags = ctx->win_flags.as<unsigned char>();
     p.p1_stride = wshift > 0 && wsize / wshift > 1 ? wsize / wshift : 1;
     if (!use_lists) p.skip_covered = 0;

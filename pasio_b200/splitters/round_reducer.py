@@ -9,7 +9,7 @@ import numpy as np
 from .. import _native
 from ..logging import logger, logging_filter
 from . import _fusion
-from .sliding_window_reducer import _set_candidates
+from .sliding_window_reducer import _set_candidates, _has_both_ends
 
 
 class RoundReducer(object):
@@ -19,7 +19,9 @@ class RoundReducer(object):
 
     def reduce_candidate_list(self, counts, split_candidates):
         plan = _fusion.rounds_plan(self)
-        if plan is not None and isinstance(counts, np.ndarray):
+        # (a candidate list without both ends is legal in the reference -- 0 and len(counts) are simply added to the
+        # result -- but not for the fused device loop: those lists take the object route below)
+        if plan is not None and isinstance(counts, np.ndarray) and _has_both_ends(split_candidates, counts):
             factory, size, shift, constraint, num_rounds = plan
             eng = _native.engine()
             eng.use_scorer(factory)

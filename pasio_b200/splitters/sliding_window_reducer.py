@@ -26,7 +26,9 @@ class SlidingWindowReducer(object):
 
     def reduce_candidate_list(self, counts, split_candidates):
         plan = _fusion.window_plan(self)
-        if plan is not None and isinstance(counts, np.ndarray):
+        # (a candidate list without both ends is legal in the reference -- 0 and len(counts) are simply added to the
+        # result -- but not for the fused device loop: those lists take the object route below)
+        if plan is not None and isinstance(counts, np.ndarray) and _has_both_ends(split_candidates, counts):
             factory, size, shift, constraint = plan
             eng = _native.engine()
             eng.use_scorer(factory)
@@ -43,6 +45,10 @@ class SlidingWindowReducer(object):
                 100 * completion, len(candidates_in_window), len(reduced)))
         logging_filter.remove_from_context('window')
         return np.array(sorted(survivors))
+
+
+def _has_both_ends(split_candidates, counts):
+    return len(split_candidates) >= 2 and split_candidates[0] == 0 and split_candidates[-1] == len(counts)
 
 
 def _set_candidates(eng, counts, split_candidates):

@@ -541,6 +541,53 @@ def test_window_prune_switch_gives_identical_rounds():
     assert sum(a[3] for a in per_round[1]) > 0
 
 
+def test_window_speculation_switch_gives_identical_rounds():
+    """the speculative block resolution of the window kernel (assume arg-max = previous row, verify, else the ordinary
+    chain) writes the same P and prev: every round of a bench-like contig gives the same candidates with it on and off,
+    and the oracle agrees with the final list"""
+    from pasio_b200 import _native
+    from pasio_b200.log_marginal_likelyhood import ScorerFactory
+    eng = _native.engine()
+    eng.use_scorer(ScorerFactory(1.0, 1.0))
+    counts = synth.dnase_like(20000000, 1000)
+    eng.invalidate()
+    eng.load(counts)
+    per_round = {}
+    try:
+        for spec in (1, 0):
+            eng.set_tuning('window_speculate', spec)
+            eng.set_candidates(None)
+            rounds = []
+            while True:
+                n_in, n_out, cells = eng.round(2500, 1250, 'constants')
+                rounds.append((n_in, n_out, cells, eng.candidates().copy()))
+                if n_in == n_out:
+                    break
+            per_round[spec] = rounds
+    finally:
+        eng.set_tuning('window_speculate', 1)
+    assert len(per_round[0]) == len(per_round[1]) and len(per_round[1]) >= 4
+    for a, b in zip(per_round[1], per_round[0]):
+        assert a[:3] == b[:3] and np.array_equal(a[3], b[3])
+    # a real alpha takes the other template instance
+    eng.use_scorer(ScorerFactory(0.75, 1.5))
+    small = synth.dnase_like(3000000, 7)
+    eng.invalidate()
+    eng.load(small)
+    finals = {}
+    try:
+        for spec in (1, 0):
+            eng.set_tuning('window_speculate', spec)
+            eng.set_candidates(None)
+            eng.rounds(2500, 1250, 'constants')
+            finals[spec] = eng.candidates().copy()
+    finally:
+        eng.set_tuning('window_speculate', 1)
+    assert np.array_equal(finals[0], finals[1])
+    want, _, _ = c_oracle.FlatOracle(small, 0.75, 1.5, threads=8).rounds(2500, 1250, 'constants')
+    assert np.array_equal(finals[1], want)
+
+
 def test_logfac_exact_and_parallel_modes():
     """logfac_cumsum: the default reproduces np.cumsum's sequential float64 sum bit for bit (sparse and dense coverage, a
     batch of contigs: every contig's sum restarts at 0); PASIO_TUNE_LOGFAC_EXACT = 0 (parallel scan) agrees to 1e-9"""
@@ -584,3 +631,44 @@ def test_logfac_exact_and_parallel_modes():
         local = splits[(splits >= offsets[k]) & (splits <= offsets[k + 1])] - offsets[k]
         want.append(po.Scorer(part, local, t).log_marginal_likelyhoods())
     assert np.array_equal(lmm, np.concatenate(want))
+
+
+def test_reducer_accepts_candidates_without_the_ends():
+    """the reference's SlidingWindowReducer takes any ascending candidate list and adds 0 and len(counts) to the result
+    (sliding_window_reducer.py:22); the fused device loop needs both ends, so such lists take the object route"""
+    counts = synth.dnase_like(5000, 3, hotspot_share=0.5)
+    cands = np.arange(5001)[7:-9:3]
+    factory = ScorerFactory(1.0, 1.0)
+    base = ReducerCombiner(NotConstantReducer(), SquareSplitter(factory))
+    swr = SlidingWindowReducer(SlidingWindow(100, 50), base)
+    got = swr.reduce_candidate_list(counts, cands)
+    want = po.sliding_window_round(counts, cands, po.Tables(1, 1.0), 100, 50, 'constants')
+    assert np.array_equal(got, want) and got[0] == 0 and got[-1] == 5000
+
+
+def test_mutated_arrays_are_not_served_from_the_identity_cache():
+    """the engine caches the loaded contig / candidates by array identity; an array changed in place between calls (the
+    reference recomputes from the array every time) is detected by the sampled fingerprint and uploaded again"""
+    counts = synth.dnase_like(20000, 8, hotspot_share=0.5)
+    factory = ScorerFactory(1.0, 1.0)
+    sq = SquareSplitter(factory)
+    cands = np.arange(0, 20001, 40)
+    a = sq.split(counts, cands)
+    counts[:] = synth.dnase_like(20000, 9, hotspot_share=0.5)          # same object, new content
+    b = sq.split(counts, cands)
+    o = po.square_split(counts, cands, po.Tables(1, 1.0))
+    assert b[0] == o[0] and np.array_equal(b[1], o[1])
+    assert a[0] != b[0]
+    cands[1:-1] += 1                                                   # same candidate object, new content
+    c = sq.split(counts, cands)
+    o = po.square_split(counts, cands, po.Tables(1, 1.0))
+    assert c[0] == o[0] and np.array_equal(c[1], o[1])
+
+
+def test_exact_dp_refuses_deep_coverage_clearly():
+    """the whole-contig DP indexes the lgamma table with the contig's total count in 32 bits: refused with a clear message
+    before any table is built (the default rounds pipeline handles such contigs, test_deep_coverage_total_beyond_int32)"""
+    from pasio_b200 import _native
+    counts = np.full(3000000, 1000, dtype=np.int64)                    # total 3e9 > 2^31
+    with pytest.raises(_native.PasioDeviceError, match='2\\^31'):
+        SquareSplitter(ScorerFactory(1.0, 1.0)).split(counts, np.array([0, 1000000, 3000000]))

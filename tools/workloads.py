@@ -45,7 +45,7 @@ def exact(args, which):
         score, splits = eng.square_split()
         wall = time.perf_counter() - t0
         times.append((wall, eng.timing()['exact_dp'][0]))
-    wall, kern = min(times[1:])
+    wall, kern = min(times[1:] if len(times) > 1 else times)
     cells = N * (N - 1) // 2
     _, skipped = eng.round_stats()
     peak = 148 * 64 * 1.965e9
