@@ -19,152 +19,154 @@ __device__ __forceinline__ u64 pack_state(u64 flag, i64 v) { return (flag << 62)
 __device__ __forceinline__ u64 ld_state(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
 __device__ __forceinline__ void st_state(u64 *p, u64 v) { *reinterpret_cast<volatile u64 *>(p) = v; }
 
-constexpr int SCAN_PER_THREAD = SCAN_TILE / SCAN_THREADS;          // 16 consecutive elements per thread
-// element e of the tile lives at e + 2 * (e / 16) in shared memory: a thread's 16 elements are 8 aligned 16-byte pairs,
-// and the 144-byte stride between threads spreads them over the banks
-__device__ __forceinline__ int scan_slot(int e) { return e + 2 * (e >> 4); }
+__device__ __forceinline__ u64 spread_bits(unsigned x)   // bit k of x -> bit 2k
+{
+    u64 v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
 
-// The tile is read with fully coalesced 512-byte warp accesses, transposed through shared memory so that every thread
-// owns 16 CONSECUTIVE elements (a local running sum, the change-point tests and the sign / maximum checks are then a
-// dozen instructions per element instead of the per-slab warp scans of the first version, which made the kernel
-// issue-bound: profiles/r02_window_dp_scan_ncu_full_bench_chr1.txt, 92 instructions per element, 49 % of the copy
-// peak), scanned across threads once per tile, and written back the same coalesced way.  cg[p] is the EXCLUSIVE prefix
-// at p, so the (cg[2m], cg[2m+1]) pair is an aligned 16-byte store.
-__global__ void __launch_bounds__(SCAN_THREADS, 3)
+// Each warp owns SCAN_WARP_ELEMS consecutive elements: SCAN_SLABS slabs of 32 lanes x one 16-byte pair, so every load
+// and store instruction of a warp is one fully coalesced 512-byte access.  cg[p] is the EXCLUSIVE
+// prefix at p, which makes the (cg[2m], cg[2m+1]) pair an aligned 16-byte store.  The change-point
+// bits of a slab come from two ballots interleaved into one 64-bit word.
+__global__ void __launch_bounds__(SCAN_THREADS)
 scan_counts_kernel(const i64 *__restrict__ counts, i64 n, i64 *__restrict__ cg,
                    u64 *__restrict__ cpwords, u64 *tile_state, unsigned *tile_counter, i64 first_tile, i64 n_tiles,
                    i64 *scalars /* [0]=total, [1]=negative seen, [2]=largest count */)
 {
-    __shared__ __align__(16) i64 sbuf[SCAN_TILE + 2 * (SCAN_TILE / 16)];
     __shared__ unsigned s_tile;
     __shared__ i64 s_warp[SCAN_THREADS / 32];
     __shared__ i64 s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // Persistent CTAs (one resident wave) take tile numbers from a per-launch counter: tiles start in issue order, so the
-    // look-back never waits on an unscheduled tile.
+    // look-back never waits on an unscheduled tile, and a chr1-sized contig is 60 000 tiles but only a few hundred CTAs
+    // (the CTA launch rate, not HBM, bounded the one-tile-per-CTA version: profiles/r02_scan_*).
     while (true) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-        __syncthreads();
-        if ((i64)s_tile >= n_tiles) break;
-        const i64 tile = first_tile + s_tile;
-        const i64 tbase = tile * SCAN_TILE;
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    if ((i64)s_tile >= n_tiles) break;
+    const i64 tile = first_tile + s_tile;
+    const i64 wbase = tile * SCAN_TILE + (i64)warp * SCAN_WARP_ELEMS;     // first element of this warp's chunk
 
-        // ---- coalesced load -> shared memory (warp w: elements [512w, 512w + 512), 8 slabs of 32 lanes x one pair) ----
+    i64 v0[SCAN_SLABS], v1[SCAN_SLABS];
+    bool neg = false;
+    i64 vmax = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_SLABS; ++k) {
+        const i64 e = wbase + 64 * k + 2 * lane;
+        if (e + 1 < n) {
+            const longlong2 t = __ldg(reinterpret_cast<const longlong2 *>(counts + e));
+            v0[k] = t.x;
+            v1[k] = t.y;
+        } else {
+            v0[k] = (e < n) ? __ldg(counts + e) : 0;
+            v1[k] = 0;
+        }
+        neg |= (v0[k] < 0) | (v1[k] < 0);
+        vmax = max(vmax, max(v0[k], v1[k]));
+    }
+    if (neg) scalars[1] = 1;
+    // largest count (the log-factorial table must reach it): one atomic per warp, and only when it raises the maximum
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    if (lane == 0 && vmax > *reinterpret_cast<volatile i64 *>(scalars + 2)) atomicMax(reinterpret_cast<long long *>(scalars + 2), vmax);
+
+    // change-point words: position p flagged when counts[p-1] != counts[p], 1 <= p <= n-1
+    {
+        i64 carry = (wbase > 0 && wbase - 1 < n) ? __ldg(counts + wbase - 1) : 0;   // element before the chunk
+        u64 word[SCAN_SLABS];
 #pragma unroll
         for (int k = 0; k < SCAN_SLABS; ++k) {
-            const int e = warp * SCAN_WARP_ELEMS + 64 * k + 2 * lane;
-            const i64 g = tbase + e;
-            longlong2 t = make_longlong2(0, 0);
-            if (g + 1 < n) t = __ldg(reinterpret_cast<const longlong2 *>(counts + g));
-            else if (g < n) t.x = __ldg(counts + g);
-            *reinterpret_cast<longlong2 *>(sbuf + scan_slot(e)) = t;
+            const i64 e = wbase + 64 * k + 2 * lane;
+            i64 before = __shfl_up_sync(0xffffffffu, v1[k], 1);
+            if (lane == 0) before = carry;
+            const bool f0 = (e >= 1) && (e <= n - 1) && (v0[k] != before);
+            const bool f1 = (e + 1 <= n - 1) && (v1[k] != v0[k]);
+            const unsigned b0 = __ballot_sync(0xffffffffu, f0);
+            const unsigned b1 = __ballot_sync(0xffffffffu, f1);
+            word[k] = spread_bits(b0) | (spread_bits(b1) << 1);
+            carry = __shfl_sync(0xffffffffu, v1[k], 31);
         }
-        const i64 before_tile = (tid == 0 && tbase > 0 && tbase - 1 < n) ? __ldg(counts + tbase - 1) : 0;
-        __syncthreads();
+        u64 mine = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_SLABS; ++k)
+            if (lane == k) mine = word[k];
+        if (lane < SCAN_SLABS && wbase + 64 * lane <= n) cpwords[(wbase >> 6) + lane] = mine;
+    }
 
-        // ---- 16 consecutive elements per thread ----
-        const int e0 = tid * SCAN_PER_THREAD;
-        const i64 p0 = tbase + e0;                      // position of this thread's first element
-        i64 v[SCAN_PER_THREAD];
+    // warp-level inclusive scans of the pair sums, slab by slab
+    i64 ex[SCAN_SLABS];
+    i64 run = 0;
 #pragma unroll
-        for (int q = 0; q < SCAN_PER_THREAD / 2; ++q) {
-            const longlong2 t = *reinterpret_cast<const longlong2 *>(sbuf + scan_slot(e0) + 2 * q);
-            v[2 * q] = t.x;
-            v[2 * q + 1] = t.y;
-        }
-        i64 prev = __shfl_up_sync(0xffffffffu, v[SCAN_PER_THREAD - 1], 1);
-        if (lane == 0) prev = tid == 0 ? before_tile : sbuf[scan_slot(e0 - 1)];
-        i64 run = 0, any = 0, vmax = 0;
-        unsigned bits = 0;
-#pragma unroll
-        for (int k = 0; k < SCAN_PER_THREAD; ++k) {
-            const i64 p = p0 + k;
-            // change point at p: counts[p-1] != counts[p], 1 <= p <= n-1 (constants_reducer.py:16-17)
-            if (v[k] != prev && p >= 1 && p <= n - 1) bits |= 1u << k;
-            prev = v[k];
-            any |= v[k];
-            vmax = max(vmax, v[k]);
-            const i64 x = v[k];
-            v[k] = run;                                 // exclusive prefix inside the thread
-            run += x;
-        }
-        if (any < 0) scalars[1] = 1;                    // a negative count sets the sign bit of the OR
-        // largest count (the log-factorial table must reach it): one atomic per warp, and only when it raises the maximum
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-        if (lane == 0 && vmax > *reinterpret_cast<volatile i64 *>(scalars + 2)) atomicMax(reinterpret_cast<long long *>(scalars + 2), vmax);
-        // change-point words: four threads per 64-bit word
-        {
-            u64 w = (u64)bits << (16 * (lane & 3));
-            w |= __shfl_xor_sync(0xffffffffu, w, 1);
-            w |= __shfl_xor_sync(0xffffffffu, w, 2);
-            if ((lane & 3) == 0 && p0 <= n) cpwords[p0 >> 6] = w;
-        }
-        // scan of the thread totals over the warp, then over the CTA
-        i64 incl = run;
+    for (int k = 0; k < SCAN_SLABS; ++k) {
+        const i64 pair = v0[k] + v1[k];
+        i64 incl = pair;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const i64 o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        i64 warp_off = 0, aggregate = 0;
+        ex[k] = run + incl - pair;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_warp[warp] = run;
+    __syncthreads();
+    i64 warp_off = 0, aggregate = 0;
 #pragma unroll
-        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-            const i64 t = s_warp[w];
-            if (w < warp) warp_off += t;
-            aggregate += t;
-        }
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        const i64 t = s_warp[w];
+        if (w < warp) warp_off += t;
+        aggregate += t;
+    }
 
-        // decoupled look-back over predecessor tiles (warp 0)
-        if (warp == 0) {
-            i64 running = 0;
-            if (tile > 0) {
-                if (lane == 0) st_state(tile_state + tile, pack_state(1, aggregate));
-                i64 look = tile - 1;
-                while (true) {
-                    const i64 idx = look - lane;
-                    u64 st;
-                    do {
-                        st = (idx >= 0) ? ld_state(tile_state + idx) : pack_state(2, 0);
-                    } while (__any_sync(0xffffffffu, (st >> 62) == 0));
-                    const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-                    const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
-                    i64 val = (lane <= stop) ? (i64)(st & 0x3fffffffffffffffull) : 0;
+    // decoupled look-back over predecessor tiles (warp 0)
+    if (warp == 0) {
+        i64 running = 0;
+        if (tile > 0) {
+            if (lane == 0) st_state(tile_state + tile, pack_state(1, aggregate));
+            i64 look = tile - 1;
+            while (true) {
+                const i64 idx = look - lane;
+                u64 st;
+                do {
+                    st = (idx >= 0) ? ld_state(tile_state + idx) : pack_state(2, 0);
+                } while (__any_sync(0xffffffffu, (st >> 62) == 0));
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                const int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+                i64 val = (lane <= stop) ? (i64)(st & 0x3fffffffffffffffull) : 0;
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                    running += val;
-                    if (has_prefix) break;
-                    look -= 32;
-                }
-            }
-            if (lane == 0) {
-                st_state(tile_state + tile, pack_state(2, running + aggregate));
-                s_prefix = running;
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                running += val;
+                if (has_prefix) break;
+                look -= 32;
             }
         }
-        __syncthreads();
-        const i64 off = s_prefix + warp_off + incl - run;
-        // prefix sums back to shared memory (same slots: every thread rewrites its own 16), then coalesced stores
-#pragma unroll
-        for (int q = 0; q < SCAN_PER_THREAD / 2; ++q)
-            *reinterpret_cast<longlong2 *>(sbuf + scan_slot(e0) + 2 * q) = make_longlong2(off + v[2 * q], off + v[2 * q + 1]);
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < SCAN_SLABS; ++k) {
-            const int e = warp * SCAN_WARP_ELEMS + 64 * k + 2 * lane;
-            const i64 g = tbase + e;
-            const longlong2 t = *reinterpret_cast<const longlong2 *>(sbuf + scan_slot(e));
-            if (g + 1 <= n) {
-                *reinterpret_cast<longlong2 *>(cg + g) = t;
-                if (g + 1 == n) scalars[0] = t.y;
-            } else if (g <= n) {
-                cg[g] = t.x;
-                if (g == n) scalars[0] = t.x;
-            }
+        if (lane == 0) {
+            st_state(tile_state + tile, pack_state(2, running + aggregate));
+            s_prefix = running;
         }
+    }
+    __syncthreads();
+    const i64 off = s_prefix + warp_off;
+#pragma unroll
+    for (int k = 0; k < SCAN_SLABS; ++k) {
+        const i64 e = wbase + 64 * k + 2 * lane;
+        const i64 c0 = off + ex[k];
+        const i64 c1 = c0 + v0[k];
+        if (e + 1 <= n) {
+            *reinterpret_cast<longlong2 *>(cg + e) = make_longlong2(c0, c1);
+            if (e + 1 == n) scalars[0] = c1;
+        } else if (e <= n) {
+            cg[e] = c0;
+            if (e == n) scalars[0] = c0;
+        }
+    }
     }   // next tile
 }
 

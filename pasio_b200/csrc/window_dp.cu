@@ -104,12 +104,12 @@ __host__ __device__ inline size_t window_smem_bytes(int cap)
            + NEAR_Q * 32 * 8        // sPartV
            + DP_JB * DP_JB * 8      // sTri            (back-trace: sMark lives here, needs capr <= 8192)
            + NEAR_Q * 32 * 4        // sPartA
-           + 16 * 4                 // sMisc
+           + 24 * 4                 // sMisc (+ the list counters)
            + capr * 2               // sPrev
            + (capr / PR_CB) * sizeof(CoarseRec)   // sCoarse  (back-trace: sJump lives here, capr*2 bytes)
-           + 32 * sizeof(float4)                  // sRow: the 32 rows being bounded (lower bound, C, L as floats)
+           + 2 * 32 * sizeof(float4)              // sRow: the 32 rows being bounded (lower bound, C, L as floats), two blocks
            + capr * 2                             // sList: fine rectangles that survived both bounds (< PR_DENSE per block)
-           + (capr / PR_CB) * 2 + 16              // sDense: blocks to sweep whole
+           + 2 * ((capr / PR_CB) * 2 + 16)        // sDense: blocks to sweep whole; sSurv: blocks that survived level 1
            + 2 * WD_FARW * 32 * (8 + 4)           // sFarV, sFarA: per-warp far results of the 32 rows, double-buffered
            + 8 * 8;                 // sScal
 }
@@ -193,15 +193,17 @@ __device__ __forceinline__ double tilted_row_min(const float4 *sRow, int r0, int
 }
 
 // Far columns [1, 1 + 32*nfar) of the 32-row block starting at row jb, run by warps 1..7 while warp 0 chains the
-// block before it.  Part 1: coarse block cb is bounded by far warp cb % 7, lane cb / 7; the survivors are split into
-// 4-row x 8-column rectangles (one lane each) and what survives again goes to a shared list.  Part 2 (after a
-// barrier among the far warps): the listed rectangles are dealt round-robin and evaluated exactly, 4 in flight per
+// block before it.  Level 1: coarse block cb is bounded by far warp cb / 32, lane cb % 32 (a lane per rectangle costs a
+// warp the same for 1 or 32 rectangles, so they are packed); the survivors go to a shared list and, after a barrier among
+// the far warps, are dealt round-robin and split into 4-row x 8-column rectangles (level 2, one lane each); what
+// survives again goes to a second list.  Level 3 (after another barrier): the listed rectangles are dealt round-robin and evaluated exactly, 4 in flight per
 // warp, lane = (row of the group, column of the sub-block).  Every far warp keeps a running (max, first arg-max) for
 // all 32 rows (lane = row) and publishes it in its slice of sFarV / sFarA; far warp 0 also covers column 0, which
 // is in no block.  Returns the number of cells skipped (per lane; the caller sums).
 template <bool AI>
 __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *sCol, const CoarseRec *sCoarse,
-                                        const float4 *sRow, double lbabs, unsigned short *sList, unsigned short *sDense, int *sListCount,
+                                        const float4 *sRow, double lbabs, unsigned short *sList, unsigned short *sDense,
+                                        unsigned short *sSurv, int *sListCount /* [0] fine list, [1] dense list, [2] level-1 survivors */,
                                         double *sFarVW, int *sFarAW, double delta,
                                         const double *__restrict__ gtab, const double *__restrict__ ltab,
                                         int alpha_int, double alpha PROF_ARGS)
@@ -226,74 +228,65 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
     const int r0 = 4 * rg, r1 = min(r0 + 3, nrows - 1);
     const bool act2 = r0 < nrows;
     const int2 gF = col_lc(sCol, jb + min(r0, nrows - 1)), gL = col_lc(sCol, jb + r1);
-    const float4 myrow = sRow[lane];                        // level 1: lane = row
 
-    for (int base = 0; base < nfar; base += 32 * WD_FARW) {
-        // ---- level 1: 32 rows x 32 columns, one lane per rectangle ----
-        const int cb = base + lane * WD_FARW + w7;
-        const bool act1 = cb < nfar;
-        double a1 = 0.0, b1 = 0.0, ub1 = 0.0;
-        if (act1) {
+    // ---- level 1: 32 rows x 32 columns, one lane per rectangle, the rectangles packed into as few warps as they fill
+    // (77 blocks of a 2500-candidate window: 3 warps; the others go straight to the barrier) ----
+    for (int base = 0; base + 32 * w7 < nfar; base += 32 * WD_FARW) {
+        const int cb = base + 32 * w7 + lane;
+        bool surv1 = false;
+        if (cb < nfar) {
             const CoarseRec *rec = sCoarse + cb;
             const int4 ends = *reinterpret_cast<const int4 *>(rec);
-            a1 = rec->a;
-            b1 = rec->b;
-            ub1 = rec->mpt + tilted_box_max<AI>(rowF.y - ends.y, rowL.y - ends.x, rowF.x - ends.w, rowL.x - ends.z, a1, b1,
-                                                gtab, ltab, alpha_int, alpha);
-        }
-        // min_r (lb_r + a*C_r + b*L_r) of every rectangle of this warp: lane = row, one warp-wide integer min per rectangle
-        // (floats compare like their sign-folded bit patterns)
-        const int nact = __popc(__ballot_sync(0xffffffffu, act1));       // active lanes are 0 .. nact-1
-        const float a1f = (float)a1, b1f = (float)b1;
-        int key1 = 0;
-        for (int i = 0; i < nact; ++i) {
-            const float af = __shfl_sync(0xffffffffu, a1f, i), bf = __shfl_sync(0xffffffffu, b1f, i);
-            const float v = lane < nrows ? fmaf(af, myrow.y, fmaf(bf, myrow.z, myrow.x)) : INFINITY;
-            const int bits = __float_as_int(v);
-            const int mn = __reduce_min_sync(0xffffffffu, bits >= 0 ? bits : bits ^ 0x7fffffff);
-            if (lane == i) key1 = mn;
-        }
-        bool surv1 = false;
-        if (act1) {
-            const float m3f = __int_as_float(key1 >= 0 ? key1 : key1 ^ 0x7fffffff);
-            const double err = (lbabs + fabs(a1) * (double)rowL.y + fabs(b1) * (double)rowL.x) * 9.5367431640625e-07;   // 2^-20
-            surv1 = !(ub1 - ((double)m3f - err) + delta < 0.0);          // NaN keeps the block
+            const double a1 = rec->a, b1 = rec->b;
+            const double ub1 = rec->mpt + tilted_box_max<AI>(rowF.y - ends.y, rowL.y - ends.x, rowF.x - ends.w, rowL.x - ends.z,
+                                                             a1, b1, gtab, ltab, alpha_int, alpha);
+            // min_r (lb_r + a*C_r + b*L_r): every lane walks the 32 rows (broadcast reads of sRow)
+            const double m3 = tilted_row_min(sRow, 0, nrows - 1, a1, b1, lbabs, rowL.y, rowL.x);
+            surv1 = !(ub1 - m3 + delta < 0.0);                           // NaN keeps the block
             if (!surv1) skipped += (u64)(PR_CB * nrows);
         }
-        unsigned mask1 = __ballot_sync(0xffffffffu, surv1);
-        PROF_T(4);
-
-        // ---- level 2: a surviving block as 8 row groups x 4 sub-blocks of 8 columns, one lane per rectangle ----
-        while (mask1) {
-            const int cb1 = base + (__ffs(mask1) - 1) * WD_FARW + w7;
-            mask1 &= mask1 - 1;
-            const CoarseRec *rec = sCoarse + cb1;
-            const double a = rec->a, b = rec->b;
-            bool surv2 = false;
-            if (act2) {
-                const int i0 = 1 + PR_CB * cb1 + PR_FB * q;
-                const int2 cF = col_lc(sCol, i0), cL = col_lc(sCol, i0 + PR_FB - 1);
-                const double m2 = tilted_box_max<AI>(gF.y - cL.y, gL.y - cF.y, gF.x - cL.x, gL.x - cF.x, a, b,
-                                                     gtab, ltab, alpha_int, alpha);
-                const double m3 = tilted_row_min(sRow, r0, r1, a, b, lbabs, gL.y, gL.x);
-                surv2 = !(rec->mpt8[q] + m2 - m3 + delta < 0.0);
-                if (!surv2) skipped += (u64)(PR_FB * (r1 - r0 + 1));
-            }
-            const unsigned mask2 = __ballot_sync(0xffffffffu, surv2);
-            const int n2 = __popc(mask2);
-            if (n2 >= PR_DENSE) {
-                // most of the block is needed: the whole 32 x 32 block goes to the sweep list (its rectangles are not skipped)
-                if (act2 && !surv2) skipped -= (u64)(PR_FB * (r1 - r0 + 1));
-                if (lane == 0) sDense[atomicAdd(sListCount + 1, 1)] = (unsigned short)cb1;
-            } else if (n2) {
-                int slot = 0;
-                if (lane == 0) slot = atomicAdd(sListCount, n2);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (surv2) sList[slot + __popc(mask2 & ((1u << lane) - 1u))] = (unsigned short)((cb1 << 5) | lane);
-            }
+        const unsigned mask1 = __ballot_sync(0xffffffffu, surv1);
+        if (mask1) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(sListCount + 2, __popc(mask1));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (surv1) sSurv[slot + __popc(mask1 & ((1u << lane) - 1u))] = (unsigned short)cb;
         }
-        PROF_T(5);
     }
+    PROF_T(4);
+    asm volatile("bar.sync 1, %0;" ::"n"(WD_FARW * 32) : "memory");
+    const int nsurv = *reinterpret_cast<volatile int *>(sListCount + 2);
+
+    // ---- level 2: a surviving block as 8 row groups x 4 sub-blocks of 8 columns, one lane per rectangle; the surviving
+    // blocks are dealt round-robin to the far warps ----
+    for (int e = w7; e < nsurv; e += WD_FARW) {
+        const int cb1 = sSurv[e];
+        const CoarseRec *rec = sCoarse + cb1;
+        const double a = rec->a, b = rec->b;
+        bool surv2 = false;
+        if (act2) {
+            const int i0 = 1 + PR_CB * cb1 + PR_FB * q;
+            const int2 cF = col_lc(sCol, i0), cL = col_lc(sCol, i0 + PR_FB - 1);
+            const double m2 = tilted_box_max<AI>(gF.y - cL.y, gL.y - cF.y, gF.x - cL.x, gL.x - cF.x, a, b,
+                                                 gtab, ltab, alpha_int, alpha);
+            const double m3 = tilted_row_min(sRow, r0, r1, a, b, lbabs, gL.y, gL.x);
+            surv2 = !(rec->mpt8[q] + m2 - m3 + delta < 0.0);
+            if (!surv2) skipped += (u64)(PR_FB * (r1 - r0 + 1));
+        }
+        const unsigned mask2 = __ballot_sync(0xffffffffu, surv2);
+        const int n2 = __popc(mask2);
+        if (n2 >= PR_DENSE) {
+            // most of the block is needed: the whole 32 x 32 block goes to the sweep list (its rectangles are not skipped)
+            if (act2 && !surv2) skipped -= (u64)(PR_FB * (r1 - r0 + 1));
+            if (lane == 0) sDense[atomicAdd(sListCount + 1, 1)] = (unsigned short)cb1;
+        } else if (n2) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(sListCount, n2);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (surv2) sList[slot + __popc(mask2 & ((1u << lane) - 1u))] = (unsigned short)((cb1 << 5) | lane);
+        }
+    }
+    PROF_T(5);
     // ---- all far warps: the list is complete ----
     asm volatile("bar.sync 1, %0;" ::"n"(WD_FARW * 32) : "memory");
     const int total = *reinterpret_cast<volatile int *>(sListCount);
@@ -375,22 +368,23 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
 }
 
 // The nearest 32 columns [jb-32, jb) (all final) and the triangle self scores of the block starting at row jb,
-// by warps 1..7.  The rectangle is 16 tasks of 8 rows x 8 columns (a lane: 2 rows, 4 apart, one column; so the 32
+// by NW warps.  The rectangle is 16 tasks of 8 rows x 8 columns (a lane: 2 rows, 4 apart, one column; so the 32
 // addresses of one gather span 4+8 candidates); task t covers row group t & 3, column chunk t >> 2.  Per-chunk
 // (max, first arg-max) go to sPartV / sPartA [chunk*32 + row].
-template <bool AI>
-__device__ __forceinline__ void near_tri_farwarps(int jb, int N, const ColRec *sCol, double *sPartV, int *sPartA, double *sTri,
+template <bool AI, int NW>
+__device__ __forceinline__ void near_tri_farwarps(int w7 /* 0 .. NW-1 */, int jb, int N, const ColRec *sCol, double *sPartV,
+                                                  int *sPartA, double *sTri,
                                                   const double *__restrict__ gtab, const double *__restrict__ ltab,
                                                   int alpha_int, double alpha)
 {
-    const int lane = threadIdx.x & 31, w7 = (threadIdx.x >> 5) - 1;
+    const int lane = threadIdx.x & 31;
     const int rr = lane & 3, cc = lane >> 2;
-    constexpr int NT = (16 + WD_FARW - 1) / WD_FARW;     // tasks per warp (3)
+    constexpr int NT = (16 + NW - 1) / NW;               // tasks per warp
     double tv[NT][2];
     int tcol[NT];
 #pragma unroll
     for (int u = 0; u < NT; ++u) {
-        const int t = w7 + u * WD_FARW;
+        const int t = w7 + u * NW;
         const int grp = t & 3, qc = (t >> 2) & 3;
         tcol[u] = jb - PR_CB + qc * 8 + cc;
         const ColRec a = sCol[tcol[u]];
@@ -405,11 +399,11 @@ __device__ __forceinline__ void near_tri_farwarps(int jb, int N, const ColRec *s
     // triangle: lane = row, this warp's columns k = w7, w7+7, ...
     const int2 mt = col_lc(sCol, min(jb + lane, N - 1));
     const RowConst<AI> rt = make_row<AI>(mt.y, mt.x, alpha_int, alpha);
-    constexpr int NK = (DP_JB + WD_FARW - 1) / WD_FARW;  // 5
+    constexpr int NK = (DP_JB + NW - 1) / NW;
     double w[NK];
 #pragma unroll
     for (int kk = 0; kk < NK; ++kk) {
-        const int k = w7 + kk * WD_FARW;
+        const int k = w7 + kk * NW;
         w[kk] = 0.0;
         if (k < lane && jb + lane < N) {
             const int2 a = col_lc(sCol, jb + k);
@@ -418,7 +412,7 @@ __device__ __forceinline__ void near_tri_farwarps(int jb, int N, const ColRec *s
     }
 #pragma unroll
     for (int u = 0; u < NT; ++u) {
-        const int t = w7 + u * WD_FARW;
+        const int t = w7 + u * NW;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             double best = tv[u][k];
@@ -433,7 +427,7 @@ __device__ __forceinline__ void near_tri_farwarps(int jb, int N, const ColRec *s
     }
 #pragma unroll
     for (int kk = 0; kk < NK; ++kk) {
-        const int k = w7 + kk * WD_FARW;
+        const int k = w7 + kk * NW;
         if (k < lane && jb + lane < N) sTri[k * DP_JB + lane] = w[kk];
     }
 }
@@ -458,14 +452,14 @@ window_dp_kernel(WinDpParams p)
     double *sTri = sPartV + NEAR_Q * 32;
     int *sPartA = reinterpret_cast<int *>(sTri + DP_JB * DP_JB);
     int *sMisc = sPartA + NEAR_Q * 32;
-    unsigned short *sPrev = reinterpret_cast<unsigned short *>(sMisc + 16);
+    unsigned short *sPrev = reinterpret_cast<unsigned short *>(sMisc + 24);
     CoarseRec *sCoarse = reinterpret_cast<CoarseRec *>(sPrev + capr);   // capr*2 bytes is a multiple of 16
     float4 *sRow = reinterpret_cast<float4 *>(sCoarse + capr / PR_CB);
-    double *sFarV = reinterpret_cast<double *>(sRow + 32);              // [2][WD_FARW][32]
+    double *sFarV = reinterpret_cast<double *>(sRow + 2 * 32);          // [2][WD_FARW][32]   (sRow: [2][32], by parity of the block)
     int *sFarA = reinterpret_cast<int *>(sFarV + 2 * WD_FARW * 32);     // [2][WD_FARW][32]
-    double *sScal = reinterpret_cast<double *>(sFarA + 2 * WD_FARW * 32);   // [0] magnitude of the window's largest self score, [1] max |P|, [2], [3] tilt scales, [4] max |lb| of sRow
+    double *sScal = reinterpret_cast<double *>(sFarA + 2 * WD_FARW * 32);   // [0] magnitude of the window's largest self score, [1] max |P|, [2], [3] tilt scales, [4], [5] max |lb| of the two sRow buffers
     unsigned short *sList = reinterpret_cast<unsigned short *>(sScal + 8);
-    int *sListCount = sMisc + 12;
+    int *sListCount = sMisc + 16;                                        // [2][4], by parity of the block
     // the back-trace runs after the DP, when these are dead
     unsigned short *sJump = reinterpret_cast<unsigned short *>(sCoarse); // capr*2 bytes <= (capr/32)*80
     unsigned char *sMark = reinterpret_cast<unsigned char *>(sTri);     // capr <= 8192 bytes
@@ -492,8 +486,24 @@ window_dp_kernel(WinDpParams p)
                 const volatile unsigned char *f = p.done_flags;
                 while (!f[lo] || (hi < p.list_len && !f[hi])) __nanosleep(200);
                 __threadfence();
+                // fast path: both neighbours kept every one of their candidates (flag bit 1) and together they cover this
+                // window, so every candidate of this window is a survivor already -- no need to read them
+                i64 skip_cells = -1;
+                if (hi < p.list_len && (f[lo] & 2) && (f[hi] & 2)) {
+                    i64 s0, e0, s1, e1, s2, e2;
+                    window_range(p.geom, w, s0, e0);
+                    window_range(p.geom, p.w_begin + lo, s1, e1);
+                    window_range(p.geom, p.w_begin + hi, s2, e2);
+                    if (s1 <= s0 && e1 >= s2 && e2 >= e0) skip_cells = (e0 - s0) * (e0 - s0 - 1) / 2;
+                }
+                if (skip_cells >= 0) {
+                    atomicAdd(p.cells, (u64)skip_cells);
+                    atomicAdd(p.cells_skipped, (u64)skip_cells);
+                }
+                sMisc[1] = skip_cells >= 0;
             }
             __syncthreads();
+            if (sMisc[1]) continue;
         }
         int kept_all = 1;                           // phase 2: are all candidates of this window survivors already?
 
@@ -614,11 +624,21 @@ window_dp_kernel(WinDpParams p)
         };
         auto far_delta = [&]() { return (sScal[0] + sScal[1] + fabs(p.pen) * DP_JB) * 5.684341886080802e-14; };   // 2^-44
         // warp 0: lower bounds of the rows of block [jbn, jbn+32) for the far pass that runs next
+        // warp 0: lower bounds of the rows of block [jbn, jbn+32) for the far pass that runs one phase later, from the P of the
+        // rows before jbp (jbp = jbn - 32: the block between is still to be chained).  Buffers by parity of the block.
         auto prepare_rows = [&](int jbn) {
+            const int par = ((jbn - 1) / DP_JB) & 1;
             const double delta_path = (sScal[0] + sScal[1] + fabs(p.pen) * DP_JB) * 1.8189894035458565e-12;   // 2^-39
-            compute_row_lb<AI>(jbn - DP_JB, jbn, N, sCol, sRow, sScal + 4, delta_path, p.pen, p.gtab, p.ltab,
+            compute_row_lb<AI>(jbn - DP_JB, jbn, N, sCol, sRow + 32 * par, sScal + 4 + par, delta_path, p.pen, p.gtab, p.ltab,
                                p.alpha_int, p.alpha);
-            if (lane == 0) { sListCount[0] = 0; sListCount[1] = 0; }
+            if (lane == 0) { sListCount[4 * par] = 0; sListCount[4 * par + 1] = 0; sListCount[4 * par + 2] = 0; }
+        };
+        auto run_far = [&](int jbf) {               // warps 1..7: far pass of the block starting at row jbf
+            const int kf = (jbf - 1) / DP_JB, par = kf & 1;
+            skipped += far_pass<AI>(jbf, N, kf - 1, sCol, sCoarse, sRow + 32 * par, sScal[4 + par], sList, sList + capr,
+                                    sList + capr + capr / PR_CB + 8, sListCount + 4 * par, sFarV + (par * WD_FARW + warp - 1) * 32,
+                                    sFarA + (par * WD_FARW + warp - 1) * 32,
+                                    far_delta(), p.gtab, p.ltab, p.alpha_int, p.alpha PROF_PASS);
         };
         int jb = 1;
         // the first two blocks (and everything without pruning, and small windows, where bounding costs more than
@@ -634,27 +654,19 @@ window_dp_kernel(WinDpParams p)
         PROF_T(6);
         if (pipelined && jb < N) {
             // Software pipeline over the remaining blocks k = 2, 3, ...:
-            //   phase X(k): warp 0 turns block k-1 into a column block and prepares the row bounds of block k+1;
-            //               warps 1..7 sweep the nearest 32 columns and the triangle of block k
-            //   phase Y(k): warp 0 merges and resolves the chain of block k; warps 1..7 run the far pass of block k+1
+            //   phase X(k): all warps sweep the nearest 32 columns (block k-1) and the triangle of block k
+            //   phase Y(k): warp 0 resolves the chain of block k, turns the block into a column block and prepares the row
+            //               bounds of block k+2; warps 1..7 run the far pass of block k+1 (columns up to block k-1, row
+            //               bounds prepared one phase earlier)
             int spec_wait = 0, spec_back = 1;       // warp 0: blocks to sit out before speculating again, and the next back-off
             if (warp == 0) prepare_rows(jb);
             __syncthreads();
-            if (warp > 0) {
-                const int buf = ((jb - 1) / DP_JB) & 1;
-                skipped += far_pass<AI>(jb, N, (jb - 1) / PR_CB - 1, sCol, sCoarse, sRow, sScal[4], sList, sList + capr, sListCount,
-                                        sFarV + (buf * WD_FARW + warp - 1) * 32, sFarA + (buf * WD_FARW + warp - 1) * 32,
-                                        far_delta(), p.gtab, p.ltab, p.alpha_int, p.alpha PROF_PASS);
-            }
+            if (warp > 0) run_far(jb);
+            else if (jb + DP_JB < N) prepare_rows(jb + DP_JB);
             __syncthreads();
             for (; jb < N; jb += DP_JB) {
                 const int k = (jb - 1) / DP_JB, buf = k & 1;
-                if (warp == 0) {
-                    if (k > 2) finish_block(jb - DP_JB);
-                    if (jb + DP_JB < N) prepare_rows(jb + DP_JB);
-                } else {
-                    near_tri_farwarps<AI>(jb, N, sCol, sPartV, sPartA, sTri, p.gtab, p.ltab, p.alpha_int, p.alpha);
-                }
+                near_tri_farwarps<AI, WD_WARPS>(warp, jb, N, sCol, sPartV, sPartA, sTri, p.gtab, p.ltab, p.alpha_int, p.alpha);
                 PROF_T(1);
                 __syncthreads();
                 PROF_T(6);
@@ -682,11 +694,11 @@ window_dp_kernel(WinDpParams p)
                         --spec_wait;
                     }
                     if (!resolved) block_chain<NEAR_Q>(jb, N, sCol, sPrev, nullptr, sPartV, sPartA, sTri, p.pen, ib, ia, 0, nullptr);
+                    __syncwarp();
+                    finish_block(jb);
+                    if (jb + 2 * DP_JB < N) prepare_rows(jb + 2 * DP_JB);
                 } else if (jb + DP_JB < N) {
-                    skipped += far_pass<AI>(jb + DP_JB, N, k, sCol, sCoarse, sRow, sScal[4], sList, sList + capr, sListCount,
-                                            sFarV + ((buf ^ 1) * WD_FARW + warp - 1) * 32,
-                                            sFarA + ((buf ^ 1) * WD_FARW + warp - 1) * 32,
-                                            far_delta(), p.gtab, p.ltab, p.alpha_int, p.alpha PROF_PASS);
+                    run_far(jb + DP_JB);
                 }
                 PROF_T(2);
                 __syncthreads();
@@ -706,18 +718,21 @@ window_dp_kernel(WinDpParams p)
             __syncthreads();
             unsigned short *t = ja; ja = jb2; jb2 = t;
         }
+        int every = N == nq;                         // did every candidate of the window (none filtered) survive?
         for (int k = tid; k < N; k += WD_THREADS) {
             if (sMark[k]) {
                 const i64 pos = first + sCol[k].L;
                 atomicOr(p.keepbits + (pos >> 5), 1u << (pos & 31));
+            } else {
+                every = 0;
             }
         }
         if (!second && p.skip_covered && p.n_p1 < p.nwin) {             // phase-2 windows wait for this
             __threadfence();
-            __syncthreads();
+            every = __syncthreads_and(every);
             if (tid == 0) {
                 __threadfence();
-                *reinterpret_cast<volatile unsigned char *>(p.done_flags + (w - p.w_begin)) = 1;
+                *reinterpret_cast<volatile unsigned char *>(p.done_flags + (w - p.w_begin)) = every ? 3 : 1;
             }
         }
         if (tid == 0) atomicAdd(p.cells, (u64)N * (u64)(N - 1) / 2);
