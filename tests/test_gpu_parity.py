@@ -270,6 +270,10 @@ PRUNED_EXACT_CASES = {
     'pp_cands': lambda: (synth.piecewise_poisson(300000, 9), synth.random_candidates(300000, 25000, 9)),
     'long_segments': lambda: (np.repeat(np.random.RandomState(4).poisson(20, 12), 2500).astype(np.int64)
                               + np.random.RandomState(5).poisson(3, 30000), None),
+    # every candidate is a split point (levels far apart, candidates exactly at the steps): the dependency chains inside a
+    # 32-row block are long (the opposite of the other cases, where the arg-max is far behind the block)
+    'all_split': lambda: (np.repeat(np.arange(9000) % 2 * 400 + np.arange(9000) % 7 * 60, 5).astype(np.int64),
+                          np.arange(0, 45001, 5, dtype=np.int64)),
 }
 
 
