@@ -33,6 +33,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -55,17 +56,58 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread of this process (a sample every
+    few ms: the timed region of a short run is ~0.1 s, less than nvidia-smi needs to start on an 8-GPU box), with the
+    nvidia-smi loop of the profiling recipe as the fallback when the NVML binding is missing."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    REASON_BITS = [(0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap')]
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
+        self.uuid = uuid
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.mx = [], set(), None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for bit, name in self.REASON_BITS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            self.stop_flag.wait(0.004)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = None
+            if self.uuid:
+                for cand in (self.uuid, 'GPU-' + self.uuid):
+                    try:
+                        handle = nv.nvmlDeviceGetHandleByUUID(cand.encode() if hasattr(cand, 'encode') else cand)
+                        break
+                    except Exception:
+                        handle = None
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         fd, self.path = tempfile.mkstemp(suffix='.csv')
         os.close(fd)
         try:
@@ -77,6 +119,13 @@ class ClockSampler(object):
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.mx, reasons=sorted(self.reasons),
+                           samples=len(self.sm), source='nvml')
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -100,7 +149,8 @@ class ClockSampler(object):
                     reasons.add(name)
         os.unlink(self.path)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       source='nvidia-smi')
         return out
 
 
@@ -355,7 +405,7 @@ def run_b200(args):
         m_final, score = step_resident()
     fp64_peak_measured = eng.fp64_peak() if rank == 0 else 0.0
     eng.timing_reset(True)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, str(getattr(torch.cuda.get_device_properties(local), 'uuid', '') or ''))
     barrier(dist, torch)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -505,7 +555,7 @@ def run_b200(args):
         'kernel_ms_per_step': {k: timing[k][0] / args.steps for k in timing},
         'wall_ms_per_step': wall / args.steps * 1e3,
         'clocks': {'sm_mhz': clocks['sm_mhz'], 'sm_max_mhz': clocks['sm_max_mhz'], 'reasons': clocks['reasons'],
-                   'samples': clocks['samples']},
+                   'samples': clocks['samples'], 'source': clocks.get('source')},
         'roofline': roofline, 'cpu_baseline': cpu, 'parity': parity, 'exact_dp': exact, 'genome': genome,
     }
     print(json.dumps(line))
