@@ -455,6 +455,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_timing = eng.timing()
+    e2e_wire_bytes = int(eng.upload_stats())
     eng.timing_reset(False)
     e2e_rows = gather_rows([e2e_s * 1e3], dist, device, world)
     e2e_s = max(r[0] for r in e2e_rows) * 1e-3
@@ -547,6 +548,10 @@ def run_b200(args):
         'dp_cells_per_step': cells, 'dp_cells_per_s': cells * world / (step_ms * 1e-3),
         'window_dp_cells_per_s_kernel_only': cells / (wd_ms / args.steps * 1e-3),
         'e2e': {'value': e2e_value, 'unit': 'nt/s', 'h2d_bytes_per_step': int(n * 8),
+                'h2d_wire_bytes_per_step': e2e_wire_bytes,
+                'h2d_note': 'h2d_bytes_per_step = the int64 counts tensor handed to the API (pinned host memory); the library packs '
+                            'counts that fit 31 bits to int32 on host threads before the DMA and widens them on the device, '
+                            'h2d_wire_bytes_per_step is what crossed PCIe',
                 'd2h_bytes_per_step': int(final * 8 * 4), 'ms_per_step': e2e_s * 1e3,
                 'api': 'pasio_b200.segmentation.segment_on_device(counts_pinned_host, plan)',
                 'device_ms_per_step': {k: e2e_timing[k][0] / e2e_steps for k in e2e_timing},

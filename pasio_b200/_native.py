@@ -18,7 +18,7 @@ E_CUDA, E_ARG, E_COUNTS, E_CANDIDATES, E_TABLE_TOO_SHORT, E_STATE, E_TOO_LARGE, 
 TAB_LOG, TAB_LGAMMA, TAB_LGAMMA_ALPHA = 0, 1, 2
 CONSTRAINTS = {'none': 0, 'zeros': 1, 'constants': 2}
 TUNE = {'window_prune': 0, 'window_phases': 1, 'exact_prune': 2, 'exact_lag': 3, 'exact_ring': 4, 'logfac_exact': 5,
-        'window_speculate': 6}
+        'window_speculate': 6, 'upload_narrow': 7}
 TIMING_FAMILIES = ['scan', 'window_dp', 'compact', 'exact_dp', 'score', 'h2d', 'd2h']
 
 _i64 = ctypes.c_int64
@@ -47,6 +47,7 @@ SIGNATURES = {
     'pasio_filter_candidates': (ctypes.c_int, [_vp, ctypes.c_int, _i64p, _i64p]),
     'pasio_round': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64p, _i64p, _i64p]),
     'pasio_round_stats': (ctypes.c_int, [_vp, _i64p, _i64p]),
+    'pasio_upload_stats': (ctypes.c_int, [_vp, _i64p]),
     'pasio_set_tuning': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     'pasio_rounds': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64, _i64p, _i64p, _i64p, _i64p, _i64]),
     'pasio_square_split': (ctypes.c_int, [_vp, _i64p, _i64, _i64p, _f64p, _f64p, _i64p]),
@@ -378,6 +379,12 @@ class Engine(object):
     def set_tuning(self, key, value):
         """kernel variant switches (TUNE); results never depend on them"""
         self._check(self.lib.pasio_set_tuning(self.ctx, TUNE[key], int(value)))
+
+    def upload_stats(self):
+        """bytes the last load_and_round put on the PCIe link (half of counts.nbytes when the counts went up as int32)"""
+        b = _i64(0)
+        self._check(self.lib.pasio_upload_stats(self.ctx, ctypes.byref(b)))
+        return b.value
 
     def round_stats(self):
         """(algorithmic cells, cells skipped by the exact bound) of the most recent round"""

@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <thread>
+#include <atomic>
+#include <chrono>
+#include <memory>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -165,6 +168,149 @@ static int upload(pasio_ctx *ctx, void *dst, const void *src, size_t bytes, cuda
     return PASIO_OK;
 }
 
+// ---- narrowed upload ------------------------------------------------------------------------------
+// Coverage counts are small numbers in 8-byte slots, and a chr1-sized upload is bound by the PCIe link (2 GB at 55 GB/s =
+// 36 ms of an 80 ms end-to-end step).  Host threads therefore pack the counts to int32 into page-locked slices (reading the
+// caller's buffer -- pinned or pageable -- at memory bandwidth: 87 GB/s with 16 threads on the bench box,
+// profiles/r02_host_narrow_probe.txt), each slice is DMA'd as soon as it is packed and widened to the int64 layout the
+// kernels use by a small kernel behind the copy on the same stream.  A slice that holds a count outside [0, 2^31) goes up
+// as it is (the scan then reports negative counts as before).  Slices are handed out in order; the thread that completes
+// a chunk records the chunk's event, and the loading thread waits (host side) for that record before it makes its
+// stream wait for the event.
+__global__ void __launch_bounds__(256) widen_counts_kernel(const int4 *__restrict__ src, longlong2 *__restrict__ dst, i64 n4)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (i64)gridDim.x * blockDim.x) {
+        const int4 v = __ldg(src + i);
+        dst[2 * i] = make_longlong2(v.x, v.y);
+        dst[2 * i + 1] = make_longlong2(v.z, v.w);
+    }
+}
+
+// dst[i] = (int32) src[i]; returns the OR of all values (bits 31..63 set <=> some count is negative or >= 2^31); textio.cpp
+uint64_t pasio_narrow_slice(int32_t *dst, const int64_t *src, size_t n);
+#define narrow_slice pasio_narrow_slice
+
+namespace {
+struct NarrowUpload {
+    static constexpr size_t SLICE = (size_t)1 << 19;       // elements per slice: 4 MB of int64 -> 2 MB of int32
+    pasio_ctx *ctx = nullptr;
+    const int64_t *src = nullptr;
+    i64 n = 0, chunk_elems = 0, n_chunks = 0, n_slices = 0;
+    std::vector<std::thread> threads;
+    std::atomic<i64> next_slice{0};
+    std::atomic<int> cancel{0}, failed{0};
+    std::unique_ptr<std::atomic<int>[]> left_in_chunk, recorded;
+    std::atomic<i64> wire_bytes{0};
+    int limit_bits = 31;                                // slices whose counts all fit this many bits are narrowed
+
+    // every slice lies inside one chunk (chunk_elems is a multiple of SLICE)
+    int start(pasio_ctx *c, const int64_t *counts, i64 n_, i64 chunk_elems_, i64 n_chunks_)
+    {
+        ctx = c; src = counts; n = n_; chunk_elems = chunk_elems_; n_chunks = n_chunks_;
+        n_slices = (n + (i64)SLICE - 1) / (i64)SLICE;
+        unsigned hc = std::thread::hardware_concurrency();
+        const int T = (int)std::max(1u, std::min(16u, hc ? hc : 4u));
+        if (ctx->nstage_threads < T) {
+            if (ctx->nstage_host) { cudaFreeHost(ctx->nstage_host); ctx->nstage_host = nullptr; }
+            if (ctx->nstage_dev) { cudaFree(ctx->nstage_dev); ctx->nstage_dev = nullptr; }
+            for (cudaEvent_t e : ctx->nstage_free) cudaEventDestroy(e);
+            ctx->nstage_free.clear();
+            ctx->nstage_threads = 0;
+            if (cudaHostAlloc(&ctx->nstage_host, (size_t)T * 2 * SLICE * 4, cudaHostAllocDefault) != cudaSuccess ||
+                cudaMalloc(&ctx->nstage_dev, (size_t)T * 2 * SLICE * 4) != cudaSuccess) {
+                cudaGetLastError();
+                if (ctx->nstage_host) { cudaFreeHost(ctx->nstage_host); ctx->nstage_host = nullptr; }
+                return 1;                                   // no staging memory: the caller copies plainly
+            }
+            for (int k = 0; k < 2 * T; ++k) {
+                cudaEvent_t e;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return 1; }
+                ctx->nstage_free.push_back(e);
+            }
+            ctx->nstage_threads = T;
+        }
+        left_in_chunk.reset(new std::atomic<int>[(size_t)n_chunks]);
+        recorded.reset(new std::atomic<int>[(size_t)n_chunks]);
+        for (i64 q = 0; q < n_chunks; ++q) {
+            const i64 e0 = q * chunk_elems, e1 = std::min<i64>(n, (q + 1) * chunk_elems);
+            const i64 cnt = e1 > e0 ? (e1 - e0 + (i64)SLICE - 1) / (i64)SLICE : 0;
+            left_in_chunk[(size_t)q].store((int)cnt);
+            recorded[(size_t)q].store(0);
+            if (cnt == 0) {                                 // (a chunk past the end of the counts: only position n)
+                cudaEventRecord(ctx->chunk_events[(size_t)q], ctx->stream_copy);
+                recorded[(size_t)q].store(1, std::memory_order_release);
+            }
+        }
+        for (int t = 0; t < T; ++t) threads.emplace_back([this, t] { work(t); });
+        return 0;
+    }
+
+    void work(int t)
+    {
+        cudaSetDevice(ctx->device);
+        bool used[2] = {false, false};
+        int which = 0;
+        while (!cancel.load(std::memory_order_relaxed)) {
+            const i64 sidx = next_slice.fetch_add(1);
+            if (sidx >= n_slices) break;
+            const i64 e0 = sidx * (i64)SLICE, e1 = std::min<i64>(n, e0 + (i64)SLICE), len = e1 - e0;
+            const int buf = 2 * t + which;
+            which ^= 1;
+            int32_t *hst = (int32_t *)ctx->nstage_host + (size_t)buf * SLICE;
+            int32_t *dev = (int32_t *)ctx->nstage_dev + (size_t)buf * SLICE;
+            i64 *dst = ctx->counts.as<i64>() + e0;
+            bool ok = true;
+            if (used[buf & 1]) ok = cudaEventSynchronize(ctx->nstage_free[(size_t)buf]) == cudaSuccess;   // its last copy has left
+            const uint64_t bits = ok ? narrow_slice(hst, src + e0, (size_t)len) : 0;
+            if (ok && (bits >> limit_bits) == 0 && (len & 3) == 0) {
+                ok = cudaMemcpyAsync(dev, hst, (size_t)len * 4, cudaMemcpyHostToDevice, ctx->stream_copy) == cudaSuccess;
+                if (ok) {
+                    ok = cudaEventRecord(ctx->nstage_free[(size_t)buf], ctx->stream_copy) == cudaSuccess;
+                    used[buf & 1] = true;
+                    const i64 n4 = len / 4;
+                    widen_counts_kernel<<<(unsigned)std::min<i64>((n4 + 255) / 256, 296), 256, 0, ctx->stream_copy>>>(
+                        reinterpret_cast<const int4 *>(dev), reinterpret_cast<longlong2 *>(dst), n4);
+                    // (the next copy into `dev` is ordered behind this kernel by the stream)
+                    ok = ok && cudaGetLastError() == cudaSuccess;
+                    wire_bytes.fetch_add(len * 4);
+                }
+            } else if (ok) {
+                // a count outside [0, 2^31), or the ragged last slice: as it is
+                ok = cudaMemcpyAsync(dst, src + e0, (size_t)len * 8, cudaMemcpyHostToDevice, ctx->stream_copy) == cudaSuccess;
+                wire_bytes.fetch_add(len * 8);
+            }
+            if (!ok) { cudaGetLastError(); failed.store(1); cancel.store(1); }
+            const i64 q = e0 / chunk_elems;
+            if (left_in_chunk[(size_t)q].fetch_sub(1) == 1) {
+                // every slice of chunk q has been queued (by this or another thread, before its decrement)
+                if (cudaEventRecord(ctx->chunk_events[(size_t)q], ctx->stream_copy) != cudaSuccess) { cudaGetLastError(); failed.store(1); }
+                recorded[(size_t)q].store(1, std::memory_order_release);
+            }
+        }
+    }
+
+    // host-side wait until chunk q's event has been recorded; false if the upload failed or was cancelled
+    bool wait_recorded(i64 q)
+    {
+        while (!recorded[(size_t)q].load(std::memory_order_acquire)) {
+            if (failed.load() || cancel.load()) return false;
+            std::this_thread::sleep_for(std::chrono::microseconds(20));      // (not a spin: the packing threads want every core)
+        }
+        return !failed.load();
+    }
+
+    void finish()
+    {
+        for (auto &th : threads) th.join();
+        threads.clear();
+    }
+    ~NarrowUpload()
+    {
+        if (!threads.empty()) { cancel.store(1); finish(); }
+    }
+};
+}  // namespace
+
 static void drop_borrowed_counts(pasio_ctx *ctx)
 {
     if (ctx->counts_borrowed) { ctx->counts.p = nullptr; ctx->counts.bytes = 0; ctx->counts_borrowed = false; }
@@ -228,6 +374,7 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->tune[PASIO_TUNE_EXACT_RING] = env_int("PASIO_XD_RING", 1);
     ctx->tune[PASIO_TUNE_LOGFAC_EXACT] = env_int("PASIO_B200_EXACT_LMM", 1);
     ctx->tune[PASIO_TUNE_WINDOW_SPECULATE] = env_int("PASIO_WD_SPECULATE", 1);
+    ctx->tune[PASIO_TUNE_UPLOAD_NARROW] = env_int("PASIO_B200_UPLOAD_NARROW", 1);
     if (ctx->tune[PASIO_TUNE_EXACT_LAG] < 3 || ctx->tune[PASIO_TUNE_EXACT_LAG] > 4) ctx->tune[PASIO_TUNE_EXACT_LAG] = 3;
     *out = ctx;
     return PASIO_OK;
@@ -250,6 +397,11 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     for (int k = 0; k < 3; ++k) {
         if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+        if (k == 0) {
+            if (ctx->nstage_host) cudaFreeHost(ctx->nstage_host);
+            if (ctx->nstage_dev) cudaFree(ctx->nstage_dev);
+            for (cudaEvent_t e : ctx->nstage_free) cudaEventDestroy(e);
+        }
         if (ctx->stage_free[k]) cudaEventDestroy(ctx->stage_free[k]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -485,12 +637,34 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
         return PASIO_OK;
     };
 
+    // large loads go up narrowed to int32 by a team of host threads (NarrowUpload above) while this thread drives the GPU
+    NarrowUpload narrow;
+    std::unique_ptr<TimingScope> narrow_span;
+    bool narrow_on = false;
+    if (ctx->tune[PASIO_TUNE_UPLOAD_NARROW] && n >= ((i64)1 << 24) && (chunk_tiles * tile_elems) % (i64)NarrowUpload::SLICE == 0) {
+        narrow_span.reset(new TimingScope(ctx, TF_H2D, 1, ctx->stream_copy));
+        if (ctx->tune[PASIO_TUNE_UPLOAD_NARROW] >= 2 && ctx->tune[PASIO_TUNE_UPLOAD_NARROW] < 31) narrow.limit_bits = ctx->tune[PASIO_TUNE_UPLOAD_NARROW];   // (tests: mixes narrowed and plain slices)
+        narrow_on = narrow.start(ctx, counts, n, chunk_tiles * tile_elems, n_chunks) == 0;
+        if (!narrow_on) narrow_span.reset();
+    }
+    auto stop_upload = [&]() {                      // before any return: nothing may read the caller's buffer afterwards
+        if (narrow_on) { narrow.cancel.store(1); narrow.finish(); narrow_span.reset(); }
+    };
+
     const i64 nwin_total = (ctx->m - 1 + window_shift - 1) / window_shift;
     i64 w_done = 0;
     int table_rc = ctx->have_params ? PASIO_OK : pasio_fail(ctx, PASIO_E_STATE, "pasio_set_params has not been called");
     bool first_dp = true;
     for (i64 c = 0; c < n_chunks; ++c) {
-        PASIO_TRY(queue_copies(c + 3));
+        if (narrow_on) {
+            if (!narrow.wait_recorded(c)) {
+                stop_upload();
+                cudaStreamSynchronize(ctx->stream_copy);
+                return pasio_fail(ctx, PASIO_E_CUDA, "narrowed upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+        } else {
+            PASIO_TRY(queue_copies(c + 3));
+        }
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[(size_t)c], 0));
         const i64 t1 = std::min<i64>(n_tiles, (c + 1) * chunk_tiles);
         PASIO_TRY(launch_scan_tiles(ctx, t1 - c * chunk_tiles));
@@ -510,6 +684,7 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
             PASIO_TRY(launch_window_prepass(ctx, w_ready - w_done, (int)window_size, (int)window_shift, &max_span, &max_cnt,
                                             constraint, w_done));
             if (ctx->h_scalars[1]) {
+                stop_upload();
                 cudaStreamSynchronize(ctx->stream_copy);      // the caller's buffer must not be read after we return
                 return pasio_fail(ctx, PASIO_E_COUNTS, "counts must be >= 0");
             }
@@ -523,6 +698,17 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
             }
             w_done = w_ready;
         }
+    }
+    if (narrow_on) {
+        narrow.finish();
+        narrow_span.reset();
+        ctx->last_wire_bytes = narrow.wire_bytes.load();
+        if (narrow.failed.load()) {
+            cudaStreamSynchronize(ctx->stream_copy);
+            return pasio_fail(ctx, PASIO_E_CUDA, "narrowed upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    } else {
+        ctx->last_wire_bytes = n * 8;
     }
     PASIO_TRY(d2h(ctx, ctx->h_scalars, ctx->scalars.p, 3 * sizeof(i64)));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream_copy));
@@ -786,6 +972,13 @@ extern "C" int pasio_rounds(pasio_ctx *ctx, int64_t window_size, int64_t window_
     if (n_out) *n_out = ctx->m;
     if (cells) *cells = total_cells;
     return rc;
+}
+
+extern "C" int pasio_upload_stats(const pasio_ctx *ctx, int64_t *wire_bytes)
+{
+    if (!ctx || !wire_bytes) return PASIO_E_ARG;
+    *wire_bytes = ctx->last_wire_bytes;
+    return PASIO_OK;
 }
 
 extern "C" int pasio_round_stats(const pasio_ctx *ctx, int64_t *cells, int64_t *cells_skipped)

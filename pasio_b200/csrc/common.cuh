@@ -42,6 +42,12 @@ struct pasio_ctx {
     cudaEvent_t stage_free[3] = {nullptr, nullptr, nullptr};
     bool stage_used[3] = {false, false, false};
     int stage_next = 0;
+    // narrowed upload (api.cu: NarrowUpload): per host thread two page-locked slices and two device slices of int32
+    void *nstage_host = nullptr;
+    void *nstage_dev = nullptr;
+    std::vector<cudaEvent_t> nstage_free;
+    int nstage_threads = 0;
+    i64 last_wire_bytes = 0;       // bytes the last pasio_contig_load_round put on the PCIe link
     std::string err;
 
     // scorer parameters (log_marginal_likelyhood.py:6-16,62)

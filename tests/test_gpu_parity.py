@@ -445,6 +445,36 @@ def test_load_and_round_equals_load_then_round(eng, n, constraint):
     assert np.array_equal(eng.candidates(), want)
 
 
+def test_load_and_round_narrowed_upload(eng):
+    """counts that fit 31 bits cross PCIe as int32 (host threads pack them, a kernel widens them): same state and same
+    first round as with plain copies, half the bytes on the link; with the limit lowered to 3 bits (test switch) slices
+    with larger counts go up as they are, in the same run as narrowed ones"""
+    n = 40000000
+    counts = synth.dnase_like(n, 78, hotspot_share=0.2)
+    eng.use_scorer(factory(1.0, 1.0))
+    got = {}
+    try:
+        for mode in (0, 1, 3):
+            eng.set_tuning('upload_narrow', mode)
+            eng.invalidate()
+            first = eng.load_and_round(counts, 2500, 1250, 'constants')
+            got[mode] = (first, eng.info(), eng.candidates().copy(), eng.upload_stats())
+    finally:
+        eng.set_tuning('upload_narrow', 1)
+    for mode in (1, 3):
+        assert got[mode][0] == got[0][0] and got[mode][1] == got[0][1]
+        assert np.array_equal(got[mode][2], got[0][2])
+    assert got[0][1][1] == int(counts.sum())
+    assert got[0][3] == 8 * n
+    assert 4 * n <= got[1][3] < 4 * n + 8 * (1 << 19)          # all but (at most) the ragged last slice
+    assert got[1][3] < got[3][3] < 8 * n                       # some slices narrowed, some not
+    # the dense profile on the device is what was sent: scores of a few fixed segments need the true prefix sums
+    eng.set_candidates(np.array([0, 5, n // 3, n - 7, n], dtype=np.int64))
+    cg = eng.cumsum_at_candidates()
+    want = np.concatenate([[0], np.cumsum(counts)])[[0, 5, n // 3, n - 7, n]]
+    assert np.array_equal(cg, want)
+
+
 def test_load_and_round_asserts_and_table_growth(eng):
     """negative counts still raise; a first round that needs longer tables falls back to load + grow + round"""
     eng.use_scorer(ScorerFactory(1.0, 1.0))            # fresh factory: tables at their initial 2^20 entries
