@@ -65,7 +65,11 @@ enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (defaul
                                          them into page-locked slices, a kernel widens them on arrival): half the PCIe bytes;
                                          a slice holding a larger or negative count goes up as it is.  0: plain copies;
                                          k in 2..30 (tests): only slices whose counts fit k bits are narrowed */
-       PASIO_TUNE_COUNT = 8 };
+       PASIO_TUNE_LOGFAC_EAGER = 8,   /* 1: pasio_contig_load_round also forms the sequential log-factorial sums, chunk by chunk on a
+                                         side stream behind the upload (set it when log_marginal_likelyhoods() / the LMM column
+                                         will be asked for: the 30 ms sum of a chr1-sized contig is then done when the upload is).
+                                         0 (default): on demand, or pasio_logfac_prefetch */
+       PASIO_TUNE_COUNT = 9 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int pasio_ctx_create(int device, pasio_ctx **out);

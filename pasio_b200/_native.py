@@ -18,7 +18,8 @@ E_CUDA, E_ARG, E_COUNTS, E_CANDIDATES, E_TABLE_TOO_SHORT, E_STATE, E_TOO_LARGE, 
 TAB_LOG, TAB_LGAMMA, TAB_LGAMMA_ALPHA = 0, 1, 2
 CONSTRAINTS = {'none': 0, 'zeros': 1, 'constants': 2}
 TUNE = {'window_prune': 0, 'window_phases': 1, 'exact_prune': 2, 'exact_lag': 3, 'exact_ring': 4, 'logfac_exact': 5,
-        'window_speculate': 6, 'upload_narrow': 7}
+        'window_speculate': 6, 'upload_narrow': 7,
+        'logfac_eager': 8}
 TIMING_FAMILIES = ['scan', 'window_dp', 'compact', 'exact_dp', 'score', 'h2d', 'd2h']
 
 _i64 = ctypes.c_int64
@@ -262,9 +263,10 @@ class Engine(object):
         self._loaded_print = self._fingerprint(counts)
         self._loaded_offsets = None if offsets is None else np.array(offsets, dtype=np.int64)
 
-    def load_and_round(self, counts, window_size, window_shift, constraint):
+    def load_and_round(self, counts, window_size, window_shift, constraint, want_logfac=False):
         """load(counts) fused with the first round(): the upload overlaps the scan and the round (pasio_contig_load_round).
-        Returns (n_in, n_out, cells) of that round."""
+        want_logfac: the sequential log-factorial sums (LMM column) will be asked for -- they then follow the chunks of
+        the upload on a side stream.  Returns (n_in, n_out, cells) of that round."""
         assert isinstance(counts, np.ndarray)
         assert counts.dtype == int
         assert len(counts) > 0
@@ -272,9 +274,14 @@ class Engine(object):
         self._loaded = None
         self._cands_obj = None
         n_in, n_out, cells = _i64(0), _i64(0), _i64(0)
-        rc = self.lib.pasio_contig_load_round(self.ctx, _ptr(c, ctypes.c_int64), len(c), window_size, window_shift,
-                                              CONSTRAINTS[constraint], ctypes.byref(n_in), ctypes.byref(n_out),
-                                              ctypes.byref(cells))
+        self.set_tuning('logfac_eager', 1 if want_logfac else 0)
+        try:
+            rc = self.lib.pasio_contig_load_round(self.ctx, _ptr(c, ctypes.c_int64), len(c), window_size, window_shift,
+                                                  CONSTRAINTS[constraint], ctypes.byref(n_in), ctypes.byref(n_out),
+                                                  ctypes.byref(cells))
+        finally:
+            if want_logfac:
+                self.set_tuning('logfac_eager', 0)
         if rc != E_TABLE_TOO_SHORT:
             self._check(rc)
         self._loaded = counts

@@ -375,6 +375,7 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->tune[PASIO_TUNE_LOGFAC_EXACT] = env_int("PASIO_B200_EXACT_LMM", 1);
     ctx->tune[PASIO_TUNE_WINDOW_SPECULATE] = env_int("PASIO_WD_SPECULATE", 1);
     ctx->tune[PASIO_TUNE_UPLOAD_NARROW] = env_int("PASIO_B200_UPLOAD_NARROW", 1);
+    ctx->tune[PASIO_TUNE_LOGFAC_EAGER] = env_int("PASIO_B200_LOGFAC_EAGER", 0);
     if (ctx->tune[PASIO_TUNE_EXACT_LAG] < 3 || ctx->tune[PASIO_TUNE_EXACT_LAG] > 4) ctx->tune[PASIO_TUNE_EXACT_LAG] = 3;
     *out = ctx;
     return PASIO_OK;
@@ -390,7 +391,7 @@ extern "C" int pasio_ctx_destroy(pasio_ctx *ctx)
                       &ctx->bounds, &ctx->brank, &ctx->cand[0], &ctx->cand[1], &ctx->candC[0], &ctx->candC[1], &ctx->win_st, &ctx->win_en, &ctx->win_small, &ctx->win_medium, &ctx->win_large, &ctx->win_flags,
                       &ctx->blocksum, &ctx->tilestate, &ctx->scalars, &ctx->dpL, &ctx->dpC, &ctx->dpP, &ctx->dpPrev,
                       &ctx->dpPart, &ctx->dpPartArg, &ctx->dpMark, &ctx->dpJump, &ctx->fscan, &ctx->logfac_full,
-                      &ctx->xpRing, &ctx->xpRec, &ctx->xpTasks, &ctx->regLR, &ctx->regNR, &ctx->lxPos, &ctx->lxSum, &ctx->lxFirst};
+                      &ctx->xpRing, &ctx->xpRec, &ctx->xpTasks, &ctx->regLR, &ctx->regNR, &ctx->lxPos, &ctx->lxSum, &ctx->lxFirst, &ctx->lxState};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -519,6 +520,7 @@ static int check_load_args(pasio_ctx *ctx, int64_t n, const int64_t *offsets, in
         ctx->logfac_pending = false;
     }
     ctx->logfac_ready = false;
+    ctx->logfac_eager = false;
     ctx->have_contig = false;
     if (n < 1) return pasio_fail(ctx, PASIO_E_COUNTS, "contig is empty");            // len(counts) > 0
     if (n > 2147483645LL) return pasio_fail(ctx, PASIO_E_TOO_LARGE, "contig of %lld nt exceeds 2^31-3", (long long)n);
@@ -637,6 +639,13 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
         return PASIO_OK;
     };
 
+    // the sequential log-factorial sums follow the chunks on the side stream when the caller announced that it wants them
+    // (PASIO_TUNE_LOGFAC_EAGER; the lgamma table in place decides whether the terms can be looked up at all)
+    const bool eager = ctx->tune[PASIO_TUNE_LOGFAC_EXACT] && ctx->tune[PASIO_TUNE_LOGFAC_EAGER] && ctx->ntab[PASIO_TAB_LGAMMA] > 2;
+    if (eager) {
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_lx, ctx->ev_fork, 0));
+        PASIO_TRY(launch_logfac_exact_begin(ctx, ctx->stream_lx));
+    }
     // large loads go up narrowed to int32 by a team of host threads (NarrowUpload above) while this thread drives the GPU
     NarrowUpload narrow;
     std::unique_ptr<TimingScope> narrow_span;
@@ -649,6 +658,7 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
     }
     auto stop_upload = [&]() {                      // before any return: nothing may read the caller's buffer afterwards
         if (narrow_on) { narrow.cancel.store(1); narrow.finish(); narrow_span.reset(); }
+        if (eager) cudaStreamSynchronize(ctx->stream_lx);
     };
 
     const i64 nwin_total = (ctx->m - 1 + window_shift - 1) / window_shift;
@@ -666,6 +676,11 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
             PASIO_TRY(queue_copies(c + 3));
         }
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[(size_t)c], 0));
+        if (eager) {
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_lx, ctx->chunk_events[(size_t)c], 0));
+            PASIO_TRY(launch_logfac_exact_chunk(ctx, c * chunk_tiles * tile_elems, std::min<i64>(n, (c + 1) * chunk_tiles * tile_elems),
+                                                ctx->stream_lx));
+        }
         const i64 t1 = std::min<i64>(n_tiles, (c + 1) * chunk_tiles);
         PASIO_TRY(launch_scan_tiles(ctx, t1 - c * chunk_tiles));
         // positions < scanned are final (prefix sums and change-point bits); the last chunk covers position n as well
@@ -716,6 +731,13 @@ extern "C" int pasio_contig_load_round(pasio_ctx *ctx, const int64_t *counts, in
     ctx->total = ctx->h_scalars[0];
     ctx->max_count = ctx->h_scalars[2];
     ctx->have_contig = true;
+    if (eager) {                                       // the sums are (nearly) done on the side stream; verdict at first use
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_lx1, ctx->stream_lx));
+        ctx->logfac_ready = true;
+        ctx->logfac_is_exact = true;
+        ctx->logfac_pending = true;
+        ctx->logfac_eager = true;
+    }
     PASIO_TRY(launch_boundary_ranks(ctx));
     ctx->h_brank = ctx->h_bounds;
     if (n_in) *n_in = ctx->m;
@@ -998,6 +1020,7 @@ extern "C" int pasio_set_tuning(pasio_ctx *ctx, int key, int value)
     if (key == PASIO_TUNE_LOGFAC_EXACT) {
         if (ctx->logfac_pending) { cudaStreamSynchronize(ctx->stream_lx); ctx->logfac_pending = false; }
         ctx->logfac_ready = false;
+        ctx->logfac_eager = false;
     }
     return PASIO_OK;
 }
@@ -1111,6 +1134,13 @@ static int ensure_logfac(pasio_ctx *ctx)
     if (ctx->logfac_pending) {                 // prefetched on the side stream: order the consumers behind it
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lx1, 0));
         ctx->logfac_pending = false;
+    }
+    if (ctx->logfac_eager) {                   // formed chunk by chunk behind the upload: how many terms, and were they all in the table?
+        ctx->logfac_eager = false;
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_lx1));
+        bool usable = false;
+        PASIO_TRY(logfac_exact_chunks_result(ctx, &usable));
+        if (!usable) ctx->logfac_ready = false;           // the ordinary path below checks the table and reports what is wrong
     }
     if (ctx->logfac_ready) return PASIO_OK;
     if (ctx->tune[PASIO_TUNE_LOGFAC_EXACT]) {

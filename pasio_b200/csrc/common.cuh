@@ -36,6 +36,7 @@ struct pasio_ctx {
     cudaStream_t stream_copy = nullptr;  // host->device chunks of pasio_contig_load_round
     cudaStream_t stream_lx = nullptr;    // log-factorial sums prefetched beside the rounds (pasio_logfac_prefetch)
     cudaEvent_t ev_lx0 = nullptr, ev_lx1 = nullptr;
+    bool logfac_eager = false;     // the pending sums were formed chunk by chunk behind the upload: verdict still to be read
     bool logfac_pending = false;         // the prefetch is in flight: consumers wait for ev_lx1 first
     std::vector<cudaEvent_t> chunk_events;
     void *stage[3] = {nullptr, nullptr, nullptr};   // page-locked staging ring for uploads from pageable memory
@@ -96,7 +97,7 @@ struct pasio_ctx {
     // scratch
     DevBuf blocksum, tilestate, scalars, dpL, dpC, dpP, dpPrev, dpPart, dpPartArg, dpMark, dpJump, fscan, logfac_full;
     DevBuf xpRing, xpRec, xpTasks, regLR, regNR;
-    DevBuf lxPos, lxSum, lxFirst;    // logfac_exact.cu: positions / running sums of the non-zero log-factorial terms, first term per contig
+    DevBuf lxPos, lxSum, lxFirst, lxState;    // logfac_exact.cu: positions / running sums of the non-zero log-factorial terms, first term per contig
     i64 lx_terms = 0;
     i64 scan_tiles_done = 0;     // tiles of the loaded contig already scanned (pasio_contig_load_round scans chunk by chunk)   // exact_pruned.cu: self-score ring, column-block records, task list
 
@@ -185,6 +186,9 @@ int launch_lmm(pasio_ctx *ctx, const double *d_scores, const double *d_logfac_fu
 
 // logfac_exact.cu: logfac_cumsum with the reference's sequential rounding
 int launch_logfac_exact(pasio_ctx *ctx, cudaStream_t stream = nullptr);
+int launch_logfac_exact_begin(pasio_ctx *ctx, cudaStream_t stream);                  // the same chunk by chunk behind an upload ...
+int launch_logfac_exact_chunk(pasio_ctx *ctx, i64 p0, i64 p1, cudaStream_t stream);   // ... positions [p0, p1) ...
+int logfac_exact_chunks_result(pasio_ctx *ctx, bool *usable);                        // ... and, after the stream finished, the verdict
 int launch_lmm_exact(pasio_ctx *ctx, const double *d_scores, double *d_lmm);
 int launch_logfac_at_candidates_exact(pasio_ctx *ctx, double *d_out);
 int logfac_exact_total(pasio_ctx *ctx, double *h_out);

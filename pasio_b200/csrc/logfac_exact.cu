@@ -21,20 +21,30 @@ constexpr int LX_THREADS = 256;
 constexpr int LX_ITEMS = 8;
 constexpr int LX_TILE = LX_THREADS * LX_ITEMS;
 
-__device__ __forceinline__ double term_of(const i64 *__restrict__ counts, i64 p, const double *__restrict__ gtab)
+// gammaln(counts + 1) from the host-built table.  CHECK: the chunked variant runs before anybody has looked at the
+// counts: a count outside the table (or negative) raises *flag and contributes nothing; the host then discards the sums and takes the ordinary path, which
+// reports negative counts and grows the table
+template <bool CHECK>
+__device__ __forceinline__ double term_at(const i64 *__restrict__ counts, i64 p, const double *__restrict__ gtab, i64 ntab, int *flag)
 {
-    return __ldg(gtab + __ldg(counts + p) + 1);          // gammaln(counts + 1) from the host-built table
+    const i64 c = __ldg(counts + p);
+    if (CHECK && (c < 0 || c + 1 >= ntab)) { *flag = 1; return 0.0; }
+    return __ldg(gtab + c + 1);
 }
 
+// tile0: first tile of the launch (chunked variant: the tiles of the chunk that has just arrived)
+template <bool CHECK>
 __global__ void __launch_bounds__(LX_THREADS)
-nonzero_count_kernel(const i64 *__restrict__ counts, i64 n, const double *__restrict__ gtab, unsigned *__restrict__ tile_count)
+nonzero_count_kernel(const i64 *__restrict__ counts, i64 n, const double *__restrict__ gtab, unsigned *__restrict__ tile_count,
+                     i64 tile0, i64 ntab, int *flag)
 {
-    const i64 base = (i64)blockIdx.x * LX_TILE;
+    const i64 tile = tile0 + blockIdx.x;
+    const i64 base = tile * LX_TILE;
     int c = 0;
 #pragma unroll
     for (int k = 0; k < LX_ITEMS; ++k) {
         const i64 p = base + (i64)k * LX_THREADS + threadIdx.x;
-        if (p < n && term_of(counts, p, gtab) != 0.0) ++c;
+        if (p < n && term_at<CHECK>(counts, p, gtab, ntab, flag) != 0.0) ++c;
     }
     c = __reduce_add_sync(0xffffffffu, c);
     __shared__ int s[LX_THREADS / 32];
@@ -43,17 +53,19 @@ nonzero_count_kernel(const i64 *__restrict__ counts, i64 n, const double *__rest
     if (threadIdx.x == 0) {
         int t = 0;
         for (int w = 0; w < LX_THREADS / 32; ++w) t += s[w];
-        tile_count[blockIdx.x] = (unsigned)t;
+        tile_count[tile] = (unsigned)t;
     }
 }
 
 // exclusive scan of the tile counts in place (one CTA); total -> *total
+// running != nullptr (chunked variant): the scan starts at running[0] (terms of the chunks before), which moves to
+// running[1], and running[0] becomes the new total
 __global__ void __launch_bounds__(1024)
-tile_offsets_kernel(unsigned *tile_count, i64 n_tiles, i64 *total)
+tile_offsets_kernel(unsigned *tile_count, i64 n_tiles, i64 *total, i64 *running)
 {
     __shared__ i64 s_warp[32];
     __shared__ i64 s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) s_carry = running ? running[0] : 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (i64 base = 0; base < n_tiles; base += 1024) {
@@ -82,22 +94,28 @@ tile_offsets_kernel(unsigned *tile_count, i64 n_tiles, i64 *total)
         if (threadIdx.x == 0) s_carry = carry + tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = s_carry;
+    if (threadIdx.x == 0) {
+        if (running) { running[1] = running[0]; running[0] = s_carry; }
+        else *total = s_carry;
+    }
 }
 
+template <bool CHECK>
 __global__ void __launch_bounds__(LX_THREADS)
 nonzero_scatter_kernel(const i64 *__restrict__ counts, i64 n, const double *__restrict__ gtab,
-                       const unsigned *__restrict__ tile_offset, int32_t *__restrict__ pos_out, double *__restrict__ term_out)
+                       const unsigned *__restrict__ tile_offset, int32_t *__restrict__ pos_out, double *__restrict__ term_out,
+                       i64 tile0, i64 ntab, int *flag)
 {
     __shared__ int s_warp[LX_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i64 base = (i64)blockIdx.x * LX_TILE;
-    i64 at = tile_offset[blockIdx.x];
+    const i64 tile = tile0 + blockIdx.x;
+    const i64 base = tile * LX_TILE;
+    i64 at = tile_offset[tile];
 #pragma unroll 1
     for (int k = 0; k < LX_ITEMS; ++k) {                  // positions ascend with k, then with the thread index
         const i64 p = base + (i64)k * LX_THREADS + threadIdx.x;
         double x = 0.0;
-        if (p < n) x = term_of(counts, p, gtab);
+        if (p < n) x = term_at<CHECK>(counts, p, gtab, ntab, flag);
         const bool keep = x != 0.0;
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp[warp] = __popc(bal);
@@ -153,6 +171,30 @@ __global__ void sequential_sum_kernel(const int32_t *__restrict__ pos, double *_
             terms_to_sums[k] = s;
         }
     }
+}
+
+// Chunked variant, one contig: continue the running sum over the terms the chunk added, [running[1], running[0]).
+__global__ void sequential_append_kernel(double *__restrict__ terms_to_sums, const i64 *__restrict__ running, double *carry)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    const i64 k0 = running[1], k1 = running[0];
+    double s = *carry;
+    i64 k = k0;
+    for (; k + 7 < k1; k += 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = terms_to_sums[k + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = __dadd_rn(s, x[u]);
+            terms_to_sums[k + u] = s;
+        }
+    }
+    for (; k < k1; ++k) {
+        s = __dadd_rn(s, terms_to_sums[k]);
+        terms_to_sums[k] = s;
+    }
+    *carry = s;
 }
 
 __device__ __forceinline__ double cumsum_at(const int32_t *__restrict__ pos, const double *__restrict__ sums, i64 n_terms,
@@ -227,21 +269,69 @@ int launch_logfac_exact(pasio_ctx *ctx, cudaStream_t stream)
     unsigned *d_tiles = ctx->fscan.as<unsigned>();
     i64 *d_total = ctx->scalars.as<i64>() + 9;
     TimingScope ts(ctx, TF_SCORE, 4, stream);
-    nonzero_count_kernel<<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles);
-    tile_offsets_kernel<<<1, 1024, 0, stream>>>(d_tiles, tiles, d_total);
+    nonzero_count_kernel<false><<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles, 0, 0, nullptr);
+    tile_offsets_kernel<<<1, 1024, 0, stream>>>(d_tiles, tiles, d_total, nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 9, d_total, 8, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(stream));
     const i64 n_terms = ctx->h_scalars[9];
     PASIO_TRY(pasio_reserve(ctx, ctx->lxPos, (size_t)(n_terms + 1) * 4));
     PASIO_TRY(pasio_reserve(ctx, ctx->lxSum, (size_t)(n_terms + 1) * 8));
-    nonzero_scatter_kernel<<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles,
-                                                                           ctx->lxPos.as<int32_t>(), ctx->lxSum.as<double>());
+    nonzero_scatter_kernel<false><<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), n, gtab, d_tiles,
+                                                                                  ctx->lxPos.as<int32_t>(), ctx->lxSum.as<double>(), 0, 0, nullptr);
     const unsigned g = (unsigned)((ctx->n_contigs + 63) / 64);
     sequential_sum_kernel<<<g < 1 ? 1 : g, 64, 0, stream>>>(ctx->lxPos.as<int32_t>(), ctx->lxSum.as<double>(), n_terms,
                                                                  ctx->bounds.as<int32_t>(), ctx->n_contigs, ctx->lxFirst.as<i64>());
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->lx_terms = n_terms;
+    return PASIO_OK;
+}
+
+// ---- the same sums chunk by chunk behind an upload (pasio_contig_load_round with PASIO_TUNE_LOGFAC_EAGER) ----------
+// One contig.  The chunks' terms are appended in order on `stream` (each launch waits for its chunk's event there), so the
+// sequential sum -- 30 ms of one thread for a chr1-sized contig -- is nearly finished when the upload is, instead of
+// starting then.  Device state (ctx->lxState): [0] terms so far, [1] terms before the current chunk, [2] running sum,
+// [3] flag: a count outside the lgamma table or negative was seen (the sums are then discarded by the host).
+int launch_logfac_exact_begin(pasio_ctx *ctx, cudaStream_t stream)
+{
+    const i64 n = ctx->n;
+    const i64 tiles = (n + LX_TILE - 1) / LX_TILE;
+    PASIO_TRY(pasio_reserve(ctx, ctx->fscan, (size_t)tiles * 4 + 16));
+    PASIO_TRY(pasio_reserve(ctx, ctx->lxFirst, 8));
+    PASIO_TRY(pasio_reserve(ctx, ctx->lxState, 64));
+    PASIO_TRY(pasio_reserve(ctx, ctx->lxPos, (size_t)(n + 1) * 4));         // worst case: every position carries a term
+    PASIO_TRY(pasio_reserve(ctx, ctx->lxSum, (size_t)(n + 1) * 8));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->lxState.p, 0, 64, stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->lxFirst.p, 0, 8, stream));
+    return PASIO_OK;
+}
+
+int launch_logfac_exact_chunk(pasio_ctx *ctx, i64 p0, i64 p1, cudaStream_t stream)     // positions [p0, p1), p0 a multiple of the tile
+{
+    if (p1 <= p0) return PASIO_OK;
+    const double *gtab = ctx->tab[PASIO_TAB_LGAMMA].as<double>();
+    const i64 ntab = ctx->ntab[PASIO_TAB_LGAMMA];
+    const i64 tile0 = p0 / LX_TILE, tiles = (p1 - p0 + LX_TILE - 1) / LX_TILE;
+    unsigned *d_tiles = ctx->fscan.as<unsigned>();
+    i64 *st = ctx->lxState.as<i64>();
+    int *flag = reinterpret_cast<int *>(st + 3);
+    TimingScope ts(ctx, TF_SCORE, 4, stream);
+    nonzero_count_kernel<true><<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), p1, gtab, d_tiles, tile0, ntab, flag);
+    tile_offsets_kernel<<<1, 1024, 0, stream>>>(d_tiles + tile0, tiles, nullptr, st);
+    nonzero_scatter_kernel<true><<<(unsigned)tiles, LX_THREADS, 0, stream>>>(ctx->counts.as<i64>(), p1, gtab, d_tiles,
+                                                                                 ctx->lxPos.as<int32_t>(), ctx->lxSum.as<double>(), tile0, ntab, flag);
+    sequential_append_kernel<<<1, 32, 0, stream>>>(ctx->lxSum.as<double>(), st, reinterpret_cast<double *>(st + 2));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PASIO_OK;
+}
+
+// after the stream has finished: number of terms; *usable = false if the sums must be discarded
+int logfac_exact_chunks_result(pasio_ctx *ctx, bool *usable)
+{
+    i64 h[4];
+    CUDA_TRY(ctx, cudaMemcpy(h, ctx->lxState.p, sizeof h, cudaMemcpyDeviceToHost));
+    ctx->lx_terms = h[0];
+    *usable = (int)(h[3] & 0xffffffff) == 0;
     return PASIO_OK;
 }
 

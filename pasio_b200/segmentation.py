@@ -62,7 +62,7 @@ def segment_on_device(counts, plan, want_lmm=True):
         # the first round always starts from all positions: run it while the counts are still going up
         _, factory, size, shift, constraint = steps[0][:5]
         eng.use_scorer(factory)
-        first = eng.load_and_round(counts, size, shift, constraint)
+        first = eng.load_and_round(counts, size, shift, constraint, want_logfac=want_lmm)
         if want_lmm:
             eng.logfac_prefetch()                 # the sequential log-factorial sums run beside the remaining rounds
         return run_loaded_pipeline(eng, plan, want_lmm, first=first)

@@ -633,6 +633,35 @@ def test_logfac_exact_and_parallel_modes():
     assert np.array_equal(lmm, np.concatenate(want))
 
 
+def test_logfac_sums_behind_the_upload():
+    """load_and_round(want_logfac=True) forms the sequential log-factorial sums chunk by chunk behind the upload (40 Mb = two
+    chunks): logfac_cumsum, the LMM column and the total are the numpy values bit for bit, the same as on demand; a count
+    beyond the lgamma table makes the library discard those sums and take the ordinary path (which grows the table)"""
+    from pasio_b200 import _native
+    eng = _native.engine()
+    t = po.Tables(1, 1.0)
+    for n, poke in [(40000000, None), (3000000, None), (700000, 1500000)]:
+        counts = synth.dnase_like(n, 21, hotspot_share=0.3)
+        if poke:
+            counts[n // 2] = poke                       # gammaln table of a fresh factory has 2^20 entries
+        results = []
+        for eager in (True, False):
+            eng.use_scorer(ScorerFactory(1.0, 1.0))
+            eng.invalidate()
+            eng.load_and_round(counts, 2500, 1250, 'constants', want_logfac=eager)
+            eng.rounds(2500, 1250, 'constants', 1)
+            splits = eng.candidates().copy()
+            lmm, total = eng.segment_lmm()
+            lf = eng.segment_scores(scores=False, logfac=True)[3]
+            results.append((splits, lmm.copy(), total, lf.copy()))
+        a, b = results
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and np.array_equal(a[3], b[3])
+        from scipy.special import gammaln
+        want = np.concatenate([[0.0], np.cumsum(gammaln(counts + 1))])
+        assert np.array_equal(a[3], want[a[0]])
+        assert a[2] == want[-1]
+
+
 def test_reducer_accepts_candidates_without_the_ends():
     """the reference's SlidingWindowReducer takes any ascending candidate list and adds 0 and len(counts) to the result
     (sliding_window_reducer.py:22); the fused device loop needs both ends, so such lists take the object route"""
