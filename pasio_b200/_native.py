@@ -61,8 +61,8 @@ SIGNATURES = {
     'pasio_logfac_prefetch': (ctypes.c_int, [_vp]),
     'pasio_host_alloc': (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     'pasio_host_free': (ctypes.c_int, [_vp]),
-    'pasio_bedgraph_count_lines': (_i64, [ctypes.c_char_p, _i64]),
-    'pasio_bedgraph_parse': (ctypes.c_int, [ctypes.c_char_p, _i64, _i64, _i64p, _i64p, _i64p, _i64p,
+    'pasio_bedgraph_count_lines': (_i64, [ctypes.c_void_p, _i64]),
+    'pasio_bedgraph_parse': (ctypes.c_int, [ctypes.c_void_p, _i64, _i64, _i64p, _i64p, _i64p, _i64p,
                                             ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8), _i64p, _i64p]),
     'pasio_bedgraph_runs': (_i64, [_i64p, _i64p, _i64p, ctypes.POINTER(ctypes.c_uint8), _i64, ctypes.c_int, _i64p, _i64p, _i64p,
                                    _i64p, _i64p]),
@@ -534,25 +534,30 @@ class Engine(object):
         return out
 
 
-def parse_bedgraph_text(data):
-    """data: bytes of a bedgraph file.  Returns dict of arrays: starts, stops, counts (int64), name_off, name_len,
-    new_chrom, plus n_float (counts that needed int(float(x)))."""
+def parse_bedgraph_text(data, front=0, length=None):
+    """data: bytes of a bedgraph file (or a bytearray, of which the first `length` bytes are parsed in place).  Returns dict of arrays: starts, stops, counts (int64), name_off, name_len,
+    new_chrom, plus n_float (counts that needed int(float(x))).  front: leave that many unfilled slots before the parsed
+    lines in every array (the streaming reader puts the lines of a contig that began in the previous piece there, instead of
+    concatenating whole arrays piece after piece); name_off / name_len / new_chrom of those slots are the caller's too."""
     lib = load_library()
-    cap = lib.pasio_bedgraph_count_lines(data, len(data))
-    starts = np.empty(cap, dtype=np.int64)
-    stops = np.empty(cap, dtype=np.int64)
-    counts = np.empty(cap, dtype=np.int64)
-    name_off = np.empty(cap, dtype=np.int64)
-    name_len = np.empty(cap, dtype=np.int32)
-    new_chrom = np.empty(cap, dtype=np.uint8)
+    nbytes = len(data) if length is None else int(length)
+    if isinstance(data, bytearray):
+        data = (ctypes.c_char * len(data)).from_buffer(data) if len(data) else None
+    cap = lib.pasio_bedgraph_count_lines(data, nbytes)
+    starts = np.empty(front + cap, dtype=np.int64)
+    stops = np.empty(front + cap, dtype=np.int64)
+    counts = np.empty(front + cap, dtype=np.int64)
+    name_off = np.empty(front + cap, dtype=np.int64)
+    name_len = np.empty(front + cap, dtype=np.int32)
+    new_chrom = np.empty(front + cap, dtype=np.uint8)
     n, nfloat = _i64(0), _i64(0)
-    rc = lib.pasio_bedgraph_parse(data, len(data), cap, _ptr(starts, ctypes.c_int64), _ptr(stops, ctypes.c_int64),
-                                  _ptr(counts, ctypes.c_int64), _ptr(name_off, ctypes.c_int64),
-                                  _ptr(name_len, ctypes.c_int32), _ptr(new_chrom, ctypes.c_uint8),
+    rc = lib.pasio_bedgraph_parse(data, nbytes, cap, _ptr(starts[front:], ctypes.c_int64), _ptr(stops[front:], ctypes.c_int64),
+                                  _ptr(counts[front:], ctypes.c_int64), _ptr(name_off[front:], ctypes.c_int64),
+                                  _ptr(name_len[front:], ctypes.c_int32), _ptr(new_chrom[front:], ctypes.c_uint8),
                                   ctypes.byref(n), ctypes.byref(nfloat))
     if rc != OK:
         raise ValueError('malformed bedgraph line %d (need: chrom start stop count)' % (n.value + 1))
-    k = n.value
+    k = front + n.value
     return dict(starts=starts[:k], stops=stops[:k], counts=counts[:k], name_off=name_off[:k], name_len=name_len[:k],
                 new_chrom=new_chrom[:k], n_float=nfloat.value)
 

@@ -7,6 +7,8 @@ is parsed by one C++ pass (csrc/textio.cpp) instead of a per-line Python loop, c
 GPU as run-length intervals (pasio_contig_load_rle expands them on the device: the dense 8 B/nt profile
 never exists on the host), and the output lines are formatted in C++.
 """
+import os
+import sys
 import numpy as np
 
 from . import _native
@@ -49,6 +51,18 @@ def interval_groups(intervals, split_at_gaps):
 CHUNK_BYTES = 64 << 20        # the input is read in pieces of this size, cut at line starts
 
 
+class _Reader(object):
+    """read(n) -> bytes, plus readinto(buffer) -> n when the object underneath has it (files, BytesIO, gzip): the
+    streaming reader then fills its one reusable buffer without intermediate bytes objects"""
+
+    def __init__(self, read, readinto=None):
+        self.read = read
+        self.readinto = readinto
+
+    def __call__(self, n):
+        return self.read(n)
+
+
 def _binary_reader(stream):
     """read(n) -> bytes over the input.  A text stream over a binary one (open(..., 'rt'), gzip.open(..., 'rt'),
     sys.stdin) is read through the binary object underneath instead of decoding gigabytes of ASCII to str and
@@ -62,16 +76,16 @@ def _binary_reader(stream):
                 pos = stream.tell()              # byte offset of the next character (plain cookie for ASCII / UTF-8)
                 if 0 <= pos < (1 << 62):
                     raw.seek(pos)
-                    return raw.read
+                    return _Reader(raw.read, getattr(raw, 'readinto', None))
             else:
-                return raw.read
+                return _Reader(raw.read, getattr(raw, 'readinto', None))
         except (OSError, ValueError, AttributeError):
             pass
 
     def read_text(n):
         data = stream.read(n)
         return data.encode() if isinstance(data, str) else bytes(data)
-    return read_text
+    return _Reader(read_text)
 
 
 def _read_all(stream):
@@ -95,41 +109,66 @@ def _contig_runs_chunked(read, split_at_gaps=False):
     lines of one chromosome form a group; with split_at_gaps a group also ends where an interval does not start at the
     previous stop; otherwise a zero run is inserted between non-adjacent intervals (when the previous stop is non-zero,
     as in the reference's `if previous_stop and ...`).  Runs of non-positive length contribute nothing."""
-    tail = b''
+    # one reusable buffer: the unfinished last line of a piece is moved to its front, the next piece is read behind it and
+    # parsed in place (no bytes object per piece, no concatenation, no slicing copies)
+    data = bytearray(CHUNK_BYTES + (1 << 16))
+    readinto = getattr(read, 'readinto', None)
+    tail_len = 0
     pend = None          # lines of the last (possibly unfinished) group: (chrom, starts, stops, counts)
     while True:
-        chunk = read(CHUNK_BYTES)
-        eof = len(chunk) == 0
-        data = tail + chunk if tail else chunk
+        filled = tail_len
+        eof = False
+        while filled - tail_len < CHUNK_BYTES // 2:              # (gzip and pipes return short reads)
+            room = min(len(data) - filled, CHUNK_BYTES - (filled - tail_len))
+            if room <= 0:
+                break
+            if readinto is not None:
+                with memoryview(data) as mv:
+                    got = readinto(mv[filled:filled + room])
+                got = 0 if got is None else got
+            else:
+                piece = read(room)
+                got = len(piece)
+                data[filled:filled + got] = piece
+            if got == 0:
+                eof = True
+                break
+            filled += got
         if eof:
-            tail = b''
+            cut = filled
         else:
-            cut = data.rfind(b'\n') + 1
-            tail = data[cut:]
-            data = data[:cut]
-        rec = _native.parse_bedgraph_text(data) if data else None
-        n_new = len(rec['starts']) if rec is not None else 0
+            cut = data.rfind(b'\n', 0, filled) + 1
+            if cut == 0 and filled == len(data):                 # a line longer than the buffer: grow and keep reading
+                data.extend(bytes(len(data)))
+                tail_len = filled
+                continue
+        # the lines of the contig in progress (from the pieces before) go in front of this piece's lines, in place
+        n_old = len(pend[1]) if pend is not None else 0
+        rec = _native.parse_bedgraph_text(data, front=n_old, length=cut) if cut else None
+        n_new = len(rec['starts']) - n_old if rec is not None else 0
         if rec is not None and rec['n_float']:
             logger.warning("Pasio cannot be used with floating point counts. %d count(s) were automatically converted "
                            "to integers as an approximation. Make sure these values were designed to actually be "
                            "integer counts." % rec['n_float'])
         if n_new == 0 and not eof:
+            tail_len = filled - cut
+            data[0:tail_len] = data[cut:filled]
             continue
         if pend is not None:
-            n_old = len(pend[1])
             if n_new:
-                first = data[rec['name_off'][0]:rec['name_off'][0] + rec['name_len'][0]]
-                new_chrom = np.concatenate([np.zeros(n_old, dtype=np.uint8), rec['new_chrom']])
-                new_chrom[0] = 1
-                new_chrom[n_old] = first != pend[0]
-                lines = dict(starts=np.concatenate([pend[1], rec['starts']]), stops=np.concatenate([pend[2], rec['stops']]),
-                             counts=np.concatenate([pend[3], rec['counts']]), new_chrom=new_chrom)
+                first = bytes(data[rec['name_off'][n_old]:rec['name_off'][n_old] + rec['name_len'][n_old]])
+                rec['starts'][:n_old] = pend[1]
+                rec['stops'][:n_old] = pend[2]
+                rec['counts'][:n_old] = pend[3]
+                rec['new_chrom'][:n_old] = 0
+                rec['new_chrom'][0] = 1
+                rec['new_chrom'][n_old] = first != pend[0]
+                lines = rec
             else:
                 new_chrom = np.zeros(n_old, dtype=np.uint8)
                 new_chrom[0] = 1
                 lines = dict(starts=pend[1], stops=pend[2], counts=pend[3], new_chrom=new_chrom)
         elif n_new:
-            n_old = 0
             lines = rec
         else:
             return                                   # end of an empty input
@@ -143,8 +182,8 @@ def _contig_runs_chunked(read, split_at_gaps=False):
             gl = first_line[k]
             if gl < n_old:
                 return pend[0]
-            off, ln = int(rec['name_off'][gl - n_old]), int(rec['name_len'][gl - n_old])
-            return data[off:off + ln]
+            off, ln = int(rec['name_off'][gl]), int(rec['name_len'][gl])
+            return bytes(data[off:off + ln])
         done = n_groups if eof else n_groups - 1     # the last group may continue in the next piece
         for k in range(done):
             yield name_of(k).decode(), run_len[bounds[k]:bounds[k + 1]], run_val[bounds[k]:bounds[k + 1]], first_start[k]
@@ -153,6 +192,8 @@ def _contig_runs_chunked(read, split_at_gaps=False):
         gl = first_line[-1]
         pend = (bytes(name_of(n_groups - 1)), lines['starts'][gl:].copy(), lines['stops'][gl:].copy(),
                 lines['counts'][gl:].copy())
+        tail_len = filled - cut                      # the unfinished last line moves to the front (names were read above)
+        data[0:tail_len] = data[cut:filled]
 
 
 def contig_runs(data, split_at_gaps=False):
@@ -348,7 +389,21 @@ def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=F
         return
     import queue
     import threading
-    parsed = _Stage(_batches(contigs, plan), lambda b: b)          # thread 1: read + parse + group
+    busy = {'read': 0.0, 'device': 0.0, 'write': 0.0}               # seconds of work per stage (PASIO_B200_STAGE_TIMES=1 prints them)
+    import time as _time
+
+    def timed_batches():
+        it = iter(_batches(contigs, plan))
+        while True:
+            t0 = _time.perf_counter()
+            try:
+                b = next(it)
+            except StopIteration:
+                return
+            finally:
+                busy['read'] += _time.perf_counter() - t0
+            yield b
+    parsed = _Stage(timed_batches(), lambda b: b)                  # thread 1: read + parse + group
     out_q = queue.Queue(maxsize=2)
     writer_error = []
 
@@ -359,7 +414,9 @@ def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=F
                 if item is None:
                     return
                 batch, result = item
+                t0 = _time.perf_counter()
                 _write(output_stream, _format_batch(result, mode))
+                busy['write'] += _time.perf_counter() - t0
                 for chrom, _, _, _ in batch:
                     logger.info('Output of chromosome %s finished' % chrom)
         except BaseException as e:           # noqa: BLE001 -- re-raised below
@@ -372,12 +429,18 @@ def split_bedgraph_stream(input_stream, output_stream, splitter, split_at_gaps=F
         for batch in parsed:                                       # this thread: the device
             if writer_error:
                 break
-            out_q.put((batch, _segment_batch(splitter, plan, batch, mode)))
+            t0 = _time.perf_counter()
+            result = _segment_batch(splitter, plan, batch, mode)
+            busy['device'] += _time.perf_counter() - t0
+            out_q.put((batch, result))
     except BaseException:
         parsed.cancel()
         raise
     finally:
         out_q.put(None)
         thread.join()
+    if os.environ.get('PASIO_B200_STAGE_TIMES'):
+        sys.stderr.write('[pasio_b200 stages] read+parse %.3f s, device %.3f s, format+write %.3f s (busy time per thread)\n'
+                         % (busy['read'], busy['device'], busy['write']))
     if writer_error:
         raise writer_error[0]
