@@ -170,7 +170,8 @@ static int upload(pasio_ctx *ctx, void *dst, const void *src, size_t bytes, cuda
 
 // ---- narrowed upload ------------------------------------------------------------------------------
 // Coverage counts are small numbers in 8-byte slots, and a chr1-sized upload is bound by the PCIe link (2 GB at 55 GB/s =
-// 36 ms of an 80 ms end-to-end step).  Host threads therefore pack the counts to int32 into page-locked slices (reading the
+// 36 ms of an 80 ms end-to-end step).  Host threads therefore pack the counts to uint16 (int32 for a slice that holds a
+// count of 2^16 or more) into page-locked slices (reading the
 // caller's buffer -- pinned or pageable -- at memory bandwidth: 87 GB/s with 16 threads on the bench box,
 // profiles/r02_host_narrow_probe.txt), each slice is DMA'd as soon as it is packed and widened to the int64 layout the
 // kernels use by a small kernel behind the copy on the same stream.  A slice that holds a count outside [0, 2^31) goes up
@@ -188,7 +189,19 @@ __global__ void __launch_bounds__(256) widen_counts_kernel(const int4 *__restric
 
 // dst[i] = (int32) src[i]; returns the OR of all values (bits 31..63 set <=> some count is negative or >= 2^31); textio.cpp
 uint64_t pasio_narrow_slice(int32_t *dst, const int64_t *src, size_t n);
+uint64_t pasio_narrow_slice16(uint16_t *dst, const int64_t *src, size_t n);     // the same to uint16 (saturating)
 #define narrow_slice pasio_narrow_slice
+
+__global__ void __launch_bounds__(256) widen_counts16_kernel(const uint4 *__restrict__ src, longlong2 *__restrict__ dst, i64 n8)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (i64)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(src + i);                    // 8 counts
+        dst[4 * i] = make_longlong2(v.x & 0xffffu, v.x >> 16);
+        dst[4 * i + 1] = make_longlong2(v.y & 0xffffu, v.y >> 16);
+        dst[4 * i + 2] = make_longlong2(v.z & 0xffffu, v.z >> 16);
+        dst[4 * i + 3] = make_longlong2(v.w & 0xffffu, v.w >> 16);
+    }
+}
 
 namespace {
 struct NarrowUpload {
@@ -201,7 +214,7 @@ struct NarrowUpload {
     std::atomic<int> cancel{0}, failed{0};
     std::unique_ptr<std::atomic<int>[]> left_in_chunk, recorded;
     std::atomic<i64> wire_bytes{0};
-    int limit_bits = 31;                                // slices whose counts all fit this many bits are narrowed
+    int limit_bits = 31;                                // test switch (< 31): slices fitting this many bits go as uint16, 6 bits more as int32
 
     // every slice lies inside one chunk (chunk_elems is a multiple of SLICE)
     int start(pasio_ctx *c, const int64_t *counts, i64 n_, i64 chunk_elems_, i64 n_chunks_)
@@ -261,8 +274,22 @@ struct NarrowUpload {
             i64 *dst = ctx->counts.as<i64>() + e0;
             bool ok = true;
             if (used[buf & 1]) ok = cudaEventSynchronize(ctx->nstage_free[(size_t)buf]) == cudaSuccess;   // its last copy has left
-            const uint64_t bits = ok ? narrow_slice(hst, src + e0, (size_t)len) : 0;
-            if (ok && (bits >> limit_bits) == 0 && (len & 3) == 0) {
+            // most coverage fits 16 bits: try that first (a quarter of the bytes); its OR says whether to redo the slice wider
+            uint64_t bits = ok ? pasio_narrow_slice16(reinterpret_cast<uint16_t *>(hst), src + e0, (size_t)len) : 0;
+            const int lim16 = limit_bits < 16 ? limit_bits : 16, lim32 = limit_bits < 25 ? limit_bits + 6 : 31;   // (test switch: three-way mix)
+            if (ok && (bits >> lim16) == 0 && (len & 7) == 0) {
+                ok = cudaMemcpyAsync(dev, hst, (size_t)len * 2, cudaMemcpyHostToDevice, ctx->stream_copy) == cudaSuccess;
+                if (ok) {
+                    ok = cudaEventRecord(ctx->nstage_free[(size_t)buf], ctx->stream_copy) == cudaSuccess;
+                    used[buf & 1] = true;
+                    const i64 n8 = len / 8;
+                    widen_counts16_kernel<<<(unsigned)std::min<i64>((n8 + 255) / 256, 296), 256, 0, ctx->stream_copy>>>(
+                        reinterpret_cast<const uint4 *>(dev), reinterpret_cast<longlong2 *>(dst), n8);
+                    ok = ok && cudaGetLastError() == cudaSuccess;
+                    wire_bytes.fetch_add(len * 2);
+                }
+            } else if (ok && (bits >> lim32) == 0 && (len & 3) == 0) {
+                narrow_slice(hst, src + e0, (size_t)len);
                 ok = cudaMemcpyAsync(dev, hst, (size_t)len * 4, cudaMemcpyHostToDevice, ctx->stream_copy) == cudaSuccess;
                 if (ok) {
                     ok = cudaEventRecord(ctx->nstage_free[(size_t)buf], ctx->stream_copy) == cudaSuccess;
@@ -537,9 +564,39 @@ extern "C" int pasio_contig_load(pasio_ctx *ctx, const int64_t *counts, int64_t 
     ctx->n = n;
     drop_borrowed_counts(ctx);
     PASIO_TRY(pasio_reserve(ctx, ctx->counts, (size_t)n * 8 + 16));
-    {
+    bool sent = false;
+    if (ctx->tune[PASIO_TUNE_UPLOAD_NARROW] && n >= ((i64)1 << 24)) {
+        // a large batch: packed to int32 by the host threads on the way (NarrowUpload), as one chunk
+        if (ctx->chunk_events.empty()) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->chunk_events.push_back(e);
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));      // the buffers may still be in use by earlier work
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_fork, 0));
+        NarrowUpload narrow;
+        std::unique_ptr<TimingScope> span(new TimingScope(ctx, TF_H2D, 1, ctx->stream_copy));
+        if (ctx->tune[PASIO_TUNE_UPLOAD_NARROW] >= 2 && ctx->tune[PASIO_TUNE_UPLOAD_NARROW] < 31) narrow.limit_bits = ctx->tune[PASIO_TUNE_UPLOAD_NARROW];
+        const i64 one_chunk = (n + (i64)NarrowUpload::SLICE - 1) / (i64)NarrowUpload::SLICE * (i64)NarrowUpload::SLICE;
+        if (narrow.start(ctx, counts, n, one_chunk, 1) == 0) {
+            const bool ok = narrow.wait_recorded(0);
+            narrow.finish();
+            span.reset();
+            ctx->last_wire_bytes = narrow.wire_bytes.load();
+            if (!ok || narrow.failed.load()) {
+                cudaStreamSynchronize(ctx->stream_copy);
+                return pasio_fail(ctx, PASIO_E_CUDA, "narrowed upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[0], 0));
+            sent = true;
+        } else {
+            span.reset();
+        }
+    }
+    if (!sent) {
         TimingScope ts(ctx, TF_H2D);
         PASIO_TRY(upload(ctx, ctx->counts.p, counts, (size_t)n * 8, ctx->stream));
+        ctx->last_wire_bytes = n * 8;
     }
     return finish_load(ctx, offsets, n_contigs);
 }

@@ -404,6 +404,39 @@ __attribute__((target("avx2"))) static uint64_t narrow_slice_avx2(int32_t *dst, 
     return r;
 }
 
+// the same to uint16 (coverage counts almost always fit): values >= 2^16 saturate, the returned OR tells the caller to redo the slice wider
+__attribute__((target("avx2"))) static uint64_t narrow_slice16_avx2(uint16_t *dst, const int64_t *src, size_t n)
+{
+    __m256i acc = _mm256_setzero_si256();
+    const __m256i idx = _mm256_setr_epi32(0, 2, 4, 6, 0, 0, 0, 0);
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (; i + 8 <= n; i += 8) {
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 4));
+            acc = _mm256_or_si256(acc, _mm256_or_si256(a, b));
+            const __m128i lo = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(a, idx));
+            const __m128i hi = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(b, idx));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_packus_epi32(lo, hi));
+        }
+    }
+    uint64_t o[4];
+    _mm256_storeu_si256(reinterpret_cast<__m256i *>(o), acc);
+    uint64_t r = o[0] | o[1] | o[2] | o[3];
+    for (; i < n; ++i) { r |= (uint64_t)src[i]; dst[i] = (uint16_t)src[i]; }
+    _mm_sfence();
+    return r;
+}
+
+__attribute__((visibility("hidden"))) uint64_t pasio_narrow_slice16(uint16_t *dst, const int64_t *src, size_t n)
+{
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return narrow_slice16_avx2(dst, src, n);
+    uint64_t r = 0;
+    for (size_t i = 0; i < n; ++i) { r |= (uint64_t)src[i]; dst[i] = (uint16_t)src[i]; }
+    return r;
+}
+
 __attribute__((visibility("hidden"))) uint64_t pasio_narrow_slice(int32_t *dst, const int64_t *src, size_t n)
 {
     static const bool have_avx2 = __builtin_cpu_supports("avx2");

@@ -446,11 +446,14 @@ def test_load_and_round_equals_load_then_round(eng, n, constraint):
 
 
 def test_load_and_round_narrowed_upload(eng):
-    """counts that fit 31 bits cross PCIe as int32 (host threads pack them, a kernel widens them): same state and same
-    first round as with plain copies, half the bytes on the link; with the limit lowered to 3 bits (test switch) slices
-    with larger counts go up as they are, in the same run as narrowed ones"""
+    """counts cross PCIe as uint16 / int32 where they fit (host threads pack them, kernels widen them): same state and same
+    first round as with plain copies, a quarter of the bytes on the link; with the limits lowered (test switch: uint16 below
+    2^3, int32 below 2^9) all three kinds of slices occur in one run"""
     n = 40000000
     counts = synth.dnase_like(n, 78, hotspot_share=0.2)
+    counts[counts >= 8] = 7                          # (so that whole slices fit 3 bits ...)
+    counts[3000000:9000000:997] = 300                # (... some need int32 under the test switch ...)
+    counts[30000001] = 70000                         # (... one needs int32 even by default, and is plain under the switch)
     eng.use_scorer(factory(1.0, 1.0))
     got = {}
     try:
@@ -466,13 +469,24 @@ def test_load_and_round_narrowed_upload(eng):
         assert np.array_equal(got[mode][2], got[0][2])
     assert got[0][1][1] == int(counts.sum())
     assert got[0][3] == 8 * n
-    assert 4 * n <= got[1][3] < 4 * n + 8 * (1 << 19)          # all but (at most) the ragged last slice
+    assert 2 * n <= got[1][3] < 2 * n + 10 * (1 << 19)         # all but the ragged last slice (plain) and one int32 slice
     assert got[1][3] < got[3][3] < 8 * n                       # some slices narrowed, some not
     # the dense profile on the device is what was sent: scores of a few fixed segments need the true prefix sums
-    eng.set_candidates(np.array([0, 5, n // 3, n - 7, n], dtype=np.int64))
-    cg = eng.cumsum_at_candidates()
     want = np.concatenate([[0], np.cumsum(counts)])[[0, 5, n // 3, n - 7, n]]
-    assert np.array_equal(cg, want)
+    eng.set_candidates(np.array([0, 5, n // 3, n - 7, n], dtype=np.int64))
+    assert np.array_equal(eng.cumsum_at_candidates(), want)
+    # the plain load (batches of contigs) takes the same route
+    try:
+        for mode, lo, hi in [(1, 2 * n, 2 * n + 10 * (1 << 19)), (3, 2 * n + 1, 8 * n - 1), (0, 8 * n, 8 * n)]:
+            eng.set_tuning('upload_narrow', mode)
+            eng.invalidate()
+            eng.load(counts)
+            assert lo <= eng.upload_stats() <= hi
+            assert eng.info() == (n, int(counts.sum()), 1)
+            eng.set_candidates(np.array([0, 5, n // 3, n - 7, n], dtype=np.int64))
+            assert np.array_equal(eng.cumsum_at_candidates(), want)
+    finally:
+        eng.set_tuning('upload_narrow', 1)
 
 
 def test_load_and_round_asserts_and_table_growth(eng):
