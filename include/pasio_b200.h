@@ -61,10 +61,10 @@ enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (defaul
        PASIO_TUNE_WINDOW_SPECULATE = 6, /* 1 (default): window DP first resolves a 32-row block assuming every row's arg-max is the
                                          row before it (true for nearly all rows of the later rounds), verifies, and falls
                                          back to the ordinary chain where the assumption fails */
-       PASIO_TUNE_UPLOAD_NARROW = 7,  /* 1 (default): large uploads send counts packed to uint16 (a slice whose counts all fit 16 bits) or
-                                         int32 (31 bits): host threads pack them into page-locked slices, a kernel widens them on
-                                         arrival; a slice holding a larger or negative count goes up as it is.  0: plain copies;
-                                         k in 2..24 (tests): uint16 if the slice fits k bits, int32 if it fits k + 6, else plain */
+       PASIO_TUNE_UPLOAD_NARROW = 7,  /* 1 (default): large uploads send counts packed to uint8, uint16 or int32 (whatever every count of
+                                         a 4 MB slice fits): host threads pack them into page-locked slices, a kernel widens them on
+                                         arrival; a slice holding a negative count or one >= 2^31 goes up as it is.  0: plain copies;
+                                         k in 2..24 (tests): uint8 if the slice fits k bits, uint16 k + 3, int32 k + 6, else plain */
        PASIO_TUNE_LOGFAC_EAGER = 8,   /* 1: pasio_contig_load_round also forms the sequential log-factorial sums, chunk by chunk on a
                                          side stream behind the upload (set it when log_marginal_likelyhoods() / the LMM column
                                          will be asked for: the 30 ms sum of a chr1-sized contig is then done when the upload is).
@@ -150,7 +150,7 @@ int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int c
  * pasio_square_split: the same two numbers for the whole-contig DP. */
 int pasio_round_stats(const pasio_ctx *ctx, int64_t *cells, int64_t *cells_skipped);
 /* Bytes the most recent pasio_contig_load_round put on the PCIe link (counts travel as uint16 or int32 where they fit,
- * PASIO_TUNE_UPLOAD_NARROW): 2 * n when every slice fitted 16 bits, 8 * n with plain copies. */
+ * PASIO_TUNE_UPLOAD_NARROW): n when every slice fitted 8 bits, 8 * n with plain copies. */
 int pasio_upload_stats(const pasio_ctx *ctx, int64_t *wire_bytes);
 /* Switch a kernel variant on or off (PASIO_TUNE_*).  Every variant returns identical results
  * (the bounds are exact); defaults come from PASIO_WD_PRUNE / PASIO_WD_PHASES / PASIO_XD_PRUNE /

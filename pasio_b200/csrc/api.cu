@@ -170,8 +170,8 @@ static int upload(pasio_ctx *ctx, void *dst, const void *src, size_t bytes, cuda
 
 // ---- narrowed upload ------------------------------------------------------------------------------
 // Coverage counts are small numbers in 8-byte slots, and a chr1-sized upload is bound by the PCIe link (2 GB at 55 GB/s =
-// 36 ms of an 80 ms end-to-end step).  Host threads therefore pack the counts to uint16 (int32 for a slice that holds a
-// count of 2^16 or more) into page-locked slices (reading the
+// 36 ms of an 80 ms end-to-end step).  Host threads therefore pack the counts to uint8 (uint16 / int32 for a slice that
+// holds a count of 2^8 / 2^16 or more) into page-locked slices (reading the
 // caller's buffer -- pinned or pageable -- at memory bandwidth: 87 GB/s with 16 threads on the bench box,
 // profiles/r02_host_narrow_probe.txt), each slice is DMA'd as soon as it is packed and widened to the int64 layout the
 // kernels use by a small kernel behind the copy on the same stream.  A slice that holds a count outside [0, 2^31) goes up
@@ -190,6 +190,20 @@ __global__ void __launch_bounds__(256) widen_counts_kernel(const int4 *__restric
 // dst[i] = (int32) src[i]; returns the OR of all values (bits 31..63 set <=> some count is negative or >= 2^31); textio.cpp
 uint64_t pasio_narrow_slice(int32_t *dst, const int64_t *src, size_t n);
 uint64_t pasio_narrow_slice16(uint16_t *dst, const int64_t *src, size_t n);     // the same to uint16 (saturating)
+uint64_t pasio_narrow_slice8(uint8_t *dst, const int64_t *src, size_t n);       // and to uint8
+
+__global__ void __launch_bounds__(256) widen_counts8_kernel(const uint4 *__restrict__ src, longlong2 *__restrict__ dst, i64 n16)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (i64)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(src + i);                    // 16 counts
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dst[8 * i + 2 * k] = make_longlong2(w[k] & 0xffu, (w[k] >> 8) & 0xffu);
+            dst[8 * i + 2 * k + 1] = make_longlong2((w[k] >> 16) & 0xffu, w[k] >> 24);
+        }
+    }
+}
 #define narrow_slice pasio_narrow_slice
 
 __global__ void __launch_bounds__(256) widen_counts16_kernel(const uint4 *__restrict__ src, longlong2 *__restrict__ dst, i64 n8)
@@ -214,7 +228,7 @@ struct NarrowUpload {
     std::atomic<int> cancel{0}, failed{0};
     std::unique_ptr<std::atomic<int>[]> left_in_chunk, recorded;
     std::atomic<i64> wire_bytes{0};
-    int limit_bits = 31;                                // test switch (< 31): slices fitting this many bits go as uint16, 6 bits more as int32
+    int limit_bits = 31;                                // test switch (< 25): slices fitting this many bits go as uint8, 3 more as uint16, 6 more as int32
 
     // every slice lies inside one chunk (chunk_elems is a multiple of SLICE)
     int start(pasio_ctx *c, const int64_t *counts, i64 n_, i64 chunk_elems_, i64 n_chunks_)
@@ -274,10 +288,23 @@ struct NarrowUpload {
             i64 *dst = ctx->counts.as<i64>() + e0;
             bool ok = true;
             if (used[buf & 1]) ok = cudaEventSynchronize(ctx->nstage_free[(size_t)buf]) == cudaSuccess;   // its last copy has left
-            // most coverage fits 16 bits: try that first (a quarter of the bytes); its OR says whether to redo the slice wider
-            uint64_t bits = ok ? pasio_narrow_slice16(reinterpret_cast<uint16_t *>(hst), src + e0, (size_t)len) : 0;
-            const int lim16 = limit_bits < 16 ? limit_bits : 16, lim32 = limit_bits < 25 ? limit_bits + 6 : 31;   // (test switch: three-way mix)
-            if (ok && (bits >> lim16) == 0 && (len & 7) == 0) {
+            // most coverage fits 8 bits: try that first (an eighth of the bytes); the OR of the slice says whether to redo it wider
+            const uint64_t bits = ok ? pasio_narrow_slice8(reinterpret_cast<uint8_t *>(hst), src + e0, (size_t)len) : 0;
+            const bool sw = limit_bits < 25;                                           // (test switch: a mix of all four kinds)
+            const int lim8 = sw ? limit_bits : 8, lim16 = sw ? limit_bits + 3 : 16, lim32 = sw ? limit_bits + 6 : 31;
+            if (ok && (bits >> lim8) == 0 && (len & 15) == 0) {
+                ok = cudaMemcpyAsync(dev, hst, (size_t)len, cudaMemcpyHostToDevice, ctx->stream_copy) == cudaSuccess;
+                if (ok) {
+                    ok = cudaEventRecord(ctx->nstage_free[(size_t)buf], ctx->stream_copy) == cudaSuccess;
+                    used[buf & 1] = true;
+                    const i64 n16 = len / 16;
+                    widen_counts8_kernel<<<(unsigned)std::min<i64>((n16 + 255) / 256, 296), 256, 0, ctx->stream_copy>>>(
+                        reinterpret_cast<const uint4 *>(dev), reinterpret_cast<longlong2 *>(dst), n16);
+                    ok = ok && cudaGetLastError() == cudaSuccess;
+                    wire_bytes.fetch_add(len);
+                }
+            } else if (ok && (bits >> lim16) == 0 && (len & 7) == 0) {
+                pasio_narrow_slice16(reinterpret_cast<uint16_t *>(hst), src + e0, (size_t)len);
                 ok = cudaMemcpyAsync(dev, hst, (size_t)len * 2, cudaMemcpyHostToDevice, ctx->stream_copy) == cudaSuccess;
                 if (ok) {
                     ok = cudaEventRecord(ctx->nstage_free[(size_t)buf], ctx->stream_copy) == cudaSuccess;

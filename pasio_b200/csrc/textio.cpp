@@ -428,6 +428,43 @@ __attribute__((target("avx2"))) static uint64_t narrow_slice16_avx2(uint16_t *ds
     return r;
 }
 
+// and to uint8 (most coverage is below 256 everywhere)
+__attribute__((target("avx2"))) static uint64_t narrow_slice8_avx2(uint8_t *dst, const int64_t *src, size_t n)
+{
+    __m256i acc = _mm256_setzero_si256();
+    const __m256i idx = _mm256_setr_epi32(0, 2, 4, 6, 0, 0, 0, 0);
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (; i + 16 <= n; i += 16) {
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 4));
+            const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 8));
+            const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 12));
+            acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(a, b), _mm256_or_si256(c, d)));
+            const __m128i ab = _mm_packus_epi32(_mm256_castsi256_si128(_mm256_permutevar8x32_epi32(a, idx)),
+                                                _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(b, idx)));
+            const __m128i cd = _mm_packus_epi32(_mm256_castsi256_si128(_mm256_permutevar8x32_epi32(c, idx)),
+                                                _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(d, idx)));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_packus_epi16(ab, cd));
+        }
+    }
+    uint64_t o[4];
+    _mm256_storeu_si256(reinterpret_cast<__m256i *>(o), acc);
+    uint64_t r = o[0] | o[1] | o[2] | o[3];
+    for (; i < n; ++i) { r |= (uint64_t)src[i]; dst[i] = (uint8_t)src[i]; }
+    _mm_sfence();
+    return r;
+}
+
+__attribute__((visibility("hidden"))) uint64_t pasio_narrow_slice8(uint8_t *dst, const int64_t *src, size_t n)
+{
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return narrow_slice8_avx2(dst, src, n);
+    uint64_t r = 0;
+    for (size_t i = 0; i < n; ++i) { r |= (uint64_t)src[i]; dst[i] = (uint8_t)src[i]; }
+    return r;
+}
+
 __attribute__((visibility("hidden"))) uint64_t pasio_narrow_slice16(uint16_t *dst, const int64_t *src, size_t n)
 {
     static const bool have_avx2 = __builtin_cpu_supports("avx2");

@@ -229,38 +229,8 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
     const bool act2 = r0 < nrows;
     const int2 gF = col_lc(sCol, jb + min(r0, nrows - 1)), gL = col_lc(sCol, jb + r1);
 
-    // ---- level 1: 32 rows x 32 columns, one lane per rectangle, the rectangles packed into as few warps as they fill
-    // (77 blocks of a 2500-candidate window: 3 warps; the others go straight to the barrier) ----
-    for (int base = 0; base + 32 * w7 < nfar; base += 32 * WD_FARW) {
-        const int cb = base + 32 * w7 + lane;
-        bool surv1 = false;
-        if (cb < nfar) {
-            const CoarseRec *rec = sCoarse + cb;
-            const int4 ends = *reinterpret_cast<const int4 *>(rec);
-            const double a1 = rec->a, b1 = rec->b;
-            const double ub1 = rec->mpt + tilted_box_max<AI>(rowF.y - ends.y, rowL.y - ends.x, rowF.x - ends.w, rowL.x - ends.z,
-                                                             a1, b1, gtab, ltab, alpha_int, alpha);
-            // min_r (lb_r + a*C_r + b*L_r): every lane walks the 32 rows (broadcast reads of sRow)
-            const double m3 = tilted_row_min(sRow, 0, nrows - 1, a1, b1, lbabs, rowL.y, rowL.x);
-            surv1 = !(ub1 - m3 + delta < 0.0);                           // NaN keeps the block
-            if (!surv1) skipped += (u64)(PR_CB * nrows);
-        }
-        const unsigned mask1 = __ballot_sync(0xffffffffu, surv1);
-        if (mask1) {
-            int slot = 0;
-            if (lane == 0) slot = atomicAdd(sListCount + 2, __popc(mask1));
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (surv1) sSurv[slot + __popc(mask1 & ((1u << lane) - 1u))] = (unsigned short)cb;
-        }
-    }
-    PROF_T(4);
-    asm volatile("bar.sync 1, %0;" ::"n"(WD_FARW * 32) : "memory");
-    const int nsurv = *reinterpret_cast<volatile int *>(sListCount + 2);
-
-    // ---- level 2: a surviving block as 8 row groups x 4 sub-blocks of 8 columns, one lane per rectangle; the surviving
-    // blocks are dealt round-robin to the far warps ----
-    for (int e = w7; e < nsurv; e += WD_FARW) {
-        const int cb1 = sSurv[e];
+    // level 2: a block as 8 row groups x 4 sub-blocks of 8 columns, one lane per rectangle (a whole warp per block)
+    auto level2 = [&](int cb1) {
         const CoarseRec *rec = sCoarse + cb1;
         const double a = rec->a, b = rec->b;
         bool surv2 = false;
@@ -285,7 +255,44 @@ __device__ __forceinline__ u64 far_pass(int jb, int N, int nfar, const ColRec *s
             slot = __shfl_sync(0xffffffffu, slot, 0);
             if (surv2) sList[slot + __popc(mask2 & ((1u << lane) - 1u))] = (unsigned short)((cb1 << 5) | lane);
         }
+    };
+    // The nearest blocks nearly always survive level 1, and level 1 (packed) leaves warps idle: those warps take the nearest
+    // blocks straight to level 2 while the others bound the rest, which takes a level-2 pass off the critical path.
+    const int l1_warps = min(WD_FARW, (nfar + 31) / 32);
+    const int n_direct = max(0, min(nfar, WD_FARW - l1_warps));
+    const int nfar1 = nfar - n_direct;                     // level 1 covers blocks [0, nfar1)
+    if (w7 >= l1_warps && w7 - l1_warps < n_direct) level2(nfar - 1 - (w7 - l1_warps));
+
+    // ---- level 1: 32 rows x 32 columns, one lane per rectangle, the rectangles packed into as few warps as they fill
+    // (77 blocks of a 2500-candidate window: 3 warps) ----
+    for (int base = 0; base + 32 * w7 < nfar1 && w7 < l1_warps; base += 32 * l1_warps) {
+        const int cb = base + 32 * w7 + lane;
+        bool surv1 = false;
+        if (cb < nfar1) {
+            const CoarseRec *rec = sCoarse + cb;
+            const int4 ends = *reinterpret_cast<const int4 *>(rec);
+            const double a1 = rec->a, b1 = rec->b;
+            const double ub1 = rec->mpt + tilted_box_max<AI>(rowF.y - ends.y, rowL.y - ends.x, rowF.x - ends.w, rowL.x - ends.z,
+                                                             a1, b1, gtab, ltab, alpha_int, alpha);
+            // min_r (lb_r + a*C_r + b*L_r): every lane walks the 32 rows (broadcast reads of sRow)
+            const double m3 = tilted_row_min(sRow, 0, nrows - 1, a1, b1, lbabs, rowL.y, rowL.x);
+            surv1 = !(ub1 - m3 + delta < 0.0);                           // NaN keeps the block
+            if (!surv1) skipped += (u64)(PR_CB * nrows);
+        }
+        const unsigned mask1 = __ballot_sync(0xffffffffu, surv1);
+        if (mask1) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(sListCount + 2, __popc(mask1));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (surv1) sSurv[slot + __popc(mask1 & ((1u << lane) - 1u))] = (unsigned short)cb;
+        }
     }
+    PROF_T(4);
+    asm volatile("bar.sync 1, %0;" ::"n"(WD_FARW * 32) : "memory");
+    const int nsurv = *reinterpret_cast<volatile int *>(sListCount + 2);
+
+    // ---- level 2 of the blocks that survived level 1, dealt round-robin to the far warps ----
+    for (int e = w7; e < nsurv; e += WD_FARW) level2(sSurv[e]);
     PROF_T(5);
     // ---- all far warps: the list is complete ----
     asm volatile("bar.sync 1, %0;" ::"n"(WD_FARW * 32) : "memory");

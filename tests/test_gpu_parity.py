@@ -446,14 +446,15 @@ def test_load_and_round_equals_load_then_round(eng, n, constraint):
 
 
 def test_load_and_round_narrowed_upload(eng):
-    """counts cross PCIe as uint16 / int32 where they fit (host threads pack them, kernels widen them): same state and same
-    first round as with plain copies, a quarter of the bytes on the link; with the limits lowered (test switch: uint16 below
-    2^3, int32 below 2^9) all three kinds of slices occur in one run"""
+    """counts cross PCIe as uint8 / uint16 / int32 where they fit (host threads pack them, kernels widen them): same state
+    and same first round as with plain copies, an eighth of the bytes on the link; with the limits lowered (test switch:
+    uint8 below 2^3, uint16 below 2^6, int32 below 2^9) all four kinds of slices occur in one run"""
     n = 40000000
     counts = synth.dnase_like(n, 78, hotspot_share=0.2)
-    counts[counts >= 8] = 7                          # (so that whole slices fit 3 bits ...)
-    counts[3000000:9000000:997] = 300                # (... some need int32 under the test switch ...)
-    counts[30000001] = 70000                         # (... one needs int32 even by default, and is plain under the switch)
+    counts[counts >= 8] = 7                          # (so that whole slices fit 3 bits: uint8 under the test switch ...)
+    counts[12000000:15000000:499] = 40               # (... some need uint16 under the switch ...)
+    counts[3000000:9000000:997] = 300                # (... some int32; uint16 by default ...)
+    counts[30000001] = 70000                         # (... and one is plain under the switch, int32 by default)
     eng.use_scorer(factory(1.0, 1.0))
     got = {}
     try:
@@ -469,7 +470,7 @@ def test_load_and_round_narrowed_upload(eng):
         assert np.array_equal(got[mode][2], got[0][2])
     assert got[0][1][1] == int(counts.sum())
     assert got[0][3] == 8 * n
-    assert 2 * n <= got[1][3] < 2 * n + 10 * (1 << 19)         # all but the ragged last slice (plain) and one int32 slice
+    assert n <= got[1][3] < n + 24 * (1 << 19)                 # uint8 but for a dozen uint16 slices, one int32, the ragged last one plain
     assert got[1][3] < got[3][3] < 8 * n                       # some slices narrowed, some not
     # the dense profile on the device is what was sent: scores of a few fixed segments need the true prefix sums
     want = np.concatenate([[0], np.cumsum(counts)])[[0, 5, n // 3, n - 7, n]]
@@ -477,7 +478,7 @@ def test_load_and_round_narrowed_upload(eng):
     assert np.array_equal(eng.cumsum_at_candidates(), want)
     # the plain load (batches of contigs) takes the same route
     try:
-        for mode, lo, hi in [(1, 2 * n, 2 * n + 10 * (1 << 19)), (3, 2 * n + 1, 8 * n - 1), (0, 8 * n, 8 * n)]:
+        for mode, lo, hi in [(1, n, n + 24 * (1 << 19)), (3, n + 1, 8 * n - 1), (0, 8 * n, 8 * n)]:
             eng.set_tuning('upload_narrow', mode)
             eng.invalidate()
             eng.load(counts)
