@@ -3,7 +3,7 @@
 # a full capture of the window / scan kernels of the same bench command; plus a host memory-bandwidth probe
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=${1:-f1}
+T=${1:-f2}
 timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_gpu_tests.log 2>&1
 echo "gpu tests rc=$?" >> gpurun_out/${T}_gpu_tests.log
 timeout 1200 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
@@ -22,3 +22,6 @@ if [ $rc -eq 0 ]; then
   }
 fi
 tail -4 gpurun_out/${T}_gpu_tests.log; tail -2 gpurun_out/${T}_bench.err; head -c 500 gpurun_out/${T}_bench.json; cat gpurun_out/${T}_smoke.log | tail -2; cat gpurun_out/${T}_host_narrow.txt; head -c 400 gpurun_out/${T}_bench_reference.json
+timeout 1500 python tools/config5_stdin.py > gpurun_out/${T}_config5_stdin_text.json 2> gpurun_out/${T}_config5_stdin.err
+timeout 900 python tools/cli_e2e.py > gpurun_out/${T}_cli_e2e.log 2>&1
+cat gpurun_out/${T}_config5_stdin_text.json; tail -4 gpurun_out/${T}_cli_e2e.log
