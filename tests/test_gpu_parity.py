@@ -449,7 +449,7 @@ def test_load_and_round_narrowed_upload(eng):
     """counts cross PCIe as uint8 / uint16 / int32 where they fit (host threads pack them, kernels widen them): same state
     and same first round as with plain copies, an eighth of the bytes on the link; with the limits lowered (test switch:
     uint8 below 2^3, uint16 below 2^6, int32 below 2^9) all four kinds of slices occur in one run"""
-    n = 40000000
+    n = 40000003                                     # (a ragged last slice: it goes up as it is)
     counts = synth.dnase_like(n, 78, hotspot_share=0.2)
     counts[counts >= 8] = 7                          # (so that whole slices fit 3 bits: uint8 under the test switch ...)
     counts[12000000:15000000:499] = 40               # (... some need uint16 under the switch ...)
