@@ -228,6 +228,14 @@ struct NarrowUpload {
     std::atomic<int> cancel{0}, failed{0};
     std::unique_ptr<std::atomic<int>[]> left_in_chunk, recorded;
     std::atomic<i64> wire_bytes{0};
+    // A page-locked source can also be DMA'd as it is, at the PCIe rate and without any host thread.  Packing only pays while
+    // the host threads read faster than that -- not when eight ranks pack on one host and share its memory bandwidth (8-GPU
+    // weak-scaling run: 156 ms per rank packed, 94-127 ms plain).  So the rate of the first 512 MB decides for the rest.
+    bool src_pinned = false;
+    std::chrono::steady_clock::time_point t_start;
+    std::atomic<i64> packed_elems{0};
+    std::atomic<int> decided{0}, plain_mode{0};
+    static constexpr double PLAIN_RATE = 60e9;             // source bytes per second a plain copy from pinned memory reaches (55 GB/s) + margin
     int limit_bits = 31;                                // test switch (< 25): slices fitting this many bits go as uint8, 3 more as uint16, 6 more as int32
 
     // every slice lies inside one chunk (chunk_elems is a multiple of SLICE)
@@ -268,6 +276,8 @@ struct NarrowUpload {
                 recorded[(size_t)q].store(1, std::memory_order_release);
             }
         }
+        src_pinned = host_is_pinned(counts);
+        t_start = std::chrono::steady_clock::now();
         for (int t = 0; t < T; ++t) threads.emplace_back([this, t] { work(t); });
         return 0;
     }
@@ -287,6 +297,18 @@ struct NarrowUpload {
             int32_t *dev = (int32_t *)ctx->nstage_dev + (size_t)buf * SLICE;
             i64 *dst = ctx->counts.as<i64>() + e0;
             bool ok = true;
+            if (plain_mode.load(std::memory_order_relaxed)) {
+                ok = cudaMemcpyAsync(dst, src + e0, (size_t)len * 8, cudaMemcpyHostToDevice, ctx->stream_copy) == cudaSuccess;
+                wire_bytes.fetch_add(len * 8);
+                which ^= 1;                                   // (this slice used no staging buffer)
+                if (!ok) { cudaGetLastError(); failed.store(1); cancel.store(1); }
+                const i64 qp = e0 / chunk_elems;
+                if (left_in_chunk[(size_t)qp].fetch_sub(1) == 1) {
+                    if (cudaEventRecord(ctx->chunk_events[(size_t)qp], ctx->stream_copy) != cudaSuccess) { cudaGetLastError(); failed.store(1); }
+                    recorded[(size_t)qp].store(1, std::memory_order_release);
+                }
+                continue;
+            }
             if (used[buf & 1]) ok = cudaEventSynchronize(ctx->nstage_free[(size_t)buf]) == cudaSuccess;   // its last copy has left
             // most coverage fits 8 bits: try that first (an eighth of the bytes); the OR of the slice says whether to redo it wider
             const uint64_t bits = ok ? pasio_narrow_slice8(reinterpret_cast<uint8_t *>(hst), src + e0, (size_t)len) : 0;
@@ -334,6 +356,10 @@ struct NarrowUpload {
                 wire_bytes.fetch_add(len * 8);
             }
             if (!ok) { cudaGetLastError(); failed.store(1); cancel.store(1); }
+            if (src_pinned && packed_elems.fetch_add(len) + len >= ((i64)64 << 20) && !decided.exchange(1)) {
+                const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+                if ((double)packed_elems.load() * 8.0 < PLAIN_RATE * secs) plain_mode.store(1);
+            }
             const i64 q = e0 / chunk_elems;
             if (left_in_chunk[(size_t)q].fetch_sub(1) == 1) {
                 // every slice of chunk q has been queued (by this or another thread, before its decrement)
