@@ -69,7 +69,9 @@ enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (defaul
                                          side stream behind the upload (set it when log_marginal_likelyhoods() / the LMM column
                                          will be asked for: the 30 ms sum of a chr1-sized contig is then done when the upload is).
                                          0 (default): on demand, or pasio_logfac_prefetch */
-       PASIO_TUNE_COUNT = 9 };
+       PASIO_TUNE_EXACT_NBLOCK = 9,   /* 1 (default): the exact DP hands the first column block of the diagonal's band (block b - lag + 1
+                                         of row block b) to worker CTAs, which evaluate it exhaustively; 0: the diagonal sweeps it */
+       PASIO_TUNE_COUNT = 10 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int pasio_ctx_create(int device, pasio_ctx **out);

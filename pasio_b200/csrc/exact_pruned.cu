@@ -36,6 +36,8 @@ constexpr int XP_THREADS = 256;
 constexpr int XP_HELP = 7;            // helper warps of the diagonal CTA: six sweep the mid columns, one (warp 4) keeps the books
 constexpr int XP_MIDW = 6;
 constexpr int XP_G = 8;               // far slices per row block
+constexpr int XP_NG = 8;              // slices of the column block next to the far region, evaluated exhaustively by workers (N tasks)
+constexpr int XP_GT = XP_G + XP_NG;   // result slices per row block
 constexpr int XP_SQ = 4;              // self-score sub-tasks per row block
 constexpr int XP_RING = 64;           // row blocks of self scores kept
 constexpr int XP_SAHEAD = 16;         // self scores are produced this many blocks ahead of the diagonal
@@ -64,6 +66,7 @@ static_assert(sizeof(XpRec32) == 144 && sizeof(XpAnchors) == 160, "record layout
 
 struct XpParams {
     int N, nB, nSteps, lag, DB, n_tasks, npad;
+    int nb;                     // 1: the first column block of the band (block b - lag + 1) is evaluated by worker CTAs (N tasks), not swept by the diagonal
     int dbg;                    // PASIO_XD_DBG (timing experiments only, results become wrong): 1 no mid sweep, 2 no records,
                                 // 4 no waiting for far results, 8 no tile moves, 16 mid: loads only, 32 mid: arithmetic only
     int s_slots;                // row blocks of self scores held: nB (every block has its own slab: written once per launch,
@@ -74,11 +77,11 @@ struct XpParams {
     int *prev;
     double *Sring;              // [ring slot][d - 1][row in block]
     int *s_ready;               // [nB] finished S sub-tasks
-    int *far_ready;             // [nB] finished F slices
+    int *far_ready;             // [nB] finished F and N slices
     int *done_block;            // blocks finished and published (P, prev, records)
     unsigned *task_counter;
     const int2 *tasks;          // x = type | block << 1, y = sub index
-    double *farV;               // [nB][XP_G][128]
+    double *farV;               // [nB][XP_GT][128]: far slices, then N slices
     int *farA;
     XpRec32 *rec32;             // per 32 finished columns [1 + 32q, 33 + 32q)
     CoarseRec *rec128;          // per finished block
@@ -139,6 +142,8 @@ __device__ __forceinline__ void xp_wait_s_blocks(const XpParams &p, int need, in
 }
 
 __device__ __forceinline__ int xp_far_bound(int b, int lag) { return b >= lag - 1 ? 1 + XP_RB * (b - lag + 1) : 0; }
+// first column of the band the diagonal sweeps itself (and of the self-score slabs): with N tasks one block later than the far bound
+__device__ __forceinline__ int xp_band_bound(int b, int lag, int nb) { return xp_far_bound(b, lag) + ((nb && b >= lag - 1) ? XP_RB : 0); }
 
 __host__ __device__ inline size_t xp_diag_smem()
 {
@@ -185,7 +190,7 @@ __device__ __forceinline__ XpMid xp_mid_geometry(const XpParams &p, int step, in
 {
     XpMid g;
     const int jbn = 1 + 32 * step, bn = step >> 2;
-    const int F = xp_far_bound(bn, p.lag);
+    const int F = xp_band_bound(bn, p.lag, p.nb);
     g.j = jbn + lane;
     g.Sb = p.Sring + (size_t)(bn % p.s_slots) * p.DB * XP_RB + (step & 3) * 32 + lane;
     const int nd = jbn - F - 1;                          // distances 33 .. jbn + 31 - F over the warp
@@ -455,7 +460,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 // measured slower: profiles/r02_exact_dp_v8_notes.txt)
                 if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
                     if (lane == 0 && !(p.dbg & 4)) {
-                        while (xp_ld_flag(p.far_ready + (b + 1)) < XP_G) __nanosleep(20);
+                        while (xp_ld_flag(p.far_ready + (b + 1)) < (p.nb ? XP_GT : XP_G)) __nanosleep(20);
                         __threadfence();
                     }
                     __syncwarp();
@@ -477,8 +482,10 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 const bool do_fold = !(p.dbg & 16), do_load = !(p.dbg & 32);
                 if (have1 && do_fold) xp_mid_fold(g1, g1.dhi - 1, pre0, sP, best, arg);
                 if (have2 && do_load) xp_mid_load<RING>(g2, g2.dhi - 1, pre0);
+                // (with N tasks a warp's chunk is 22 .. 38 distances: the second batch is empty in half of the steps)
+                const bool two1 = g1.dhi - 1 - XP_MB >= g1.dlo, two2 = g2.dhi - 1 - XP_MB >= g2.dlo;      // warp-uniform
                 if (have1) {
-                    if (do_fold) xp_mid_fold(g1, g1.dhi - 1 - XP_MB, pre1, sP, best, arg);
+                    if (do_fold && two1) xp_mid_fold(g1, g1.dhi - 1 - XP_MB, pre1, sP, best, arg);
                     for (int d = g1.dhi - 1 - 2 * XP_MB; d >= g1.dlo; d -= XP_MB) {    // (lag 4: further batches, loaded here)
                         double v[XP_MB];
                         xp_mid_load<RING>(g1, d, v);
@@ -487,7 +494,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                     sMidV[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = best;
                     sMidA[(((k + 1) & 1) * XP_HELP + hw) * 32 + lane] = arg;
                 }
-                if (have2 && do_load) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
+                if (have2 && do_load && two2) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
                 if (p.dbg & 16) { double acc = 0.0; for (int u = 0; u < XP_MB; ++u) acc += pre0[u] + pre1[u]; if (acc == 1.2345) sMidV[0] = acc; }   // (keeps the loads alive)
                 { const long long t1 = xp_clock(); pq[1] += t1 - tq; tq = t1; }
                 // the tile of step k+2 (loaded during the previous step) -> shared memory; then the loads of the next one
@@ -503,15 +510,16 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                         double best = -INFINITY;
                         int arg = 0x7fffffff;
                         if (j < N) {
-                            double v[XP_G];
-                            int a[XP_G];
+                            double v[XP_GT];
+                            int a[XP_GT];
 #pragma unroll
-                            for (int g = 0; g < XP_G; ++g) {
-                                v[g] = __ldcg(p.farV + ((size_t)(b + 1) * XP_G + g) * XP_RB + hidx);
-                                a[g] = __ldcg(p.farA + ((size_t)(b + 1) * XP_G + g) * XP_RB + hidx);
+                            for (int g = 0; g < XP_GT; ++g) {
+                                const bool have = g < XP_G || p.nb;
+                                v[g] = have ? __ldcg(p.farV + ((size_t)(b + 1) * XP_GT + g) * XP_RB + hidx) : -INFINITY;
+                                a[g] = have ? __ldcg(p.farA + ((size_t)(b + 1) * XP_GT + g) * XP_RB + hidx) : 0x7fffffff;
                             }
 #pragma unroll
-                            for (int g = 0; g < XP_G; ++g)
+                            for (int g = 0; g < XP_GT; ++g)
                                 if (v[g] > best || (v[g] == best && a[g] < arg)) { best = v[g]; arg = a[g]; }
                         }
                         sFarV[((b + 1) & 1) * XP_RB + hidx] = best;
@@ -536,7 +544,7 @@ __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
 {
     int2 *sLC = reinterpret_cast<int2 *>(smem);                 // (L, C) of candidates [F, r0 + nrows)
     const int tid = threadIdx.x;
-    const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, p.N - r0), F = xp_far_bound(b, p.lag);
+    const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, p.N - r0), F = xp_band_bound(b, p.lag, p.nb);
     const long long ts0 = xp_clock();
     if (b >= p.s_slots) xp_wait_cta(p.done_block, b - p.s_slots + 1);  // ring only: the slot's previous block is finished
     const long long ts1 = xp_clock();
@@ -938,8 +946,8 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
             const int a = sWA[w * XP_RB + tid];
             if (v > best || (v == best && a < arg)) { best = v; arg = a; }
         }
-        __stcg(p.farV + ((size_t)b * XP_G + g) * XP_RB + tid, best);
-        __stcg(p.farA + ((size_t)b * XP_G + g) * XP_RB + tid, arg);
+        __stcg(p.farV + ((size_t)b * XP_GT + g) * XP_RB + tid, best);
+        __stcg(p.farA + ((size_t)b * XP_GT + g) * XP_RB + tid, arg);
     }
     if (tid == 0 && evaluated) atomicAdd(p.far_cells, evaluated);
     __syncthreads();
@@ -955,6 +963,61 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
         atomicAdd(p.prof + XQ_F_L1, (u64)tl1);
         atomicAdd(p.prof + XQ_F_L23, (u64)tl2);
         atomicAdd(p.prof + XQ_F_HEAD, (u64)thead);
+    }
+}
+
+// N(b, g): rows of block b against 16 columns of the first block of the band, [F_b + 16 g, F_b + 16 g + 16) -- the block
+// that has just been published when block b - lag + 2 starts.  Too close to the diagonal for the bounds of the F tasks to
+// be worth their latency, too far for the chain to need it soon: its 128 x 128 cells are simply evaluated, in the
+// reference's operation order, by eight worker CTAs, and reach the diagonal with the far results.  This takes a third of
+// the columns (at lag 3) out of the sweep that the diagonal's helper warps stream through one SM.
+template <bool AI>
+__device__ void xp_n_task(const XpParams &p, int b, int g, unsigned char *smem)
+{
+    double *sV = reinterpret_cast<double *>(smem);                      // [2][128]
+    int *sA = reinterpret_cast<int *>(sV + 2 * XP_RB);                  // [2][128]
+    const int tid = threadIdx.x;
+    const int N = p.N;
+    const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, N - r0);
+    const int F = xp_far_bound(b, p.lag);
+    xp_wait_cta(p.done_block, b - p.lag + 2);                           // blocks 0 .. b - lag + 1 are final
+    const int r = tid & (XP_RB - 1), h = tid >> 7;                      // row; which 8 of the slice's 16 columns
+    const int c0 = F + 16 * g + 8 * h;
+    double best = -INFINITY;
+    int arg = 0x7fffffff;
+    if (r < nrows) {
+        const int j = r0 + r;
+        const RowConst<AI> row = make_row<AI>(__ldg(p.C + j), __ldg(p.L + j), p.alpha_int, p.alpha);
+        double gq[8], lq[8], pc[8];
+        int ci[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {                                   // all gathers in flight, then the arithmetic
+            ci[u] = __ldg(p.C + c0 + u);
+            gq[u] = __ldg(p.gtab + (row.cjx - ci[u]));
+            lq[u] = __ldg(p.ltab + (row.lj - __ldg(p.L + c0 + u)));
+            pc[u] = __ldcg(p.P + c0 + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double sx = AI ? u32_to_double(row.cjx - ci[u]) : __dsub_rn(row.aj, u32_to_double(ci[u]));
+            const double t = __dadd_rn(__dsub_rn(gq[u], __dmul_rn(sx, lq[u])), pc[u]);
+            if (t > best) { best = t; arg = c0 + u; }
+        }
+    }
+    sV[h * XP_RB + r] = best;
+    sA[h * XP_RB + r] = arg;
+    __syncthreads();
+    if (tid < nrows) {
+        double v = sV[tid];
+        int a = sA[tid];
+        if (sV[XP_RB + tid] > v) { v = sV[XP_RB + tid]; a = sA[XP_RB + tid]; }      // the later columns win only when strictly greater
+        __stcg(p.farV + ((size_t)b * XP_GT + XP_G + g) * XP_RB + tid, v);
+        __stcg(p.farA + ((size_t)b * XP_GT + XP_G + g) * XP_RB + tid, a);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(p.far_ready + b, 1);
     }
 }
 
@@ -987,16 +1050,18 @@ exact_pruned_kernel(XpParams p)
         if (t >= p.n_tasks) return;
         const int2 task = __ldg(p.tasks + t);
         if ((task.x & 1) == 0) xp_s_task<AI>(p, task.x >> 1, task.y, smem);
-        else xp_f_task<AI>(p, task.x >> 1, task.y, smem);
+        else if (task.y < XP_G) xp_f_task<AI>(p, task.x >> 1, task.y, smem);
+        else xp_n_task<AI>(p, task.x >> 1, task.y - XP_G, smem);
     }
 }
 
 // S tasks run XP_SAHEAD blocks ahead of the F tasks; F(b) sits where the diagonal finishes block b - lag.
-std::vector<int2> build_tasks(int nB, int lag)
+std::vector<int2> build_tasks(int nB, int lag, int nb)
 {
     std::vector<int2> t;
     auto push_s = [&](int b) { if (b < nB) for (int q = 0; q < XP_SQ; ++q) t.push_back(make_int2(b << 1, q)); };
-    auto push_f = [&](int b) { if (b >= lag - 1 && b < nB) for (int g = 0; g < XP_G; ++g) t.push_back(make_int2((b << 1) | 1, g)); };
+    // F slices first (they are released one block earlier), then the N slices of the same row block (sub index >= XP_G)
+    auto push_f = [&](int b) { if (b >= lag - 1 && b < nB) for (int g = 0; g < (nb ? XP_GT : XP_G); ++g) t.push_back(make_int2((b << 1) | 1, g)); };
     for (int b = 0; b < XP_SAHEAD; ++b) push_s(b);
     for (int tt = 0; tt < nB; ++tt) {
         push_f(tt + lag - 1);
@@ -1014,9 +1079,10 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.nSteps = (int)((N - 1 + 31) / 32);
     p.lag = lag;
     p.dbg = getenv("PASIO_XD_DBG") ? atoi(getenv("PASIO_XD_DBG")) : 0;
-    p.DB = XP_RB * lag;
     p.npad = (int)((N + 127) & ~(i64)127);
-    const std::vector<int2> tasks = build_tasks(p.nB, lag);
+    p.nb = ctx->tune[PASIO_TUNE_EXACT_NBLOCK] ? 1 : 0;
+    p.DB = XP_RB * (lag - p.nb);                                 // distances kept per row block: the band is one block narrower with N tasks
+    const std::vector<int2> tasks = build_tasks(p.nB, lag, p.nb);
     p.n_tasks = (int)tasks.size();
 
     // every row block its own slab of self scores while that fits XP_LINEAR_BYTES (2 GB: N <= 680 000 at lag 3), else a ring
@@ -1026,7 +1092,7 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     const int slots = ring && p.nB > XP_RING ? XP_RING : p.nB;
     p.s_slots = slots;
     const size_t ring_bytes = (size_t)slots * p.DB * XP_RB * 8;
-    const size_t far_bytes = (size_t)XP_G * XP_RB * p.nB * 12;
+    const size_t far_bytes = (size_t)XP_GT * XP_RB * p.nB * 12;
     const size_t rec_bytes = ((size_t)p.nSteps + 1) * sizeof(XpRec32) + ((size_t)p.nB + 1) * (sizeof(CoarseRec) + sizeof(XpAnchors));
     const size_t flag_ints = (size_t)2 * p.nB + 8 + 64 + 8;      // + 32 u64 profile counters + 4 doubles of constants
     PASIO_TRY(pasio_reserve(ctx, ctx->xpRing, ring_bytes));
@@ -1055,7 +1121,7 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.far_ready = p.s_ready + p.nB;
     p.tasks = ctx->xpTasks.as<int2>();
     p.farV = ctx->dpPart.as<double>();
-    p.farA = reinterpret_cast<int *>(p.farV + (size_t)XP_G * XP_RB * p.nB);
+    p.farA = reinterpret_cast<int *>(p.farV + (size_t)XP_GT * XP_RB * p.nB);
     p.rec32 = ctx->xpRec.as<XpRec32>();
     p.rec128 = reinterpret_cast<CoarseRec *>(p.rec32 + p.nSteps + 1);
     p.anchors = reinterpret_cast<XpAnchors *>(p.rec128 + p.nB + 1);

@@ -34,6 +34,7 @@ def exact(args, which):
         N = len(cands)
     eng.load(counts)
     eng.set_tuning('exact_prune', args.prune)
+    eng.set_tuning('exact_nblock', args.nblock)
     eng.set_tuning('exact_lag', args.lag)
     eng.set_tuning('exact_ring', args.ring)
     times = []
@@ -156,6 +157,7 @@ if __name__ == '__main__':
     ap.add_argument('--prune', type=int, default=1, help='exact DP: 1 = bounded far columns (default), 0 = every cell')
     ap.add_argument('--ring', type=int, default=1, help='exact DP: 1 = self scores in the ring layout of very long lists')
     ap.add_argument('--lag', type=int, default=3, help='exact DP: far columns start this many blocks behind (3 or 4)')
+    ap.add_argument('--nblock', type=int, default=1, help='exact DP: 1 = first block of the band on worker CTAs (default)')
     a = ap.parse_args()
     if a.what == 'exact1':
         exact(a, 1)
