@@ -329,9 +329,11 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     }
     long long pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // per-thread phase cycles (only threads 0, 32 and 224 report)
     const long long t_begin = xp_clock();
+    long long t_last = t_begin;
     for (int k = 0; k < p.nSteps; ++k) {
         const int jb = 1 + 32 * k, b = k >> 2, s = k & 3;
         long long tq = xp_clock();
+        pq[6] += tq - t_last;                              // (between the clock read behind the barrier and this one)
         if (warp == 0) {
             // ---------------- chain warp: rows [jb, jb + 32) ----------------
             const int j = jb + lane;
@@ -530,11 +532,15 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             }
         }
         __syncthreads();
-        pq[5] += xp_clock() - tq;
+        t_last = xp_clock();
+        pq[5] += t_last - tq;
     }
-    if (tid == 0) { p.prof[XQ_CHAIN] = pq[0]; p.prof[XQ_CHAIN_BAR] = pq[5]; p.prof[XQ_DIAG_TOTAL] = xp_clock() - t_begin; }
+    if ((p.dbg & 64) && lane == 0) printf("[xp_dbg] warp %d: barrier gap %lld, phases %lld %lld %lld %lld %lld %lld cycles/step\n", warp, pq[6] / p.nSteps, pq[0] / p.nSteps, pq[1] / p.nSteps, pq[2] / p.nSteps, pq[3] / p.nSteps, pq[4] / p.nSteps, pq[5] / p.nSteps);
+    if (tid == 0) { p.prof[XQ_CHAIN] = pq[0]; p.prof[XQ_CHAIN_BAR] = pq[5]; p.prof[XQ_DIAG_TOTAL] = xp_clock() - t_begin; p.prof[31] = pq[6]; }
+    if (tid == 32) p.prof[XQ_H6_MID] = pq[6];                // (the sweeping warp's back-edge gap, in a slot the book-keeping warp never uses)
     if (tid == 32) { p.prof[XQ_H0_MID] = pq[1]; p.prof[XQ_H0_TILE] = pq[2]; p.prof[XQ_H0_SWAIT] = pq[3]; p.prof[XQ_H0_FAR] = pq[4]; p.prof[XQ_H0_BAR] = pq[5]; }
-    if (tid == 128) { p.prof[XQ_H6_REC] = pq[0]; p.prof[XQ_H6_MID] = pq[1]; p.prof[XQ_H6_TILE] = pq[2]; p.prof[XQ_H6_SWAIT] = pq[3]; p.prof[XQ_H6_FAR] = pq[4]; p.prof[XQ_H6_BAR] = pq[5]; }
+    if (warp > 0 && hw_mine < XP_MIDW && lane == 0) p.prof[hw_mine < 2 ? 14 + hw_mine : 25 + hw_mine] = pq[1];      // mid cycles of every sweeping warp (slots 14, 15, 27 .. 30)
+    if (tid == 128) { p.prof[XQ_H6_REC] = pq[0]; p.prof[XQ_H6_TILE] = pq[6]; /* (its back-edge gap; it never sweeps or moves tiles) */ p.prof[XQ_H6_SWAIT] = pq[3]; p.prof[XQ_H6_FAR] = pq[4]; p.prof[XQ_H6_BAR] = pq[5]; }
 }
 
 // ---- worker CTAs -----------------------------------------------------------------------------
@@ -1169,11 +1175,15 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
         u64 h[32];
         cudaMemcpy(h, p.prof, sizeof h, cudaMemcpyDeviceToHost);
         const double st = (double)p.nSteps;
-        fprintf(stderr, "[xp_prof] N=%d steps=%d lag=%d workers=%d | cycles/step: diag %.0f = chain %.0f + barrier wait %.0f | book-keeping warp: rec %.0f mid %.0f tile %.0f "
+        fprintf(stderr, "[xp_prof] N=%d steps=%d lag=%d workers=%d | cycles/step: diag %.0f = chain %.0f + barrier wait %.0f | book-keeping warp: rec %.0f (gaps %.0f %.0f) "
                         "s-wait %.0f far %.0f bar %.0f | sweeping warp: mid %.0f tile %.0f s-wait %.0f far %.0f bar %.0f\n",
                 p.N, p.nSteps, lag, workers, h[XQ_DIAG_TOTAL] / st, h[XQ_CHAIN] / st, h[XQ_CHAIN_BAR] / st, h[XQ_H6_REC] / st, h[XQ_H6_MID] / st,
                 h[XQ_H6_TILE] / st, h[XQ_H6_SWAIT] / st, h[XQ_H6_FAR] / st, h[XQ_H6_BAR] / st, h[XQ_H0_MID] / st, h[XQ_H0_TILE] / st,
                 h[XQ_H0_SWAIT] / st, h[XQ_H0_FAR] / st, h[XQ_H0_BAR] / st);
+        fprintf(stderr, "[xp_prof] mid cycles/step of the six sweeping warps (distance chunks 0 .. 5): %.0f %.0f %.0f %.0f %.0f %.0f\n",
+                h[14] / st, h[15] / st, h[27] / st, h[28] / st, h[29] / st, h[30] / st);
+        fprintf(stderr, "[xp_prof] wait at the step barrier (shows between the clock read behind it and the next step's: a clock read does not wait for BAR): chain warp %.0f, sweeping warp %.0f, book-keeping warp %.0f cycles/step\n",
+                h[31] / st, h[XQ_H6_MID] / st, h[XQ_H6_TILE] / st);
         const double ns = (double)(h[XQ_S_COUNT] ? h[XQ_S_COUNT] : 1), nf = (double)(h[XQ_F_COUNT] ? h[XQ_F_COUNT] : 1);
         fprintf(stderr, "[xp_prof] S tasks %llu: work %.0f cyc, wait %.0f | F tasks %llu: wait %.0f, work %.0f (max %llu) = head %.0f + L0 %.0f + L1 %.0f + L2/3 %.0f\n",
                 (unsigned long long)h[XQ_S_COUNT], h[XQ_S_WORK] / ns, h[XQ_S_WAIT] / ns, (unsigned long long)h[XQ_F_COUNT], h[XQ_F_WAIT] / nf,
