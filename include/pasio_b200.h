@@ -53,7 +53,7 @@ enum { PASIO_CONSTRAINT_NONE = 0, PASIO_CONSTRAINT_ZEROS = 1, PASIO_CONSTRAINT_C
 enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (default), 0: every cell evaluated */
        PASIO_TUNE_WINDOW_PHASES = 1,  /* 1: windows whose candidates all survived already are skipped      */
        PASIO_TUNE_EXACT_PRUNE = 2,    /* 1: whole-contig exact DP bounds far columns (csrc/exact_pruned.cu) */
-       PASIO_TUNE_EXACT_LAG = 3,      /* far columns start this many 128-row blocks behind the diagonal (3 or 4) */
+       PASIO_TUNE_EXACT_LAG = 3,      /* far columns start this many 128-row blocks behind the diagonal (3 .. 5, default 5) */
        PASIO_TUNE_EXACT_RING = 4,     /* 1 (default): self scores in an L2-resident ring of 64 row blocks; 0: one slab per row block
                                          while that fits 2 GB (measured slower: the slabs fall out of L2) */
        PASIO_TUNE_LOGFAC_EXACT = 5,   /* 1 (default): logfac_cumsum summed sequentially like np.cumsum (bit-identical LMM column);
@@ -69,8 +69,9 @@ enum { PASIO_TUNE_WINDOW_PRUNE = 0,   /* 1: window DP bounds far columns (defaul
                                          side stream behind the upload (set it when log_marginal_likelyhoods() / the LMM column
                                          will be asked for: the 30 ms sum of a chr1-sized contig is then done when the upload is).
                                          0 (default): on demand, or pasio_logfac_prefetch */
-       PASIO_TUNE_EXACT_NBLOCK = 9,   /* 1 (default): the exact DP hands the first column block of the diagonal's band (block b - lag + 1
-                                         of row block b) to worker CTAs, which evaluate it exhaustively; 0: the diagonal sweeps it */
+       PASIO_TUNE_EXACT_NBLOCK = 9,   /* the exact DP hands the first n column blocks in front of the far columns (blocks b - lag + 1 ..
+                                         of row block b) to worker CTAs, which evaluate them exhaustively; the diagonal sweeps the
+                                         remaining lag - n blocks itself.  0 .. lag - 2, default 3 (with lag 5: a band of two blocks) */
        PASIO_TUNE_COUNT = 10 };
 
 /* ---- context ------------------------------------------------------------------------ */

@@ -450,14 +450,14 @@ extern "C" int pasio_ctx_create(int device, pasio_ctx **out)
     ctx->tune[PASIO_TUNE_WINDOW_PRUNE] = env_int("PASIO_WD_PRUNE", 1);
     ctx->tune[PASIO_TUNE_WINDOW_PHASES] = env_int("PASIO_WD_PHASES", 1);
     ctx->tune[PASIO_TUNE_EXACT_PRUNE] = env_int("PASIO_XD_PRUNE", 1);
-    ctx->tune[PASIO_TUNE_EXACT_LAG] = env_int("PASIO_XD_LAG", 3);
+    ctx->tune[PASIO_TUNE_EXACT_LAG] = env_int("PASIO_XD_LAG", 5);
     ctx->tune[PASIO_TUNE_EXACT_RING] = env_int("PASIO_XD_RING", 1);
     ctx->tune[PASIO_TUNE_LOGFAC_EXACT] = env_int("PASIO_B200_EXACT_LMM", 1);
     ctx->tune[PASIO_TUNE_WINDOW_SPECULATE] = env_int("PASIO_WD_SPECULATE", 1);
     ctx->tune[PASIO_TUNE_UPLOAD_NARROW] = env_int("PASIO_B200_UPLOAD_NARROW", 1);
     ctx->tune[PASIO_TUNE_LOGFAC_EAGER] = env_int("PASIO_B200_LOGFAC_EAGER", 0);
-    ctx->tune[PASIO_TUNE_EXACT_NBLOCK] = env_int("PASIO_XD_NBLOCK", 1);
-    if (ctx->tune[PASIO_TUNE_EXACT_LAG] < 3 || ctx->tune[PASIO_TUNE_EXACT_LAG] > 4) ctx->tune[PASIO_TUNE_EXACT_LAG] = 3;
+    ctx->tune[PASIO_TUNE_EXACT_NBLOCK] = env_int("PASIO_XD_NBLOCK", 3);
+    if (ctx->tune[PASIO_TUNE_EXACT_LAG] < 3 || ctx->tune[PASIO_TUNE_EXACT_LAG] > 5) ctx->tune[PASIO_TUNE_EXACT_LAG] = 5;
     *out = ctx;
     return PASIO_OK;
 }
@@ -1126,7 +1126,7 @@ extern "C" int pasio_set_tuning(pasio_ctx *ctx, int key, int value)
 {
     if (!ctx) return PASIO_E_ARG;
     if (key < 0 || key >= PASIO_TUNE_COUNT) return pasio_fail(ctx, PASIO_E_ARG, "unknown tuning key %d", key);
-    if (key == PASIO_TUNE_EXACT_LAG && (value < 3 || value > 4)) return pasio_fail(ctx, PASIO_E_ARG, "exact lag must be 3 or 4");
+    if (key == PASIO_TUNE_EXACT_LAG && (value < 3 || value > 5)) return pasio_fail(ctx, PASIO_E_ARG, "exact lag must be 3, 4 or 5");
     ctx->tune[key] = value;
     if (key == PASIO_TUNE_LOGFAC_EXACT) {
         if (ctx->logfac_pending) { cudaStreamSynchronize(ctx->stream_lx); ctx->logfac_pending = false; }

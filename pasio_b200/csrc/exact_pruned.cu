@@ -43,7 +43,11 @@ constexpr int XP_RING = 64;           // row blocks of self scores kept
 constexpr int XP_SAHEAD = 16;         // self scores are produced this many blocks ahead of the diagonal
 constexpr int XP_PRING = 1024;        // finished P kept in the diagonal's shared memory
 constexpr int XP_ST = 63;             // self-score tile of the chain warp: distances 1..63
-constexpr int XP_MB = 30;             // mid sweep: loads per batch and lane (a multiple of 3); two batches are prefetched
+#ifndef XP_MB_N
+#define XP_MB_N 20
+#endif
+constexpr int XP_MB = XP_MB_N;             // mid sweep: loads per batch and lane; two batches are prefetched (lag 3 with N tasks: a warp's
+                                      // chunk is at most 38 distances).  Was 30: the unrolled batches are most of the sweeping warps' code
 constexpr int XP_LIST1 = 4096;
 #ifndef XP_STREAM_LOADS
 #define XP_STREAM_LOADS 1      // every self score is read once: evict-first loads keep them from displacing the tables in L1
@@ -79,8 +83,12 @@ struct XpParams {
     int *s_ready;               // [nB] finished S sub-tasks
     int *far_ready;             // [nB] finished F and N slices
     int *done_block;            // blocks finished and published (P, prev, records)
+    int *p_block;               // blocks whose P and prev are final in global memory: published a record-fit earlier than done_block (N tasks)
     unsigned *task_counter;
     const int2 *tasks;          // x = type | block << 1, y = sub index
+    double *farVm;              // [nB][128] the slices merged (first maximum) by the last task of the block; farAm likewise
+    int *farAm;
+    int *far_done;              // [nB] 1: farVm / farAm of the block are complete
     double *farV;               // [nB][XP_GT][128]: far slices, then N slices
     int *farA;
     XpRec32 *rec32;             // per 32 finished columns [1 + 32q, 33 + 32q)
@@ -88,7 +96,8 @@ struct XpParams {
     XpAnchors *anchors;         // per finished block
     double *pmax;               // running max |P|
     u64 *far_cells;             // far cells evaluated exactly
-    u64 *prof;                  // [32] cycle counters (see XP_PROF_NAMES)
+    u64 *prof;                  // [64] cycle counters; [32 + 4 * role + s]: cycles from the top of a step to the step barrier by step type
+                                // s = k & 3 (role 0 chain, 1 sweeping, 2 book-keeping warp), [44] looks at the self-score flags, [48 + s] step duration by type
     const double *gtab;
     const double *ltab;
     int alpha_int;
@@ -103,6 +112,31 @@ enum { XQ_CHAIN = 0, XQ_CHAIN_BAR, XQ_H6_REC, XQ_H6_MID, XQ_H6_TILE, XQ_H6_SWAIT
 __device__ __forceinline__ long long xp_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
 
 __device__ __forceinline__ int xp_ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ int xp_ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+// The merged far results of a block travel from global memory into the diagonal's shared memory as two bulk copies that
+// complete on an mbarrier: no register, hence no scoreboard, is tied up while they are in flight.  (A load that is issued
+// early into registers does not hide its latency here: ptxas shares the six scoreboards of a warp between loads, so the
+// next wait on a shared slot also waits for the far load -- ~1.5 k cycles to L2 and back while 147 worker CTAs gather.
+// Measured: profiles/r02_exact_dp_v9_notes.txt.)
+__device__ __forceinline__ unsigned xp_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void xp_mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xp_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void xp_mbar_expect(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xp_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xp_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(xp_smem_addr(dst)), "l"(src), "r"(bytes), "r"(xp_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void xp_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n .reg .pred p;\n XP_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra XP_DONE;\n bra XP_WAIT;\n XP_DONE:\n}"
+                 ::"r"(xp_smem_addr(bar)), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ void xp_wait_cta(const int *flag, int target)     // every thread of the CTA calls
 {
@@ -126,6 +160,7 @@ __device__ __forceinline__ void xp_wait_s_blocks(const XpParams &p, int need, in
     if (need <= *known) return;
     if ((threadIdx.x >> 5) == 4) {
         const int lane = threadIdx.x & 31;
+        if ((p.dbg & 128) && lane == 0) atomicAdd(p.prof + 44, 1ull);
         unsigned ok;
         while (true) {
             const int bq = need + lane;
@@ -143,11 +178,19 @@ __device__ __forceinline__ void xp_wait_s_blocks(const XpParams &p, int need, in
 
 __device__ __forceinline__ int xp_far_bound(int b, int lag) { return b >= lag - 1 ? 1 + XP_RB * (b - lag + 1) : 0; }
 // first column of the band the diagonal sweeps itself (and of the self-score slabs): with N tasks one block later than the far bound
-__device__ __forceinline__ int xp_band_bound(int b, int lag, int nb) { return xp_far_bound(b, lag) + ((nb && b >= lag - 1) ? XP_RB : 0); }
+// N tasks of row block b cover the nb column blocks in front of the band, [F0 + ... ) with F0 = 1 + 128 (b - lag + 1) -- which is
+// negative in the first blocks: there they start at column 0 (the "last column of block -1").  They exist once they cover more
+// than column 0.  With them the band of row block b starts nb blocks later, so that its distances fit the slab (128 (lag - nb))
+// in every block.
+__host__ __device__ __forceinline__ bool xp_has_n(int b, int lag, int nb) { return nb > 0 && 1 + XP_RB * (b - lag + 1 + nb) > 1; }
+__host__ __device__ __forceinline__ bool xp_has_far(int b, int lag, int nb) { return b >= lag - 1 || xp_has_n(b, lag, nb); }   // any results to fetch
+__host__ __device__ __forceinline__ int xp_far_count(int b, int lag, int nb) { return (b >= lag - 1 ? XP_G : 0) + (xp_has_n(b, lag, nb) ? XP_NG : 0); }
+__device__ __forceinline__ int xp_band_bound(int b, int lag, int nb) { return xp_has_n(b, lag, nb) ? 1 + XP_RB * (b - lag + 1 + nb) : xp_far_bound(b, lag); }
 
 __host__ __device__ inline size_t xp_diag_smem()
 {
-    return (size_t)2 * XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + XP_PRING * 4 + 16;
+    return (size_t)2 * XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + XP_PRING * 4 + 16
+           + 16;                                                // two mbarriers: the bulk copies of the far results
 }
 __host__ __device__ inline size_t xp_worker_smem()
 {
@@ -220,13 +263,13 @@ __device__ __forceinline__ void xp_mid_load(const XpMid &g, int d, double (&v)[X
         }
     }
 }
-// Six independent (max, first arg-max) chains over consecutive sixths of the batch -- written interleaved, so that the
+// Five independent (max, first arg-max) chains over consecutive fifths of the batch -- written interleaved, so that the
 // in-order issue finds an independent instruction every cycle -- merged in column order (a later column wins only when
 // strictly greater) = the sequential first maximum.  Column of entry u: j - d + u; its P sits at a fixed offset from
 // the first one in the mirrored ring.
 __device__ __forceinline__ void xp_mid_fold(const XpMid &g, int d, const double (&v)[XP_MB], const double *sP, double &best, int &arg)
 {
-    constexpr int NCH = 6, PER = XP_MB / NCH;
+    constexpr int NCH = XP_MB % 6 == 0 ? 6 : 5, PER = XP_MB / NCH;
     static_assert(XP_MB % NCH == 0, "batch must split into equal chains");
     const int col0 = g.j - d;
     const double *pc = sP + (col0 & (XP_PRING - 1));
@@ -285,6 +328,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     int *sFarA = sMidA + 2 * XP_HELP * 32;                      // [2][128]
     double *sScal = reinterpret_cast<double *>(sFarA + 2 * XP_RB);   // [0] running max |P|
     int *sPrevRing = reinterpret_cast<int *>(sScal + 8);             // [XP_PRING] arg-max columns of the finished rows, ring by row index
+    unsigned long long *sFarBar = reinterpret_cast<unsigned long long *>(sPrevRing + XP_PRING + 4);   // [2], behind sKnown (16 bytes)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, lag = p.lag;
 
@@ -294,6 +338,9 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
         __stcg(p.P, 0.0);
         __stcg(p.prev, 0);
         sScal[0] = 0.0;
+        xp_mbar_init(sFarBar, 1);
+        xp_mbar_init(sFarBar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int k = tid; k < 2 * XP_HELP * 32; k += XP_THREADS) { sMidV[k] = -INFINITY; sMidA[k] = 0; }
     xp_wait_cta(p.s_ready, XP_SQ);
@@ -301,6 +348,8 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     xp_load_s_tile<RING>(p, 1, sS + XP_ST * 32, tid, XP_THREADS);
     __syncthreads();
 
+    int far_first = 0;                       // first row block with far / N results (the first use of its slot's mbarrier)
+    while (far_first < p.nB && !xp_has_far(far_first, lag, p.nb)) ++far_first;
     // chain warp state: accumulator of the NEXT step's rows over the columns being chained now
     double best2 = -INFINITY, pmax = 0.0;
     int arg2 = 0;
@@ -329,17 +378,21 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     }
     long long pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // per-thread phase cycles (only threads 0, 32 and 224 report)
     const long long t_begin = xp_clock();
-    long long t_last = t_begin;
+    long long t_last = t_begin, t_prev_top = t_begin;
     for (int k = 0; k < p.nSteps; ++k) {
         const int jb = 1 + 32 * k, b = k >> 2, s = k & 3;
         long long tq = xp_clock();
+        const long long t_top = tq;
         pq[6] += tq - t_last;                              // (between the clock read behind the barrier and this one)
         if (warp == 0) {
             // ---------------- chain warp: rows [jb, jb + 32) ----------------
             const int j = jb + lane;
             double best = -INFINITY;
             int arg = 0;
-            if (b >= lag - 1) {                                  // far columns (the smallest indices)
+            if (xp_has_far(b, lag, p.nb)) {                      // far columns (the smallest indices)
+                // the bulk copies of this block's merged far results were started a step ago; a slot's n-th use completes
+                // phase n of its mbarrier
+                if (s == 0) xp_mbar_wait(sFarBar + (b & 1), (unsigned)(((b - far_first) >> 1) & 1));
                 best = sFarV[(b & 1) * XP_RB + s * 32 + lane];
                 arg = sFarA[(b & 1) * XP_RB + s * 32 + lane];
             }
@@ -357,7 +410,8 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             double mine = 0.0;
             // Always 32 iterations: in the last (partial) step the lanes past the end only produce values nobody reads.
             // The operands of 8 iterations are fetched from shared memory ahead of the dependent chain; a lane that
-            // must not take part in an update holds -inf there, so the updates need no branches.
+            // must not take part in an update holds -inf there, so the updates need no branches.  (Rolled into 4 x 8 rows
+            // the loop is 12 KB shorter and 8 cycles per row slower: profiles/r02_exact_dp_v9_notes.txt.)
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 8) {
                 double tv[8], nv[8];
@@ -403,6 +457,62 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             // shares its scheduler with the chain warp -- keeps the books: records, anchors, publishing, the far results
             const int hw = hw_mine;
             if (hw == XP_MIDW) {
+                // (first: the sweeping warps wait at a named barrier for this warp's look at the flags)
+                if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
+                { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
+                // P and prev of the block that finished with the previous step are in global memory (the chain warp stored them
+                // before the step barrier): the N tasks need nothing else, so they are released before the records are made
+                if (s == 0 && k > 0 && lane == 0) {
+                    __threadfence();
+                    *reinterpret_cast<volatile int *>(p.p_block) = b;
+                }
+                // The far results of the next block: the last worker task of the block has merged the slices into one (value,
+                // column) per row.  This warp waits for that and starts two bulk copies into the diagonal's shared memory; the
+                // chain warp waits for them on the mbarrier when it starts the block, a step later.  First thing in the step:
+                // the copies have the whole step, and nobody else does anything for the far results any more (the sweeping
+                // warps fetched and merged 16 slices per row: 2.6 k cycles per block on the critical path,
+                // profiles/r02_exact_dp_v9_notes.txt).
+                if (s == 3 && b + 1 < p.nB && xp_has_far(b + 1, lag, p.nb)) {
+                    if (lane == 0) {
+                        if (!(p.dbg & 4)) while (xp_ld_acquire(p.far_done + (b + 1)) == 0) __nanosleep(20);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        unsigned long long *bar = sFarBar + ((b + 1) & 1);
+                        xp_mbar_expect(bar, XP_RB * 12);
+                        xp_bulk_g2s(sFarV + ((b + 1) & 1) * XP_RB, p.farVm + (size_t)(b + 1) * XP_RB, XP_RB * 8, bar);
+                        xp_bulk_g2s(sFarA + ((b + 1) & 1) * XP_RB, p.farAm + (size_t)(b + 1) * XP_RB, XP_RB * 4, bar);
+                    }
+                    __syncwarp();
+                }
+                { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
+                // (first in its step: the F tasks wait for this)
+                if (s == 2 && b >= 1) {
+                    // anchors of the block that finished: its last row e and the last seven split points of the best
+                    // segmentation ending there (e -> prev[e] -> prev[prev[e]] ...): the rows ahead most likely continue
+                    // one of these, so "best up to the anchor, then one segment" bounds their maxima from below tightly
+                    const int e = XP_RB * b;
+                    // rows still in the shared-memory rings: the chain warp is writing rows e + 65 .. e + 96 in this step
+                    // (they overwrite rows 1024 further back)
+                    const int in_ring = e + 96 - XP_PRING + 64;
+                    int a = e, mine = e;
+                    for (int t = 1; t < 8; ++t) {                  // (every lane walks the same chain: uniform loads)
+                        if (a > 0) a = a > in_ring ? sPrevRing[a & (XP_PRING - 1)] : __ldcg(p.prev + a);
+                        if (lane == t) mine = a;
+                    }
+                    if (lane < 8) {
+                        mine = min(max(mine, 0), e);
+                        XpAnchors *an = p.anchors + (b - 1);
+                        an->idx[lane] = mine;
+                        an->L[lane] = __ldg(p.L + mine);
+                        an->C[lane] = __ldg(p.C + mine);
+                        an->P[lane] = mine > in_ring ? sP[mine & (XP_PRING - 1)] : (mine > 0 ? __ldcg(p.P + mine) : 0.0);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        __stcg(p.pmax, sScal[0]);
+                        __threadfence();
+                        *reinterpret_cast<volatile int *>(p.done_block) = b;
+                    }
+                }
                 if (k > 0) {
                     // records of the columns finished in step k-1 (and of the block they complete), then publish; the
                     // columns' (C, L) were loaded during the previous step
@@ -412,35 +522,16 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                     if (!(p.dbg & 2)) fit_column_record(cme, lme, sP[(jbp + lane) & (XP_PRING - 1)], &rec->r, tilt_c, tilt_l);
                     if ((lane & 7) == 0) { rec->sub[lane >> 3][0] = cme; rec->sub[lane >> 3][2] = lme; }
                     if ((lane & 7) == 7) { rec->sub[lane >> 3][1] = cme; rec->sub[lane >> 3][3] = lme; }
-                    if (s == 0) {
+                    // The work per finished block is spread over three steps, so that this warp is never the last at the step
+                    // barrier (all of it in the block's first step: 7.3 k cycles against the others' 3.8 k):  s == 0: P published
+                    // for the N tasks (above); s == 1: the 128-column record; s == 2: anchors, then done_block -- the F tasks
+                    // start 2.5 steps later than they could, which lag >= 4 affords (profiles/r02_exact_dp_v9_notes.txt)
+                    if (s == 1 && b >= 1) {
                         const int c0 = 1 + XP_RB * (b - 1);
                         double pp[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) pp[q] = sP[(c0 + lane + 32 * q) & (XP_PRING - 1)];
                         if (!(p.dbg & 2)) fit_column_record128(rec_c4, rec_l4, pp, p.rec128 + (b - 1), tilt_c, tilt_l);
-                        // anchors of the block that just finished: its last row e and the last seven split points of the best
-                        // segmentation ending there (e -> prev[e] -> prev[prev[e]] ...): the rows ahead most likely continue
-                        // one of these, so "best up to the anchor, then one segment" bounds their maxima from below tightly
-                        const int e = jb - 1;
-                        int a = e, mine = e;
-                        for (int t = 1; t < 8; ++t) {                  // (every lane walks the same chain: uniform loads)
-                            if (a > 0) a = a > e - (XP_PRING - 64) ? sPrevRing[a & (XP_PRING - 1)] : __ldcg(p.prev + a);
-                            if (lane == t) mine = a;
-                        }
-                        if (lane < 8) {
-                            mine = min(max(mine, 0), e);
-                            XpAnchors *an = p.anchors + (b - 1);
-                            an->idx[lane] = mine;
-                            an->L[lane] = __ldg(p.L + mine);
-                            an->C[lane] = __ldg(p.C + mine);
-                            an->P[lane] = mine > e - (XP_PRING - 64) ? sP[mine & (XP_PRING - 1)] : (mine > 0 ? __ldcg(p.P + mine) : 0.0);
-                        }
-                        __syncwarp();
-                        if (lane == 0) {
-                            __stcg(p.pmax, sScal[0]);
-                            __threadfence();
-                            *reinterpret_cast<volatile int *>(p.done_block) = b;
-                        }
                     }
                 }
                 // inputs of the next step's records
@@ -455,20 +546,6 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                     }
                 }
                 { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
-                if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
-                { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
-                // the far results of the next block must have arrived: this warp waits for them, the sweeping warps fetch them
-                // (looking at the flag earlier -- every step, by this warp or by every thread -- and fetching early was
-                // measured slower: profiles/r02_exact_dp_v8_notes.txt)
-                if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
-                    if (lane == 0 && !(p.dbg & 4)) {
-                        while (xp_ld_flag(p.far_ready + (b + 1)) < (p.nb ? XP_GT : XP_G)) __nanosleep(20);
-                        __threadfence();
-                    }
-                    __syncwarp();
-                    asm volatile("bar.sync 2, %0;" ::"n"(XP_HELP * 32) : "memory");
-                    { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
-                }
             } else {
                 // self scores of block (k+3)/4 must be complete before anything of step k+3 is prefetched below
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
@@ -503,34 +580,14 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_tile_store(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, hidx, XP_MIDW * 32, tile_regs);
                 if (k + 3 < p.nSteps && !(p.dbg & 8)) xp_tile_load<RING>(p, k + 3, hidx, XP_MIDW * 32, tile_regs);
                 { const long long t1 = xp_clock(); pq[2] += t1 - tq; tq = t1; }
-                // far results of the next block (the book-keeping warp saw them arrive): one row per thread, the eight
-                // slices merged by column index
-                if (s == 3 && b + 1 < p.nB && b + 1 >= lag - 1) {
-                    asm volatile("bar.sync 2, %0;" ::"n"(XP_HELP * 32) : "memory");
-                    if (hidx < XP_RB) {
-                        const int j = 1 + XP_RB * (b + 1) + hidx;
-                        double best = -INFINITY;
-                        int arg = 0x7fffffff;
-                        if (j < N) {
-                            double v[XP_GT];
-                            int a[XP_GT];
-#pragma unroll
-                            for (int g = 0; g < XP_GT; ++g) {
-                                const bool have = g < XP_G || p.nb;
-                                v[g] = have ? __ldcg(p.farV + ((size_t)(b + 1) * XP_GT + g) * XP_RB + hidx) : -INFINITY;
-                                a[g] = have ? __ldcg(p.farA + ((size_t)(b + 1) * XP_GT + g) * XP_RB + hidx) : 0x7fffffff;
-                            }
-#pragma unroll
-                            for (int g = 0; g < XP_GT; ++g)
-                                if (v[g] > best || (v[g] == best && a[g] < arg)) { best = v[g]; arg = a[g]; }
-                        }
-                        sFarV[((b + 1) & 1) * XP_RB + hidx] = best;
-                        sFarA[((b + 1) & 1) * XP_RB + hidx] = arg;
-                    }
-                    { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
-                }
             }
         }
+        if ((p.dbg & 128) && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+            const long long ta = xp_clock();
+            atomicAdd(p.prof + 32 + 4 * (warp == 0 ? 0 : (warp == 1 ? 1 : 2)) + s, (u64)(ta - t_top));
+            if (warp == 0 && k > 0) atomicAdd(p.prof + 48 + ((k - 1) & 3), (u64)(t_top - t_prev_top));
+        }
+        t_prev_top = t_top;
         __syncthreads();
         t_last = xp_clock();
         pq[5] += t_last - tq;
@@ -614,6 +671,47 @@ __device__ __forceinline__ double xp_row_min(const XpRows &R, int ra, int rb, do
     }
     for (; r <= rb; ++r) m0 = fmin(m0, R.lb[r] + (a * R.cd[r] + b * R.ld[r]));
     return fmin(fmin(m0, m1), fmin(m2, m3));
+}
+
+// Every F and N task of a row block ends here: the task that finishes last merges the block's slices -- first maximum: the
+// larger value, on a tie the smaller column -- into one (value, column) per row, farVm / farAm, and raises far_done.  The
+// diagonal copies those 1.5 KB into its shared memory in bulk; before, its sweeping warps fetched and merged the 16 slices.
+__device__ void xp_far_finish(const XpParams &p, int b)
+{
+    __shared__ int sLast;
+    const int tid = threadIdx.x;
+    __syncthreads();                                                    // this task's slice is written
+    if (tid == 0) {
+        __threadfence();
+        sLast = atomicAdd(p.far_ready + b, 1) == xp_far_count(b, p.lag, p.nb) - 1;
+        if (sLast) __threadfence();                                     // the other tasks' slices, released the same way
+    }
+    __syncthreads();
+    if (!sLast) return;
+    if (tid < XP_RB) {
+        double best = -INFINITY;
+        int arg = 0x7fffffff;
+        if (1 + XP_RB * b + tid < p.N) {
+            double v[XP_GT];
+            int a[XP_GT];
+#pragma unroll
+            for (int g = 0; g < XP_GT; ++g) {
+                const bool have = g < XP_G ? b >= p.lag - 1 : xp_has_n(b, p.lag, p.nb);
+                v[g] = have ? __ldcg(p.farV + ((size_t)b * XP_GT + g) * XP_RB + tid) : -INFINITY;
+                a[g] = have ? __ldcg(p.farA + ((size_t)b * XP_GT + g) * XP_RB + tid) : 0x7fffffff;
+            }
+#pragma unroll
+            for (int g = 0; g < XP_GT; ++g)
+                if (v[g] > best || (v[g] == best && a[g] < arg)) { best = v[g]; arg = a[g]; }
+        }
+        __stcg(p.farVm + (size_t)b * XP_RB + tid, best);
+        __stcg(p.farAm + (size_t)b * XP_RB + tid, arg);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile int *>(p.far_done + b) = 1;
+    }
 }
 
 // F(b, g): far columns of row block b that lie in the 32-column groups q = g, g + 8, ... (slice 0 also column 0): the
@@ -956,10 +1054,8 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
         __stcg(p.farA + ((size_t)b * XP_GT + g) * XP_RB + tid, arg);
     }
     if (tid == 0 && evaluated) atomicAdd(p.far_cells, evaluated);
-    __syncthreads();
+    xp_far_finish(p, b);
     if (tid == 0) {
-        __threadfence();
-        atomicAdd(p.far_ready + b, 1);
         const u64 work = (u64)(xp_clock() - tf1);
         atomicAdd(p.prof + XQ_F_WAIT, (u64)(tf1 - tf0));
         atomicAdd(p.prof + XQ_F_WORK, work);
@@ -985,29 +1081,34 @@ __device__ void xp_n_task(const XpParams &p, int b, int g, unsigned char *smem)
     const int tid = threadIdx.x;
     const int N = p.N;
     const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, N - r0);
-    const int F = xp_far_bound(b, p.lag);
-    xp_wait_cta(p.done_block, b - p.lag + 2);                           // blocks 0 .. b - lag + 1 are final
+
     const int r = tid & (XP_RB - 1), h = tid >> 7;                      // row; which 8 of the slice's 16 columns
-    const int c0 = F + 16 * g + 8 * h;
     double best = -INFINITY;
     int arg = 0x7fffffff;
-    if (r < nrows) {
+    // (two N blocks, with lag 4: the far tasks get three blocks of time instead of two, the band of the diagonal stays the same)
+    for (int nq = 0; nq < p.nb; ++nq) {                                 // ascending columns within a thread
+        // P of column block b - lag + 1 + nq is final (no records needed).  Block by block: the task has been waiting since
+        // long before, so all but its last block are evaluated before that one is released
+        xp_wait_cta(p.p_block, b - p.lag + 2 + nq);
+        const int c0 = 1 + XP_RB * (b - p.lag + 1 + nq) + 16 * g + 8 * h;   // (negative in the first blocks: column 0 is "the last of block -1")
+        if (r >= nrows || c0 + 7 < 0) continue;
         const int j = r0 + r;
         const RowConst<AI> row = make_row<AI>(__ldg(p.C + j), __ldg(p.L + j), p.alpha_int, p.alpha);
         double gq[8], lq[8], pc[8];
         int ci[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {                                   // all gathers in flight, then the arithmetic
-            ci[u] = __ldg(p.C + c0 + u);
+            const int col = max(c0 + u, 0);
+            ci[u] = __ldg(p.C + col);
             gq[u] = __ldg(p.gtab + (row.cjx - ci[u]));
-            lq[u] = __ldg(p.ltab + (row.lj - __ldg(p.L + c0 + u)));
-            pc[u] = __ldcg(p.P + c0 + u);
+            lq[u] = __ldg(p.ltab + (row.lj - __ldg(p.L + col)));
+            pc[u] = __ldcg(p.P + col);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const double sx = AI ? u32_to_double(row.cjx - ci[u]) : __dsub_rn(row.aj, u32_to_double(ci[u]));
             const double t = __dadd_rn(__dsub_rn(gq[u], __dmul_rn(sx, lq[u])), pc[u]);
-            if (t > best) { best = t; arg = c0 + u; }
+            if (c0 + u >= 0 && t > best) { best = t; arg = c0 + u; }
         }
     }
     sV[h * XP_RB + r] = best;
@@ -1016,15 +1117,13 @@ __device__ void xp_n_task(const XpParams &p, int b, int g, unsigned char *smem)
     if (tid < nrows) {
         double v = sV[tid];
         int a = sA[tid];
-        if (sV[XP_RB + tid] > v) { v = sV[XP_RB + tid]; a = sA[XP_RB + tid]; }      // the later columns win only when strictly greater
+        const double v1 = sV[XP_RB + tid];                             // first maximum = the smaller column on a tie
+        const int a1 = sA[XP_RB + tid];
+        if (v1 > v || (v1 == v && a1 < a)) { v = v1; a = a1; }
         __stcg(p.farV + ((size_t)b * XP_GT + XP_G + g) * XP_RB + tid, v);
         __stcg(p.farA + ((size_t)b * XP_GT + XP_G + g) * XP_RB + tid, a);
     }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        atomicAdd(p.far_ready + b, 1);
-    }
+    xp_far_finish(p, b);
 }
 
 // constants of the bound, once per launch (so that no far task starts with a chain of dependent loads)
@@ -1067,8 +1166,13 @@ std::vector<int2> build_tasks(int nB, int lag, int nb)
     std::vector<int2> t;
     auto push_s = [&](int b) { if (b < nB) for (int q = 0; q < XP_SQ; ++q) t.push_back(make_int2(b << 1, q)); };
     // F slices first (they are released one block earlier), then the N slices of the same row block (sub index >= XP_G)
-    auto push_f = [&](int b) { if (b >= lag - 1 && b < nB) for (int g = 0; g < (nb ? XP_GT : XP_G); ++g) t.push_back(make_int2((b << 1) | 1, g)); };
+    auto push_f = [&](int b) {
+        if (b >= nB) return;
+        if (b >= lag - 1) for (int g = 0; g < XP_G; ++g) t.push_back(make_int2((b << 1) | 1, g));
+        if (xp_has_n(b, lag, nb)) for (int g = XP_G; g < XP_GT; ++g) t.push_back(make_int2((b << 1) | 1, g));
+    };
     for (int b = 0; b < XP_SAHEAD; ++b) push_s(b);
+    for (int b = 0; b < lag - 1; ++b) push_f(b);          // (two N blocks: the row blocks that have N tasks before they have F tasks)
     for (int tt = 0; tt < nB; ++tt) {
         push_f(tt + lag - 1);
         push_s(tt + XP_SAHEAD);
@@ -1085,8 +1189,9 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.nSteps = (int)((N - 1 + 31) / 32);
     p.lag = lag;
     p.dbg = getenv("PASIO_XD_DBG") ? atoi(getenv("PASIO_XD_DBG")) : 0;
+    if (getenv("PASIO_XD_PROF")) p.dbg |= 128;                 // per-step-type counters (one RED per role and step)
     p.npad = (int)((N + 127) & ~(i64)127);
-    p.nb = ctx->tune[PASIO_TUNE_EXACT_NBLOCK] ? 1 : 0;
+    p.nb = ctx->tune[PASIO_TUNE_EXACT_NBLOCK] < 0 ? 0 : (ctx->tune[PASIO_TUNE_EXACT_NBLOCK] > lag - 2 ? lag - 2 : ctx->tune[PASIO_TUNE_EXACT_NBLOCK]);   // the band keeps >= 2 blocks
     p.DB = XP_RB * (lag - p.nb);                                 // distances kept per row block: the band is one block narrower with N tasks
     const std::vector<int2> tasks = build_tasks(p.nB, lag, p.nb);
     p.n_tasks = (int)tasks.size();
@@ -1098,9 +1203,9 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     const int slots = ring && p.nB > XP_RING ? XP_RING : p.nB;
     p.s_slots = slots;
     const size_t ring_bytes = (size_t)slots * p.DB * XP_RB * 8;
-    const size_t far_bytes = (size_t)XP_GT * XP_RB * p.nB * 12;
+    const size_t far_bytes = (size_t)(XP_GT + 1) * XP_RB * p.nB * 12;     // slices + the merged results
     const size_t rec_bytes = ((size_t)p.nSteps + 1) * sizeof(XpRec32) + ((size_t)p.nB + 1) * (sizeof(CoarseRec) + sizeof(XpAnchors));
-    const size_t flag_ints = (size_t)2 * p.nB + 8 + 64 + 8;      // + 32 u64 profile counters + 4 doubles of constants
+    const size_t flag_ints = (size_t)3 * p.nB + 8 + 128 + 8;     // + 64 u64 profile counters + 4 doubles of constants
     PASIO_TRY(pasio_reserve(ctx, ctx->xpRing, ring_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPart, far_bytes > rec_bytes ? far_bytes : rec_bytes));
     PASIO_TRY(pasio_reserve(ctx, ctx->xpRec, rec_bytes));
@@ -1119,15 +1224,19 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     p.pmax = reinterpret_cast<double *>(flags);                 // 8 bytes
     p.far_cells = reinterpret_cast<u64 *>(flags + 2);           // 8 bytes
     p.done_block = flags + 4;
+    p.p_block = flags + 6;
     p.task_counter = reinterpret_cast<unsigned *>(flags + 5);
-    p.prof = reinterpret_cast<u64 *>(flags + 8);                // 32 x 8 bytes
-    double *consts = reinterpret_cast<double *>(flags + 8 + 64);    // 4 x 8 bytes
+    p.prof = reinterpret_cast<u64 *>(flags + 8);                // 64 x 8 bytes
+    double *consts = reinterpret_cast<double *>(flags + 8 + 128);   // 4 x 8 bytes
     p.consts = consts;
-    p.s_ready = flags + 8 + 64 + 8;
+    p.s_ready = flags + 8 + 128 + 8;
     p.far_ready = p.s_ready + p.nB;
+    p.far_done = p.far_ready + p.nB;
     p.tasks = ctx->xpTasks.as<int2>();
     p.farV = ctx->dpPart.as<double>();
-    p.farA = reinterpret_cast<int *>(p.farV + (size_t)XP_GT * XP_RB * p.nB);
+    p.farVm = p.farV + (size_t)XP_GT * XP_RB * p.nB;            // (8-byte data first: the bulk copies need 16-byte aligned rows)
+    p.farA = reinterpret_cast<int *>(p.farVm + (size_t)XP_RB * p.nB);
+    p.farAm = p.farA + (size_t)XP_GT * XP_RB * p.nB;
     p.rec32 = ctx->xpRec.as<XpRec32>();
     p.rec128 = reinterpret_cast<CoarseRec *>(p.rec32 + p.nSteps + 1);
     p.anchors = reinterpret_cast<XpAnchors *>(p.rec128 + p.nB + 1);
@@ -1172,7 +1281,7 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
     ctx->last_cells_skipped = ctx->last_cells - band - ctx->h_scalars[8];
     static const bool prof = getenv("PASIO_XD_PROF") != nullptr;
     if (prof) {
-        u64 h[32];
+        u64 h[64];
         cudaMemcpy(h, p.prof, sizeof h, cudaMemcpyDeviceToHost);
         const double st = (double)p.nSteps;
         fprintf(stderr, "[xp_prof] N=%d steps=%d lag=%d workers=%d | cycles/step: diag %.0f = chain %.0f + barrier wait %.0f | book-keeping warp: rec %.0f (gaps %.0f %.0f) "
@@ -1184,6 +1293,11 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
                 h[14] / st, h[15] / st, h[27] / st, h[28] / st, h[29] / st, h[30] / st);
         fprintf(stderr, "[xp_prof] wait at the step barrier (shows between the clock read behind it and the next step's: a clock read does not wait for BAR): chain warp %.0f, sweeping warp %.0f, book-keeping warp %.0f cycles/step\n",
                 h[31] / st, h[XQ_H6_MID] / st, h[XQ_H6_TILE] / st);
+        const double sq = st / 4.0;
+        fprintf(stderr, "[xp_prof] cycles from the top of a step to the step barrier, by step type k & 3 = 0 1 2 3: chain warp %.0f %.0f %.0f %.0f | sweeping warp %.0f %.0f %.0f %.0f | "
+                        "book-keeping warp %.0f %.0f %.0f %.0f | whole step %.0f %.0f %.0f %.0f | blocking looks at the self-score flags %llu\n",
+                h[32] / sq, h[33] / sq, h[34] / sq, h[35] / sq, h[36] / sq, h[37] / sq, h[38] / sq, h[39] / sq, h[40] / sq, h[41] / sq, h[42] / sq, h[43] / sq,
+                h[48] / sq, h[49] / sq, h[50] / sq, h[51] / sq, (unsigned long long)h[44]);
         const double ns = (double)(h[XQ_S_COUNT] ? h[XQ_S_COUNT] : 1), nf = (double)(h[XQ_F_COUNT] ? h[XQ_F_COUNT] : 1);
         fprintf(stderr, "[xp_prof] S tasks %llu: work %.0f cyc, wait %.0f | F tasks %llu: wait %.0f, work %.0f (max %llu) = head %.0f + L0 %.0f + L1 %.0f + L2/3 %.0f\n",
                 (unsigned long long)h[XQ_S_COUNT], h[XQ_S_WORK] / ns, h[XQ_S_WAIT] / ns, (unsigned long long)h[XQ_F_COUNT], h[XQ_F_WAIT] / nf,

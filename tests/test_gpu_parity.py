@@ -287,20 +287,20 @@ def test_exact_pruned_vs_oracle_and_unpruned(eng, case, ab):
         cands = np.arange(len(counts) + 1, dtype=np.int64)
     o_score, o_splits, o_P, o_prev = c_oracle.FlatOracle(counts, *ab, threads=_oracle_threads()).square_split(cands)
     try:
-        for prune, lag, ring, nblock in [(1, 3, 1, 1), (1, 4, 1, 1), (1, 3, 0, 1), (0, 3, 1, 1), (1, 3, 1, 0), (1, 4, 0, 0)]:
+        for prune, lag, ring, nblock in [(1, 3, 1, 1), (1, 4, 1, 1), (1, 3, 0, 1), (0, 3, 1, 1), (1, 3, 1, 0), (1, 4, 0, 0), (1, 4, 1, 2), (1, 4, 0, 2), (1, 5, 1, 3), (1, 5, 0, 2)]:
             eng.set_tuning('exact_prune', prune)
             eng.set_tuning('exact_lag', lag)
             eng.set_tuning('exact_ring', ring)       # 1: self scores in a ring of 64 slabs (default), 0: one slab per block
-            eng.set_tuning('exact_nblock', nblock)   # 1: the band's first column block on worker CTAs (default), 0: swept by the diagonal
+            eng.set_tuning('exact_nblock', nblock)   # 1 / 2: the band's first column block(s) on worker CTAs, 0: swept by the diagonal
             score, splits, P, prev = gpu_exact(eng, counts, cands, *ab)
             assert np.array_equal(P, o_P), (case, prune, lag)
             assert np.array_equal(prev, o_prev), (case, prune, lag)
             assert score == o_score and np.array_equal(splits, o_splits)
     finally:
         eng.set_tuning('exact_prune', 1)
-        eng.set_tuning('exact_lag', 3)
+        eng.set_tuning('exact_lag', 5)
         eng.set_tuning('exact_ring', 1)
-        eng.set_tuning('exact_nblock', 1)
+        eng.set_tuning('exact_nblock', 3)
 
 
 def test_config3_prefix_property(eng):

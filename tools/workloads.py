@@ -156,8 +156,8 @@ if __name__ == '__main__':
     ap.add_argument('--contigs', type=int, default=100000)
     ap.add_argument('--prune', type=int, default=1, help='exact DP: 1 = bounded far columns (default), 0 = every cell')
     ap.add_argument('--ring', type=int, default=1, help='exact DP: 1 = self scores in the ring layout of very long lists')
-    ap.add_argument('--lag', type=int, default=3, help='exact DP: far columns start this many blocks behind (3 or 4)')
-    ap.add_argument('--nblock', type=int, default=1, help='exact DP: 1 = first block of the band on worker CTAs (default)')
+    ap.add_argument('--lag', type=int, default=5, help='exact DP: far columns start this many blocks behind (3 .. 5)')
+    ap.add_argument('--nblock', type=int, default=3, help='exact DP: column blocks in front of the far columns evaluated by worker CTAs (0 .. lag - 2)')
     a = ap.parse_args()
     if a.what == 'exact1':
         exact(a, 1)
