@@ -351,23 +351,20 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     int far_first = 0;                       // first row block with far / N results (the first use of its slot's mbarrier)
     while (far_first < p.nB && !xp_has_far(far_first, lag, p.nb)) ++far_first;
     // chain warp state: accumulator of the NEXT step's rows over the columns being chained now
-    double best2 = -INFINITY, pmax = 0.0;
+    double best2 = -INFINITY;
     int arg2 = 0;
     if (warp == 0 && 1 + lane < N) {         // rows of step 0 against column 0: distance = row index
         best2 = __dadd_rn(sS[lane * 32 + lane], 0.0);
         arg2 = 0;
     }
-    const double tilt_c = (double)__ldg(p.C + N - 1) + p.alpha, tilt_l = (double)__ldg(p.L + N - 1);
     // helper state carried from step to step: the self scores of the NEXT mid sweep and of the next tile are loaded
     // one step ahead (they do not depend on P), so a step only adds the finished P to values that have already arrived
     const int hw_mine = warp < 4 ? warp - 1 : (warp == 4 ? XP_MIDW : warp - 2);       // 0..5 sweep, 6 = the book-keeping warp
     const int hidx = hw_mine * 32 + lane;                // index among the 192 sweeping threads
     double pre0[XP_MB], pre1[XP_MB];
     double2 tile_regs[XP_TILE_NV];
-    int rec_c = 0, rec_l = 0, rec_c4[4] = {0, 0, 0, 0}, rec_l4[4] = {0, 0, 0, 0};     // book-keeping warp: (C, L) of the columns its next records cover
     int s_known = 0;                                     // block 0 is complete (waited above)
     int *sKnown = sPrevRing + XP_PRING;
-    if (warp == 4 && 1 + lane < N) { rec_c = __ldg(p.C + 1 + lane); rec_l = __ldg(p.L + 1 + lane); }
     if (warp > 0 && hw_mine < XP_MIDW) {
         if (2 < p.nSteps) xp_tile_load<RING>(p, 2, hidx, XP_MIDW * 32, tile_regs);
         if (1 < p.nSteps) {
@@ -437,19 +434,12 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                     arg2 = w2 ? jb + kk : arg2;
                 }
             }
-            double pm = 0.0;
             if (j < N) {
                 sP[j & (XP_PRING - 1)] = mine;
                 sP[(j & (XP_PRING - 1)) + XP_PRING] = mine;
                 __stcg(p.P + j, mine);
                 __stcg(p.prev + j, arg);
-                pm = fabs(mine);
             }
-            if (j < N) sPrevRing[j & (XP_PRING - 1)] = arg;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, off));
-            pmax = fmax(pmax, pm);
-            if (lane == 0) sScal[0] = pmax;
             { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
         } else {
             // ---------------- helper warps ----------------
@@ -484,67 +474,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                     __syncwarp();
                 }
                 { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
-                // (first in its step: the F tasks wait for this)
-                if (s == 2 && b >= 1) {
-                    // anchors of the block that finished: its last row e and the last seven split points of the best
-                    // segmentation ending there (e -> prev[e] -> prev[prev[e]] ...): the rows ahead most likely continue
-                    // one of these, so "best up to the anchor, then one segment" bounds their maxima from below tightly
-                    const int e = XP_RB * b;
-                    // rows still in the shared-memory rings: the chain warp is writing rows e + 65 .. e + 96 in this step
-                    // (they overwrite rows 1024 further back)
-                    const int in_ring = e + 96 - XP_PRING + 64;
-                    int a = e, mine = e;
-                    for (int t = 1; t < 8; ++t) {                  // (every lane walks the same chain: uniform loads)
-                        if (a > 0) a = a > in_ring ? sPrevRing[a & (XP_PRING - 1)] : __ldcg(p.prev + a);
-                        if (lane == t) mine = a;
-                    }
-                    if (lane < 8) {
-                        mine = min(max(mine, 0), e);
-                        XpAnchors *an = p.anchors + (b - 1);
-                        an->idx[lane] = mine;
-                        an->L[lane] = __ldg(p.L + mine);
-                        an->C[lane] = __ldg(p.C + mine);
-                        an->P[lane] = mine > in_ring ? sP[mine & (XP_PRING - 1)] : (mine > 0 ? __ldcg(p.P + mine) : 0.0);
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        __stcg(p.pmax, sScal[0]);
-                        __threadfence();
-                        *reinterpret_cast<volatile int *>(p.done_block) = b;
-                    }
-                }
-                if (k > 0) {
-                    // records of the columns finished in step k-1 (and of the block they complete), then publish; the
-                    // columns' (C, L) were loaded during the previous step
-                    const int jbp = jb - 32;
-                    const int cme = rec_c, lme = rec_l;
-                    XpRec32 *rec = p.rec32 + (k - 1);
-                    if (!(p.dbg & 2)) fit_column_record(cme, lme, sP[(jbp + lane) & (XP_PRING - 1)], &rec->r, tilt_c, tilt_l);
-                    if ((lane & 7) == 0) { rec->sub[lane >> 3][0] = cme; rec->sub[lane >> 3][2] = lme; }
-                    if ((lane & 7) == 7) { rec->sub[lane >> 3][1] = cme; rec->sub[lane >> 3][3] = lme; }
-                    // The work per finished block is spread over three steps, so that this warp is never the last at the step
-                    // barrier (all of it in the block's first step: 7.3 k cycles against the others' 3.8 k):  s == 0: P published
-                    // for the N tasks (above); s == 1: the 128-column record; s == 2: anchors, then done_block -- the F tasks
-                    // start 2.5 steps later than they could, which lag >= 4 affords (profiles/r02_exact_dp_v9_notes.txt)
-                    if (s == 1 && b >= 1) {
-                        const int c0 = 1 + XP_RB * (b - 1);
-                        double pp[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) pp[q] = sP[(c0 + lane + 32 * q) & (XP_PRING - 1)];
-                        if (!(p.dbg & 2)) fit_column_record128(rec_c4, rec_l4, pp, p.rec128 + (b - 1), tilt_c, tilt_l);
-                    }
-                }
-                // inputs of the next step's records
-                if (jb + lane < N) { rec_c = __ldg(p.C + jb + lane); rec_l = __ldg(p.L + jb + lane); }
-                if (s == 3) {
-                    const int c0 = 1 + XP_RB * b;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int col = min(c0 + lane + 32 * q, N - 1);
-                        rec_c4[q] = __ldg(p.C + col);
-                        rec_l4[q] = __ldg(p.L + col);
-                    }
-                }
+                // (the records of the finished columns, the anchors and done_block are made by worker CTAs: R tasks)
                 { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
             } else {
                 // self scores of block (k+3)/4 must be complete before anything of step k+3 is prefetched below
@@ -1068,6 +998,68 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
     }
 }
 
+// R(b): the records of the finished row block b -- its four 32-column records, its 128-column record, its anchors, its
+// largest |P| -- and then done_block = b + 1, in block order.  Everything here needs only final P / prev in global memory
+// (p_block), so it does not have to run on the diagonal's SM: there the book-keeping warp spent 2.7 k cycles per step on the
+// 32-column record alone and was the last at the step barrier in three steps out of four
+// (profiles/r02_exact_dp_v9_notes.txt).
+__device__ void xp_r_task(const XpParams &p, int b)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    xp_wait_cta(p.p_block, b + 1);                                      // P and prev of blocks 0 .. b are final
+    const double tilt_c = __ldg(p.consts + 1), tilt_l = __ldg(p.consts + 2);
+    const int c0 = 1 + XP_RB * b;                                       // (a block with an R task is never the last: 128 columns)
+    if (warp < 4) {
+        const int col = c0 + 32 * warp + lane;
+        const int cme = __ldg(p.C + col), lme = __ldg(p.L + col);
+        const double P = __ldcg(p.P + col);
+        XpRec32 *rec = p.rec32 + (4 * b + warp);
+        fit_column_record(cme, lme, P, &rec->r, tilt_c, tilt_l);
+        if ((lane & 7) == 0) { rec->sub[lane >> 3][0] = cme; rec->sub[lane >> 3][2] = lme; }
+        if ((lane & 7) == 7) { rec->sub[lane >> 3][1] = cme; rec->sub[lane >> 3][3] = lme; }
+        double pm = fabs(P);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, off));
+        // (non-negative doubles order like their bit patterns)
+        if (lane == 0) atomicMax(reinterpret_cast<u64 *>(p.pmax), (u64)__double_as_longlong(pm));
+    } else if (warp == 4) {
+        int c4[4], l4[4];
+        double p4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            c4[q] = __ldg(p.C + c0 + lane + 32 * q);
+            l4[q] = __ldg(p.L + c0 + lane + 32 * q);
+            p4[q] = __ldcg(p.P + c0 + lane + 32 * q);
+        }
+        fit_column_record128(c4, l4, p4, p.rec128 + b, tilt_c, tilt_l);
+    } else if (warp == 5) {
+        // anchors: the block's last row e and the last seven split points of the best segmentation ending there (e -> prev[e]
+        // -> prev[prev[e]] ...): the rows ahead most likely continue one of these, so "best up to the anchor, then one
+        // segment" bounds their maxima from below tightly
+        const int e = XP_RB * (b + 1);
+        int a = e, mine = e;
+        for (int t = 1; t < 8; ++t) {                                   // (every lane walks the same chain: uniform loads)
+            if (a > 0) a = __ldcg(p.prev + a);
+            if (lane == t) mine = a;
+        }
+        if (lane < 8) {
+            mine = min(max(mine, 0), e);
+            XpAnchors *an = p.anchors + b;
+            an->idx[lane] = mine;
+            an->L[lane] = __ldg(p.L + mine);
+            an->C[lane] = __ldg(p.C + mine);
+            an->P[lane] = mine > 0 ? __ldcg(p.P + mine) : 0.0;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        while (xp_ld_flag(p.done_block) < b) __nanosleep(32);           // (R(b - 1) is earlier in the task list)
+        __threadfence();
+        *reinterpret_cast<volatile int *>(p.done_block) = b + 1;
+    }
+}
+
 // N(b, g): rows of block b against 16 columns of the first block of the band, [F_b + 16 g, F_b + 16 g + 16) -- the block
 // that has just been published when block b - lag + 2 starts.  Too close to the diagonal for the bounds of the F tasks to
 // be worth their latency, too far for the chain to need it soon: its 128 x 128 cells are simply evaluated, in the
@@ -1156,7 +1148,8 @@ exact_pruned_kernel(XpParams p)
         const int2 task = __ldg(p.tasks + t);
         if ((task.x & 1) == 0) xp_s_task<AI>(p, task.x >> 1, task.y, smem);
         else if (task.y < XP_G) xp_f_task<AI>(p, task.x >> 1, task.y, smem);
-        else xp_n_task<AI>(p, task.x >> 1, task.y - XP_G, smem);
+        else if (task.y < XP_GT) xp_n_task<AI>(p, task.x >> 1, task.y - XP_G, smem);
+        else xp_r_task(p, task.x >> 1);
     }
 }
 
@@ -1174,6 +1167,7 @@ std::vector<int2> build_tasks(int nB, int lag, int nb)
     for (int b = 0; b < XP_SAHEAD; ++b) push_s(b);
     for (int b = 0; b < lag - 1; ++b) push_f(b);          // (two N blocks: the row blocks that have N tasks before they have F tasks)
     for (int tt = 0; tt < nB; ++tt) {
+        if (tt >= 1 && tt + lag - 1 < nB) t.push_back(make_int2(((tt - 1) << 1) | 1, XP_GT));     // R(tt - 1): F(tt + lag - 1) waits for it
         push_f(tt + lag - 1);
         push_s(tt + XP_SAHEAD);
     }
