@@ -79,7 +79,8 @@ struct XpParams {
     const int32_t *C;
     double *P;
     int *prev;
-    double *Sring;              // [ring slot][d - 1][row in block]
+    double *Sring;              // [ring slot][step of the block (4)][d - 1][row of the step (32)]: the tile of a step -- and every
+                                // run of distances of its 32 rows -- is one contiguous piece (one bulk copy)
     int *s_ready;               // [nB] finished S sub-tasks
     int *far_ready;             // [nB] finished F and N slices
     int *done_block;            // blocks finished and published (P, prev, records)
@@ -190,7 +191,7 @@ __device__ __forceinline__ int xp_band_bound(int b, int lag, int nb) { return xp
 __host__ __device__ inline size_t xp_diag_smem()
 {
     return (size_t)2 * XP_PRING * 8 + 3 * XP_ST * 32 * 8 + 2 * XP_HELP * 32 * 12 + 2 * XP_RB * 12 + 64 + XP_PRING * 4 + 16
-           + 16;                                                // two mbarriers: the bulk copies of the far results
+           + 48;                                                // five mbarriers: the bulk copies of the far results and of the chain warp's tiles
 }
 __host__ __device__ inline size_t xp_worker_smem()
 {
@@ -209,24 +210,24 @@ __device__ __forceinline__ void xp_load_s_tile(const XpParams &p, int step, doub
     const int jb = 1 + 32 * step;
     if (jb >= p.N) return;
     const int b = step >> 2;
-    const double *src = p.Sring + (size_t)(b % p.s_slots) * p.DB * XP_RB + (step & 3) * 32;
+    const double *src = p.Sring + ((size_t)(b % p.s_slots) * 4 + (step & 3)) * p.DB * 32;
     constexpr int NV = (XP_ST * 16 + XP_HELP * 32 - 1) / (XP_HELP * 32);      // chunks per thread with 224 threads (5)
     double2 v[NV];
 #pragma unroll
     for (int u = 0; u < NV; ++u) {                                            // all loads in flight, then the stores
         const int c = t + u * nthreads;
-        if (c < XP_ST * 16) v[u] = xp_ld_s<RING>(reinterpret_cast<const double2 *>(src + (size_t)(c >> 4) * XP_RB + (c & 15) * 2));
+        if (c < XP_ST * 16) v[u] = xp_ld_s<RING>(reinterpret_cast<const double2 *>(src + c * 2));
     }
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
         const int c = t + u * nthreads;
-        if (c < XP_ST * 16) *reinterpret_cast<double2 *>(dst + (c >> 4) * 32 + (c & 15) * 2) = v[u];
+        if (c < XP_ST * 16) *reinterpret_cast<double2 *>(dst + c * 2) = v[u];
     }
 }
 
 // Mid columns of the rows of one step, for one helper warp: the distances this warp sweeps and this lane's valid range.
 struct XpMid {
-    const double *Sb;      // self scores of this lane's row: Sb[(d - 1) * XP_RB]
+    const double *Sb;      // self scores of this lane's row: Sb[(d - 1) * 32]
     int j, dlo, dhi, lane_lo, lane_hi;
 };
 __device__ __forceinline__ XpMid xp_mid_geometry(const XpParams &p, int step, int hw, int lane)
@@ -235,7 +236,7 @@ __device__ __forceinline__ XpMid xp_mid_geometry(const XpParams &p, int step, in
     const int jbn = 1 + 32 * step, bn = step >> 2;
     const int F = xp_band_bound(bn, p.lag, p.nb);
     g.j = jbn + lane;
-    g.Sb = p.Sring + (size_t)(bn % p.s_slots) * p.DB * XP_RB + (step & 3) * 32 + lane;
+    g.Sb = p.Sring + ((size_t)(bn % p.s_slots) * 4 + (step & 3)) * p.DB * 32 + lane;
     const int nd = jbn - F - 1;                          // distances 33 .. jbn + 31 - F over the warp
     const int unit = (nd + XP_MIDW - 1) / XP_MIDW;       // six equal chunks (59 distances at lag 3: two batches)
     g.dlo = 33 + hw * unit;
@@ -250,16 +251,16 @@ __device__ __forceinline__ XpMid xp_mid_geometry(const XpParams &p, int step, in
 template <bool RING>
 __device__ __forceinline__ void xp_mid_load(const XpMid &g, int d, double (&v)[XP_MB])
 {
-    const double *top = g.Sb + (size_t)(d - 1) * XP_RB;              // entry u sits u * XP_RB doubles below
+    const double *top = g.Sb + (size_t)(d - 1) * 32;                 // entry u sits u * 32 doubles below
     const int lo_all = __reduce_max_sync(0xffffffffu, g.lane_lo), hi_all = __reduce_min_sync(0xffffffffu, g.lane_hi);
     if (d - (XP_MB - 1) >= lo_all && d <= hi_all) {
 #pragma unroll
-        for (int u = 0; u < XP_MB; ++u) v[u] = xp_ld_s<RING>(top - (size_t)u * XP_RB);
+        for (int u = 0; u < XP_MB; ++u) v[u] = xp_ld_s<RING>(top - u * 32);
     } else {
 #pragma unroll
         for (int u = 0; u < XP_MB; ++u) {
             const int dd = d - u;
-            v[u] = (dd >= g.lane_lo && dd <= g.lane_hi) ? xp_ld_s<RING>(top - (size_t)u * XP_RB) : -INFINITY;
+            v[u] = (dd >= g.lane_lo && dd <= g.lane_hi) ? xp_ld_s<RING>(top - u * 32) : -INFINITY;
         }
     }
 }
@@ -293,28 +294,21 @@ __device__ __forceinline__ void xp_mid_fold(const XpMid &g, int d, const double 
         if (qb[q] > best) { best = qb[q]; arg = col0 + qu[q]; }
 }
 
-// the chain warp's self-score tile of a step (distances 1..63 of its 32 rows): global -> registers, registers -> shared
-constexpr int XP_TILE_NV = (XP_ST * 16 + XP_MIDW * 32 - 1) / (XP_MIDW * 32);      // double2 chunks per sweeping thread (6)
-template <bool RING>
-__device__ __forceinline__ void xp_tile_load(const XpParams &p, int step, int t, int nthreads, double2 (&v)[XP_TILE_NV])
+// The chain warp's self-score tile of a step (distances 1..63 of its 32 rows: 16 KB, contiguous in the slab) travels into
+// shared memory as one bulk copy issued by the book-keeping warp, two steps ahead; the chain warp waits on the slot's mbarrier
+// when it first reads the tile.  (Before, the six sweeping warps carried the tiles through registers: 0.5 k of their 3.4 k
+// cycles per step, and they are the slowest role: profiles/r02_exact_dp_v9_notes.txt.)
+__device__ __forceinline__ void xp_tile_bulk(const XpParams &p, int step, double *dst, unsigned long long *bar, int lane)
 {
-    if (1 + 32 * step >= p.N) return;
-    const double *src = p.Sring + (size_t)((step >> 2) % p.s_slots) * p.DB * XP_RB + (step & 3) * 32;
-#pragma unroll
-    for (int u = 0; u < XP_TILE_NV; ++u) {
-        const int c = t + u * nthreads;
-        if (c < XP_ST * 16) v[u] = xp_ld_s<RING>(reinterpret_cast<const double2 *>(src + (size_t)(c >> 4) * XP_RB + (c & 15) * 2));
-    }
+    const double *src = p.Sring + ((size_t)((step >> 2) % p.s_slots) * 4 + (step & 3)) * p.DB * 32;
+    if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        xp_mbar_expect(bar, XP_ST * 32 * 8);
+        xp_bulk_g2s(dst, src, XP_ST * 32 * 8, bar);                  // (many small bulk copies are slow to issue: 63 of 256 bytes cost
+    }                                                                //  the warp 4.5 k cycles)
 }
-__device__ __forceinline__ void xp_tile_store(const XpParams &p, int step, double *dst, int t, int nthreads, const double2 (&v)[XP_TILE_NV])
-{
-    if (1 + 32 * step >= p.N) return;
-#pragma unroll
-    for (int u = 0; u < XP_TILE_NV; ++u) {
-        const int c = t + u * nthreads;
-        if (c < XP_ST * 16) *reinterpret_cast<double2 *>(dst + (c >> 4) * 32 + (c & 15) * 2) = v[u];
-    }
-}
+// parity of the mbarrier phase that the bulk copy of tile `step` completes: slot step % 3; tiles 0 and 1 are loaded directly
+__device__ __forceinline__ unsigned xp_tile_parity(int step) { return (unsigned)((step / 3 - (step % 3 == 2 ? 0 : 1)) & 1); }
 
 template <bool AI, bool RING>
 __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
@@ -338,8 +332,8 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
         __stcg(p.P, 0.0);
         __stcg(p.prev, 0);
         sScal[0] = 0.0;
-        xp_mbar_init(sFarBar, 1);
-        xp_mbar_init(sFarBar + 1, 1);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) xp_mbar_init(sFarBar + q, 1);       // [0], [1] far results; [2 + slot] tiles
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int k = tid; k < 2 * XP_HELP * 32; k += XP_THREADS) { sMidV[k] = -INFINITY; sMidA[k] = 0; }
@@ -360,13 +354,10 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
     // helper state carried from step to step: the self scores of the NEXT mid sweep and of the next tile are loaded
     // one step ahead (they do not depend on P), so a step only adds the finished P to values that have already arrived
     const int hw_mine = warp < 4 ? warp - 1 : (warp == 4 ? XP_MIDW : warp - 2);       // 0..5 sweep, 6 = the book-keeping warp
-    const int hidx = hw_mine * 32 + lane;                // index among the 192 sweeping threads
     double pre0[XP_MB], pre1[XP_MB];
-    double2 tile_regs[XP_TILE_NV];
     int s_known = 0;                                     // block 0 is complete (waited above)
     int *sKnown = sPrevRing + XP_PRING;
     if (warp > 0 && hw_mine < XP_MIDW) {
-        if (2 < p.nSteps) xp_tile_load<RING>(p, 2, hidx, XP_MIDW * 32, tile_regs);
         if (1 < p.nSteps) {
             const XpMid g = xp_mid_geometry(p, 1, hw_mine, lane);
             xp_mid_load<RING>(g, g.dhi - 1, pre0);
@@ -403,6 +394,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             arg2 = 0;
             const double *tri = sS + (k % 3) * XP_ST * 32;
             const double *nxt = sS + ((k + 1) % 3) * XP_ST * 32;
+            if (k >= 1 && k + 1 < p.nSteps && !(p.dbg & 8)) xp_mbar_wait(sFarBar + 2 + (k + 1) % 3, xp_tile_parity(k + 1));
             const bool valid2 = jb + 32 + lane < N;
             double mine = 0.0;
             // Always 32 iterations: in the last (partial) step the lanes past the end only produce values nobody reads.
@@ -450,6 +442,8 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 // (first: the sweeping warps wait at a named barrier for this warp's look at the flags)
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
                 { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
+                // the chain warp's tile of the step after next into the slot it stopped reading a step ago
+                if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_tile_bulk(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, sFarBar + 2 + (k + 2) % 3, lane);
                 // P and prev of the block that finished with the previous step are in global memory (the chain warp stored them
                 // before the step barrier): the N tasks need nothing else, so they are released before the records are made
                 if (s == 0 && k > 0 && lane == 0) {
@@ -507,8 +501,6 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 if (p.dbg & 16) { double acc = 0.0; for (int u = 0; u < XP_MB; ++u) acc += pre0[u] + pre1[u]; if (acc == 1.2345) sMidV[0] = acc; }   // (keeps the loads alive)
                 { const long long t1 = xp_clock(); pq[1] += t1 - tq; tq = t1; }
                 // the tile of step k+2 (loaded during the previous step) -> shared memory; then the loads of the next one
-                if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_tile_store(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, hidx, XP_MIDW * 32, tile_regs);
-                if (k + 3 < p.nSteps && !(p.dbg & 8)) xp_tile_load<RING>(p, k + 3, hidx, XP_MIDW * 32, tile_regs);
                 { const long long t1 = xp_clock(); pq[2] += t1 - tq; tq = t1; }
             }
         }
@@ -549,7 +541,7 @@ __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
     if (r < nrows) {
         const int2 me = sLC[j - F];
         const RowConst<AI> row = make_row<AI>(me.y, me.x, p.alpha_int, p.alpha);
-        double *Sb = p.Sring + (size_t)(b % p.s_slots) * p.DB * XP_RB + r;
+        double *Sb = p.Sring + ((size_t)(b % p.s_slots) * 4 + (r >> 5)) * p.DB * 32 + (r & 31);
         const int dmax = min(d1 - 1, j - F);                    // column j - d >= F
         constexpr int U = 4;
         for (int d = d0 + half; d <= dmax; d += 2 * U) {
@@ -569,7 +561,7 @@ __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
                 const int dd = d + 2 * u;
                 if (dd <= dmax) {
                     const double sx = AI ? u32_to_double(idx[u]) : __dsub_rn(row.aj, u32_to_double(ci[u]));
-                    Sb[(size_t)(dd - 1) * XP_RB] = __dsub_rn(g[u], __dmul_rn(sx, lg[u]));
+                    Sb[(dd - 1) * 32] = __dsub_rn(g[u], __dmul_rn(sx, lg[u]));
                 }
             }
         }

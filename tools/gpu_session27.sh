@@ -6,7 +6,7 @@ T=${1:-i6}
 timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "exact or config or pruned" > gpurun_out/${T}_gpu_tests.log 2>&1
 echo "gpu tests rc=$?" >> gpurun_out/${T}_gpu_tests.log
 tail -2 gpurun_out/${T}_gpu_tests.log
-for geo in "5 3" "4 2"; do
+for geo in "5 3"; do
 set -- $geo
 for prof in 1 0; do
 for cfg in exact1 exact3; do
