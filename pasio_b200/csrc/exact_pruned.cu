@@ -171,6 +171,7 @@ __device__ __forceinline__ void xp_wait_s_blocks(const XpParams &p, int need, in
             __nanosleep(20);
         }
         __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");          // (the slabs are read by bulk copies, too)
         if (lane == 0) *sKnown = need + __ffs(~ok | 0x80000000u) - 2 + ((ok == 0xffffffffu) ? 1 : 0);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(XP_HELP * 32) : "memory");
@@ -301,8 +302,7 @@ __device__ __forceinline__ void xp_mid_fold(const XpMid &g, int d, const double 
 __device__ __forceinline__ void xp_tile_bulk(const XpParams &p, int step, double *dst, unsigned long long *bar, int lane)
 {
     const double *src = p.Sring + ((size_t)((step >> 2) % p.s_slots) * 4 + (step & 3)) * p.DB * 32;
-    if (lane == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");
+    if (lane == 0) {                                                 // (the proxy fence sits where the slab's flag was seen: xp_wait_s_blocks)
         xp_mbar_expect(bar, XP_ST * 32 * 8);
         xp_bulk_g2s(dst, src, XP_ST * 32 * 8, bar);                  // (many small bulk copies are slow to issue: 63 of 256 bytes cost
     }                                                                //  the warp 4.5 k cycles)
@@ -378,9 +378,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             double best = -INFINITY;
             int arg = 0;
             if (xp_has_far(b, lag, p.nb)) {                      // far columns (the smallest indices)
-                // the bulk copies of this block's merged far results were started a step ago; a slot's n-th use completes
-                // phase n of its mbarrier
-                if (s == 0) xp_mbar_wait(sFarBar + (b & 1), (unsigned)(((b - far_first) >> 1) & 1));
+                // (bulk-copied by the book-keeping warp during the previous step, which also waited for them)
                 best = sFarV[(b & 1) * XP_RB + s * 32 + lane];
                 arg = sFarA[(b & 1) * XP_RB + s * 32 + lane];
             }
@@ -394,7 +392,6 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             arg2 = 0;
             const double *tri = sS + (k % 3) * XP_ST * 32;
             const double *nxt = sS + ((k + 1) % 3) * XP_ST * 32;
-            if (k >= 1 && k + 1 < p.nSteps && !(p.dbg & 8)) xp_mbar_wait(sFarBar + 2 + (k + 1) % 3, xp_tile_parity(k + 1));
             const bool valid2 = jb + 32 + lane < N;
             double mine = 0.0;
             // Always 32 iterations: in the last (partial) step the lanes past the end only produce values nobody reads.
@@ -442,8 +439,6 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 // (first: the sweeping warps wait at a named barrier for this warp's look at the flags)
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
                 { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
-                // the chain warp's tile of the step after next into the slot it stopped reading a step ago
-                if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_tile_bulk(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, sFarBar + 2 + (k + 2) % 3, lane);
                 // P and prev of the block that finished with the previous step are in global memory (the chain warp stored them
                 // before the step barrier): the N tasks need nothing else, so they are released before the records are made
                 if (s == 0 && k > 0 && lane == 0) {
@@ -467,6 +462,9 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                     }
                     __syncwarp();
                 }
+                // ... and waits for the copies it started (a slot's n-th use completes phase n of its mbarrier), so that the step
+                // barrier hands the far results to the chain warp
+                if (s == 3 && b + 1 < p.nB && xp_has_far(b + 1, lag, p.nb)) xp_mbar_wait(sFarBar + ((b + 1) & 1), (unsigned)(((b + 1 - far_first) >> 1) & 1));
                 { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
                 // (the records of the finished columns, the anchors and done_block are made by worker CTAs: R tasks)
                 { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
@@ -474,6 +472,11 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 // self scores of block (k+3)/4 must be complete before anything of step k+3 is prefetched below
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
                 { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
+                // the chain warp's tile of the step after next into the slot it stopped reading a step ago: started by the first
+                // sweeping warp (the book-keeping warp shares its scheduler with the chain warp), which also waits for it at the
+                // end of its step -- long after it has arrived -- so that the step barrier hands it to the chain warp
+                const bool tile_mine = hw == 0 && k + 2 < p.nSteps && !(p.dbg & 8);
+                if (tile_mine) xp_tile_bulk(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, sFarBar + 2 + (k + 2) % 3, lane);
                 // mid columns of the next step's rows: [F, jb), by distance, descending (= ascending column).  The two
                 // batches were loaded during the previous step; as soon as a batch is folded its registers take the loads
                 // of the step after, so the transfers run under the arithmetic
@@ -500,7 +503,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 if (have2 && do_load && two2) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
                 if (p.dbg & 16) { double acc = 0.0; for (int u = 0; u < XP_MB; ++u) acc += pre0[u] + pre1[u]; if (acc == 1.2345) sMidV[0] = acc; }   // (keeps the loads alive)
                 { const long long t1 = xp_clock(); pq[1] += t1 - tq; tq = t1; }
-                // the tile of step k+2 (loaded during the previous step) -> shared memory; then the loads of the next one
+                if (tile_mine) xp_mbar_wait(sFarBar + 2 + (k + 2) % 3, xp_tile_parity(k + 2));
                 { const long long t1 = xp_clock(); pq[2] += t1 - tq; tq = t1; }
             }
         }
