@@ -1,7 +1,8 @@
 """Code size of the loops of a kernel: largest backward branches in its SASS (cuobjdump -sass of an object file).
 
 usage: python tools/sass_loop_size.py pasio_b200/csrc/exact_pruned.o exact_pruned_kernelILb1ELb1E [min_bytes]
-The step loop of the exact DP's diagonal CTA must fit the SM's instruction cache (profiles/r02_exact_dp_v9_icache.txt)."""
+Written to test whether the step loop of the exact DP's diagonal CTA (70 KB) suffered from the 32 KB instruction cache: shrinking it
+to 48 KB changed nothing (profiles/r02_exact_dp_v9_notes.txt)."""
 import re
 import subprocess
 import sys
