@@ -607,9 +607,9 @@ __device__ void xp_far_finish(const XpParams &p, int b)
     const int tid = threadIdx.x;
     __syncthreads();                                                    // this task's slice is written
     if (tid == 0) {
-        __threadfence();
-        sLast = atomicAdd(p.far_ready + b, 1) == xp_far_count(b, p.lag, p.nb) - 1;
-        if (sLast) __threadfence();                                     // the other tasks' slices, released the same way
+        int before;                                                     // release of this slice + acquire of the others' in one
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(before) : "l"(p.far_ready + b) : "memory");
+        sLast = before == xp_far_count(b, p.lag, p.nb) - 1;
     }
     __syncthreads();
     if (!sLast) return;
@@ -633,10 +633,7 @@ __device__ void xp_far_finish(const XpParams &p, int b)
         __stcg(p.farAm + (size_t)b * XP_RB + tid, arg);
     }
     __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        *reinterpret_cast<volatile int *>(p.far_done + b) = 1;
-    }
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], 1;" ::"l"(p.far_done + b) : "memory");
 }
 
 // F(b, g): far columns of row block b that lie in the 32-column groups q = g, g + 8, ... (slice 0 also column 0): the
@@ -1072,29 +1069,37 @@ __device__ void xp_n_task(const XpParams &p, int b, int g, unsigned char *smem)
     const int r = tid & (XP_RB - 1), h = tid >> 7;                      // row; which 8 of the slice's 16 columns
     double best = -INFINITY;
     int arg = 0x7fffffff;
-    // (two N blocks, with lag 4: the far tasks get three blocks of time instead of two, the band of the diagonal stays the same)
-    for (int nq = 0; nq < p.nb; ++nq) {                                 // ascending columns within a thread
-        // P of column block b - lag + 1 + nq is final (no records needed).  Block by block: the task has been waiting since
-        // long before, so all but its last block are evaluated before that one is released
-        xp_wait_cta(p.p_block, b - p.lag + 2 + nq);
+    // Column blocks b - lag + 1 .. b - lag + nb (with lag 5 and three of them the far tasks get four blocks of time, the band of
+    // the diagonal stays two blocks), ascending columns within a thread.  Block by block: the task has been waiting since long
+    // before, so all but its last block are evaluated before that one is released -- and everything that does not depend on
+    // P (the columns' counts, the table gathers) is fetched BEFORE the wait: behind it only P is loaded (one round trip to L2,
+    // not three: this task's last block and the merge decide when the diagonal gets the block's far results)
+    const int j = min(r0 + r, N - 1);
+    const RowConst<AI> row = make_row<AI>(__ldg(p.C + j), __ldg(p.L + j), p.alpha_int, p.alpha);
+    for (int nq = 0; nq < p.nb; ++nq) {
         const int c0 = 1 + XP_RB * (b - p.lag + 1 + nq) + 16 * g + 8 * h;   // (negative in the first blocks: column 0 is "the last of block -1")
-        if (r >= nrows || c0 + 7 < 0) continue;
-        const int j = r0 + r;
-        const RowConst<AI> row = make_row<AI>(__ldg(p.C + j), __ldg(p.L + j), p.alpha_int, p.alpha);
-        double gq[8], lq[8], pc[8];
+        const bool mine = r < nrows && c0 + 7 >= 0;
+        double gq[8], lq[8];
         int ci[8];
+        if (mine) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {                                   // all gathers in flight, then the arithmetic
-            const int col = max(c0 + u, 0);
-            ci[u] = __ldg(p.C + col);
-            gq[u] = __ldg(p.gtab + (row.cjx - ci[u]));
-            lq[u] = __ldg(p.ltab + (row.lj - __ldg(p.L + col)));
-            pc[u] = __ldcg(p.P + col);
+            for (int u = 0; u < 8; ++u) {                               // all gathers in flight
+                const int col = max(c0 + u, 0);
+                ci[u] = __ldg(p.C + col);
+                gq[u] = __ldg(p.gtab + (row.cjx - ci[u]));
+                lq[u] = __ldg(p.ltab + (row.lj - __ldg(p.L + col)));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) gq[u] = __dsub_rn(gq[u], __dmul_rn(AI ? u32_to_double(row.cjx - ci[u]) : __dsub_rn(row.aj, u32_to_double(ci[u])), lq[u]));
         }
+        xp_wait_cta(p.p_block, b - p.lag + 2 + nq);                     // P of column block b - lag + 1 + nq is final (no records needed)
+        if (!mine) continue;
+        double pc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) pc[u] = __ldcg(p.P + max(c0 + u, 0));
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const double sx = AI ? u32_to_double(row.cjx - ci[u]) : __dsub_rn(row.aj, u32_to_double(ci[u]));
-            const double t = __dadd_rn(__dsub_rn(gq[u], __dmul_rn(sx, lq[u])), pc[u]);
+            const double t = __dadd_rn(gq[u], pc[u]);
             if (c0 + u >= 0 && t > best) { best = t; arg = c0 + u; }
         }
     }

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T=${1:-j1}
-for v in ${VARIANTS:-t0 t1 t2 t3}; do
+for v in ${VARIANTS:-p0 p1}; do
 for prof in 1 0; do
 for cfg in exact1 exact3; do
   if [ $prof = 1 ]; then export PASIO_XD_PROF=1; else unset PASIO_XD_PROF; fi
