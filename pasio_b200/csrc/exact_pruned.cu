@@ -398,6 +398,9 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             // The operands of 8 iterations are fetched from shared memory ahead of the dependent chain; a lane that
             // must not take part in an update holds -inf there, so the updates need no branches.  (Rolled into 4 x 8 rows
             // the loop is 12 KB shorter and 8 cycles per row slower: profiles/r02_exact_dp_v9_notes.txt.)
+            // bp = best + pen is carried along: the next row's P is (w ? t : best) + pen = w ? (t + pen) : (best + pen), bit for
+            // bit, and t + pen is formed beside the compare instead of behind the select -- one DADD less on the dependent path
+            double bp = __dadd_rn(best, p.pen);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 8) {
                 double tv[8], nv[8];
@@ -410,12 +413,13 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int kk = k0 + u;
-                    const double pf = __dadd_rn(best, p.pen);       // prefix_scores[j] = max + segment_creation_cost
-                    const double pk = __shfl_sync(0xffffffffu, pf, kk);
-                    mine = lane == kk ? pf : mine;
+                    const double pk = __shfl_sync(0xffffffffu, bp, kk);     // prefix_scores[j] = max + segment_creation_cost
+                    mine = lane == kk ? bp : mine;
                     const double t = __dadd_rn(tv[u], pk);
+                    const double tp = __dadd_rn(t, p.pen);
                     const bool w = t > best;
                     best = w ? t : best;
+                    bp = w ? tp : bp;
                     arg = w ? jb + kk : arg;
                     const double t2 = __dadd_rn(nv[u], pk);
                     const bool w2 = t2 > best2;
