@@ -382,10 +382,17 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 best = sFarV[(b & 1) * XP_RB + s * 32 + lane];
                 arg = sFarA[(b & 1) * XP_RB + s * 32 + lane];
             }
+            {   // mid columns: helper w swept the w-th distance chunk (all twelve reads first, then the merge in column order)
+                double mv[XP_MIDW];
+                int ma[XP_MIDW];
 #pragma unroll
-            for (int w = XP_MIDW - 1; w >= 0; --w) {             // mid columns: helper w swept the w-th distance chunk
-                const double v = sMidV[((k & 1) * XP_HELP + w) * 32 + lane];
-                if (v > best) { best = v; arg = sMidA[((k & 1) * XP_HELP + w) * 32 + lane]; }
+                for (int w = 0; w < XP_MIDW; ++w) {
+                    mv[w] = sMidV[((k & 1) * XP_HELP + w) * 32 + lane];
+                    ma[w] = sMidA[((k & 1) * XP_HELP + w) * 32 + lane];
+                }
+#pragma unroll
+                for (int w = XP_MIDW - 1; w >= 0; --w)
+                    if (mv[w] > best) { best = mv[w]; arg = ma[w]; }
             }
             if (best2 > best) { best = best2; arg = arg2; }     // near columns
             best2 = -INFINITY;
