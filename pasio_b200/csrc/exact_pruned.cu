@@ -476,6 +476,9 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 // ... and waits for the copies it started (a slot's n-th use completes phase n of its mbarrier), so that the step
                 // barrier hands the far results to the chain warp
                 if (s == 3 && b + 1 < p.nB && xp_has_far(b + 1, lag, p.nb)) xp_mbar_wait(sFarBar + ((b + 1) & 1), (unsigned)(((b + 1 - far_first) >> 1) & 1));
+                // the chain warp's tile of the step after next, started by the first sweeping warp at the top of this step: this
+                // warp has the time to wait for it, so that the step barrier hands it to the chain warp
+                if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_mbar_wait(sFarBar + 2 + (k + 2) % 3, xp_tile_parity(k + 2));
                 { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
                 // (the records of the finished columns, the anchors and done_block are made by worker CTAs: R tasks)
                 { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
@@ -484,8 +487,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
                 { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
                 // the chain warp's tile of the step after next into the slot it stopped reading a step ago: started by the first
-                // sweeping warp (the book-keeping warp shares its scheduler with the chain warp), which also waits for it at the
-                // end of its step -- long after it has arrived -- so that the step barrier hands it to the chain warp
+                // sweeping warp; the book-keeping warp waits for it before the step barrier
                 const bool tile_mine = hw == 0 && k + 2 < p.nSteps && !(p.dbg & 8);
                 if (tile_mine) xp_tile_bulk(p, k + 2, sS + ((k + 2) % 3) * XP_ST * 32, sFarBar + 2 + (k + 2) % 3, lane);
                 // mid columns of the next step's rows: [F, jb), by distance, descending (= ascending column).  The two
@@ -514,7 +516,6 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 if (have2 && do_load && two2) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
                 if (p.dbg & 16) { double acc = 0.0; for (int u = 0; u < XP_MB; ++u) acc += pre0[u] + pre1[u]; if (acc == 1.2345) sMidV[0] = acc; }   // (keeps the loads alive)
                 { const long long t1 = xp_clock(); pq[1] += t1 - tq; tq = t1; }
-                if (tile_mine) xp_mbar_wait(sFarBar + 2 + (k + 2) % 3, xp_tile_parity(k + 2));
                 { const long long t1 = xp_clock(); pq[2] += t1 - tq; tq = t1; }
             }
         }
