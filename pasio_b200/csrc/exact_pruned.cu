@@ -110,7 +110,16 @@ struct XpParams {
 enum { XQ_CHAIN = 0, XQ_CHAIN_BAR, XQ_H6_REC, XQ_H6_MID, XQ_H6_TILE, XQ_H6_SWAIT, XQ_H6_FAR, XQ_H6_BAR,
        XQ_H0_MID, XQ_H0_TILE, XQ_H0_SWAIT, XQ_H0_FAR, XQ_H0_BAR, XQ_DIAG_TOTAL,
        XQ_S_WORK = 16, XQ_S_WAIT, XQ_S_COUNT, XQ_F_WORK, XQ_F_WAIT, XQ_F_COUNT, XQ_F_MAX, XQ_F_L0, XQ_F_L1, XQ_F_L23, XQ_F_HEAD };
-__device__ __forceinline__ long long xp_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
+// PROF = false (the kernels that run unless PASIO_XD_PROF is set): no clock reads -- each is an asm volatile with a memory
+// clobber that the compiler schedules nothing across; without them the kernel is 1.6 - 2.2 % faster (gpurun session k3)
+template <bool PROF>
+__device__ __forceinline__ long long xp_clock()
+{
+    if (!PROF) return 0;
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
 
 __device__ __forceinline__ int xp_ld_flag(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ int xp_ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
@@ -310,7 +319,7 @@ __device__ __forceinline__ void xp_tile_bulk(const XpParams &p, int step, double
 // parity of the mbarrier phase that the bulk copy of tile `step` completes: slot step % 3; tiles 0 and 1 are loaded directly
 __device__ __forceinline__ unsigned xp_tile_parity(int step) { return (unsigned)((step / 3 - (step % 3 == 2 ? 0 : 1)) & 1); }
 
-template <bool AI, bool RING>
+template <bool AI, bool RING, bool PROF>
 __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
 {
     double *sP = reinterpret_cast<double *>(smem);              // [2 * XP_PRING] finished P, ring by column index, every entry
@@ -365,11 +374,11 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
         }
     }
     long long pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // per-thread phase cycles (only threads 0, 32 and 224 report)
-    const long long t_begin = xp_clock();
+    const long long t_begin = xp_clock<PROF>();
     long long t_last = t_begin, t_prev_top = t_begin;
     for (int k = 0; k < p.nSteps; ++k) {
         const int jb = 1 + 32 * k, b = k >> 2, s = k & 3;
-        long long tq = xp_clock();
+        long long tq = xp_clock<PROF>();
         const long long t_top = tq;
         pq[6] += tq - t_last;                              // (between the clock read behind the barrier and this one)
         if (warp == 0) {
@@ -440,7 +449,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 __stcg(p.P + j, mine);
                 __stcg(p.prev + j, arg);
             }
-            { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
+            { const long long t1 = xp_clock<PROF>(); pq[0] += t1 - tq; tq = t1; }
         } else {
             // ---------------- helper warps ----------------
             // warps 1,2,3,5,6,7 sweep the mid columns (six distance chunks, in this order) and move the tiles; warp 4 -- which
@@ -449,7 +458,7 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
             if (hw == XP_MIDW) {
                 // (first: the sweeping warps wait at a named barrier for this warp's look at the flags)
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
-                { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
+                { const long long t1 = xp_clock<PROF>(); pq[3] += t1 - tq; tq = t1; }
                 // P and prev of the block that finished with the previous step are in global memory (the chain warp stored them
                 // before the step barrier): the N tasks need nothing else, so they are released before the records are made
                 if (s == 0 && k > 0 && lane == 0) {
@@ -479,13 +488,13 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 // the chain warp's tile of the step after next, started by the first sweeping warp at the top of this step: this
                 // warp has the time to wait for it, so that the step barrier hands it to the chain warp
                 if (k + 2 < p.nSteps && !(p.dbg & 8)) xp_mbar_wait(sFarBar + 2 + (k + 2) % 3, xp_tile_parity(k + 2));
-                { const long long t1 = xp_clock(); pq[4] += t1 - tq; tq = t1; }
+                { const long long t1 = xp_clock<PROF>(); pq[4] += t1 - tq; tq = t1; }
                 // (the records of the finished columns, the anchors and done_block are made by worker CTAs: R tasks)
-                { const long long t1 = xp_clock(); pq[0] += t1 - tq; tq = t1; }
+                { const long long t1 = xp_clock<PROF>(); pq[0] += t1 - tq; tq = t1; }
             } else {
                 // self scores of block (k+3)/4 must be complete before anything of step k+3 is prefetched below
                 if (k + 3 < p.nSteps && ((k + 3) & 3) == 0) xp_wait_s_blocks(p, (k + 3) >> 2, &s_known, sKnown);
-                { const long long t1 = xp_clock(); pq[3] += t1 - tq; tq = t1; }
+                { const long long t1 = xp_clock<PROF>(); pq[3] += t1 - tq; tq = t1; }
                 // the chain warp's tile of the step after next into the slot it stopped reading a step ago: started by the first
                 // sweeping warp; the book-keeping warp waits for it before the step barrier
                 const bool tile_mine = hw == 0 && k + 2 < p.nSteps && !(p.dbg & 8);
@@ -515,22 +524,22 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
                 }
                 if (have2 && do_load && two2) xp_mid_load<RING>(g2, g2.dhi - 1 - XP_MB, pre1);
                 if (p.dbg & 16) { double acc = 0.0; for (int u = 0; u < XP_MB; ++u) acc += pre0[u] + pre1[u]; if (acc == 1.2345) sMidV[0] = acc; }   // (keeps the loads alive)
-                { const long long t1 = xp_clock(); pq[1] += t1 - tq; tq = t1; }
-                { const long long t1 = xp_clock(); pq[2] += t1 - tq; tq = t1; }
+                { const long long t1 = xp_clock<PROF>(); pq[1] += t1 - tq; tq = t1; }
+                { const long long t1 = xp_clock<PROF>(); pq[2] += t1 - tq; tq = t1; }
             }
         }
         if ((p.dbg & 128) && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
-            const long long ta = xp_clock();
+            const long long ta = xp_clock<PROF>();
             atomicAdd(p.prof + 32 + 4 * (warp == 0 ? 0 : (warp == 1 ? 1 : 2)) + s, (u64)(ta - t_top));
             if (warp == 0 && k > 0) atomicAdd(p.prof + 48 + ((k - 1) & 3), (u64)(t_top - t_prev_top));
         }
         t_prev_top = t_top;
         __syncthreads();
-        t_last = xp_clock();
+        t_last = xp_clock<PROF>();
         pq[5] += t_last - tq;
     }
     if ((p.dbg & 64) && lane == 0) printf("[xp_dbg] warp %d: barrier gap %lld, phases %lld %lld %lld %lld %lld %lld cycles/step\n", warp, pq[6] / p.nSteps, pq[0] / p.nSteps, pq[1] / p.nSteps, pq[2] / p.nSteps, pq[3] / p.nSteps, pq[4] / p.nSteps, pq[5] / p.nSteps);
-    if (tid == 0) { p.prof[XQ_CHAIN] = pq[0]; p.prof[XQ_CHAIN_BAR] = pq[5]; p.prof[XQ_DIAG_TOTAL] = xp_clock() - t_begin; p.prof[31] = pq[6]; }
+    if (tid == 0) { p.prof[XQ_CHAIN] = pq[0]; p.prof[XQ_CHAIN_BAR] = pq[5]; p.prof[XQ_DIAG_TOTAL] = xp_clock<PROF>() - t_begin; p.prof[31] = pq[6]; }
     if (tid == 32) p.prof[XQ_H6_MID] = pq[6];                // (the sweeping warp's back-edge gap, in a slot the book-keeping warp never uses)
     if (tid == 32) { p.prof[XQ_H0_MID] = pq[1]; p.prof[XQ_H0_TILE] = pq[2]; p.prof[XQ_H0_SWAIT] = pq[3]; p.prof[XQ_H0_FAR] = pq[4]; p.prof[XQ_H0_BAR] = pq[5]; }
     if (warp > 0 && hw_mine < XP_MIDW && lane == 0) p.prof[hw_mine < 2 ? 14 + hw_mine : 25 + hw_mine] = pq[1];      // mid cycles of every sweeping warp (slots 14, 15, 27 .. 30)
@@ -539,15 +548,15 @@ __device__ void xp_diagonal(const XpParams &p, unsigned char *smem)
 
 // ---- worker CTAs -----------------------------------------------------------------------------
 // S(b, q): self scores of row block b against the columns [F_b, j), distances 1 + q*DB/4 .. (q+1)*DB/4.
-template <bool AI>
+template <bool AI, bool PROF>
 __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
 {
     int2 *sLC = reinterpret_cast<int2 *>(smem);                 // (L, C) of candidates [F, r0 + nrows)
     const int tid = threadIdx.x;
     const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, p.N - r0), F = xp_band_bound(b, p.lag, p.nb);
-    const long long ts0 = xp_clock();
+    const long long ts0 = xp_clock<PROF>();
     if (b >= p.s_slots) xp_wait_cta(p.done_block, b - p.s_slots + 1);  // ring only: the slot's previous block is finished
-    const long long ts1 = xp_clock();
+    const long long ts1 = xp_clock<PROF>();
     const int cnt = r0 + nrows - F;
     for (int i = tid; i < cnt; i += XP_THREADS) sLC[i] = make_int2(__ldg(p.L + F + i), __ldg(p.C + F + i));
     __syncthreads();
@@ -586,7 +595,7 @@ __device__ void xp_s_task(const XpParams &p, int b, int q, unsigned char *smem)
         __threadfence();
         atomicAdd(p.s_ready + b, 1);
         atomicAdd(p.prof + XQ_S_WAIT, (u64)(ts1 - ts0));
-        atomicAdd(p.prof + XQ_S_WORK, (u64)(xp_clock() - ts1));
+        atomicAdd(p.prof + XQ_S_WORK, (u64)(xp_clock<PROF>() - ts1));
         atomicAdd(p.prof + XQ_S_COUNT, 1ull);
     }
 }
@@ -654,7 +663,7 @@ __device__ void xp_far_finish(const XpParams &p, int b)
 // Written for LATENCY (the diagonal reaches block b two or three blocks after this task is released): every level
 // first issues all the loads of all its rectangles, then consumes them, so a level costs one or two round trips to
 // L2 whatever its size.
-template <bool AI>
+template <bool AI, bool PROF>
 __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
 {
     int2 *sRowLC = reinterpret_cast<int2 *>(smem);                      // [128]
@@ -674,9 +683,9 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
     const int N = p.N, lag = p.lag;
     const int r0 = 1 + XP_RB * b, nrows = min(XP_RB, N - r0);
     const int ncb = b - lag + 1;                                        // far column blocks 0 .. ncb-1
-    const long long tf0 = xp_clock();
+    const long long tf0 = xp_clock<PROF>();
     xp_wait_cta(p.done_block, ncb);
-    const long long tf1 = xp_clock();
+    const long long tf1 = xp_clock<PROF>();
     long long tl0 = 0, tl1 = 0, tl2 = 0, thead = 0;
 
     // ---- phase A: rows, anchors, this thread's first level-0 record, scalars: one round trip ----
@@ -773,10 +782,10 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
     const XpRows R = {sRowLC, sLB, sCd, sLd};
     auto row_slack = [&](double a, double bb) { return (lbabs + fabs(a) * tilt_c + fabs(bb) * tilt_l) * 5.684341886080802e-14; };   // 2^-44
     u64 evaluated = 0;
-    thead = xp_clock() - tf1;
+    thead = xp_clock<PROF>() - tf1;
 
     for (int cbase = g >> 2; cbase < ncb; cbase += XP_THREADS * 2) {
-        long long tq = xp_clock();
+        long long tq = xp_clock<PROF>();
         // ---- level 0: 128 rows x 128 columns, one thread per column block; row minima in float ----
         {
             const int c = cbase + tid * 2;
@@ -809,7 +818,7 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
             }
         }
         __syncthreads();
-        { const long long t1 = xp_clock(); tl0 += t1 - tq; tq = t1; }
+        { const long long t1 = xp_clock<PROF>(); tl0 += t1 - tq; tq = t1; }
         const int n0 = sCnt[0];
         // ---- level 1: 32 rows x 32 columns (this slice's column group of every surviving block), one thread per
         //      rectangle, two rectangles in flight per thread ----
@@ -859,7 +868,7 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
                 }
         }
         __syncthreads();
-        { const long long t1 = xp_clock(); tl1 += t1 - tq; tq = t1; }
+        { const long long t1 = xp_clock<PROF>(); tl1 += t1 - tq; tq = t1; }
         const int n1 = min(sCnt[1], XP_LIST1);       // n0 <= 256 blocks x 16 = 4096: never overflows
         // ---- level 2 (4 rows x 8 columns, one lane per rectangle) then exact evaluation, XP_L2CHUNK level-1 survivors per pass ----
         for (int base = 0; base < n1; base += XP_L2CHUNK) {
@@ -970,7 +979,7 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
             }
             __syncthreads();
         }
-        tl2 += xp_clock() - tq;
+        tl2 += xp_clock<PROF>() - tq;
         if (tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
         __syncthreads();
     }
@@ -990,7 +999,7 @@ __device__ void xp_f_task(const XpParams &p, int b, int g, unsigned char *smem)
     if (tid == 0 && evaluated) atomicAdd(p.far_cells, evaluated);
     xp_far_finish(p, b);
     if (tid == 0) {
-        const u64 work = (u64)(xp_clock() - tf1);
+        const u64 work = (u64)(xp_clock<PROF>() - tf1);
         atomicAdd(p.prof + XQ_F_WAIT, (u64)(tf1 - tf0));
         atomicAdd(p.prof + XQ_F_WORK, work);
         atomicAdd(p.prof + XQ_F_COUNT, 1ull);
@@ -1141,14 +1150,14 @@ __global__ void xp_consts_kernel(const int32_t *__restrict__ L, const int32_t *_
     out[2] = (double)zL;
 }
 
-template <bool AI, bool RING>
+template <bool AI, bool RING, bool PROF>
 __global__ void __launch_bounds__(XP_THREADS, 1)
 exact_pruned_kernel(XpParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int sTask;
     if (blockIdx.x == 0) {
-        xp_diagonal<AI, RING>(p, smem);
+        xp_diagonal<AI, RING, PROF>(p, smem);
         return;
     }
     while (true) {
@@ -1158,8 +1167,8 @@ exact_pruned_kernel(XpParams p)
         const int t = sTask;
         if (t >= p.n_tasks) return;
         const int2 task = __ldg(p.tasks + t);
-        if ((task.x & 1) == 0) xp_s_task<AI>(p, task.x >> 1, task.y, smem);
-        else if (task.y < XP_G) xp_f_task<AI>(p, task.x >> 1, task.y, smem);
+        if ((task.x & 1) == 0) xp_s_task<AI, PROF>(p, task.x >> 1, task.y, smem);
+        else if (task.y < XP_G) xp_f_task<AI, PROF>(p, task.x >> 1, task.y, smem);
         else if (task.y < XP_GT) xp_n_task<AI>(p, task.x >> 1, task.y - XP_G, smem);
         else xp_r_task(p, task.x >> 1);
     }
@@ -1254,7 +1263,9 @@ int run_exact_pruned(pasio_ctx *ctx, i64 N, int lag)
 
     xp_consts_kernel<AI><<<1, 1, 0, ctx->stream>>>(p.L, p.C, p.N, p.gtab, p.ltab, p.alpha_int, p.alpha, consts);
     const size_t smem = xp_diag_smem() > xp_worker_smem() ? xp_diag_smem() : xp_worker_smem();
-    void (*kern)(XpParams) = ring ? exact_pruned_kernel<AI, true> : exact_pruned_kernel<AI, false>;
+    static const bool with_counters = getenv("PASIO_XD_PROF") != nullptr || getenv("PASIO_XD_DBG") != nullptr;
+    void (*kern)(XpParams) = with_counters ? (ring ? exact_pruned_kernel<AI, true, true> : exact_pruned_kernel<AI, false, true>)
+                                           : (ring ? exact_pruned_kernel<AI, true, false> : exact_pruned_kernel<AI, false, false>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, XP_THREADS, smem));
