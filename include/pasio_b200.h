@@ -152,6 +152,14 @@ int pasio_round(pasio_ctx *ctx, int64_t window_size, int64_t window_shift, int c
  * with the exact far-column bound (csrc/window_dp.cu) instead of evaluating them.  After
  * pasio_square_split: the same two numbers for the whole-contig DP. */
 int pasio_round_stats(const pasio_ctx *ctx, int64_t *cells, int64_t *cells_skipped);
+/* The task list of the exact DP's worker CTAs (host only, no context, nothing is launched): for a candidate list of
+ * n_candidates entries, lag and nblock as in PASIO_TUNE_EXACT_LAG / PASIO_TUNE_EXACT_NBLOCK, the tasks in the order the
+ * worker CTAs pull them, as (row block, kind, slice) triples -- kind 0: S (self scores of the block, slice = quarter),
+ * 1: F (far columns, bounded), 2: N (the column blocks in front of the band, exhaustive), 3: R (records of the finished
+ * block, then done_block).  *n_tasks receives their number; PASIO_E_ARG when cap (in triples) is too small.  The flag
+ * waits of the kernel are deadlock-free because every task only waits for tasks earlier in this list or for the
+ * diagonal: tests/test_exact_task_plan.py checks that ordering for many shapes without a GPU. */
+int pasio_exact_task_plan(int64_t n_candidates, int lag, int nblock, int32_t *triples, int64_t cap, int64_t *n_tasks);
 /* Bytes the most recent pasio_contig_load_round put on the PCIe link (counts travel as uint16 or int32 where they fit,
  * PASIO_TUNE_UPLOAD_NARROW): n when every slice fitted 8 bits, 8 * n with plain copies. */
 int pasio_upload_stats(const pasio_ctx *ctx, int64_t *wire_bytes);

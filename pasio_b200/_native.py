@@ -48,6 +48,7 @@ SIGNATURES = {
     'pasio_filter_candidates': (ctypes.c_int, [_vp, ctypes.c_int, _i64p, _i64p]),
     'pasio_round': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64p, _i64p, _i64p]),
     'pasio_round_stats': (ctypes.c_int, [_vp, _i64p, _i64p]),
+    'pasio_exact_task_plan': (ctypes.c_int, [_i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), _i64, _i64p]),
     'pasio_upload_stats': (ctypes.c_int, [_vp, _i64p]),
     'pasio_set_tuning': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     'pasio_rounds': (ctypes.c_int, [_vp, _i64, _i64, ctypes.c_int, _i64, _i64p, _i64p, _i64p, _i64p, _i64]),

@@ -1331,3 +1331,21 @@ int launch_exact_dp_pruned(pasio_ctx *ctx, i64 N, int lag)
     PASIO_TRY(pasio_reserve(ctx, ctx->dpPrev, (size_t)N * 4));
     return ctx->alpha_is_int ? run_exact_pruned<true>(ctx, N, lag) : run_exact_pruned<false>(ctx, N, lag);
 }
+
+extern "C" int pasio_exact_task_plan(int64_t n_candidates, int lag, int nblock, int32_t *triples, int64_t cap, int64_t *n_tasks)
+{
+    if (n_candidates < 2 || lag < 3 || lag > 5 || !n_tasks) return PASIO_E_ARG;
+    const int nB = (int)((n_candidates - 1 + XP_RB - 1) / XP_RB);
+    const int nb = nblock < 0 ? 0 : (nblock > lag - 2 ? lag - 2 : nblock);      // as run_exact_pruned clamps it
+    const std::vector<int2> tasks = build_tasks(nB, lag, nb);
+    *n_tasks = (int64_t)tasks.size();
+    if (!triples || cap < (int64_t)tasks.size()) return PASIO_E_ARG;
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        const int b = tasks[i].x >> 1, y = tasks[i].y;
+        const int kind = (tasks[i].x & 1) == 0 ? 0 : (y < XP_G ? 1 : (y < XP_GT ? 2 : 3));
+        triples[3 * i] = b;
+        triples[3 * i + 1] = kind;
+        triples[3 * i + 2] = kind == 2 ? y - XP_G : (kind == 3 ? 0 : y);
+    }
+    return PASIO_OK;
+}
