@@ -6,22 +6,27 @@
 // are bit-identical to evaluating every cell: a cell is either evaluated in the reference's operation order or PROVED
 // unable to hold the arg-max or a tie (bound.cuh).
 //
-// One persistent cooperative launch, one CTA per SM.  Rows in blocks of 128, steps of 32.
-//   CTA 0 (diagonal) owns the dependent chain.  For row j its columns are split by distance:
-//       triangle  [jb, j)           chain warp, one shuffle-broadcast step per row
-//       near      [jb-32, jb)       chain warp, folded while those rows are being chained (a second accumulator)
-//       mid       [F_b, jb-32)      7 helper warps, one step ahead (F_b = first row of block b - lag + 1)
-//       far       [0, F_b)          worker CTAs, 'lag' - 1 blocks ahead, pruned
-//     The diagonal never gathers from the tables: all self scores within distance 128 * lag of the diagonal
-//     (P-independent) are produced ahead of it by workers into an L2-resident ring (S tasks) and only ADDED to the
-//     finished P_i here.
-//   Workers pull tasks from a fixed list: S(b, q) = a quarter of the self-score band of row block b; F(b, g) = the
-//     far columns of row block b (column blocks c = g mod 8), released when block b - lag is final:
+// One persistent cooperative launch, one CTA per SM.  Rows in blocks of 128, steps of 32 (defaults: lag 5, 3 N blocks).
+//   CTA 0 (diagonal) owns the dependent chain and does nothing else but add.  For row j its columns are split by distance:
+//       triangle  [jb, j)              chain warp, one shuffle-broadcast step per row
+//       near      [jb-32, jb)          chain warp, folded while those rows are being chained (a second accumulator)
+//       mid       [band_b, jb-32)      6 sweeping warps, one step ahead (band_b = first row of block b - 1)
+//       N blocks  [F_b, band_b)        worker CTAs, every cell (blocks b - lag + 1 .. b - 2), released by p_block
+//       far       [0, F_b)             worker CTAs, pruned (F_b = first row of block b - lag + 1), released by done_block
+//     The diagonal never gathers from the tables: the self scores of the band (P-independent) are produced ahead of it by
+//     workers into an L2-resident ring (S tasks, laid out per 32-row step) and only ADDED to the finished P_i here; the chain
+//     warp's tile of a step and the merged far results of a block arrive by bulk copy (cp.async.bulk + mbarrier), warp 4
+//     waits for them.  The records of finished columns (tilt fits, anchors, max |P|) are made by workers, too (R tasks).
+//   Workers pull tasks from a fixed list: S(b, q) = a quarter of the self-score band of row block b; R(b) = records of the
+//     finished block b, then done_block; N(b, g) = 16 columns of each N block; F(b, g) = the far columns of row block b
+//     (column groups q = g mod 8):
 //       lower bound of every row's maximum = best exactly evaluated cell over 8 anchors (the last final row and the
 //       arg-max columns of the rows before it -- the recent change points);
 //       128 x 128 rectangles against the tilted corner bound, survivors again as 32 x 32, again as 4 x 8, the rest
-//       evaluated exactly.  On BASELINE configs 1 and 3 under 1 % of the far cells survive (profiles/r02_*).
-//   Task order makes every wait depend on tasks earlier in the list, and all CTAs are co-resident: no deadlock.
+//       evaluated exactly.  On BASELINE configs 1 and 3 about 1 % of all cells are evaluated (profiles/r02_*).
+//     The task that finishes a row block's last F / N slice merges the slices into one (value, column) per row.
+//   Task order makes every wait depend on tasks earlier in the list or on the diagonal, and all CTAs are co-resident: no
+//   deadlock (pasio_exact_task_plan + tests/test_exact_task_plan.py check the order on a CPU).
 #include "bound.cuh"
 
 #include <cstdio>
@@ -36,7 +41,7 @@ constexpr int XP_THREADS = 256;
 constexpr int XP_HELP = 7;            // helper warps of the diagonal CTA: six sweep the mid columns, one (warp 4) keeps the books
 constexpr int XP_MIDW = 6;
 constexpr int XP_G = 8;               // far slices per row block
-constexpr int XP_NG = 8;              // slices of the column block next to the far region, evaluated exhaustively by workers (N tasks)
+constexpr int XP_NG = 8;              // slices of the column blocks next to the far region, evaluated exhaustively by workers (N tasks)
 constexpr int XP_GT = XP_G + XP_NG;   // result slices per row block
 constexpr int XP_SQ = 4;              // self-score sub-tasks per row block
 constexpr int XP_RING = 64;           // row blocks of self scores kept
@@ -70,7 +75,7 @@ static_assert(sizeof(XpRec32) == 144 && sizeof(XpAnchors) == 160, "record layout
 
 struct XpParams {
     int N, nB, nSteps, lag, DB, n_tasks, npad;
-    int nb;                     // 1: the first column block of the band (block b - lag + 1) is evaluated by worker CTAs (N tasks), not swept by the diagonal
+    int nb;                     // column blocks in front of the far columns (blocks b - lag + 1 ..) evaluated by worker CTAs (N tasks), not swept by the diagonal
     int dbg;                    // PASIO_XD_DBG (timing experiments only, results become wrong): 1 no mid sweep, 2 no records,
                                 // 4 no waiting for far results, 8 no tile moves, 16 mid: loads only, 32 mid: arithmetic only
     int s_slots;                // row blocks of self scores held: nB (every block has its own slab: written once per launch,
